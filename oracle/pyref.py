@@ -1,0 +1,67 @@
+"""Import shim for the scratch build of the Python reference (see build_pyref.py).
+
+TEST INFRASTRUCTURE ONLY - used in the build container to generate golden
+fixtures and by CPU tests that are skipped when the scratch build is absent.
+The product never imports this module.
+
+``import_anuga()`` registers stub modules for the third-party packages that
+the reference imports at module scope but that are not installed in this image
+ and returns the ``anuga`` package from the scratch
+tree.
+"""
+import os
+import sys
+import types
+
+PYREF_DIR = os.environ.get("ANUGA_PYREF", "/tmp/anuga_pyref")
+
+_STUBS = [
+    "matplotlib", "matplotlib.pyplot", "matplotlib.tri", "matplotlib.cm",
+    "matplotlib.colors", "matplotlib.animation", "matplotlib.figure",
+    "matplotlib.backends", "matplotlib.backends.backend_agg",
+    "netCDF4", "utm", "pyproj", "affine", "meshpy", "meshpy.triangle",
+    "pymetis", "osgeo", "osgeo.gdal", "osgeo.osr", "openpyxl", "xarray", "git",
+    "tomli",
+]
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Stub(self.__name__ + "." + name)
+
+    def __call__(self, *a, **k):
+        raise RuntimeError("stubbed third-party module %s was called" % self.__name__)
+
+
+def available():
+    return os.path.isdir(os.path.join(PYREF_DIR, "anuga"))
+
+
+def import_anuga(epart_fn=None):
+    """Return the reference ``anuga`` package.
+
+    epart_fn(nparts, adjacency) -> list  is installed as ``pymetis.part_graph``
+    so that partition tests can inject a deterministic element partition
+    (pymetis itself is absent).
+    """
+    if not available():
+        raise ImportError("python reference not built: run oracle/build_pyref.py")
+    for name in _STUBS:
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = _Stub(name)
+    if epart_fn is not None:
+        def part_graph(nparts, adjacency=None, **kw):
+            return 0, list(epart_fn(nparts, adjacency))
+        sys.modules["pymetis"].part_graph = part_graph
+    if PYREF_DIR not in sys.path:
+        sys.path.insert(0, PYREF_DIR)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import anuga
+    return anuga
