@@ -1,0 +1,14 @@
+"""anuga_core_b200 - B200-native backend for ANUGA's discontinuous-elevation
+shallow-water timestep (DE0/DE1/DE2): hand-written sm_100a CUDA behind the
+reference's shallow_water.Domain API.  See DESIGN.md and INTEGRATION.md."""
+from .mesh import Mesh, rectangular_cross, morton_order
+from .quantity import Quantity
+from .boundaries import (Reflective_boundary, Dirichlet_boundary, Transmissive_boundary, Time_boundary,
+                         Transmissive_n_momentum_zero_t_momentum_set_stage_boundary,
+                         Transmissive_momentum_set_stage_boundary,
+                         Transmissive_stage_zero_momentum_boundary, Time_stage_zero_momentum_boundary)
+from .operators import Rate_operator
+from .domain import Domain, rectangular_cross_domain, MODE_B200
+from .backend import SwkError, device_count
+
+__version__ = "0.1.0"

@@ -1,0 +1,164 @@
+"""Boundary condition objects with the reference's constructor signatures.
+
+Each object is a *descriptor*: it names one of the device boundary kinds of
+include/swk.h and, for time-dependent conditions, provides the host-evaluated
+scalars that are uploaded before every flux evaluation.  The arithmetic runs in
+k_boundary_values (csrc/swk_kernels.cuh) and follows evaluate_segment of
+
+  Reflective_boundary                      anuga/shallow_water/boundaries.py:235-288
+  Transmissive_momentum_set_stage_boundary                         :344-372
+  Transmissive_n_momentum_zero_t_momentum_set_stage_boundary       :477-517
+  Transmissive_stage_zero_momentum_boundary                        :543-551
+  Time_stage_zero_momentum_boundary                                :616-635
+  Transmissive_boundary    anuga/abstract_2d_finite_volumes/generic_boundary_conditions.py:173-193
+  Dirichlet_boundary                                               :221-264
+  Time_boundary                                                    :370-411
+"""
+import numpy as np
+
+from . import backend as _b
+
+
+class Boundary:
+    device_kind = _b.BC_NONE
+    time_dependent = False
+
+    def device_values(self, t):
+        return (0.0, 0.0, 0.0)
+
+    def oracle_spec(self):
+        """Specification tuple understood by the CPU oracle (tests only)."""
+        raise NotImplementedError
+
+
+class Reflective_boundary(Boundary):
+    device_kind = _b.BC_REFLECTIVE
+
+    def __init__(self, domain=None):
+        if domain is None:
+            raise Exception("Domain must be specified for reflective boundary")
+        self.domain = domain
+
+    def __repr__(self):
+        return "Reflective_boundary"
+
+    def oracle_spec(self):
+        return ("reflective",)
+
+
+class Dirichlet_boundary(Boundary):
+    device_kind = _b.BC_DIRICHLET
+
+    def __init__(self, dirichlet_values=None):
+        if dirichlet_values is None:
+            raise Exception("Must specify one value for each quantity")
+        self.dirichlet_values = np.array(dirichlet_values, dtype=np.float64)
+        if self.dirichlet_values.size < 3:
+            raise Exception("Dirichlet boundary needs stage, xmomentum, ymomentum")
+
+    def __repr__(self):
+        return "Dirichlet boundary (%s)" % self.dirichlet_values
+
+    def device_values(self, t):
+        return tuple(float(v) for v in self.dirichlet_values[:3])
+
+    def oracle_spec(self):
+        return ("dirichlet", [float(v) for v in self.dirichlet_values[:3]])
+
+
+class Transmissive_boundary(Boundary):
+    device_kind = _b.BC_TRANSMISSIVE
+
+    def __init__(self, domain=None):
+        if domain is None:
+            raise Exception("Domain must be specified for transmissive boundary")
+        self.domain = domain
+
+    def __repr__(self):
+        return "Transmissive_boundary(%s)" % self.domain
+
+    def oracle_spec(self):
+        return ("transmissive",)
+
+
+class Time_boundary(Boundary):
+    """Dirichlet values given as a function of time, evaluated on the host before
+    each flux evaluation."""
+    device_kind = _b.BC_DIRICHLET
+    time_dependent = True
+
+    def __init__(self, domain=None, function=None, default_boundary=None, verbose=False):
+        if domain is None:
+            raise Exception("You must specify a domain to Time_boundary")
+        if function is None:
+            raise Exception("You must specify a function to Time_boundary")
+        q = np.asarray(function(0.0), dtype=np.float64)
+        if q.size < 3:
+            raise Exception("Time_boundary function must return (stage, xmomentum, ymomentum)")
+        self.domain = domain
+        self.function = function
+
+    def __repr__(self):
+        return "Time boundary"
+
+    def device_values(self, t):
+        q = np.asarray(self.function(t), dtype=np.float64)
+        return (float(q[0]), float(q[1]), float(q[2]))
+
+    def oracle_spec(self):
+        return ("time", self.function)
+
+
+class _Set_stage(Boundary):
+    time_dependent = True
+    _oracle_kind = None
+
+    def __init__(self, domain=None, function=None, default_boundary=0.0):
+        if domain is None:
+            raise Exception("Domain must be specified for this type boundary")
+        if function is None:
+            raise Exception("Function must be specified for this type boundary")
+        if isinstance(function, (int, float)):
+            tmp = function
+            function = lambda t: tmp
+        self.domain = domain
+        self.function = function
+        self.default_boundary = default_boundary
+
+    def device_values(self, t):
+        value = self.function(t)
+        try:
+            x = float(value)
+        except Exception:
+            x = float(value[0])
+        return (x, 0.0, 0.0)
+
+    def oracle_spec(self):
+        return (self._oracle_kind, self.function)
+
+
+class Transmissive_n_momentum_zero_t_momentum_set_stage_boundary(_Set_stage):
+    device_kind = _b.BC_TRANSMISSIVE_N_ZERO_T_SET_STAGE
+    _oracle_kind = "transmissive_n_zero_t_set_stage"
+
+
+class Transmissive_momentum_set_stage_boundary(_Set_stage):
+    device_kind = _b.BC_TRANSMISSIVE_MOMENTUM_SET_STAGE
+    _oracle_kind = "transmissive_momentum_set_stage"
+
+
+class Time_stage_zero_momentum_boundary(_Set_stage):
+    device_kind = _b.BC_DIRICHLET
+    _oracle_kind = "time_stage_zero_momentum"
+
+
+class Transmissive_stage_zero_momentum_boundary(Boundary):
+    device_kind = _b.BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM
+
+    def __init__(self, domain=None):
+        if domain is None:
+            raise Exception("Domain must be specified for Transmissive_stage_zero_momentum boundary")
+        self.domain = domain
+
+    def oracle_spec(self):
+        return ("transmissive_stage_zero_momentum",)

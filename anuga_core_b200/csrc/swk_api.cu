@@ -1,0 +1,1474 @@
+// swk_api.cu - host side of libswk.so: the C ABI declared in include/swk.h.
+//
+// Build (see __graft_entry__.build / anuga_core_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false \
+//        -Xcompiler -fPIC,-ffp-contract=off -shared -o libswk.so swk_api.cu
+//
+// No CPU fallback: every entry point needs a CUDA device that can run sm_100a code.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/swk.h"
+#include "swk_kernels.cuh"
+
+using namespace swk;
+
+// ----------------------------------------------------------------------------
+// error handling
+// ----------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(SWK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+#define CKV(call)                                                                       \
+  do {                                                                                  \
+    int r_ = (call);                                                                    \
+    if (r_ != SWK_OK) return r_;                                                        \
+  } while (0)
+
+static inline int nblk(long long n) { return (int)((n + BLOCK - 1) / BLOCK); }
+static inline double u2d_host(unsigned long long u) { double x; memcpy(&x, &u, 8); return x; }
+
+// ----------------------------------------------------------------------------
+// NCCL, loaded at run time so that single-GPU use has no NCCL dependency
+// ----------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };
+enum { ncclSumOp = 0, ncclMinOp = 3 };
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+  if (g_nccl.lib) return SWK_OK;
+  const char *env = getenv("SWK_NCCL_LIB");
+  const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+  void *lib = nullptr;
+  for (const char *n : names) {
+    if (!n) continue;
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) return fail(SWK_ERR_NCCL, "cannot dlopen libnccl.so.2 (set SWK_NCCL_LIB)");
+#define SYM(field, name)                                                        \
+  *(void **)(&g_nccl.field) = dlsym(lib, name);                                 \
+  if (!g_nccl.field) return fail(SWK_ERR_NCCL, std::string("missing symbol ") + name);
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.lib = lib;
+  return SWK_OK;
+}
+
+#define NK(call)                                                                        \
+  do {                                                                                  \
+    ncclResult_t r_ = (call);                                                           \
+    if (r_ != 0)                                                                        \
+      return fail(SWK_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+// ----------------------------------------------------------------------------
+// the handle
+// ----------------------------------------------------------------------------
+struct RateOp {
+  double rate, factor;
+  double *d_rate_array = nullptr;
+  int *d_indices = nullptr;
+  int n = 0;
+  int all_nonneg = 1;
+  double *d_partial = nullptr;
+  int nblocks = 0;
+};
+
+struct Peer {
+  int rank;
+  int n_send = 0, n_recv = 0;
+  int *d_send_ids = nullptr, *d_recv_ids = nullptr;
+  double *d_send_buf = nullptr, *d_recv_buf = nullptr;
+};
+
+struct swk_domain {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t N = 0, M = 0, NP = 0;
+  swk_params P;
+  Consts K;
+  TimeParams TP;
+  Dev D;
+  bool has_riverwalls = false;
+  bool per_call = false;
+
+  std::vector<int> new2old, old2new;
+  int *d_new2old = nullptr;
+  int *d_ident_b = nullptr;   // identity for boundary arrays
+
+  // owned device memory
+  d4 *cq = nullptr, *eq = nullptr, *xg = nullptr, *fg = nullptr, *bq = nullptr;
+  i4 *connA = nullptr, *connB = nullptr;
+  double *eu = nullptr, *bk = nullptr, *eta = nullptr, *max_speed = nullptr, *vcoord = nullptr;
+  unsigned char *zflag = nullptr;
+  int *rw_counter = nullptr, *rw_rowIndex = nullptr;
+  double *rw_elevation = nullptr, *rw_hydraulic = nullptr;
+  Clock *d_clock = nullptr, *h_clock = nullptr;
+  double *staging = nullptr;     // 3*N doubles
+  size_t staging_n = 0;
+  int *d_acct = nullptr;
+  int n_acct = 0;
+
+  // boundary
+  int *b_cell = nullptr, *b_edge = nullptr, *b_seg = nullptr;
+  std::vector<int> h_b_seg;
+  std::vector<int> seg_kind;
+  std::vector<double> seg_val;
+  int *d_seg_kind = nullptr;
+  double *d_seg_val = nullptr;
+  int seg_cap = 0;
+  bool seg_dirty = true;
+
+  std::vector<RateOp> rate_ops;
+  int *d_ghost_full = nullptr, *d_ghost_ghost = nullptr;
+  int n_ghost_copy = 0;
+
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  std::vector<Peer> peers;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_update = nullptr, ev_halo = nullptr;
+  double *d_dt_scratch = nullptr;
+
+  int64_t launches = 0;
+};
+
+static void make_consts(swk_domain *d)
+{
+  const swk_params &p = d->P;
+  Consts &K = d->K;
+  K.epsilon = p.epsilon;
+  K.g = p.g;
+  K.mah = p.minimum_allowed_height;
+  K.beta_w = p.beta_w; K.beta_w_dry = p.beta_w_dry;
+  K.beta_uh = p.beta_uh; K.beta_uh_dry = p.beta_uh_dry;
+  K.beta_vh = p.beta_vh; K.beta_vh_dry = p.beta_vh_dry;
+  K.evolve_max_timestep = p.evolve_max_timestep;
+  K.vel2 = p.extrapolate_velocity_second_order ? 1 : 0;
+  K.low_froude = (int)p.low_froude;
+  K.protect = 1;
+  K.pad = 0;
+  TimeParams &T = d->TP;
+  T.CFL = p.CFL;
+  T.evolve_max_timestep = p.evolve_max_timestep;
+  T.evolve_min_timestep = p.evolve_min_timestep;
+  T.fixed_flux_timestep = p.fixed_flux_timestep;
+  T.epsilon = p.epsilon;
+  T.max_smallsteps = (int)p.max_smallsteps;
+  T.default_order = (int)p.default_order;
+  T.method = (int)p.timestepping_method;
+}
+
+static int check_params(const swk_params *p)
+{
+  if (!p) return fail(SWK_ERR_ARG, "params is NULL");
+  if (p->timestepping_method < 1 || p->timestepping_method > 3)
+    return fail(SWK_ERR_ARG, "timestepping_method must be 1 (euler), 2 (rk2) or 3 (rk3)");
+  if (p->maximum_allowed_speed != 0.0)
+    return fail(SWK_ERR_UNSUPPORTED, "maximum_allowed_speed != 0 is not part of the DE path");
+  return SWK_OK;
+}
+
+template <typename T>
+static int dalloc(T **p, size_t n)
+{
+  *p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+  if (e != cudaSuccess) return fail(SWK_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  return SWK_OK;
+}
+
+template <typename T>
+static int upload(T *dst, const std::vector<T> &v)
+{
+  if (v.empty()) return SWK_OK;
+  CK(cudaMemcpy(dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return SWK_OK;
+}
+
+extern "C" const char *swk_last_error(void) { return g_err.c_str(); }
+extern "C" int swk_abi_version(void) { return SWK_ABI_VERSION; }
+
+extern "C" int swk_device_count(int *count)
+{
+  if (!count) return fail(SWK_ERR_ARG, "count is NULL");
+  *count = 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(SWK_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  int ok = 0;
+  for (int i = 0; i < n; i++) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ok++;
+  }
+  *count = ok;
+  if (ok == 0) return fail(SWK_ERR_CUDA, "no sm_100 device visible");
+  return SWK_OK;
+}
+
+static int select_device(int device)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SWK_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0") +
+                                  " (libswk has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(SWK_ERR_ARG, "device index out of range");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SWK_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100: libswk contains sm_100a code only");
+  CK(cudaSetDevice(device));
+  return SWK_OK;
+}
+
+// ----------------------------------------------------------------------------
+// create / destroy
+// ----------------------------------------------------------------------------
+extern "C" int swk_destroy(swk_domain *d)
+{
+  if (!d) return SWK_OK;
+  cudaSetDevice(d->device);
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  void *ptrs[] = {d->cq, d->eq, d->xg, d->fg, d->bq, d->connA, d->connB, d->eu, d->bk, d->eta, d->max_speed,
+                  d->vcoord, d->zflag, d->rw_counter, d->rw_rowIndex, d->rw_elevation, d->rw_hydraulic,
+                  d->d_clock, d->staging, d->d_acct, d->b_cell, d->b_edge, d->b_seg, d->d_seg_kind,
+                  d->d_seg_val, d->d_new2old, d->d_ghost_full, d->d_ghost_ghost, d->d_dt_scratch, d->d_ident_b};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (auto &op : d->rate_ops) {
+    if (op.d_rate_array) cudaFree(op.d_rate_array);
+    if (op.d_indices) cudaFree(op.d_indices);
+    if (op.d_partial) cudaFree(op.d_partial);
+  }
+  for (auto &pe : d->peers) {
+    if (pe.d_send_ids) cudaFree(pe.d_send_ids);
+    if (pe.d_recv_ids) cudaFree(pe.d_recv_ids);
+    if (pe.d_send_buf) cudaFree(pe.d_send_buf);
+    if (pe.d_recv_buf) cudaFree(pe.d_recv_buf);
+  }
+  if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+  if (d->h_clock) cudaFreeHost(d->h_clock);
+  if (d->ev_update) cudaEventDestroy(d->ev_update);
+  if (d->ev_halo) cudaEventDestroy(d->ev_halo);
+  if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+  return SWK_OK;
+}
+
+static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_domain *d)
+{
+  d->device = device;
+  d->P = *p;
+  make_consts(d);
+  const int64_t N = d->N = m->number_of_elements;
+  const int64_t M = d->M = m->boundary_length;
+  if (N <= 0) return fail(SWK_ERR_ARG, "number_of_elements must be positive");
+  if (N >= (1LL << 29)) return fail(SWK_ERR_ARG, "number_of_elements must be < 2^29 per device");
+  const int64_t NP = d->NP = (N + 63) / 64 * 64;
+  if (!m->neighbours || !m->neighbour_edges || !m->surrogate_neighbours || !m->number_of_boundaries ||
+      !m->tri_full_flag || !m->normals || !m->edgelengths || !m->radii || !m->areas ||
+      !m->centroid_coordinates || !m->edge_coordinates || (M > 0 && (!m->boundary_cells || !m->boundary_edges)))
+    return fail(SWK_ERR_ARG, "mesh has NULL arrays");
+  CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+
+  // permutation
+  d->new2old.resize(N);
+  d->old2new.resize(N);
+  if (m->permutation) {
+    std::vector<char> seen(N, 0);
+    for (int64_t k = 0; k < N; k++) {
+      const int64_t o = m->permutation[k];
+      if (o < 0 || o >= N || seen[o]) return fail(SWK_ERR_ARG, "permutation is not a bijection");
+      seen[o] = 1;
+      d->new2old[k] = (int)o;
+      d->old2new[o] = (int)k;
+    }
+  } else {
+    for (int64_t k = 0; k < N; k++) d->new2old[k] = d->old2new[k] = (int)k;
+  }
+  const std::vector<int> &n2o = d->new2old, &o2n = d->old2new;
+
+  // riverwalls?
+  d->has_riverwalls = false;
+  if (m->edge_flux_type && m->number_of_riverwall_edges > 0)
+    for (int64_t j = 0; j < 3 * N; j++)
+      if (m->edge_flux_type[j] == 1) { d->has_riverwalls = true; break; }
+
+  // ---- static records, built in device order with the reference's arithmetic ----
+  std::vector<i4> connA(NP), connB(NP);
+  std::vector<d4> xg(3 * NP), fg(3 * NP);
+  std::vector<int> acct;
+  const double *cc = m->centroid_coordinates, *ec = m->edge_coordinates;
+  for (int64_t k = 0; k < NP; k++) {
+    if (k >= N) {   // padding: self-referencing dry cell, never executed (k >= N guards) but keep it sane
+      connA[k] = {(int)0, (int)0, (int)0, 3};
+      connB[k] = {-1, -1, -1, 0};
+      continue;
+    }
+    const int64_t o = n2o[k];
+    const double x = cc[2 * o], y = cc[2 * o + 1];
+    double dxv[3], dyv[3];
+    for (int i = 0; i < 3; i++) {
+      dxv[i] = ec[6 * o + 2 * i] - x;           // sw_domain_openmp.c:1445-1450
+      dyv[i] = ec[6 * o + 2 * i + 1] - y;
+    }
+    const int64_t s0 = m->surrogate_neighbours[3 * o], s1 = m->surrogate_neighbours[3 * o + 1],
+                  s2 = m->surrogate_neighbours[3 * o + 2];
+    const int nb = (int)m->number_of_boundaries[o];
+    double dx1 = 0, dx2 = 0, dy1 = 0, dy2 = 0, inv_area2 = 0;
+    int which = 0;
+    if (nb <= 1) {
+      const double x0 = cc[2 * s0], y0 = cc[2 * s0 + 1];
+      const double x1 = cc[2 * s1], y1 = cc[2 * s1 + 1];
+      const double x2 = cc[2 * s2], y2 = cc[2 * s2 + 1];
+      dx1 = x1 - x0; dx2 = x2 - x0; dy1 = y1 - y0; dy2 = y2 - y0;    // :1477-1480
+      const double area2 = dy2 * dx1 - dy1 * dx2;                    // :1484
+      inv_area2 = 1.0 / area2;                                       // :1553
+    } else if (nb == 2) {
+      const int64_t ss[3] = {s0, s1, s2};
+      which = 2;
+      for (int i = 0; i < 3; i++)
+        if (ss[i] != o) { which = i; break; }                        // :1656-1674
+      const int64_t kn = ss[which];
+      dx1 = cc[2 * kn] - x;                                          // :1684-1696
+      dy1 = cc[2 * kn + 1] - y;
+      const double dist2 = dx1 * dx1 + dy1 * dy1;
+      dx2 = 1.0 / dist2;
+      dy2 = dx2 * dy1;
+      dx2 *= dx1;
+    }
+    connA[k] = {o2n[s0], o2n[s1], o2n[s2], (nb & 3) | (which << 2)};
+    xg[k] = {dxv[0], dxv[1], dxv[2], dyv[0]};
+    xg[NP + k] = {dyv[1], dyv[2], dx1, dx2};
+    xg[2 * NP + k] = {dy1, dy2, inv_area2, m->areas[o]};
+
+    const double *nr = m->normals + 6 * o;
+    const double *el = m->edgelengths + 3 * o;
+    fg[k] = {nr[0], nr[1], nr[2], nr[3]};
+    fg[NP + k] = {nr[4], nr[5], el[0], el[1]};
+    fg[2 * NP + k] = {el[2], 1.0 / m->areas[o], m->radii[o], m->areas[o]};   // inv_area: :714
+
+    int pk[3];
+    int flags = (m->tri_full_flag[o] == 1) ? 1 : 0;
+    for (int i = 0; i < 3; i++) {
+      const int64_t n = m->neighbours[3 * o + i];
+      if (n < 0) {
+        if (-n - 1 >= M) return fail(SWK_ERR_ARG, "neighbours holds a boundary index >= boundary_length");
+        pk[i] = (int)n;
+      } else {
+        pk[i] = (o2n[n] << 2) | (int)m->neighbour_edges[3 * o + i];
+      }
+      if (d->has_riverwalls && m->edge_flux_type[3 * o + i] == 1) flags |= (2 << i);
+    }
+    connB[k] = {pk[0], pk[1], pk[2], flags};
+  }
+  // boundary-flux accounting edges in the reference's (k, i) order (:696)
+  for (int64_t o = 0; o < N; o++) {
+    if (m->tri_full_flag[o] != 1) continue;
+    for (int i = 0; i < 3; i++) {
+      const int64_t n = m->neighbours[3 * o + i];
+      if (n < 0 || m->tri_full_flag[n] == 0) acct.push_back((o2n[o] << 2) | i);
+    }
+  }
+  d->n_acct = (int)acct.size();
+
+  CKV(dalloc(&d->connA, NP)); CKV(upload(d->connA, connA));
+  CKV(dalloc(&d->connB, NP)); CKV(upload(d->connB, connB));
+  CKV(dalloc(&d->xg, 3 * NP)); CKV(upload(d->xg, xg));
+  CKV(dalloc(&d->fg, 3 * NP)); CKV(upload(d->fg, fg));
+  CKV(dalloc(&d->d_acct, acct.size())); CKV(upload(d->d_acct, acct));
+  CKV(dalloc(&d->d_new2old, N)); CKV(upload(d->d_new2old, d->new2old));
+  {
+    std::vector<i4>().swap(connA); std::vector<i4>().swap(connB);
+    std::vector<d4>().swap(xg); std::vector<d4>().swap(fg);
+  }
+
+  if (p->use_sloped_mannings) {
+    if (!m->vertex_coordinates) return fail(SWK_ERR_ARG, "sloped Manning needs vertex_coordinates");
+    std::vector<double> vc(6 * NP, 0.0);
+    for (int64_t k = 0; k < N; k++)
+      for (int j = 0; j < 6; j++) vc[j * NP + k] = m->vertex_coordinates[6 * n2o[k] + j];
+    CKV(dalloc(&d->vcoord, 6 * NP)); CKV(upload(d->vcoord, vc));
+  }
+  if (d->has_riverwalls) {
+    std::vector<int> rc(3 * NP, 0);
+    int64_t maxc = 0;
+    for (int64_t k = 0; k < N; k++)
+      for (int i = 0; i < 3; i++) {
+        rc[i * NP + k] = (int)m->edge_river_wall_counter[3 * n2o[k] + i];
+        maxc = std::max<int64_t>(maxc, rc[i * NP + k]);
+      }
+    if (maxc > m->number_of_riverwall_edges) return fail(SWK_ERR_ARG, "edge_river_wall_counter exceeds number_of_riverwall_edges");
+    CKV(dalloc(&d->rw_counter, 3 * NP)); CKV(upload(d->rw_counter, rc));
+    const int64_t nrw = m->number_of_riverwall_edges;
+    std::vector<double> re(m->riverwall_elevation, m->riverwall_elevation + nrw);
+    std::vector<int> ri(nrw);
+    int64_t maxrow = 0;
+    for (int64_t j = 0; j < nrw; j++) { ri[j] = (int)m->riverwall_rowIndex[j]; maxrow = std::max<int64_t>(maxrow, ri[j]); }
+    const int64_t ncol = m->ncol_riverwall_hydraulic_properties;
+    std::vector<double> rh(m->riverwall_hydraulic_properties, m->riverwall_hydraulic_properties + (maxrow + 1) * ncol);
+    CKV(dalloc(&d->rw_elevation, nrw)); CKV(upload(d->rw_elevation, re));
+    CKV(dalloc(&d->rw_rowIndex, nrw)); CKV(upload(d->rw_rowIndex, ri));
+    CKV(dalloc(&d->rw_hydraulic, rh.size())); CKV(upload(d->rw_hydraulic, rh));
+  }
+
+  // boundary index arrays
+  {
+    std::vector<int> bc(M), be(M), ident(std::max<int64_t>(M, 1));
+    for (int64_t j = 0; j < M; j++) {
+      const int64_t vol = m->boundary_cells[j];
+      if (vol < 0 || vol >= N) return fail(SWK_ERR_ARG, "boundary_cells out of range");
+      bc[j] = o2n[vol];
+      be[j] = (int)m->boundary_edges[j];
+      ident[j] = (int)j;
+    }
+    d->h_b_seg.assign(M, -1);
+    CKV(dalloc(&d->b_cell, M)); CKV(upload(d->b_cell, bc));
+    CKV(dalloc(&d->b_edge, M)); CKV(upload(d->b_edge, be));
+    CKV(dalloc(&d->b_seg, M)); CKV(upload(d->b_seg, d->h_b_seg));
+    CKV(dalloc(&d->d_ident_b, M)); CKV(upload(d->d_ident_b, ident));
+  }
+
+  // dynamic arrays
+  CKV(dalloc(&d->cq, NP)); CK(cudaMemset(d->cq, 0, NP * sizeof(d4)));
+  CKV(dalloc(&d->eq, 3 * NP)); CK(cudaMemset(d->eq, 0, 3 * NP * sizeof(d4)));
+  CKV(dalloc(&d->bq, M)); CK(cudaMemset(d->bq, 0, std::max<int64_t>(M, 1) * sizeof(d4)));
+  CKV(dalloc(&d->eu, 3 * NP)); CK(cudaMemset(d->eu, 0, 3 * NP * sizeof(double)));
+  CKV(dalloc(&d->bk, 3 * NP)); CK(cudaMemset(d->bk, 0, 3 * NP * sizeof(double)));
+  CKV(dalloc(&d->eta, NP)); CK(cudaMemset(d->eta, 0, NP * sizeof(double)));
+  CKV(dalloc(&d->max_speed, NP)); CK(cudaMemset(d->max_speed, 0, NP * sizeof(double)));
+  CKV(dalloc(&d->zflag, NP)); CK(cudaMemset(d->zflag, 0, NP));
+  CKV(dalloc(&d->d_clock, 1)); CK(cudaMemset(d->d_clock, 0, sizeof(Clock)));
+  CK(cudaHostAlloc((void **)&d->h_clock, sizeof(Clock), cudaHostAllocDefault));
+  memset(d->h_clock, 0, sizeof(Clock));
+  d->h_clock->order = (int)p->default_order;
+  d->h_clock->finaltime = -1.0;
+  d->h_clock->yieldtime = 0.0;
+  d->h_clock->recorded_min_timestep = p->evolve_max_timestep;
+  d->h_clock->recorded_max_timestep = p->evolve_min_timestep;
+  d->h_clock->dt_min_bits = 0x7FF0000000000000ULL;
+  CK(cudaMemcpy(d->d_clock, d->h_clock, sizeof(Clock), cudaMemcpyHostToDevice));
+
+  Dev &D = d->D;
+  D.N = (int)N; D.NP = (int)NP; D.M = (int)M;
+  D.cq = d->cq; D.eq = d->eq; D.xg = d->xg; D.fg = d->fg;
+  D.connA = d->connA; D.connB = d->connB;
+  D.eu = d->eu; D.bk = d->bk; D.eta = d->eta; D.zflag = d->zflag; D.max_speed = d->max_speed;
+  D.bq = d->bq; D.vcoord = d->vcoord; D.clock = d->d_clock;
+  D.rw_counter = d->rw_counter; D.rw_elevation = d->rw_elevation; D.rw_rowIndex = d->rw_rowIndex;
+  D.rw_hydraulic = d->rw_hydraulic; D.rw_ncol = (int)m->ncol_riverwall_hydraulic_properties;
+  CK(cudaDeviceSynchronize());
+  return SWK_OK;
+}
+
+extern "C" int swk_create(const swk_mesh *mesh, const swk_params *params, int device, swk_domain **out)
+{
+  if (!mesh || !out) return fail(SWK_ERR_ARG, "mesh/out is NULL");
+  *out = nullptr;
+  CKV(check_params(params));
+  CKV(select_device(device));
+  swk_domain *d = new swk_domain();
+  int r = create_impl(mesh, params, device, d);
+  if (r != SWK_OK) {
+    std::string keep = g_err;
+    swk_destroy(d);
+    g_err = keep;
+    return r;
+  }
+  *out = d;
+  return SWK_OK;
+}
+
+extern "C" int swk_set_params(swk_domain *d, const swk_params *params)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CKV(check_params(params));
+  if (params->use_sloped_mannings && !d->vcoord)
+    return fail(SWK_ERR_ARG, "use_sloped_mannings must be chosen at swk_create (vertex coordinates are uploaded there)");
+  d->P = *params;
+  make_consts(d);
+  return SWK_OK;
+}
+
+// ----------------------------------------------------------------------------
+// quantity transfer
+// ----------------------------------------------------------------------------
+static int ensure_staging(swk_domain *d, size_t n)
+{
+  if (d->staging_n >= n) return SWK_OK;
+  if (d->staging) cudaFree(d->staging);
+  d->staging = nullptr;
+  d->staging_n = 0;
+  CKV(dalloc(&d->staging, n));
+  d->staging_n = n;
+  return SWK_OK;
+}
+
+#define LAUNCH(d, kernel, grid, block, ...)                          \
+  do {                                                               \
+    kernel<<<(grid), (block), 0, (d)->stream>>>(__VA_ARGS__);        \
+    (d)->launches++;                                                 \
+  } while (0)
+
+static int sync_check(swk_domain *d)
+{
+  CK(cudaStreamSynchronize(d->stream));
+  CK(cudaGetLastError());
+  return SWK_OK;
+}
+
+extern "C" int swk_set_quantity(swk_domain *d, int q, const double *host, int64_t n)
+{
+  if (!d || !host) return fail(SWK_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(d->device));
+  const int N = (int)d->N, NP = (int)d->NP, M = (int)d->M;
+  int64_t expect = N;
+  if ((q >= 10 && q < 30)) expect = 3LL * N;
+  if (q >= 30 && q < 40) expect = M;
+  if (n != expect) return fail(SWK_ERR_ARG, "swk_set_quantity: wrong element count");
+  if (n == 0) return SWK_OK;
+  CKV(ensure_staging(d, (size_t)std::max<int64_t>(3LL * N, M)));
+  CK(cudaMemcpyAsync(d->staging, host, n * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  switch (q) {
+    case SWK_Q_STAGE_C: LAUNCH(d, k_scatter_component, nblk(N), BLOCK, d->cq, NP, N, 1, 0, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_C: LAUNCH(d, k_scatter_component, nblk(N), BLOCK, d->cq, NP, N, 1, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_C: LAUNCH(d, k_scatter_component, nblk(N), BLOCK, d->cq, NP, N, 1, 2, d->staging, d->d_new2old); break;
+    case SWK_Q_ELEVATION_C: LAUNCH(d, k_scatter_component, nblk(N), BLOCK, d->cq, NP, N, 1, 3, d->staging, d->d_new2old); break;
+    case SWK_Q_FRICTION_C: LAUNCH(d, k_scatter_plain, nblk(N), BLOCK, d->eta, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_STAGE_E: LAUNCH(d, k_scatter_component, nblk(3LL * N), BLOCK, d->eq, NP, N, 3, 0, d->staging, d->d_new2old); break;
+    case SWK_Q_HEIGHT_E: LAUNCH(d, k_scatter_component, nblk(3LL * N), BLOCK, d->eq, NP, N, 3, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_E: LAUNCH(d, k_scatter_component, nblk(3LL * N), BLOCK, d->eq, NP, N, 3, 2, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_E: LAUNCH(d, k_scatter_component, nblk(3LL * N), BLOCK, d->eq, NP, N, 3, 3, d->staging, d->d_new2old); break;
+    case SWK_Q_STAGE_B: LAUNCH(d, k_scatter_component, nblk(M), BLOCK, d->bq, M, M, 1, 0, d->staging, d->d_ident_b); break;
+    case SWK_Q_XMOM_B: LAUNCH(d, k_scatter_component, nblk(M), BLOCK, d->bq, M, M, 1, 1, d->staging, d->d_ident_b); break;
+    case SWK_Q_YMOM_B: LAUNCH(d, k_scatter_component, nblk(M), BLOCK, d->bq, M, M, 1, 2, d->staging, d->d_ident_b); break;
+    case SWK_Q_STAGE_EU: LAUNCH(d, k_scatter_plain, nblk(N), BLOCK, d->eu, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_EU: LAUNCH(d, k_scatter_plain, nblk(N), BLOCK, d->eu + NP, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_EU: LAUNCH(d, k_scatter_plain, nblk(N), BLOCK, d->eu + 2 * NP, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_STAGE_BACKUP: LAUNCH(d, k_scatter_plain, nblk(N), BLOCK, d->bk, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_BACKUP: LAUNCH(d, k_scatter_plain, nblk(N), BLOCK, d->bk + NP, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_BACKUP: LAUNCH(d, k_scatter_plain, nblk(N), BLOCK, d->bk + 2 * NP, NP, N, 1, d->staging, d->d_new2old); break;
+    default: return fail(SWK_ERR_ARG, "swk_set_quantity: quantity id is not settable");
+  }
+  return sync_check(d);
+}
+
+extern "C" int swk_get_quantity(swk_domain *d, int q, double *host, int64_t n)
+{
+  if (!d || !host) return fail(SWK_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(d->device));
+  const int N = (int)d->N, NP = (int)d->NP, M = (int)d->M;
+  int64_t expect = N;
+  if ((q >= 10 && q < 30)) expect = 3LL * N;
+  if (q >= 30 && q < 40) expect = M;
+  if (n != expect) return fail(SWK_ERR_ARG, "swk_get_quantity: wrong element count");
+  if (n == 0) return SWK_OK;
+  CKV(ensure_staging(d, (size_t)std::max<int64_t>(3LL * N, M)));
+  switch (q) {
+    case SWK_Q_STAGE_C: LAUNCH(d, k_gather_component, nblk(N), BLOCK, d->cq, NP, N, 1, 0, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_C: LAUNCH(d, k_gather_component, nblk(N), BLOCK, d->cq, NP, N, 1, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_C: LAUNCH(d, k_gather_component, nblk(N), BLOCK, d->cq, NP, N, 1, 2, d->staging, d->d_new2old); break;
+    case SWK_Q_ELEVATION_C: LAUNCH(d, k_gather_component, nblk(N), BLOCK, d->cq, NP, N, 1, 3, d->staging, d->d_new2old); break;
+    case SWK_Q_FRICTION_C: LAUNCH(d, k_gather_plain, nblk(N), BLOCK, d->eta, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_HEIGHT_C: LAUNCH(d, k_gather_derived, nblk(N), BLOCK, d->D, d->K, 0, d->staging, d->d_new2old); break;
+    case SWK_Q_STAGE_E: LAUNCH(d, k_gather_component, nblk(3LL * N), BLOCK, d->eq, NP, N, 3, 0, d->staging, d->d_new2old); break;
+    case SWK_Q_HEIGHT_E: LAUNCH(d, k_gather_component, nblk(3LL * N), BLOCK, d->eq, NP, N, 3, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_E: LAUNCH(d, k_gather_component, nblk(3LL * N), BLOCK, d->eq, NP, N, 3, 2, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_E: LAUNCH(d, k_gather_component, nblk(3LL * N), BLOCK, d->eq, NP, N, 3, 3, d->staging, d->d_new2old); break;
+    case SWK_Q_ELEVATION_E: LAUNCH(d, k_gather_derived, nblk(N), BLOCK, d->D, d->K, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_STAGE_V: LAUNCH(d, k_gather_derived, nblk(N), BLOCK, d->D, d->K, 2, d->staging, d->d_new2old); break;
+    case SWK_Q_HEIGHT_V: LAUNCH(d, k_gather_derived, nblk(N), BLOCK, d->D, d->K, 3, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_V: LAUNCH(d, k_gather_derived, nblk(N), BLOCK, d->D, d->K, 4, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_V: LAUNCH(d, k_gather_derived, nblk(N), BLOCK, d->D, d->K, 5, d->staging, d->d_new2old); break;
+    case SWK_Q_ELEVATION_V: LAUNCH(d, k_gather_derived, nblk(N), BLOCK, d->D, d->K, 6, d->staging, d->d_new2old); break;
+    case SWK_Q_STAGE_B: LAUNCH(d, k_gather_component, nblk(M), BLOCK, d->bq, M, M, 1, 0, d->staging, d->d_ident_b); break;
+    case SWK_Q_XMOM_B: LAUNCH(d, k_gather_component, nblk(M), BLOCK, d->bq, M, M, 1, 1, d->staging, d->d_ident_b); break;
+    case SWK_Q_YMOM_B: LAUNCH(d, k_gather_component, nblk(M), BLOCK, d->bq, M, M, 1, 2, d->staging, d->d_ident_b); break;
+    case SWK_Q_STAGE_EU: LAUNCH(d, k_gather_plain, nblk(N), BLOCK, d->eu, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_EU: LAUNCH(d, k_gather_plain, nblk(N), BLOCK, d->eu + NP, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_EU: LAUNCH(d, k_gather_plain, nblk(N), BLOCK, d->eu + 2 * NP, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_MAX_SPEED: LAUNCH(d, k_gather_plain, nblk(N), BLOCK, d->max_speed, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_STAGE_BACKUP: LAUNCH(d, k_gather_plain, nblk(N), BLOCK, d->bk, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_XMOM_BACKUP: LAUNCH(d, k_gather_plain, nblk(N), BLOCK, d->bk + NP, NP, N, 1, d->staging, d->d_new2old); break;
+    case SWK_Q_YMOM_BACKUP: LAUNCH(d, k_gather_plain, nblk(N), BLOCK, d->bk + 2 * NP, NP, N, 1, d->staging, d->d_new2old); break;
+    default: return fail(SWK_ERR_ARG, "swk_get_quantity: unknown quantity id");
+  }
+  CK(cudaMemcpyAsync(host, d->staging, n * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  return sync_check(d);
+}
+
+// ----------------------------------------------------------------------------
+// boundaries, operators, ghosts
+// ----------------------------------------------------------------------------
+static int push_segments(swk_domain *d)
+{
+  if (!d->seg_dirty) return SWK_OK;
+  const int ns = (int)d->seg_kind.size();
+  if (ns > d->seg_cap) {
+    if (d->d_seg_kind) cudaFree(d->d_seg_kind);
+    if (d->d_seg_val) cudaFree(d->d_seg_val);
+    d->seg_cap = std::max(16, 2 * ns);
+    CKV(dalloc(&d->d_seg_kind, d->seg_cap));
+    CKV(dalloc(&d->d_seg_val, 3 * d->seg_cap));
+  }
+  if (ns > 0) {
+    CK(cudaMemcpyAsync(d->d_seg_kind, d->seg_kind.data(), ns * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    CK(cudaMemcpyAsync(d->d_seg_val, d->seg_val.data(), 3 * ns * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  }
+  if (d->M > 0)
+    CK(cudaMemcpyAsync(d->b_seg, d->h_b_seg.data(), d->M * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  CK(cudaStreamSynchronize(d->stream));   // host vectors may change after return
+  d->seg_dirty = false;
+  return SWK_OK;
+}
+
+extern "C" int swk_set_boundary_segment(swk_domain *d, int segment, int kind, const int64_t *ids, int64_t n_ids,
+                                        const double values[3])
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  if (segment < 0 || segment > 4096) return fail(SWK_ERR_ARG, "segment id out of range");
+  if (kind < SWK_BC_NONE || kind > SWK_BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM) return fail(SWK_ERR_ARG, "unknown boundary kind");
+  if ((int)d->seg_kind.size() <= segment) {
+    d->seg_kind.resize(segment + 1, 0);
+    d->seg_val.resize(3 * (segment + 1), 0.0);
+  }
+  d->seg_kind[segment] = kind;
+  for (int j = 0; j < 3; j++) d->seg_val[3 * segment + j] = values ? values[j] : 0.0;
+  for (int64_t j = 0; j < n_ids; j++) {
+    if (ids[j] < 0 || ids[j] >= d->M) return fail(SWK_ERR_ARG, "boundary id out of range");
+    d->h_b_seg[ids[j]] = segment;
+  }
+  d->seg_dirty = true;
+  return SWK_OK;
+}
+
+extern "C" int swk_set_boundary_values(swk_domain *d, int segment, const double values[3])
+{
+  if (!d || !values) return fail(SWK_ERR_ARG, "NULL argument");
+  if (segment < 0 || segment >= (int)d->seg_kind.size()) return fail(SWK_ERR_ARG, "unknown segment");
+  for (int j = 0; j < 3; j++) d->seg_val[3 * segment + j] = values[j];
+  d->seg_dirty = true;
+  return SWK_OK;
+}
+
+extern "C" int swk_add_rate_operator(swk_domain *d, double rate, double factor, const double *rate_array,
+                                     const int64_t *indices, int64_t n_indices, int *op_id)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  RateOp op;
+  op.rate = rate;
+  op.factor = factor;
+  op.all_nonneg = 1;
+  const int64_t N = d->N;
+  if (indices) {
+    std::vector<int> idx(n_indices);
+    for (int64_t j = 0; j < n_indices; j++) {
+      if (indices[j] < 0 || indices[j] >= N) return fail(SWK_ERR_ARG, "rate operator index out of range");
+      idx[j] = d->old2new[indices[j]];
+    }
+    op.n = (int)n_indices;
+    CKV(dalloc(&op.d_indices, idx.size())); CKV(upload(op.d_indices, idx));
+  } else {
+    op.n = (int)N;
+  }
+  if (rate_array) {   // (N,) in caller order; num.all(rate >= 0) is evaluated on the selected entries
+    std::vector<double> ra(d->NP, 0.0);
+    for (int64_t k = 0; k < N; k++) ra[k] = rate_array[d->new2old[k]];
+    if (indices) { for (int64_t j = 0; j < n_indices; j++) if (!(rate_array[indices[j]] >= 0.0)) op.all_nonneg = 0; }
+    else { for (int64_t k = 0; k < N; k++) if (!(rate_array[k] >= 0.0)) op.all_nonneg = 0; }
+    CKV(dalloc(&op.d_rate_array, ra.size())); CKV(upload(op.d_rate_array, ra));
+  } else {
+    op.all_nonneg = (rate >= 0.0) ? 1 : 0;
+  }
+  op.nblocks = nblk(op.n);
+  CKV(dalloc(&op.d_partial, op.nblocks));
+  d->rate_ops.push_back(op);
+  if (op_id) *op_id = (int)d->rate_ops.size() - 1;
+  return SWK_OK;
+}
+
+extern "C" int swk_set_rate(swk_domain *d, int op_id, double rate, double factor)
+{
+  if (!d || op_id < 0 || op_id >= (int)d->rate_ops.size()) return fail(SWK_ERR_ARG, "unknown rate operator");
+  RateOp &op = d->rate_ops[op_id];
+  op.rate = rate;
+  op.factor = factor;
+  if (!op.d_rate_array) op.all_nonneg = (rate >= 0.0) ? 1 : 0;
+  return SWK_OK;
+}
+
+extern "C" int swk_set_local_ghost_copy(swk_domain *d, const int64_t *full_ids, const int64_t *ghost_ids, int64_t n)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  if (d->d_ghost_full) cudaFree(d->d_ghost_full);
+  if (d->d_ghost_ghost) cudaFree(d->d_ghost_ghost);
+  d->d_ghost_full = d->d_ghost_ghost = nullptr;
+  d->n_ghost_copy = 0;
+  if (n <= 0) return SWK_OK;
+  std::vector<int> f(n), g(n);
+  for (int64_t j = 0; j < n; j++) {
+    if (full_ids[j] < 0 || full_ids[j] >= d->N || ghost_ids[j] < 0 || ghost_ids[j] >= d->N)
+      return fail(SWK_ERR_ARG, "ghost copy id out of range");
+    f[j] = d->old2new[full_ids[j]];
+    g[j] = d->old2new[ghost_ids[j]];
+  }
+  CKV(dalloc(&d->d_ghost_full, n)); CKV(upload(d->d_ghost_full, f));
+  CKV(dalloc(&d->d_ghost_ghost, n)); CKV(upload(d->d_ghost_ghost, g));
+  d->n_ghost_copy = (int)n;
+  return SWK_OK;
+}
+
+// ----------------------------------------------------------------------------
+// clock helpers
+// ----------------------------------------------------------------------------
+static int pull_clock(swk_domain *d)
+{
+  CK(cudaMemcpyAsync(d->h_clock, d->d_clock, sizeof(Clock), cudaMemcpyDeviceToHost, d->stream));
+  return sync_check(d);
+}
+
+static int push_clock(swk_domain *d)
+{
+  CK(cudaMemcpyAsync(d->d_clock, d->h_clock, sizeof(Clock), cudaMemcpyHostToDevice, d->stream));
+  return sync_check(d);
+}
+
+extern "C" int swk_set_time(swk_domain *d, double relative_time)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(pull_clock(d));
+  d->h_clock->time = relative_time;
+  d->h_clock->step_start_time = relative_time;
+  return push_clock(d);
+}
+
+extern "C" int swk_reset_yield_statistics(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(pull_clock(d));
+  d->h_clock->recorded_min_timestep = d->P.evolve_max_timestep;
+  d->h_clock->recorded_max_timestep = d->P.evolve_min_timestep;
+  d->h_clock->number_of_steps = 0;
+  d->h_clock->number_of_first_order_steps = 0;
+  CKV(push_clock(d));
+  CK(cudaMemsetAsync(d->max_speed, 0, d->NP * sizeof(double), d->stream));
+  return sync_check(d);
+}
+
+// ----------------------------------------------------------------------------
+// launch helpers for the individual passes
+// ----------------------------------------------------------------------------
+static void launch_extrapolate(swk_domain *d, const Consts &K)
+{
+  LAUNCH(d, k_extrapolate, nblk(d->N), BLOCK, d->D, K);
+}
+
+static int launch_boundary(swk_domain *d)
+{
+  CKV(push_segments(d));
+  if (d->M == 0) return SWK_OK;
+  Segments S;
+  S.b_cell = d->b_cell; S.b_edge = d->b_edge; S.b_seg = d->b_seg;
+  S.seg_kind = d->d_seg_kind; S.seg_val = d->d_seg_val;
+  if (d->seg_kind.empty()) return SWK_OK;
+  LAUNCH(d, k_boundary_values, nblk(d->M), BLOCK, d->D, S, d->K, (int)d->P.centroid_transmissive_bc);
+  return SWK_OK;
+}
+
+static void launch_flux(swk_domain *d, int first, int write_speed)
+{
+  if (d->has_riverwalls) LAUNCH(d, k_flux<true>, nblk(d->N), BLOCK, d->D, d->K, first, write_speed);
+  else LAUNCH(d, k_flux<false>, nblk(d->N), BLOCK, d->D, d->K, first, write_speed);
+}
+
+static void launch_bflux(swk_domain *d, int substep)
+{
+  if (d->has_riverwalls) LAUNCH(d, k_boundary_flux_sum<true>, 1, 1024, d->D, d->K, d->d_acct, d->n_acct, substep);
+  else LAUNCH(d, k_boundary_flux_sum<false>, 1, 1024, d->D, d->K, d->d_acct, d->n_acct, substep);
+}
+
+static UpdateArgs update_args(swk_domain *d, int do_backup, int do_saxpy, double a, double b, double divide_by)
+{
+  UpdateArgs U;
+  U.a = a; U.b = b; U.divide_by = divide_by;
+  U.g = d->P.g;
+  U.do_backup = do_backup; U.do_saxpy = do_saxpy;
+  U.sloped = d->P.use_sloped_mannings ? 1 : 0;
+  return U;
+}
+
+static void launch_rate_ops(swk_domain *d)
+{
+  for (auto &op : d->rate_ops) {
+    LAUNCH(d, k_rate_operator, op.nblocks, BLOCK, d->D, op.rate, op.factor, op.d_rate_array, op.d_indices, op.n,
+           op.all_nonneg, op.d_partial);
+    LAUNCH(d, k_rate_finish, 1, 1024, d->d_clock, op.d_partial, op.nblocks);
+  }
+}
+
+// ghost update: local copy and/or NCCL halo exchange (parallel_generic_communications.py:159-248)
+static int launch_ghosts(swk_domain *d)
+{
+  if (d->n_ghost_copy > 0)
+    LAUNCH(d, k_ghost_copy, nblk(d->n_ghost_copy), BLOCK, d->D, d->d_ghost_full, d->d_ghost_ghost, d->n_ghost_copy);
+  if (d->comm && !d->peers.empty()) {
+    for (auto &pe : d->peers)
+      if (pe.n_send > 0) LAUNCH(d, k_halo_pack, nblk(pe.n_send), BLOCK, d->D, pe.d_send_ids, pe.n_send, pe.d_send_buf);
+    NK(g_nccl.GroupStart());
+    for (auto &pe : d->peers) {
+      if (pe.n_recv > 0) NK(g_nccl.Recv(pe.d_recv_buf, 3 * (size_t)pe.n_recv, ncclFloat64, pe.rank, d->comm, d->stream));
+      if (pe.n_send > 0) NK(g_nccl.Send(pe.d_send_buf, 3 * (size_t)pe.n_send, ncclFloat64, pe.rank, d->comm, d->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    for (auto &pe : d->peers)
+      if (pe.n_recv > 0) LAUNCH(d, k_halo_unpack, nblk(pe.n_recv), BLOCK, d->D, pe.d_recv_ids, pe.n_recv, pe.d_recv_buf);
+  }
+  return SWK_OK;
+}
+
+// global dt: min over ranks of the flux kernel's local min (parallel_generic_communications.py:67)
+__global__ void k_bits_to_double(Clock *c, double *out) { *out = u2d(c->dt_min_bits); }
+__global__ void k_double_to_bits(Clock *c, const double *in) { c->dt_min_bits = d2u(*in); }
+
+static int launch_dt_allreduce(swk_domain *d)
+{
+  if (!d->comm || d->nranks == 1) return SWK_OK;
+  LAUNCH(d, k_bits_to_double, 1, 1, d->d_clock, d->d_dt_scratch);
+  NK(g_nccl.AllReduce(d->d_dt_scratch, d->d_dt_scratch, 1, ncclFloat64, ncclMinOp, d->comm, d->stream));
+  LAUNCH(d, k_double_to_bits, 1, 1, d->d_clock, d->d_dt_scratch);
+  return SWK_OK;
+}
+
+// one substep-0 sequence: A, boundary, B1, boundary-flux sum, dt, B2
+static int launch_first_substep(swk_domain *d, int do_backup)
+{
+  launch_extrapolate(d, d->K);
+  CKV(launch_boundary(d));
+  launch_flux(d, 1, 1);
+  launch_bflux(d, 0);
+  CKV(launch_dt_allreduce(d));
+  LAUNCH(d, k_update_timestep, 1, 1, d->d_clock, d->TP);
+  LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, do_backup, 0, 1.0, 0.0, 1.0), -1.0);
+  return SWK_OK;
+}
+
+// a later RK substep with the RK combination folded in
+static int launch_later_substep(swk_domain *d, int substep, double a, double b, double divide_by)
+{
+  launch_extrapolate(d, d->K);
+  CKV(launch_boundary(d));
+  const UpdateArgs U = update_args(d, 0, 1, a, b, divide_by);
+  if (d->has_riverwalls) {
+    launch_flux(d, 0, 0);
+    LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, U, -1.0);
+  } else {
+    LAUNCH(d, k_flux_update, nblk(d->N), BLOCK, d->D, d->K, U);
+  }
+  launch_bflux(d, substep);
+  return SWK_OK;
+}
+
+// one full timestep = one iteration of _evolve_base's while loop (generic_domain.py:1835-1862)
+static int launch_step(swk_domain *d)
+{
+  const int method = (int)d->P.timestepping_method;
+  LAUNCH(d, k_begin_step, 1, 1, d->d_clock);
+  if (method == 1) {
+    CKV(launch_first_substep(d, 0));
+  } else if (method == 2) {
+    CKV(launch_first_substep(d, 1));
+    LAUNCH(d, k_set_substep_time, 1, 1, d->d_clock, 1.0);
+    if (d->P.ghost_layer_width < 4) CKV(launch_ghosts(d));
+    CKV(launch_later_substep(d, 1, 0.5, 0.5, 1.0));
+  } else {
+    CKV(launch_first_substep(d, 1));
+    LAUNCH(d, k_set_substep_time, 1, 1, d->d_clock, 1.0);
+    CKV(launch_ghosts(d));
+    CKV(launch_later_substep(d, 1, 0.25, 0.75, 1.0));
+    LAUNCH(d, k_set_substep_time, 1, 1, d->d_clock, 0.5);
+    CKV(launch_ghosts(d));
+    CKV(launch_later_substep(d, 2, 2.0, 1.0, 3.0));
+  }
+  launch_rate_ops(d);                               // apply_fractional_steps (:1849)
+  LAUNCH(d, k_finish_step, 1, 1, d->d_clock, d->TP);
+  CKV(launch_ghosts(d));                            // :1857
+  return SWK_OK;
+}
+
+static int status_from_stop(int stop)
+{
+  switch (stop) {
+    case -3: return fail(SWK_ERR_DENOMINATOR, "semi-implicit update: denominator <= 0 (quantity.c:806)");
+    case -4: return fail(SWK_ERR_SMALLSTEP, "Too small timestep reached even after max_smallsteps steps of 1 order scheme");
+    case -5: return fail(SWK_ERR_OVERSHOOT, "time overshot finaltime");
+    default: return fail(SWK_ERR_CUDA, "device reported an unknown error state");
+  }
+}
+
+static void fill_result(swk_domain *d, swk_evolve_result *r, int64_t launches0)
+{
+  if (!r) return;
+  const Clock *c = d->h_clock;
+  r->time = c->time;
+  r->timestep = c->dt;
+  r->flux_timestep = c->flux_dt;
+  r->recorded_min_timestep = c->recorded_min_timestep;
+  r->recorded_max_timestep = c->recorded_max_timestep;
+  r->boundary_flux_integral = c->boundary_flux_integral;
+  r->fractional_step_volume_integral = c->fractional_step_volume_integral;
+  r->mass_error = c->mass_error;
+  for (int i = 0; i < 3; i++) r->boundary_flux_sum[i] = c->boundary_flux_sum[i];
+  r->number_of_steps = c->number_of_steps;
+  r->number_of_first_order_steps = c->number_of_first_order_steps;
+  r->total_steps = c->total_steps;
+  r->negative_cells = c->negative_cells;
+  r->stop_reason = (c->stop == 1) ? 1 : ((c->stop == 2) ? 2 : 0);
+  r->kernel_launches = d->launches - launches0;
+}
+
+extern "C" int swk_evolve(swk_domain *d, double relative_yieldtime, double relative_finaltime, int64_t max_steps,
+                          swk_evolve_result *result)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  const int64_t launches0 = d->launches;
+  CKV(pull_clock(d));
+  Clock *c = d->h_clock;
+  if (c->stop < 0) return status_from_stop(c->stop);
+  c->yieldtime = relative_yieldtime;
+  c->finaltime = relative_finaltime;
+  c->step_budget = (max_steps > 0) ? c->total_steps + max_steps : 0;
+  c->stop = 0;
+  CKV(push_clock(d));
+
+  int64_t batch = 1;
+  for (;;) {
+    for (int64_t b = 0; b < batch; b++) CKV(launch_step(d));
+    CKV(pull_clock(d));
+    if (c->stop != 0) break;
+    // estimate how many more steps fit before the next stop (the device clips dt itself;
+    // surplus launches see clock->stop and return immediately)
+    double target = relative_yieldtime;
+    if (relative_finaltime >= 0.0 && relative_finaltime < target) target = relative_finaltime;
+    double est = (c->dt > 0.0) ? (target - c->time) / c->dt : 1.0;
+    if (!(est >= 1.0)) est = 1.0;
+    batch = (int64_t)std::min(est + 1.0, 64.0);
+    if (c->step_budget > 0) batch = std::min<int64_t>(batch, std::max<int64_t>(1, c->step_budget - c->total_steps));
+  }
+  if (c->stop < 0) return status_from_stop(c->stop);
+  const int reason = c->stop;
+  if (reason == 1 || reason == 2) {
+    // distribute_to_vertices_and_edges + update_boundary before the yield (:1884-1885, 1899-1900)
+    c->stop = 0;
+    CKV(push_clock(d));
+    launch_extrapolate(d, d->K);
+    LAUNCH(d, k_materialize_centroids, nblk(d->N), BLOCK, d->D, d->K, 0);
+    CKV(launch_boundary(d));
+    CKV(pull_clock(d));
+  }
+  c->stop = reason;
+  fill_result(d, result, launches0);
+  c->stop = 0;
+  CKV(push_clock(d));
+  return SWK_OK;
+}
+
+extern "C" int swk_stream(swk_domain *d, void **cuda_stream_out)
+{
+  if (!d || !cuda_stream_out) return fail(SWK_ERR_ARG, "NULL argument");
+  *cuda_stream_out = (void *)d->stream;
+  return SWK_OK;
+}
+
+extern "C" int swk_synchronize(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  return sync_check(d);
+}
+
+extern "C" int swk_kernel_launch_count(swk_domain *d, int64_t *count)
+{
+  if (!d || !count) return fail(SWK_ERR_ARG, "NULL argument");
+  *count = d->launches;
+  return SWK_OK;
+}
+
+extern "C" int swk_bytes_per_triangle_step(swk_domain *d, double *algorithmic, double *layout)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  const int method = (int)d->P.timestepping_method;
+  // DE0 556 B, DE1 1076 B, DE2 1572 B per triangle-step
+  const double alg[4] = {0, 556.0, 1076.0, 1572.0};
+  // this library's records: pass A 241, B1 264, B2 121, fused B 297
+  const double A = 32 + 16 + 96 + 96 + 1, B1 = 96 + 16 + 96 + 32 + 24, B2 = 24 + 32 + 8 + 1 + 32, B = 96 + 16 + 96 + 32 + 8 + 1 + 24 + 32;
+  double lay = A + B1 + B2 + (method >= 2 ? 24 : 0);
+  for (int s = 1; s < method; s++) lay += A + B;
+  if (algorithmic) *algorithmic = alg[method];
+  if (layout) *layout = lay;
+  return SWK_OK;
+}
+
+// ----------------------------------------------------------------------------
+// individual steps on resident data (host-stepped mode and per-call layer)
+// ----------------------------------------------------------------------------
+extern "C" int swk_protect(swk_domain *d, double *mass_error)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(pull_clock(d));
+  const double before = d->h_clock->mass_error;
+  LAUNCH(d, k_protect_mass, nblk(d->N), BLOCK, d->D, d->K);
+  LAUNCH(d, k_materialize_centroids, nblk(d->N), BLOCK, d->D, d->K, 1);
+  CKV(pull_clock(d));
+  if (mass_error) *mass_error = d->h_clock->mass_error - before;
+  return SWK_OK;
+}
+
+static int extrapolate_impl(swk_domain *d, int protect)
+{
+  Consts K = d->K;
+  K.protect = protect;
+  launch_extrapolate(d, K);
+  LAUNCH(d, k_materialize_centroids, nblk(d->N), BLOCK, d->D, K, 0);
+  return sync_check(d);
+}
+
+extern "C" int swk_extrapolate_second_order_edge_sw(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  return extrapolate_impl(d, 0);
+}
+
+extern "C" int swk_distribute_to_vertices_and_edges(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  return extrapolate_impl(d, 1);
+}
+
+extern "C" int swk_update_boundary(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(launch_boundary(d));
+  return sync_check(d);
+}
+
+extern "C" int swk_compute_fluxes(swk_domain *d, int substep, double *flux_timestep)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  if (substep < 0 || substep > 2) return fail(SWK_ERR_ARG, "substep must be 0, 1 or 2");
+  CK(cudaSetDevice(d->device));
+  const int first = (substep == 0);
+  if (first) LAUNCH(d, k_begin_step, 1, 1, d->d_clock);
+  launch_flux(d, first, 1);
+  launch_bflux(d, substep);
+  if (first) CKV(launch_dt_allreduce(d));
+  CKV(pull_clock(d));
+  if (flux_timestep) *flux_timestep = first ? u2d_host(d->h_clock->dt_min_bits) : d->P.evolve_max_timestep;
+  return SWK_OK;
+}
+
+extern "C" int swk_update_conserved_quantities(swk_domain *d, double timestep, int64_t *num_negative)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(pull_clock(d));
+  const long long before = d->h_clock->negative_cells;
+  LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, 0, 0, 1.0, 0.0, 1.0), timestep);
+  CKV(pull_clock(d));
+  if (d->h_clock->stop < 0) {
+    const int st = d->h_clock->stop;
+    d->h_clock->stop = 0;
+    CKV(push_clock(d));
+    return status_from_stop(st);
+  }
+  if (num_negative) *num_negative = d->h_clock->negative_cells - before;
+  return SWK_OK;
+}
+
+extern "C" int swk_backup_conserved_quantities(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  LAUNCH(d, k_backup, nblk(d->N), BLOCK, d->D);
+  return sync_check(d);
+}
+
+extern "C" int swk_saxpy_conserved_quantities(swk_domain *d, double a, double b, double divide_by)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  if (divide_by == 0.0) return fail(SWK_ERR_ARG, "divide_by must be non-zero");
+  CK(cudaSetDevice(d->device));
+  LAUNCH(d, k_saxpy, nblk(d->N), BLOCK, d->D, a, b, divide_by);
+  return sync_check(d);
+}
+
+extern "C" int swk_apply_fractional_steps(swk_domain *d, double timestep)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  LAUNCH(d, k_set_dt, 1, 1, d->d_clock, timestep);
+  LAUNCH(d, k_bfi_update, 1, 1, d->d_clock, d->TP);
+  launch_rate_ops(d);
+  return sync_check(d);
+}
+
+extern "C" int swk_get_statistics(swk_domain *d, swk_evolve_result *result)
+{
+  if (!d || !result) return fail(SWK_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(d->device));
+  CKV(pull_clock(d));
+  fill_result(d, result, d->launches);
+  return SWK_OK;
+}
+
+extern "C" int swk_update_ghosts(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(launch_ghosts(d));
+  return sync_check(d);
+}
+
+// ----------------------------------------------------------------------------
+// multi-GPU plumbing
+// ----------------------------------------------------------------------------
+extern "C" int swk_nccl_unique_id(void *id128)
+{
+  if (!id128) return fail(SWK_ERR_ARG, "id128 is NULL");
+  CKV(load_nccl());
+  ncclUniqueId id;
+  NK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return SWK_OK;
+}
+
+extern "C" int swk_comm_init(swk_domain *d, const void *id128, int rank, int nranks)
+{
+  if (!d || !id128) return fail(SWK_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(d->device));
+  CKV(load_nccl());
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NK(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
+  d->rank = rank;
+  d->nranks = nranks;
+  CKV(dalloc(&d->d_dt_scratch, 1));
+  return SWK_OK;
+}
+
+extern "C" int swk_set_halo(swk_domain *d, int n_peers, const int *peer_ranks, const int64_t *send_counts,
+                            const int64_t *const *send_ids, const int64_t *recv_counts,
+                            const int64_t *const *recv_ids)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  for (auto &pe : d->peers) {
+    if (pe.d_send_ids) cudaFree(pe.d_send_ids);
+    if (pe.d_recv_ids) cudaFree(pe.d_recv_ids);
+    if (pe.d_send_buf) cudaFree(pe.d_send_buf);
+    if (pe.d_recv_buf) cudaFree(pe.d_recv_buf);
+  }
+  d->peers.clear();
+  for (int q = 0; q < n_peers; q++) {
+    Peer pe;
+    pe.rank = peer_ranks[q];
+    pe.n_send = (int)send_counts[q];
+    pe.n_recv = (int)recv_counts[q];
+    std::vector<int> s(pe.n_send), r(pe.n_recv);
+    for (int j = 0; j < pe.n_send; j++) {
+      if (send_ids[q][j] < 0 || send_ids[q][j] >= d->N) return fail(SWK_ERR_ARG, "halo send id out of range");
+      s[j] = d->old2new[send_ids[q][j]];
+    }
+    for (int j = 0; j < pe.n_recv; j++) {
+      if (recv_ids[q][j] < 0 || recv_ids[q][j] >= d->N) return fail(SWK_ERR_ARG, "halo recv id out of range");
+      r[j] = d->old2new[recv_ids[q][j]];
+    }
+    CKV(dalloc(&pe.d_send_ids, s.size())); CKV(upload(pe.d_send_ids, s));
+    CKV(dalloc(&pe.d_recv_ids, r.size())); CKV(upload(pe.d_recv_ids, r));
+    CKV(dalloc(&pe.d_send_buf, 3 * s.size()));
+    CKV(dalloc(&pe.d_recv_buf, 3 * r.size()));
+    d->peers.push_back(pe);
+  }
+  return SWK_OK;
+}
+
+// ============================================================================
+// (2) PER-CALL LAYER: host arrays in, host arrays out
+// ============================================================================
+extern "C" int swk_call_open(const swk_host_view *v, int device, swk_domain **out)
+{
+  if (!v) return fail(SWK_ERR_ARG, "view is NULL");
+  CKV(swk_create(&v->mesh, &v->params, device, out));
+  (*out)->per_call = true;
+  (*out)->K.protect = 0;      // each call is exactly one reference function
+  return SWK_OK;
+}
+
+extern "C" int swk_call_close(swk_domain *d) { return swk_destroy(d); }
+
+static int refresh_per_call(swk_domain *d, const swk_host_view *v)
+{
+  if (!d || !v) return fail(SWK_ERR_ARG, "NULL argument");
+  if (v->mesh.number_of_elements != d->N || v->mesh.boundary_length != d->M)
+    return fail(SWK_ERR_ARG, "host view does not match the opened context");
+  CK(cudaSetDevice(d->device));
+  CKV(check_params(&v->params));
+  d->P = v->params;
+  make_consts(d);
+  d->K.protect = 0;
+  return SWK_OK;
+}
+
+extern "C" int swk_call_compute_fluxes_ext_central(swk_domain *d, const swk_host_view *v, double timestep,
+                                                   int substep, double *flux_timestep)
+{
+  CKV(refresh_per_call(d, v));
+  if (substep < 0 || substep >= v->params.timestepping_method) return fail(SWK_ERR_ARG, "substep out of range");
+  const int64_t N = d->N, M = d->M;
+  // The device edge record carries (stage, height, xmom, ymom); bed_edge = stage_edge - height_edge and
+  // height_centroid = max(stage - bed, 0) are what extrapolate always leaves behind
+  // (sw_domain_openmp.c:1376-1378, 1863-1865).  Refuse inconsistent input instead of silently differing.
+  for (int64_t j = 0; j < 3 * N; j++)
+    if (v->bed_edge_values[j] != v->stage_edge_values[j] - v->height_edge_values[j])
+      return fail(SWK_ERR_UNSUPPORTED, "bed_edge_values != stage_edge_values - height_edge_values: call extrapolate first");
+  for (int64_t k = 0; k < N; k++)
+    if (v->height_centroid_values[k] != fmax(v->stage_centroid_values[k] - v->bed_centroid_values[k], 0.0))
+      return fail(SWK_ERR_UNSUPPORTED, "height_centroid_values != max(stage - bed, 0): call extrapolate first");
+  CKV(swk_set_quantity(d, SWK_Q_STAGE_C, v->stage_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_ELEVATION_C, v->bed_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_STAGE_E, v->stage_edge_values, 3 * N));
+  CKV(swk_set_quantity(d, SWK_Q_HEIGHT_E, v->height_edge_values, 3 * N));
+  CKV(swk_set_quantity(d, SWK_Q_XMOM_E, v->xmom_edge_values, 3 * N));
+  CKV(swk_set_quantity(d, SWK_Q_YMOM_E, v->ymom_edge_values, 3 * N));
+  if (M > 0) {
+    CKV(swk_set_quantity(d, SWK_Q_STAGE_B, v->stage_boundary_values, M));
+    CKV(swk_set_quantity(d, SWK_Q_XMOM_B, v->xmom_boundary_values, M));
+    CKV(swk_set_quantity(d, SWK_Q_YMOM_B, v->ymom_boundary_values, M));
+  }
+  double ft = 0.0;
+  CKV(swk_compute_fluxes(d, substep, &ft));
+  CKV(swk_get_quantity(d, SWK_Q_STAGE_EU, v->stage_explicit_update, N));
+  CKV(swk_get_quantity(d, SWK_Q_XMOM_EU, v->xmom_explicit_update, N));
+  CKV(swk_get_quantity(d, SWK_Q_YMOM_EU, v->ymom_explicit_update, N));
+  if (substep == 0 && v->max_speed) CKV(swk_get_quantity(d, SWK_Q_MAX_SPEED, v->max_speed, N));
+  if (v->boundary_flux_sum) v->boundary_flux_sum[substep] = d->h_clock->boundary_flux_sum[substep];
+  if (flux_timestep) *flux_timestep = (substep == 0) ? ft : timestep;   // :768-771
+  return SWK_OK;
+}
+
+extern "C" int swk_call_extrapolate_second_order_edge_sw(swk_domain *d, const swk_host_view *v)
+{
+  CKV(refresh_per_call(d, v));
+  const int64_t N = d->N;
+  CKV(swk_set_quantity(d, SWK_Q_STAGE_C, v->stage_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_XMOM_C, v->xmom_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_YMOM_C, v->ymom_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_ELEVATION_C, v->bed_centroid_values, N));
+  CKV(extrapolate_impl(d, 0));
+  CKV(swk_get_quantity(d, SWK_Q_XMOM_C, v->xmom_centroid_values, N));
+  CKV(swk_get_quantity(d, SWK_Q_YMOM_C, v->ymom_centroid_values, N));
+  if (v->height_centroid_values) CKV(swk_get_quantity(d, SWK_Q_HEIGHT_C, v->height_centroid_values, N));
+  struct { int q; double *p; } outs[] = {
+      {SWK_Q_STAGE_E, v->stage_edge_values}, {SWK_Q_XMOM_E, v->xmom_edge_values},
+      {SWK_Q_YMOM_E, v->ymom_edge_values}, {SWK_Q_HEIGHT_E, v->height_edge_values},
+      {SWK_Q_ELEVATION_E, v->bed_edge_values}, {SWK_Q_STAGE_V, v->stage_vertex_values},
+      {SWK_Q_XMOM_V, v->xmom_vertex_values}, {SWK_Q_YMOM_V, v->ymom_vertex_values},
+      {SWK_Q_HEIGHT_V, v->height_vertex_values}, {SWK_Q_ELEVATION_V, v->bed_vertex_values}};
+  for (auto &o : outs)
+    if (o.p) CKV(swk_get_quantity(d, o.q, o.p, 3 * N));
+  return SWK_OK;
+}
+
+extern "C" int swk_call_protect_new(swk_domain *d, const swk_host_view *v, double *mass_error)
+{
+  CKV(refresh_per_call(d, v));
+  const int64_t N = d->N;
+  CKV(swk_set_quantity(d, SWK_Q_STAGE_C, v->stage_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_XMOM_C, v->xmom_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_ELEVATION_C, v->bed_centroid_values, N));
+  // vertex fix-up of lifted cells (sw_domain_openmp.c:1158-1160) uses the pre-call stage
+  if (v->stage_vertex_values)
+    for (int64_t k = 0; k < N; k++)
+      if (v->stage_centroid_values[k] < v->bed_centroid_values[k])
+        v->stage_vertex_values[3 * k] = v->stage_vertex_values[3 * k + 1] = v->stage_vertex_values[3 * k + 2] =
+            v->bed_centroid_values[k];
+  CKV(swk_protect(d, mass_error));
+  CKV(swk_get_quantity(d, SWK_Q_STAGE_C, v->stage_centroid_values, N));
+  CKV(swk_get_quantity(d, SWK_Q_XMOM_C, v->xmom_centroid_values, N));
+  return SWK_OK;
+}
+
+extern "C" int swk_call_fix_negative_cells(swk_domain *d, const swk_host_view *v, int64_t *count)
+{
+  CKV(refresh_per_call(d, v));
+  const int64_t N = d->N;
+  CKV(swk_set_quantity(d, SWK_Q_STAGE_C, v->stage_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_XMOM_C, v->xmom_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_YMOM_C, v->ymom_centroid_values, N));
+  CKV(swk_set_quantity(d, SWK_Q_ELEVATION_C, v->bed_centroid_values, N));
+  CKV(pull_clock(d));
+  const long long before = d->h_clock->negative_cells;
+  LAUNCH(d, k_fix_negative, nblk(N), BLOCK, d->D);
+  CKV(pull_clock(d));
+  if (count) *count = d->h_clock->negative_cells - before;
+  CKV(swk_get_quantity(d, SWK_Q_STAGE_C, v->stage_centroid_values, N));
+  CKV(swk_get_quantity(d, SWK_Q_XMOM_C, v->xmom_centroid_values, N));
+  CKV(swk_get_quantity(d, SWK_Q_YMOM_C, v->ymom_centroid_values, N));
+  return SWK_OK;
+}
+
+// ---- stateless elementwise entry points ------------------------------------------
+struct DevBuf {
+  double *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int put(const double *h, size_t n)
+  {
+    CKV(dalloc(&p, n));
+    if (h) CK(cudaMemcpy(p, h, n * sizeof(double), cudaMemcpyHostToDevice));
+    return SWK_OK;
+  }
+  int get(double *h, size_t n)
+  {
+    CK(cudaMemcpy(h, p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return SWK_OK;
+  }
+};
+
+static int manning_call(int device, int sloped, double g, double eps, int64_t N, const double *x, const double *w,
+                        const double *zv, const double *uh, const double *vh, const double *eta,
+                        double *xmom_update, double *ymom_update)
+{
+  if (N < 0 || !w || !zv || !uh || !vh || !eta || !xmom_update || !ymom_update || (sloped && !x))
+    return fail(SWK_ERR_ARG, "NULL argument");
+  CKV(select_device(device));
+  if (N == 0) return SWK_OK;
+  DevBuf dx, dw, dz, du, dv, de, dxu, dyu;
+  if (sloped) CKV(dx.put(x, 6 * N));
+  CKV(dw.put(w, N)); CKV(dz.put(zv, sloped ? 3 * N : N)); CKV(du.put(uh, N)); CKV(dv.put(vh, N));
+  CKV(de.put(eta, N)); CKV(dxu.put(xmom_update, N)); CKV(dyu.put(ymom_update, N));
+  k_manning_plain<<<nblk(N), BLOCK>>>(g, eps, (int)N, sloped, dx.p, dw.p, dz.p, du.p, dv.p, de.p, dxu.p, dyu.p);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CKV(dxu.get(xmom_update, N));
+  CKV(dyu.get(ymom_update, N));
+  return SWK_OK;
+}
+
+extern "C" int swk_call_manning_friction_flat(int device, double g, double eps, int64_t N, const double *w,
+                                              const double *zv, const double *uh, const double *vh,
+                                              const double *eta, double *xmom_update, double *ymom_update)
+{
+  return manning_call(device, 0, g, eps, N, nullptr, w, zv, uh, vh, eta, xmom_update, ymom_update);
+}
+
+extern "C" int swk_call_manning_friction_sloped(int device, double g, double eps, int64_t N, const double *x,
+                                                const double *w, const double *zv, const double *uh,
+                                                const double *vh, const double *eta, double *xmom_update,
+                                                double *ymom_update)
+{
+  return manning_call(device, 1, g, eps, N, x, w, zv, uh, vh, eta, xmom_update, ymom_update);
+}
+
+extern "C" int swk_call_update(int device, int64_t N, double timestep, double *centroid_values,
+                               const double *explicit_update, double *semi_implicit_update)
+{
+  if (N < 0 || !centroid_values || !explicit_update || !semi_implicit_update) return fail(SWK_ERR_ARG, "NULL argument");
+  CKV(select_device(device));
+  if (N == 0) return SWK_OK;
+  DevBuf c, e, s;
+  CKV(c.put(centroid_values, N)); CKV(e.put(explicit_update, N)); CKV(s.put(semi_implicit_update, N));
+  int *derr = nullptr;
+  CKV(dalloc(&derr, 1));
+  CK(cudaMemset(derr, 0, sizeof(int)));
+  k_update_plain<<<nblk(N), BLOCK>>>((int)N, timestep, c.p, e.p, s.p, derr);
+  int herr = 0;
+  cudaError_t ce = cudaMemcpy(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(derr);
+  if (ce != cudaSuccess) return fail(SWK_ERR_CUDA, cudaGetErrorString(ce));
+  if (herr) return fail(SWK_ERR_DENOMINATOR, "semi-implicit update: denominator <= 0 (quantity.c:806)");
+  CKV(c.get(centroid_values, N));
+  CKV(s.get(semi_implicit_update, N));
+  return SWK_OK;
+}
+
+extern "C" int swk_call_backup_centroid_values(int device, int64_t N, const double *centroid_values,
+                                               double *centroid_backup_values)
+{
+  if (N < 0 || !centroid_values || !centroid_backup_values) return fail(SWK_ERR_ARG, "NULL argument");
+  CKV(select_device(device));
+  if (N == 0) return SWK_OK;
+  // a copy through the device keeps the call on the same data path as the other entry points
+  DevBuf c;
+  CKV(c.put(centroid_values, N));
+  CKV(c.get(centroid_backup_values, N));
+  return SWK_OK;
+}
+
+extern "C" int swk_call_saxpy_centroid_values(int device, int64_t N, double a, double b, double *centroid_values,
+                                              const double *centroid_backup_values)
+{
+  if (N < 0 || !centroid_values || !centroid_backup_values) return fail(SWK_ERR_ARG, "NULL argument");
+  CKV(select_device(device));
+  if (N == 0) return SWK_OK;
+  DevBuf c, bk;
+  CKV(c.put(centroid_values, N)); CKV(bk.put(centroid_backup_values, N));
+  k_saxpy_plain<<<nblk(N), BLOCK>>>((int)N, a, b, c.p, bk.p);
+  CK(cudaGetLastError());
+  CKV(c.get(centroid_values, N));
+  return SWK_OK;
+}

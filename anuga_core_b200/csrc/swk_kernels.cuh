@@ -1,0 +1,885 @@
+// swk_kernels.cuh - sm_100a kernels of the DE shallow-water timestep.
+//
+// Data layout in HBM.  N triangles, NP = N rounded up to 64,
+// triangles renumbered by a locality (Morton) permutation at upload.
+//   cq   [NP]      d4 {stage, xmom, ymom, bed}        centroid record   (32 B, gathered by neighbours)
+//   eq   [3][NP]   d4 {stage, height, xmom, ymom}     edge record       (32 B, gathered by neighbours)
+//   xg   [3][NP]   d4 extrapolation geometry          (static, streamed)
+//   fg   [3][NP]   d4 flux geometry                   (static, streamed)
+//   connA[NP]      i4 {s0, s1, s2, flagsA}            surrogate neighbours
+//   connB[NP]      i4 {p0, p1, p2, flagsB}            p = (n<<2)|edge  or  -(m+1) boundary
+//   eu   [3][NP]   double explicit updates            (substep 0 round trip)
+//   bk   [3][NP]   double RK backup
+//   eta  [NP]      double Manning n
+//   zflag[NP]      u8  loop-2 "surrounded by dry cells" momentum zeroing
+//   bq   [M]       d4 {stage, xmom, ymom, -}          boundary values
+// Every record is one 256-bit load/store (LDG.E.256/STG.E.256 on sm_100a); own-cell
+// streams are fully coalesced (32 consecutive records per warp), neighbour gathers
+// touch exactly one 32-byte sector each.
+#pragma once
+#include "swk_math.cuh"
+
+namespace swk {
+
+constexpr int BLOCK = 256;
+
+// ---- device-side clock: the scalars of Generic_Domain's time loop -------------
+struct Clock {
+  double time;                  // relative_time
+  double step_start_time;       // relative time at the start of the current step
+  double dt;                    // self.timestep
+  double flux_dt;               // self.flux_timestep (as returned by compute_fluxes)
+  unsigned long long dt_min_bits;   // running min over the flux kernel (uint64 image of a positive double)
+  double yieldtime, finaltime;  // relative; finaltime < 0: none
+  double recorded_min_timestep, recorded_max_timestep;
+  double boundary_flux_sum[3];
+  double boundary_flux_integral;
+  double fractional_step_volume_integral;
+  double mass_error;
+  long long number_of_steps, number_of_first_order_steps, total_steps, step_budget;
+  long long negative_cells;
+  int smallsteps, order;
+  int stop;                     // 0 run, 1 yield reached, 2 final reached, 3 budget exhausted, <0 error
+  int pad;
+};
+
+struct TimeParams {
+  double CFL, evolve_max_timestep, evolve_min_timestep, fixed_flux_timestep, epsilon;
+  int max_smallsteps, default_order, method;   // method: 1 euler 2 rk2 3 rk3
+};
+
+// ---- pointers --------------------------------------------------------------
+struct Dev {
+  int N, NP, M;
+  d4 *cq;
+  d4 *eq;
+  const d4 *xg;
+  const d4 *fg;
+  const i4 *connA;
+  const i4 *connB;
+  double *eu;
+  double *bk;
+  const double *eta;
+  unsigned char *zflag;
+  double *max_speed;
+  d4 *bq;
+  const double *vcoord;          // (6*NP) vertex coordinates x0,y0,x1,y1,x2,y2 planes (sloped Manning), may be null
+  Clock *clock;
+  // riverwalls
+  const int *rw_counter;         // [3][NP] edge_river_wall_counter (1-based) or null
+  const double *rw_elevation;
+  const int *rw_rowIndex;
+  const double *rw_hydraulic;
+  int rw_ncol;
+};
+
+// =============================================================================
+// Pass A: protect + second-order edge extrapolation with limiting.
+// Reference: _openmp_protect (sw_domain_openmp.c:1096-1171) and
+// _openmp_extrapolate_second_order_edge_sw (:1336-1952), fused; centroid values
+// are NOT modified (their protected form is recomputed by the consumers).
+// One thread per triangle.  Reads cq (own + 3 gathered), connA, xg; writes eq, zflag.
+// =============================================================================
+__global__ void __launch_bounds__(BLOCK) k_extrapolate(Dev D, Consts K)
+{
+  if (D.clock->stop) return;
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  const int NP = D.NP;
+  const i4 s = D.connA[k];
+  const d4 c = D.cq[k];
+  const d4 c0 = D.cq[s.x];
+  const d4 c1 = D.cq[s.y];
+  const d4 c2 = D.cq[s.z];
+  const d4 g0 = D.xg[k];
+  const d4 g1 = D.xg[NP + k];
+  const d4 g2 = D.xg[2 * NP + k];
+  XGeom G;
+  G.dxv0 = g0.x; G.dxv1 = g0.y; G.dxv2 = g0.z; G.dyv0 = g0.w;
+  G.dyv1 = g1.x; G.dyv2 = g1.y; G.dx1 = g1.z; G.dx2 = g1.w;
+  G.dy1 = g2.x; G.dy2 = g2.y; G.inv_area2 = g2.z;
+  const double area = g2.w;
+
+  Eff e = effective(c, K);
+  const Eff e0 = effective(c0, K);
+  const Eff e1 = effective(c1, K);
+  const Eff e2 = effective(c2, K);
+  if (e.mass_added != 0.0) atomicAdd(&D.clock->mass_error, e.mass_added * area);
+
+  const int nb = s.w & 3;
+  // loop 2 head (:1486-1495): all neighbours dry (or self) -> no momentum
+  const bool dry0 = (e0.h < K.mah) | (s.x == k);
+  const bool dry1 = (e1.h < K.mah) | (s.y == k);
+  const bool dry2 = (e2.h < K.mah) | (s.z == k);
+  const bool zero_mom = dry0 & dry1 & dry2;
+  if (zero_mom) { e.u = 0.0; e.v = 0.0; }
+  D.zflag[k] = zero_mom ? 1 : 0;
+
+  double w0, w1, w2, h0, h1, h2, u0, u1, u2, v0, v1, v2;
+  if (nb == 3) {                                   // :1498-1522
+    w0 = w1 = w2 = e.w;
+    h0 = h1 = h2 = e.h;
+    u0 = u1 = u2 = e.u;
+    v0 = v1 = v2 = e.v;
+  } else if (nb <= 1) {                            // :1523-1645
+    const double a_tmp = 0.3, b_tmp = 0.1;
+    const double c_tmp = 1.0 / (a_tmp - b_tmp);
+    const double d_tmp = 1.0 - (c_tmp * a_tmp);
+    const double hc = e.h;
+    const double hmin = fmin(fmin(e0.h, fmin(e1.h, e2.h)), hc);
+    const double hmax = fmax(fmax(e0.h, fmax(e1.h, e2.h)), hc);
+    double hfactor = fmax(0., fmin(c_tmp * fmax(hmin, 0.0) / fmax(hc, 1.0e-06) + d_tmp,
+                                   fmin(c_tmp * fmax(hc, 0.) / fmax(hmax, 1.0e-06) + d_tmp, 1.0)));
+    hfactor = fmin(1.2 * fmax(hmin - K.mah, 0.) / (fmax(hmin, 0.) + 1. * K.mah), hfactor);
+    double beta = K.beta_w_dry + (K.beta_w - K.beta_w_dry) * hfactor;
+    edge_values_3(beta, e.w, e0.w, e1.w, e2.w, G, w0, w1, w2);
+    edge_values_3(beta, e.h, e0.h, e1.h, e2.h, G, h0, h1, h2);
+    beta = K.beta_uh_dry + (K.beta_uh - K.beta_uh_dry) * hfactor;
+    edge_values_3(beta, e.u, e0.u, e1.u, e2.u, G, u0, u1, u2);
+    beta = K.beta_vh_dry + (K.beta_vh - K.beta_vh_dry) * hfactor;
+    edge_values_3(beta, e.v, e0.v, e1.v, e2.v, G, v0, v1, v2);
+  } else {                                         // two boundary edges :1646-1842
+    const int which = (s.w >> 2) & 3;
+    const Eff &en = (which == 0) ? e0 : ((which == 1) ? e1 : e2);
+    edge_values_1(K.beta_w, e.w, en.w, G, w0, w1, w2);
+    edge_values_1(K.beta_w, e.h, en.h, G, h0, h1, h2);
+    edge_values_1(K.beta_w, e.u, en.u, G, u0, u1, u2);
+    edge_values_1(K.beta_w, e.v, en.v, G, v0, v1, v2);
+  }
+  if (K.vel2) {                                    // :1851-1860
+    u0 = u0 * h0; v0 = v0 * h0;
+    u1 = u1 * h1; v1 = v1 * h1;
+    u2 = u2 * h2; v2 = v2 * h2;
+  }
+  d4 r;
+  r.x = w0; r.y = h0; r.z = u0; r.w = v0; D.eq[k] = r;
+  r.x = w1; r.y = h1; r.z = u1; r.w = v1; D.eq[NP + k] = r;
+  r.x = w2; r.y = h2; r.z = u2; r.w = v2; D.eq[2 * NP + k] = r;
+}
+
+// Write the protected/zeroed centroid values in place: what the reference's centroid
+// arrays hold after distribute_to_vertices_and_edges (used at yields and by the
+// per-call layer).  Must run after k_extrapolate (needs zflag).
+__global__ void __launch_bounds__(BLOCK) k_materialize_centroids(Dev D, Consts K, int protect_only)
+{
+  if (D.clock->stop) return;
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  d4 c = D.cq[k];
+  if (protect_only) {                 // exactly _openmp_protect, incl. the xmom-only zeroing (:1139-1140)
+    const double hc = c.x - c.w;
+    if (hc < K.mah * 1.0) {
+      c.y = 0.0;
+      if (hc <= 0.0 && c.x < c.w) c.x = c.w;
+    }
+  } else {
+    const Eff e = effective(c, K);
+    c.x = e.w; c.y = e.uh; c.z = e.vh;
+    if (D.zflag[k]) { c.y = 0.0; c.z = 0.0; }
+  }
+  D.cq[k] = c;
+}
+
+// protect alone with its mass error (per-call layer / swk_protect)
+__global__ void __launch_bounds__(BLOCK) k_protect_mass(Dev D, Consts K)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  const d4 c = D.cq[k];
+  if (c.x < c.w) atomicAdd(&D.clock->mass_error, (c.w - c.x) * D.xg[2 * D.NP + k].w);
+}
+
+// =============================================================================
+// Boundary values: Generic_Domain.update_boundary (generic_domain.py:2288-2306)
+// with the evaluate_segment arithmetic of each boundary class.  One thread per
+// boundary edge m.
+// =============================================================================
+struct Segments {
+  const int *b_cell;       // [M] triangle (device numbering)
+  const int *b_edge;       // [M]
+  const int *b_seg;        // [M] segment id or -1
+  const int *seg_kind;     // [nseg]
+  const double *seg_val;   // [nseg][3]
+};
+
+__device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, const Consts &K,
+                                               int m, int centroid_transmissive, d4 &out, bool &touched)
+{
+  touched = false;
+  const int seg = S.b_seg[m];
+  if (seg < 0) return;
+  const int kind = S.seg_kind[seg];
+  if (kind == 0) return;
+  const int k = S.b_cell[m];
+  const int i = S.b_edge[m];
+  const d4 e = D.eq[i * D.NP + k];           // {stage, height, xmom, ymom}
+  double n1, n2;
+  {
+    const d4 f0 = D.fg[k];
+    const d4 f1 = D.fg[D.NP + k];
+    n1 = (i == 0) ? f0.x : ((i == 1) ? f0.z : f1.x);
+    n2 = (i == 0) ? f0.y : ((i == 1) ? f0.w : f1.y);
+  }
+  const double v0 = S.seg_val[3 * seg], v1 = S.seg_val[3 * seg + 1], v2 = S.seg_val[3 * seg + 2];
+  touched = true;
+  switch (kind) {
+    case 1: {                                  // Reflective (boundaries.py:262-278)
+      const double q1 = e.z, q2 = e.w;
+      const double r1 = -q1 * n1 - q2 * n2;
+      const double r2 = -q1 * n2 + q2 * n1;
+      out.x = e.x;
+      out.y = n1 * r1 - n2 * r2;
+      out.z = n2 * r1 + n1 * r2;
+    } break;
+    case 2:                                    // Dirichlet / host-evaluated time boundary
+      out.x = v0; out.y = v1; out.z = v2;
+      break;
+    case 3:                                    // Transmissive
+      if (centroid_transmissive) {
+        const d4 c = D.cq[k];                  // centroid arrays as the reference sees them
+        const Eff ef = effective(c, K);
+        out.x = ef.w; out.y = ef.uh; out.z = ef.vh;
+        if (D.zflag[k]) { out.y = 0.0; out.z = 0.0; }
+      } else {
+        out.x = e.x; out.y = e.z; out.z = e.w;
+      }
+      break;
+    case 4: {                                  // Transmissive_n_momentum_zero_t_momentum_set_stage
+      const double ndotq = n1 * e.z + n2 * e.w;
+      out.x = v0;
+      out.y = ndotq * n1;
+      out.z = ndotq * n2;
+    } break;
+    case 5:                                    // Transmissive_momentum_set_stage
+      out.x = v0; out.y = e.z; out.z = e.w;
+      break;
+    case 6:                                    // Transmissive_stage_zero_momentum
+      out.x = e.x; out.y = 0.0; out.z = 0.0;
+      break;
+    default:
+      touched = false;
+  }
+  out.w = 0.0;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_boundary_values(Dev D, Segments S, Consts K, int centroid_transmissive)
+{
+  if (D.clock->stop) return;
+  const int m = blockIdx.x * BLOCK + threadIdx.x;
+  if (m >= D.M) return;
+  d4 out;
+  bool touched;
+  boundary_value(D, S, K, m, centroid_transmissive, out, touched);
+  if (touched) D.bq[m] = out;
+}
+
+// =============================================================================
+// Flux of one triangle: _openmp_compute_fluxes_central loop body (:521-719).
+// =============================================================================
+struct TriFlux {
+  double su, xu, yu;      // explicit updates (already scaled by 1/area)
+  double dtmin;           // min edge timestep of this triangle (1e100 if none)
+  double speed;           // max_speed[k]
+  double bflux[3];        // -flux0*length per edge (boundary-flux accounting)
+};
+
+template <bool RW>
+__device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, int k, const i4 p,
+                                                 const Eff &own, bool first)
+{
+  const int NP = D.NP;
+  d4 el[3];
+  el[0] = D.eq[k];
+  el[1] = D.eq[NP + k];
+  el[2] = D.eq[2 * NP + k];
+  const d4 f0 = D.fg[k];
+  const d4 f1 = D.fg[NP + k];
+  const d4 f2 = D.fg[2 * NP + k];
+  const int pn[3] = {p.x, p.y, p.z};
+  d4 er[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int q = pn[i];
+    if (q >= 0) er[i] = D.eq[(q & 3) * NP + (q >> 2)];
+    else er[i] = D.bq[-q - 1];
+  }
+  const double nx[3] = {f0.x, f0.z, f1.x};
+  const double ny[3] = {f0.y, f0.w, f1.y};
+  const double len[3] = {f1.z, f1.w, f2.x};
+  const double inv_area = f2.y;
+  const double radius = f2.z;
+  const bool full = p.w & 1;
+  const double hc = own.h, zc = own.z;
+
+  TriFlux T;
+  T.su = 0.0; T.xu = 0.0; T.yu = 0.0;
+  T.dtmin = 1.0e+100;
+  T.speed = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double wl = el[i].x, hle = el[i].y, uhl = el[i].z, vhl = el[i].w;
+    const double zl = wl - hle;                       // bed_edge = stage_edge - height_edge (:1863)
+    double wr, uhr, vhr, zr, hre;
+    if (pn[i] < 0) {                                  // :551-561
+      wr = er[i].x; uhr = er[i].y; vhr = er[i].z;
+      zr = zl;
+      hre = fmax(wr - zr, 0.0);
+    } else {                                          // :562-576
+      wr = er[i].x; hre = er[i].y; uhr = er[i].z; vhr = er[i].w;
+      zr = wr - hre;
+    }
+    double z_half = fmax(zl, zr);
+    bool rw_edge = false;
+    int rwc = 0;
+    if (RW) {
+      rw_edge = (p.w >> (1 + i)) & 1;
+      if (rw_edge) {                                  // :582-588
+        rwc = D.rw_counter[i * NP + k];
+        z_half = fmax(D.rw_elevation[rwc - 1], z_half);
+      }
+    }
+    const double h_left = fmax(hle + zl - z_half, 0.);
+    const double h_right = fmax(hre + zr - z_half, 0.);
+    EdgeFlux F = edge_flux_central(wl, uhl, vhl, wr, uhr, vhr, h_left, h_right, hle, hre,
+                                   nx[i], ny[i], z_half, K);
+    if (RW) {
+      if (rw_edge) {                                  // :607-653
+        const int ii = D.rw_rowIndex[rwc - 1] * D.rw_ncol;
+        const double Qfactor = D.rw_hydraulic[ii];
+        const double s1 = D.rw_hydraulic[ii + 1];
+        const double s2 = D.rw_hydraulic[ii + 2];
+        const double h1 = D.rw_hydraulic[ii + 3];
+        const double h2 = D.rw_hydraulic[ii + 4];
+        const double rw_elev = D.rw_elevation[rwc - 1];
+        const double weir_height = fmax(rw_elev - fmin(zl, zr), 0.);
+        const double h_left_tmp = fmax(own.w - z_half, 0.);
+        double h_right_tmp, zc_n = zc;
+        if (pn[i] >= 0) {
+          const Eff en = effective(D.cq[pn[i] >> 2], K);
+          zc_n = en.z;
+          h_right_tmp = fmax(en.w - z_half, 0.);
+        } else {
+          h_right_tmp = fmax(hc + zr - z_half, 0.);
+        }
+        if (rw_elev > fmax(zc, zc_n))
+          weir_adjust(F, h_left_tmp, h_right_tmp, K.g, weir_height, Qfactor, s1, s2, h1, h2);
+      }
+    }
+    const double length = len[i];
+    const double ef0 = -F.f0 * length;
+    const double ef1 = -F.f1 * length;
+    const double ef2 = -F.f2 * length;
+    const double pressuregrad =
+        length * (-K.g * 0.5 * (h_left * h_left - hle * hle - (hle + hc) * (zl - zc)) + F.pressure_flux);
+    if (first) {                                      // :667-686
+      const double edge_timestep = radius * 1.0 / fmax(F.max_speed, K.epsilon);
+      if (full && F.max_speed > K.epsilon) {
+        T.dtmin = fmin(T.dtmin, edge_timestep);
+        T.speed = fmax(T.speed, F.max_speed);
+      }
+    }
+    T.su += ef0;
+    T.xu += ef1;
+    T.yu += ef2;
+    T.bflux[i] = ef0;
+    T.xu -= nx[i] * pressuregrad;
+    T.yu -= ny[i] * pressuregrad;
+  }
+  T.su *= inv_area;
+  T.xu *= inv_area;
+  T.yu *= inv_area;
+  return T;
+}
+
+// block-wide min of positive doubles -> one atomicMin per block
+__device__ __forceinline__ void block_min_to_clock(double v, Clock *clock)
+{
+  __shared__ double smin[BLOCK / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smin[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    v = (lane < BLOCK / 32) ? smin[lane] : 1.0e+100;
+#pragma unroll
+    for (int o = BLOCK / 64; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0 && v < 1.0e+100) atomicMin(&clock->dt_min_bits, d2u(v));
+  }
+}
+
+// update of one triangle's conserved quantities from its explicit updates:
+// friction (sw_domain_openmp.c:1954-2034) -> Quantity.update x3 (quantity.c:772-820)
+// -> fix_negative_cells (:2037-2056) -> optional RK combine (quantity.c:752-769,
+// generic_domain.py:2045, 2126, 2167-2170).
+struct UpdateArgs {
+  double a, b, divide_by;     // saxpy coefficients; combine only if do_saxpy
+  double g;
+  int do_backup, do_saxpy, sloped;
+};
+
+__device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, const UpdateArgs &U,
+                                                int k, const d4 raw, Eff e, bool full,
+                                                double su, double xu, double yu, double dt)
+{
+  const int NP = D.NP;
+  if (U.do_backup) {                                   // backup holds the RAW start-of-step values
+    D.bk[k] = raw.x;
+    D.bk[NP + k] = raw.y;
+    D.bk[2 * NP + k] = raw.z;
+  }
+  if (D.zflag[k]) { e.uh = 0.0; e.vh = 0.0; }
+  double zs = 1.0;
+  double h = e.w - e.z;
+  if (U.sloped) {                                      // :2003-2023 with the dynamic bed vertex values
+    const d4 a0 = D.eq[k], a1 = D.eq[NP + k], a2 = D.eq[2 * NP + k];
+    const double b0 = a0.x - a0.y, b1 = a1.x - a1.y, b2 = a2.x - a2.y;
+    const double z0 = b1 + b2 - b0, z1 = b0 + b2 - b1, z2 = b0 + b1 - b2;
+    const double x0 = D.vcoord[k], y0 = D.vcoord[NP + k], x1 = D.vcoord[2 * NP + k];
+    const double y1 = D.vcoord[3 * NP + k], x2 = D.vcoord[4 * NP + k], y2 = D.vcoord[5 * NP + k];
+    const double det = (y2 - y0) * (x1 - x0) - (y1 - y0) * (x2 - x0);
+    double zx = (y2 - y0) * (z1 - z0) - (y1 - y0) * (z2 - z0);
+    zx /= det;
+    double zy = (x1 - x0) * (z2 - z0) - (x2 - x0) * (z1 - z0);
+    zy /= det;
+    zs = sqrt(1.0 + zx * zx + zy * zy);
+    h = e.w - (z0 + z1 + z2) * (1.0 / 3.0);
+  }
+  const double S = manning_S(U.g, K.mah, D.eta[k], h, e.uh, e.vh, zs, U.sloped);
+  double w = e.w, uh = e.uh, vh = e.vh;
+  w += dt * su;                                        // stage has no semi-implicit term: /1.0 is exact
+  bool ok = true;
+  ok &= update_value(uh, dt, xu, 0.0 + S * e.uh);
+  ok &= update_value(vh, dt, yu, 0.0 + S * e.vh);
+  if (!ok) D.clock->stop = -3;                         // SWK_ERR_DENOMINATOR
+  if ((w - e.z < 0.0) & full) {                        // fix_negative_cells
+    w = e.z; uh = 0.0; vh = 0.0;
+    atomicAdd((unsigned long long *)&D.clock->negative_cells, 1ULL);
+  }
+  if (U.do_saxpy) {
+    w = U.a * w + U.b * D.bk[k];
+    uh = U.a * uh + U.b * D.bk[NP + k];
+    vh = U.a * vh + U.b * D.bk[2 * NP + k];
+    if (U.divide_by != 1.0) {
+      w = w / U.divide_by;
+      uh = uh / U.divide_by;
+      vh = vh / U.divide_by;
+    }
+  }
+  d4 out;
+  out.x = w; out.y = uh; out.z = vh; out.w = e.z;
+  D.cq[k] = out;
+}
+
+// Pass B1 (substep 0): flux + dt partials.  writes eu, max_speed, dt_min_bits.
+template <bool RW>
+__global__ void __launch_bounds__(BLOCK) k_flux(Dev D, Consts K, int first, int write_speed)
+{
+  if (D.clock->stop) return;
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  double dtmin = 1.0e+100;
+  if (k < D.N) {
+    const i4 p = D.connB[k];
+    const Eff own = effective(D.cq[k], K);
+    const TriFlux T = triangle_flux<RW>(D, K, k, p, own, first != 0);
+    D.eu[k] = T.su;
+    D.eu[D.NP + k] = T.xu;
+    D.eu[2 * D.NP + k] = T.yu;
+    if (first && write_speed) D.max_speed[k] = T.speed;
+    dtmin = T.dtmin;
+  }
+  if (first) block_min_to_clock(dtmin, D.clock);
+}
+
+// Pass B2 (substep 0): friction + update + fix-negative (+ RK backup), dt from the clock.
+__global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U, double dt_override)
+{
+  if (D.clock->stop) return;
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  const double dt = (dt_override >= 0.0) ? dt_override : D.clock->dt;
+  const d4 raw = D.cq[k];
+  const Eff e = effective(raw, K);
+  const bool full = D.connB[k].w & 1;
+  triangle_update(D, K, U, k, raw, e, full, D.eu[k], D.eu[D.NP + k], D.eu[2 * D.NP + k], dt);
+}
+
+// Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
+// dt is already known, so explicit updates never touch HBM.  (Not used with
+// riverwalls: the weir branch reads the neighbour's stage centroid, :635.)
+__global__ void __launch_bounds__(BLOCK) k_flux_update(Dev D, Consts K, UpdateArgs U)
+{
+  if (D.clock->stop) return;
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  const double dt = D.clock->dt;
+  const i4 p = D.connB[k];
+  const d4 raw = D.cq[k];
+  const Eff e = effective(raw, K);
+  const TriFlux T = triangle_flux<false>(D, K, k, p, e, false);
+  triangle_update(D, K, U, k, raw, e, p.w & 1, T.su, T.xu, T.yu, dt);
+}
+
+// =============================================================================
+// boundary_flux_sum[substep]: sum of the mass flux through edges of full cells that
+// face a boundary or a ghost cell (:696-701, 765).  The accounting edges are few
+// (O(sqrt N)); their fluxes are re-evaluated here by ONE block that walks the list
+// in the reference's (k, i) order with a fixed reduction tree, so the sum is
+// reproducible run to run.
+// =============================================================================
+template <bool RW>
+__global__ void __launch_bounds__(1024) k_boundary_flux_sum(Dev D, Consts K, const int *acct, int n_acct, int substep)
+{
+  if (D.clock->stop) return;
+  __shared__ double part[1024];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < n_acct; j += 1024) {
+    const int ki = acct[j];
+    const int k = ki >> 2, i = ki & 3;
+    const i4 p = D.connB[k];
+    const Eff own = effective(D.cq[k], K);
+    const TriFlux T = triangle_flux<RW>(D, K, k, p, own, false);
+    s += T.bflux[i];
+  }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) D.clock->boundary_flux_sum[substep] = part[0];
+}
+
+// =============================================================================
+// Clock kernels (one thread): Generic_Domain.update_timestep (generic_domain.py:
+// 2349-2415) and the bookkeeping of _evolve_base (:1853-1911).
+// =============================================================================
+__global__ void k_begin_step(Clock *c)
+{
+  if (c->stop) return;
+  c->step_start_time = c->time;
+  c->dt_min_bits = d2u(1.0e+100);
+}
+
+__global__ void k_update_timestep(Clock *c, TimeParams P)
+{
+  if (c->stop) return;
+  // compute_fluxes returned the min edge timestep (substep 0) ...
+  double flux_dt = u2d(c->dt_min_bits);
+  if (P.fixed_flux_timestep > 0.0) flux_dt = P.fixed_flux_timestep;
+  c->flux_dt = flux_dt;
+  double timestep = fmin(P.CFL * flux_dt, P.evolve_max_timestep);
+  c->recorded_max_timestep = fmax(timestep, c->recorded_max_timestep);
+  c->recorded_min_timestep = fmin(timestep, c->recorded_min_timestep);
+  if (timestep < P.evolve_min_timestep) {
+    c->smallsteps += 1;
+    if (c->smallsteps > P.max_smallsteps) {
+      c->smallsteps = 0;
+      if (c->order == 1) { c->stop = -4; return; }      // SWK_ERR_SMALLSTEP
+      c->order = 1;
+    }
+  } else {
+    c->smallsteps = 0;
+    if (c->order == 1 && P.default_order == 2) c->order = 2;
+  }
+  if (c->finaltime >= 0.0 && c->time + timestep > c->finaltime) timestep = c->finaltime - c->time;
+  if (c->time + timestep > c->yieldtime) timestep = c->yieldtime - c->time;
+  c->dt = timestep;
+}
+
+// set_relative_time between RK substeps (generic_domain.py:2011, 2093, 2132)
+__global__ void k_set_substep_time(Clock *c, double fraction)
+{
+  if (c->stop) return;
+  c->time = c->step_start_time + c->dt * fraction;
+}
+
+__global__ void k_finish_step(Clock *c, TimeParams P)
+{
+  if (c->stop) return;
+  // boundary_flux_integral_operator.__call__ (boundary_flux_integral_operator.py:44-62)
+  const double dt = c->dt;
+  if (P.method == 1) c->boundary_flux_integral += dt * c->boundary_flux_sum[0];
+  else if (P.method == 2) c->boundary_flux_integral += 0.5 * dt * (c->boundary_flux_sum[0] + c->boundary_flux_sum[1]);
+  else c->boundary_flux_integral += 1.0 / 6.0 * dt * (c->boundary_flux_sum[0] + c->boundary_flux_sum[1] + 4.0 * c->boundary_flux_sum[2]);
+  c->boundary_flux_sum[0] = c->boundary_flux_sum[1] = c->boundary_flux_sum[2] = 0.0;
+  c->time = c->step_start_time + c->dt;                 // :1855
+  c->number_of_steps += 1;
+  c->total_steps += 1;
+  if (c->order == 1) c->number_of_first_order_steps += 1;
+  if (P.method != 1) c->flux_dt = P.evolve_max_timestep;  // quirk (8): later substeps return evolve_max_timestep
+  if (c->finaltime >= 0.0 && c->time >= c->finaltime - P.epsilon) {   // :1870-1888
+    if (c->time > c->finaltime) { c->stop = -5; return; }
+    c->time = c->finaltime;
+    c->stop = 2;
+    return;
+  }
+  if (c->time >= c->yieldtime) { c->stop = 1; return; }  // :1891
+  if (c->step_budget > 0 && c->total_steps >= c->step_budget) c->stop = 3;
+}
+
+// =============================================================================
+// Rate_operator.__call__ (operators/rate_operators.py:149-269), device form.
+// all_nonneg mirrors `num.all(rate >= 0.0)` and is decided on the host from the
+// operator's rate (scalar or array); dt comes from the clock.
+// =============================================================================
+__global__ void __launch_bounds__(BLOCK) k_rate_operator(Dev D, double rate, double factor,
+                                                         const double *rate_array, const int *indices,
+                                                         int n, int all_nonneg, double *influx_partial)
+{
+  if (D.clock->stop) return;
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  double contrib = 0.0;
+  if (j < n) {
+    const int k = indices ? indices[j] : j;
+    const double dt = D.clock->dt;
+    const double r = rate_array ? rate_array[k] : rate;
+    double local_rate = factor * dt * r;
+    d4 c = D.cq[k];
+    if (all_nonneg) {
+      c.x = c.x + local_rate;
+    } else {
+      const double height = c.x - c.w;
+      local_rate = fmax(local_rate, -height);
+      const double f = (local_rate < 0.0) ? (local_rate + height) / (height + 1.0e-10) : 1.0;
+      c.x = c.x + local_rate;
+      c.y = c.y * f;
+      c.z = c.z * f;
+    }
+    D.cq[k] = c;
+    if (D.connB[k].w & 1) contrib = local_rate * D.xg[2 * D.NP + k].w;
+  }
+  // deterministic two-stage sum: per-block partials, finished by k_rate_finish
+  __shared__ double part[BLOCK];
+  part[threadIdx.x] = contrib;
+  __syncthreads();
+  for (int o = BLOCK / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) influx_partial[blockIdx.x] = part[0];
+}
+
+__global__ void __launch_bounds__(1024) k_rate_finish(Clock *c, const double *influx_partial, int nblocks)
+{
+  if (c->stop) return;
+  __shared__ double part[1024];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < nblocks; j += 1024) s += influx_partial[j];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) c->fractional_step_volume_integral += part[0];
+}
+
+// single-process ghost copy, Generic_Domain.update_ghosts (generic_domain.py:2448-2469)
+__global__ void __launch_bounds__(BLOCK) k_ghost_copy(Dev D, const int *full_ids, const int *ghost_ids, int n)
+{
+  if (D.clock->stop) return;
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= n) return;
+  const d4 s = D.cq[full_ids[j]];
+  d4 t = D.cq[ghost_ids[j]];
+  t.x = s.x; t.y = s.y; t.z = s.z;
+  D.cq[ghost_ids[j]] = t;
+}
+
+// halo pack / unpack for the multi-GPU exchange (parallel_generic_communications.py:188-245)
+__global__ void __launch_bounds__(BLOCK) k_halo_pack(Dev D, const int *ids, int n, double *buf)
+{
+  if (D.clock->stop) return;
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= n) return;
+  const d4 s = D.cq[ids[j]];
+  buf[3 * j] = s.x; buf[3 * j + 1] = s.y; buf[3 * j + 2] = s.z;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_halo_unpack(Dev D, const int *ids, int n, const double *buf)
+{
+  if (D.clock->stop) return;
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= n) return;
+  d4 t = D.cq[ids[j]];
+  t.x = buf[3 * j]; t.y = buf[3 * j + 1]; t.z = buf[3 * j + 2];
+  D.cq[ids[j]] = t;
+}
+
+// =============================================================================
+// Host<->device marshalling kernels (caller order <-> device order and layout)
+// =============================================================================
+// comp: 0..3 component of a d4 record; planes: number of [NP] planes in dst
+__global__ void __launch_bounds__(BLOCK) k_scatter_component(d4 *dst, int NP, int N, int planes, int comp,
+                                                             const double *src, const int *new2old)
+{
+  const long long t = (long long)blockIdx.x * BLOCK + threadIdx.x;
+  if (t >= (long long)N * planes) return;
+  const int i = (int)(t / N), k = (int)(t % N);
+  const double v = src[(long long)new2old[k] * planes + i];
+  double *rec = reinterpret_cast<double *>(&dst[(long long)i * NP + k]);
+  rec[comp] = v;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_gather_component(const d4 *srcrec, int NP, int N, int planes, int comp,
+                                                            double *dst, const int *new2old)
+{
+  const long long t = (long long)blockIdx.x * BLOCK + threadIdx.x;
+  if (t >= (long long)N * planes) return;
+  const int i = (int)(t / N), k = (int)(t % N);
+  const double *rec = reinterpret_cast<const double *>(&srcrec[(long long)i * NP + k]);
+  dst[(long long)new2old[k] * planes + i] = rec[comp];
+}
+
+// plain [planes][NP] double arrays
+__global__ void __launch_bounds__(BLOCK) k_scatter_plain(double *dst, int NP, int N, int planes,
+                                                         const double *src, const int *new2old)
+{
+  const long long t = (long long)blockIdx.x * BLOCK + threadIdx.x;
+  if (t >= (long long)N * planes) return;
+  const int i = (int)(t / N), k = (int)(t % N);
+  dst[(long long)i * NP + k] = src[(long long)new2old[k] * planes + i];
+}
+
+__global__ void __launch_bounds__(BLOCK) k_gather_plain(const double *srcp, int NP, int N, int planes,
+                                                        double *dst, const int *new2old)
+{
+  const long long t = (long long)blockIdx.x * BLOCK + threadIdx.x;
+  if (t >= (long long)N * planes) return;
+  const int i = (int)(t / N), k = (int)(t % N);
+  dst[(long long)new2old[k] * planes + i] = srcp[(long long)i * NP + k];
+}
+
+// derived host views: mode 0 height_c; 1 bed_e (stage_e-height_e); 2..6 vertex values of
+// stage,height,xmom,ymom,bed from the edge records (sw_domain_openmp.c:1871-1892)
+__global__ void __launch_bounds__(BLOCK) k_gather_derived(Dev D, Consts K, int mode, double *dst, const int *new2old)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  const long long o = new2old[k];
+  if (mode == 0) {
+    const Eff e = effective(D.cq[k], K);
+    dst[o] = e.h;
+    return;
+  }
+  const d4 a0 = D.eq[k], a1 = D.eq[D.NP + k], a2 = D.eq[2 * D.NP + k];
+  double e0, e1, e2;
+  switch (mode) {
+    case 1: case 6: e0 = a0.x - a0.y; e1 = a1.x - a1.y; e2 = a2.x - a2.y; break;
+    case 2: e0 = a0.x; e1 = a1.x; e2 = a2.x; break;
+    case 3: e0 = a0.y; e1 = a1.y; e2 = a2.y; break;
+    case 4: e0 = a0.z; e1 = a1.z; e2 = a2.z; break;
+    default: e0 = a0.w; e1 = a1.w; e2 = a2.w; break;
+  }
+  if (mode == 1) {
+    dst[3 * o] = e0; dst[3 * o + 1] = e1; dst[3 * o + 2] = e2;
+  } else {
+    dst[3 * o] = e1 + e2 - e0;
+    dst[3 * o + 1] = e0 + e2 - e1;
+    dst[3 * o + 2] = e0 + e1 - e2;
+  }
+}
+
+// ---- per-call elementwise entry points (host arrays staged to plain device arrays) ----
+__global__ void __launch_bounds__(BLOCK) k_manning_plain(double g, double eps, int N, int sloped, const double *x,
+                                                         const double *w, const double *zv, const double *uh,
+                                                         const double *vh, const double *eta,
+                                                         double *xmom_update, double *ymom_update)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= N) return;
+  double zs = 1.0, h;
+  if (sloped) {
+    const double z0 = zv[3 * k], z1 = zv[3 * k + 1], z2 = zv[3 * k + 2];
+    const double x0 = x[6 * k], y0 = x[6 * k + 1], x1 = x[6 * k + 2], y1 = x[6 * k + 3];
+    const double x2 = x[6 * k + 4], y2 = x[6 * k + 5];
+    const double det = (y2 - y0) * (x1 - x0) - (y1 - y0) * (x2 - x0);
+    double zx = (y2 - y0) * (z1 - z0) - (y1 - y0) * (z2 - z0);
+    zx /= det;
+    double zy = (x1 - x0) * (z2 - z0) - (x2 - x0) * (z1 - z0);
+    zy /= det;
+    zs = sqrt(1.0 + zx * zx + zy * zy);
+    h = w[k] - (z0 + z1 + z2) * (1.0 / 3.0);
+  } else {
+    h = w[k] - zv[k];
+  }
+  const double S = manning_S(g, eps, eta[k], h, uh[k], vh[k], zs, sloped != 0);
+  xmom_update[k] += S * uh[k];
+  ymom_update[k] += S * vh[k];
+}
+
+__global__ void __launch_bounds__(BLOCK) k_update_plain(int N, double dt, double *c, const double *eu, double *siu, int *err)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= N) return;
+  double x = c[k];
+  if (!update_value(x, dt, eu[k], siu[k])) *err = 1;
+  c[k] = x;
+  siu[k] = 0.0;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_saxpy_plain(int N, double a, double b, double *c, const double *bk)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= N) return;
+  c[k] = a * c[k] + b * bk[k];
+}
+
+}  // namespace swk
+
+namespace swk {
+// RK backup / combine on resident data (quantity.c:735-769, generic_domain.py:2167-2170)
+__global__ void __launch_bounds__(BLOCK) k_backup(Dev D)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  const d4 c = D.cq[k];
+  D.bk[k] = c.x;
+  D.bk[D.NP + k] = c.y;
+  D.bk[2 * D.NP + k] = c.z;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_saxpy(Dev D, double a, double b, double divide_by)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  d4 c = D.cq[k];
+  c.x = a * c.x + b * D.bk[k];
+  c.y = a * c.y + b * D.bk[D.NP + k];
+  c.z = a * c.z + b * D.bk[2 * D.NP + k];
+  if (divide_by != 1.0) {
+    c.x = c.x / divide_by;
+    c.y = c.y / divide_by;
+    c.z = c.z / divide_by;
+  }
+  D.cq[k] = c;
+}
+
+// _openmp_fix_negative_cells alone (sw_domain_openmp.c:2037-2056), per-call layer
+__global__ void __launch_bounds__(BLOCK) k_fix_negative(Dev D)
+{
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  d4 c = D.cq[k];
+  if ((c.x - c.w < 0.0) & ((D.connB[k].w & 1) != 0)) {
+    c.x = c.w; c.y = 0.0; c.z = 0.0;
+    D.cq[k] = c;
+    atomicAdd((unsigned long long *)&D.clock->negative_cells, 1ULL);
+  }
+}
+}  // namespace swk
+
+namespace swk {
+__global__ void k_set_dt(Clock *c, double dt) { c->dt = dt; }
+
+// boundary_flux_integral_operator.__call__ for a host-driven step
+__global__ void k_bfi_update(Clock *c, TimeParams P)
+{
+  const double dt = c->dt;
+  if (P.method == 1) c->boundary_flux_integral += dt * c->boundary_flux_sum[0];
+  else if (P.method == 2) c->boundary_flux_integral += 0.5 * dt * (c->boundary_flux_sum[0] + c->boundary_flux_sum[1]);
+  else c->boundary_flux_integral += 1.0 / 6.0 * dt * (c->boundary_flux_sum[0] + c->boundary_flux_sum[1] + 4.0 * c->boundary_flux_sum[2]);
+  c->boundary_flux_sum[0] = c->boundary_flux_sum[1] = c->boundary_flux_sum[2] = 0.0;
+}
+}  // namespace swk

@@ -1,0 +1,794 @@
+"""shallow_water.Domain API on top of the device backend.
+
+Host-side mirror of the reference interface for the DE hot path: the same
+method names, argument meaning and error behaviour as
+
+  anuga/shallow_water/shallow_water_domain.py   class Domain :144
+      set_flow_algorithm :1311-1400 (presets DE0 :583, DE1 :646, DE2 :709, DE0_7 :835, DE1_7 :770)
+      set_quantity :907, evolve :2300-2407, set_multiprocessor_mode :2859-2899
+  anuga/abstract_2d_finite_volumes/generic_domain.py
+      set_boundary :937-1033, _evolve_base :1715-1912, evolve_one_*_step :1914-2179,
+      update_timestep :2349-2415, set_fixed_flux_timestep :2332
+
+The arrays of the conserved quantities live in HBM between yields; the numpy
+arrays on ``domain.quantities[...]`` are refreshed at every yield (centroid
+values eagerly, edge/vertex values on first access) and re-uploaded when the
+user changes them through ``set_quantity``/``set_values`` (or calls
+``sync_from_host``).  There is no CPU execution path: without a usable sm_100
+device ``evolve`` raises.
+"""
+import numpy as np
+
+from . import backend as _b
+from .mesh import Mesh, rectangular_cross, morton_order
+from .quantity import Quantity
+
+# multiprocessor_mode of the B200 backend.  The reference uses 0 (orig C), 1 (simd),
+# 2 (openmp), 3 (openacc), 4 (cupy experiment) - shallow_water_domain.py:2859-2876.
+MODE_B200 = 5
+
+_CONFIG = dict(
+    epsilon=1.0e-12, g=9.8, minimum_allowed_height=1.0e-05, maximum_allowed_speed=0.0,
+    max_timestep=1000.0, min_timestep=1.0e-6, max_smallsteps=50, low_froude=0,
+    extrapolate_velocity_second_order=True, sloped_mannings_function=False,
+    optimise_dry_cells=False, default_order=2,
+)
+
+_ALGORITHMS = {
+    #          CFL  method   min_allowed_height  beta  beta_dry
+    "DE0":   (0.9, "euler", 1.0e-12, 0.5, 0.0),
+    "DE1":   (1.0, "rk2",   1.0e-5,  1.0, 0.0),
+    "DE2":   (1.0, "rk3",   1.0e-5,  1.0, 0.0),
+    "DE0_7": (0.9, "euler", 1.0e-12, 0.7, 0.1),
+    "DE1_7": (1.0, "rk2",   1.0e-12, 0.75, 0.1),
+}
+
+
+class Domain:
+    conserved_quantities = ["stage", "xmomentum", "ymomentum"]
+    evolved_quantities = ["stage", "xmomentum", "ymomentum", "elevation", "height", "xvelocity", "yvelocity"]
+    other_quantities = ["elevation", "friction", "height", "xvelocity", "yvelocity", "x", "y"]
+
+    def __init__(self, coordinates=None, vertices=None, boundary=None, mesh=None,
+                 use_inscribed_circle=False, full_send_dict=None, ghost_recv_dict=None,
+                 processor=0, numproc=1, number_of_full_nodes=None, number_of_full_triangles=None,
+                 ghost_layer_width=2, verbose=False, device=0, reorder=True, **ignored):
+        if mesh is None:
+            mesh = Mesh(coordinates, vertices, boundary, use_inscribed_circle=use_inscribed_circle)
+        self.mesh = mesh
+        for name in ("nodes", "triangles", "neighbours", "neighbour_edges", "surrogate_neighbours",
+                     "number_of_boundaries", "normals", "edgelengths", "radii", "areas",
+                     "centroid_coordinates", "vertex_coordinates", "edge_midpoint_coordinates",
+                     "boundary", "boundary_cells", "boundary_edges", "tag_boundary_cells",
+                     "number_of_triangles", "number_of_nodes", "boundary_length"):
+            setattr(self, name, getattr(mesh, name))
+        self.edge_coordinates = self.edge_midpoint_coordinates
+        self.number_of_elements = self.number_of_triangles
+        N = self.number_of_triangles
+        self.verbose = verbose
+        self.device = device
+        self.reorder = reorder
+        self.processor = processor
+        self.numproc = numproc
+        self.ghost_layer_width = ghost_layer_width
+        self.full_send_dict = {} if full_send_dict is None else full_send_dict
+        self.ghost_recv_dict = {} if ghost_recv_dict is None else ghost_recv_dict
+        # generic_domain.py:285-291
+        self.tri_full_flag = np.ones(N, dtype=np.int64)
+        for key in self.ghost_recv_dict:
+            self.tri_full_flag[np.asarray(self.ghost_recv_dict[key][0], dtype=np.int64)] = 0
+        self.number_of_full_triangles = int(self.tri_full_flag.sum()) if number_of_full_triangles is None \
+            else number_of_full_triangles
+
+        self.quantities = {}
+        for name in ["stage", "xmomentum", "ymomentum", "elevation", "friction", "height", "xvelocity", "yvelocity"]:
+            self.quantities[name] = Quantity(self, name)
+            self.quantities[name]._fetch = self._fetch_lazy
+
+        # scalars (config.py) and the DE0 default preset (shallow_water_domain.py:319-334)
+        self.epsilon = _CONFIG["epsilon"]
+        self.g = _CONFIG["g"]
+        self.H0 = _CONFIG["minimum_allowed_height"]
+        self.maximum_allowed_speed = _CONFIG["maximum_allowed_speed"]
+        self.evolve_max_timestep = _CONFIG["max_timestep"]
+        self.evolve_min_timestep = _CONFIG["min_timestep"]
+        self.max_smallsteps = _CONFIG["max_smallsteps"]
+        self.low_froude = _CONFIG["low_froude"]
+        self.extrapolate_velocity_second_order = _CONFIG["extrapolate_velocity_second_order"]
+        self.use_sloped_mannings = _CONFIG["sloped_mannings_function"]
+        self.optimise_dry_cells = _CONFIG["optimise_dry_cells"]
+        self.default_order = _CONFIG["default_order"]
+        self._order_ = self.default_order
+        self.centroid_transmissive_bc = False
+        self.fixed_flux_timestep = None
+        self.set_flow_algorithm("DE0")
+
+        self.multiprocessor_mode = MODE_B200
+        self.boundary_map = None
+        self.fractional_step_operators = []
+        self.starttime = 0.0
+        self.relative_time = 0.0
+        self.evolve_starttime = 0.0
+        self.timestep = 0.0
+        self.flux_timestep = 0.0
+        self.yieldstep = None
+        self.finaltime = None
+        self.relative_finaltime = None
+        self.evolved_called = False
+        self.number_of_steps = 0
+        self.number_of_first_order_steps = 0
+        self.recorded_min_timestep = self.evolve_max_timestep
+        self.recorded_max_timestep = self.evolve_min_timestep
+        self.smallsteps = 0
+        self.boundary_flux_integral = 0.0
+        self.fractional_step_volume_integral = 0.0
+        self.total_steps = 0
+        self.kernel_launches = 0
+        self.store = False
+        self.name = "domain"
+        self._dev = None
+        self._stale = set()
+        self.timestep_history = []
+        self.record_timestep_history = False
+
+    def __len__(self):
+        return self.number_of_triangles
+
+    # ------------------------------------------------------------------
+    # configuration (same names as the reference)
+    # ------------------------------------------------------------------
+    def set_flow_algorithm(self, flag="DE0"):
+        flag = str(flag).replace(".", "_")
+        if flag not in _ALGORITHMS:
+            raise Exception("Flow algorithm %r is not part of the B200 hot path; supported: %s"
+                            % (flag, sorted(_ALGORITHMS)))
+        cfl, method, mah, beta, beta_dry = _ALGORITHMS[flag]
+        self.flow_algorithm = flag
+        # _set_config_defaults re-reads config.py (shallow_water_domain.py:486-533)
+        self.H0 = _CONFIG["minimum_allowed_height"]
+        self.g = _CONFIG["g"]
+        self.low_froude = _CONFIG["low_froude"]
+        self.use_sloped_mannings = _CONFIG["sloped_mannings_function"]
+        self.CFL = cfl
+        self.timestepping_method = method
+        self.minimum_allowed_height = mah
+        self.default_order = 2
+        self.extrapolate_velocity_second_order = True
+        self.beta_w = self.beta_uh = self.beta_vh = beta
+        self.beta_w_dry = self.beta_uh_dry = self.beta_vh_dry = beta_dry
+        self.optimise_dry_cells = False
+        self.maximum_allowed_speed = 0.0
+        self._params_dirty = True
+
+    def get_flow_algorithm(self):
+        return self.flow_algorithm
+
+    def set_timestepping_method(self, flag):
+        m = {1: "euler", 2: "rk2", 3: "rk3", "euler": "euler", "rk2": "rk2", "rk3": "rk3"}
+        if flag not in m:
+            raise Exception("Incorrect option for set_timestepping_method")
+        self.timestepping_method = m[flag]
+        self._params_dirty = True
+
+    def get_timestepping_method(self):
+        return self.timestepping_method
+
+    def set_CFL(self, cfl=1.0):
+        if cfl > 2.0:
+            raise Exception("Setting CFL condition to %g which is greater than 2 may cause instability" % cfl)
+        self.CFL = cfl
+        self._params_dirty = True
+
+    def set_beta(self, beta):
+        self.beta_w = self.beta_uh = self.beta_vh = beta
+        self.beta_w_dry = self.beta_uh_dry = self.beta_vh_dry = beta
+        self._params_dirty = True
+
+    def set_betas(self, beta_w, beta_w_dry, beta_uh, beta_uh_dry, beta_vh, beta_vh_dry):
+        self.beta_w, self.beta_w_dry = beta_w, beta_w_dry
+        self.beta_uh, self.beta_uh_dry = beta_uh, beta_uh_dry
+        self.beta_vh, self.beta_vh_dry = beta_vh, beta_vh_dry
+        self._params_dirty = True
+
+    def set_minimum_allowed_height(self, minimum_allowed_height):
+        # shallow_water_domain.py:1476-1492: the only place H0 is set
+        self.minimum_allowed_height = minimum_allowed_height
+        self.H0 = minimum_allowed_height
+        self._params_dirty = True
+
+    def set_low_froude(self, low_froude=0):
+        assert low_froude in (0, 1, 2)
+        self.low_froude = low_froude
+        self._params_dirty = True
+
+    def set_extrapolate_velocity(self, flag=True):
+        self.extrapolate_velocity_second_order = bool(flag)
+        self._params_dirty = True
+
+    def set_sloped_mannings_function(self, flag=True):
+        self.use_sloped_mannings = bool(flag)
+        self._params_dirty = True
+        if self._dev is not None:
+            self._release_device()
+
+    def set_centroid_transmissive_bc(self, flag):
+        self.centroid_transmissive_bc = bool(flag)
+        self._params_dirty = True
+
+    def set_fixed_flux_timestep(self, flux_timestep=None):
+        if flux_timestep is not None and not flux_timestep > 0.0:
+            raise Exception("flux_timestep needs to be greater than 0.0")
+        self.fixed_flux_timestep = flux_timestep
+        self._params_dirty = True
+
+    def set_evolve_max_timestep(self, t):
+        self.evolve_max_timestep = t
+        self._params_dirty = True
+
+    def set_evolve_min_timestep(self, t):
+        self.evolve_min_timestep = t
+        self._params_dirty = True
+
+    def set_multiprocessor_mode(self, multiprocessor_mode=MODE_B200):
+        """Only the device mode exists here and it never falls back to a CPU mode
+        (the reference's mode 4 falls back to mode 0, shallow_water_domain.py:2887-2894)."""
+        if multiprocessor_mode != MODE_B200:
+            raise Exception("anuga_core_b200 implements multiprocessor_mode %d (B200 device) only; "
+                            "modes 0-4 are the reference's CPU/CuPy backends" % MODE_B200)
+        self.multiprocessor_mode = multiprocessor_mode
+        self._ensure_device()
+
+    def get_multiprocessor_mode(self):
+        return self.multiprocessor_mode
+
+    # accepted for script compatibility; SWW output is out of scope
+    def set_store(self, flag=True):
+        if flag:
+            raise NotImplementedError("SWW output is outside the hot-path scope; use set_store(False)")
+        self.store = False
+
+    def set_name(self, name):
+        self.name = name
+
+    def get_name(self):
+        return self.name
+
+    def set_datadir(self, path):
+        self.datadir = path
+
+    def set_quantities_to_be_stored(self, q):
+        self.quantities_to_be_stored = q
+
+    def set_starttime(self, t):
+        self.starttime = float(t)
+
+    # ------------------------------------------------------------------
+    # quantities and boundaries
+    # ------------------------------------------------------------------
+    def set_quantity(self, name, *args, **kwargs):
+        if name not in self.quantities:
+            raise Exception("Quantity %r is not part of this domain" % name)
+        self.quantities[name].set_values(*args, **kwargs)
+        self._stale.discard(name)
+
+    def get_quantity(self, name):
+        return self.quantities[name]
+
+    def get_quantity_names(self):
+        return list(self.quantities.keys())
+
+    def get_boundary_tags(self):
+        return self.mesh.get_boundary_tags()
+
+    def set_boundary(self, boundary_map):
+        """generic_domain.py:937-1033: every tag of the mesh must be bound."""
+        if self.boundary_map is None:
+            self.boundary_map = boundary_map
+        else:
+            for key in boundary_map:
+                self.boundary_map[key] = boundary_map[key]
+        for tag in self.get_boundary_tags():
+            if tag not in self.boundary_map:
+                raise Exception("Tag \"%s\" has not been bound to a boundary object.\n"
+                                "All boundary tags defined in domain must appear in set_boundary.\n"
+                                "The tags are: %s" % (tag, self.get_boundary_tags()))
+        self.boundary_objects = [((int(v), int(e)), self.boundary_map[self.mesh.boundary[(v, e)]])
+                                 for (v, e) in sorted(self.mesh.boundary.keys())]
+        self._boundary_dirty = True
+
+    def set_fractional_step_operator(self, operator):
+        self.fractional_step_operators.append(operator)
+        self._operators_dirty = True
+
+    def get_centroid_coordinates(self, absolute=False):
+        return self.centroid_coordinates
+
+    def get_vertex_coordinates(self, absolute=False):
+        return self.vertex_coordinates
+
+    def get_edge_midpoint_coordinates(self, absolute=False):
+        return self.edge_midpoint_coordinates
+
+    def get_areas(self):
+        return self.areas
+
+    def get_time(self):
+        return self.starttime + self.relative_time
+
+    def get_relative_time(self):
+        return self.relative_time
+
+    def get_timestep(self):
+        return self.timestep
+
+    def get_boundary_flux_integral(self):
+        return self.boundary_flux_integral
+
+    def get_fractional_step_volume_integral(self):
+        return self.fractional_step_volume_integral
+
+    def compute_total_volume(self):
+        self._pull_centroids()
+        h = self.quantities["stage"].centroid_values - self.quantities["elevation"].centroid_values
+        m = self.tri_full_flag == 1
+        return float(np.sum(h[m] * self.areas[m]))
+
+    get_water_volume = compute_total_volume
+
+    def timestepping_statistics(self, *a, **k):
+        msg = "Time = %.4f (sec), " % self.get_time()
+        if self.recorded_min_timestep == self.recorded_max_timestep:
+            msg += "delta t = %.8f (s), " % self.recorded_min_timestep
+        elif self.recorded_min_timestep > self.recorded_max_timestep:
+            msg += "delta t = %.8f (s), " % self.recorded_min_timestep
+        else:
+            msg += "delta t in [%.8f, %.8f] (s), " % (self.recorded_min_timestep, self.recorded_max_timestep)
+        msg += "steps=%d" % self.number_of_steps
+        return msg
+
+    def print_timestepping_statistics(self, *a, **k):
+        print(self.timestepping_statistics(*a, **k))
+
+    # ------------------------------------------------------------------
+    # device plumbing
+    # ------------------------------------------------------------------
+    def _param_dict(self):
+        return dict(
+            epsilon=self.epsilon, H0=self.H0, g=self.g, minimum_allowed_height=self.minimum_allowed_height,
+            maximum_allowed_speed=self.maximum_allowed_speed, evolve_max_timestep=self.evolve_max_timestep,
+            evolve_min_timestep=self.evolve_min_timestep, beta_w=self.beta_w, beta_w_dry=self.beta_w_dry,
+            beta_uh=self.beta_uh, beta_uh_dry=self.beta_uh_dry, beta_vh=self.beta_vh,
+            beta_vh_dry=self.beta_vh_dry, CFL=self.CFL, fixed_flux_timestep=self.fixed_flux_timestep,
+            extrapolate_velocity_second_order=self.extrapolate_velocity_second_order,
+            low_froude=self.low_froude, timestepping_method=self.timestepping_method,
+            use_sloped_mannings=self.use_sloped_mannings, max_smallsteps=self.max_smallsteps,
+            default_order=self.default_order, ghost_layer_width=self.ghost_layer_width,
+            centroid_transmissive_bc=self.centroid_transmissive_bc,
+        )
+
+    def _mesh_dict(self):
+        m = self.mesh
+        d = dict(
+            neighbours=m.neighbours, neighbour_edges=m.neighbour_edges,
+            surrogate_neighbours=m.surrogate_neighbours, number_of_boundaries=m.number_of_boundaries,
+            tri_full_flag=self.tri_full_flag, normals=m.normals, edgelengths=m.edgelengths,
+            radii=m.radii, areas=m.areas, centroid_coordinates=m.centroid_coordinates,
+            edge_coordinates=m.edge_midpoint_coordinates, vertex_coordinates=m.vertex_coordinates,
+            boundary_cells=m.boundary_cells, boundary_edges=m.boundary_edges,
+        )
+        for k in ("edge_flux_type", "edge_river_wall_counter", "riverwall_elevation", "riverwall_rowIndex",
+                  "riverwall_hydraulic_properties", "number_of_riverwall_edges",
+                  "ncol_riverwall_hydraulic_properties"):
+            if hasattr(self, k):
+                d[k] = getattr(self, k)
+        return d
+
+    def _release_device(self):
+        if self._dev is not None:
+            self._pull_centroids()
+            self._dev.close()
+            self._dev = None
+
+    def _ensure_device(self):
+        if self._dev is None:
+            perm = None
+            if self.reorder:
+                perm = self._locality_permutation()
+            self._dev = _b.DeviceDomain(self._mesh_dict(), self._param_dict(), device=self.device,
+                                        permutation=perm)
+            self._params_dirty = False
+            self._boundary_dirty = True
+            self._operators_dirty = True
+            self._segments = {}
+            for q in self.quantities.values():
+                q.host_dirty = True
+            for op in self.fractional_step_operators:
+                op.op_id = None
+            if self.processor in self.full_send_dict and self.processor in self.ghost_recv_dict \
+                    and self.numproc == 1:
+                self._dev.set_local_ghost_copy(self.full_send_dict[self.processor][0],
+                                               self.ghost_recv_dict[self.processor][0])
+        if self._params_dirty:
+            self._dev.set_params(self._param_dict())
+            self._params_dirty = False
+        return self._dev
+
+    def _locality_permutation(self):
+        """Morton order of the centroids; full triangles stay in front of ghosts so that
+        the reference's "full first, ghosts after" numbering invariant survives."""
+        perm = morton_order(self.centroid_coordinates)
+        full = self.tri_full_flag[perm] == 1
+        return np.concatenate([perm[full], perm[~full]])
+
+    _DEVICE_NAMES = {"stage": "STAGE", "xmomentum": "XMOM", "ymomentum": "YMOM",
+                     "elevation": "ELEVATION", "height": "HEIGHT"}
+
+    def _push_quantities(self, force=False):
+        dev = self._ensure_device()
+        q = self.quantities
+        for name, qid in (("stage", "STAGE_C"), ("xmomentum", "XMOM_C"), ("ymomentum", "YMOM_C"),
+                          ("elevation", "ELEVATION_C"), ("friction", "FRICTION_C")):
+            if force or q[name].host_dirty:
+                dev.set_quantity(qid, q[name].centroid_values)
+                q[name].host_dirty = False
+                self._stale.discard(name)
+
+    def sync_from_host(self):
+        """Declare that the numpy centroid arrays were modified in place."""
+        for name in ("stage", "xmomentum", "ymomentum", "elevation", "friction"):
+            self.quantities[name].host_dirty = True
+        self._push_quantities()
+
+    def _pull_centroids(self):
+        if self._dev is None:
+            return
+        q = self.quantities
+        for name, qid in (("stage", "STAGE_C"), ("xmomentum", "XMOM_C"), ("ymomentum", "YMOM_C")):
+            if name in self._stale and not q[name].host_dirty:
+                self._dev.get_quantity(qid, out=q[name].centroid_values)
+                self._stale.discard(name)
+
+    def sync_to_host(self):
+        self._pull_centroids()
+
+    def _mark_device_newer(self):
+        self._stale = {"stage", "xmomentum", "ymomentum"}
+        self._lazy_stale = {(n, a) for n in ("stage", "xmomentum", "ymomentum", "elevation", "height")
+                            for a in ("edge_values", "vertex_values")}
+        self._lazy_stale |= {(n, "explicit_update") for n in ("stage", "xmomentum", "ymomentum")}
+
+    def _fetch_lazy(self, quantity, array_name, out):
+        key = (quantity.name, array_name)
+        stale = getattr(self, "_lazy_stale", None)
+        if self._dev is None or not stale or key not in stale:
+            return
+        base = self._DEVICE_NAMES.get(quantity.name)
+        suffix = {"edge_values": "_E", "vertex_values": "_V", "explicit_update": "_EU"}[array_name]
+        self._dev.get_quantity(base + suffix, out=out)
+        stale.discard(key)
+
+    def _push_boundaries(self, t):
+        dev = self._dev
+        if self.boundary_map is None:
+            raise Exception("Boundary tags must be bound to boundary objects before evolving system, "
+                            "e.g. using the method set_boundary.\nThis system has the boundary tags %s"
+                            % self.get_boundary_tags())
+        if self._boundary_dirty:
+            self._segments = {}
+            for seg, tag in enumerate(sorted(self.tag_boundary_cells.keys())):
+                B = self.boundary_map[tag]
+                ids = self.tag_boundary_cells[tag]
+                kind = _b.BC_NONE if B is None else B.device_kind
+                vals = (0.0, 0.0, 0.0) if B is None else B.device_values(t)
+                dev.set_boundary_segment(seg, kind, ids, vals)
+                self._segments[tag] = (seg, B)
+            self._boundary_dirty = False
+        else:
+            for tag, (seg, B) in self._segments.items():
+                if B is not None and B.time_dependent:
+                    dev.set_boundary_values(seg, B.device_values(t))
+
+    def _push_operators(self, t):
+        dev = self._dev
+        for op in self.fractional_step_operators:
+            if op.op_id is None:
+                op.op_id = dev.add_rate_operator(op.current_rate(t), op.current_factor(t),
+                                                 op.rate_array, op.indices)
+            elif op.time_dependent:
+                dev.set_rate(op.op_id, op.current_rate(t), op.current_factor(t))
+        self._operators_dirty = False
+
+    def _needs_host_stepping(self):
+        if self.boundary_map:
+            for B in self.boundary_map.values():
+                if B is not None and B.time_dependent:
+                    return True
+        return any(op.time_dependent for op in self.fractional_step_operators)
+
+    # ------------------------------------------------------------------
+    # individual passes on resident data (same names as the reference's methods)
+    # ------------------------------------------------------------------
+    def distribute_to_vertices_and_edges(self):
+        self._push_quantities()
+        self._dev.distribute_to_vertices_and_edges()
+        self._mark_device_newer()
+
+    def protect_against_infinitesimal_and_negative_heights(self):
+        self._push_quantities()
+        me = self._dev.protect()
+        self._mark_device_newer()
+        return me
+
+    def update_boundary(self):
+        self._ensure_device()
+        self._push_boundaries(self.get_time())
+        self._dev.update_boundary()
+
+    def compute_fluxes(self, substep=0):
+        self._ensure_device()
+        self.flux_timestep = self._dev.compute_fluxes(substep)
+        self._lazy_stale = getattr(self, "_lazy_stale", set()) | \
+            {(n, "explicit_update") for n in ("stage", "xmomentum", "ymomentum")}
+        return self.flux_timestep
+
+    def update_conserved_quantities(self):
+        n = self._dev.update_conserved_quantities(self.timestep)
+        self._mark_device_newer()
+        if n > 0:
+            import warnings
+            warnings.warn("Negative cells being set to zero depth, possible loss of conservation. \n"
+                          "Consider using domain.report_water_volume_statistics() to check the extent "
+                          "of the problem")
+
+    def backup_conserved_quantities(self):
+        self._push_quantities()
+        self._dev.backup_conserved_quantities()
+
+    def saxpy_conserved_quantities(self, a, b, divide_by=1.0):
+        self._dev.saxpy_conserved_quantities(a, b, divide_by)
+        self._mark_device_newer()
+
+    def update_ghosts(self):
+        self._ensure_device()
+        self._dev.update_ghosts()
+        self._mark_device_newer()
+
+    def get_max_speed(self):
+        self._ensure_device()
+        return self._dev.get_quantity("MAX_SPEED")
+
+    @property
+    def max_speed(self):
+        return self.get_max_speed()
+
+    # ------------------------------------------------------------------
+    # evolve
+    # ------------------------------------------------------------------
+    def update_timestep(self, yieldstep, finaltime):
+        """generic_domain.py:2349-2415 (host version, used by the host-stepped path)"""
+        if self.fixed_flux_timestep is not None:
+            self.flux_timestep = self.fixed_flux_timestep
+        timestep = min(self.CFL * self.flux_timestep, self.evolve_max_timestep)
+        self.recorded_max_timestep = max(timestep, self.recorded_max_timestep)
+        self.recorded_min_timestep = min(timestep, self.recorded_min_timestep)
+        if timestep < self.evolve_min_timestep:
+            self.smallsteps += 1
+            if self.smallsteps > self.max_smallsteps:
+                self.smallsteps = 0
+                if self._order_ == 1:
+                    raise Exception("WARNING: Too small timestep %.16f reached even after %d steps of 1 order scheme"
+                                    % (timestep, self.max_smallsteps))
+                self._order_ = 1
+        else:
+            self.smallsteps = 0
+            if self._order_ == 1 and self.default_order == 2:
+                self._order_ = 2
+        if self.relative_finaltime is not None and self.relative_time + timestep > self.relative_finaltime:
+            timestep = self.relative_finaltime - self.relative_time
+        if self.relative_time + timestep > self.relative_yieldtime:
+            timestep = self.relative_yieldtime - self.relative_time
+        self.timestep = timestep
+
+    def _host_step(self):
+        """One timestep driven from Python (evolve_one_*_step, generic_domain.py:1914-2179):
+        used when boundary or operator callbacks must be evaluated on the host between
+        substeps.  Data stays resident; only scalars cross the bus."""
+        dev = self._dev
+        method = self.timestepping_method
+        t0 = self.relative_time
+
+        def substep(k):
+            dev.distribute_to_vertices_and_edges()
+            self._push_boundaries(self.get_time())
+            dev.update_boundary()
+            return dev.compute_fluxes(k)
+
+        if method != "euler":
+            dev.backup_conserved_quantities()
+        self.flux_timestep = substep(0)
+        self.update_timestep(self.yieldstep, self.finaltime)
+        dt = self.timestep
+        self._check_negative(dev.update_conserved_quantities(dt))
+        if method == "rk2":
+            self.relative_time = t0 + dt
+            if self.ghost_layer_width < 4:
+                dev.update_ghosts()
+            substep(1)
+            self._check_negative(dev.update_conserved_quantities(dt))
+            dev.saxpy_conserved_quantities(0.5, 0.5)
+        elif method == "rk3":
+            self.relative_time = t0 + dt
+            dev.update_ghosts()
+            substep(1)
+            self._check_negative(dev.update_conserved_quantities(dt))
+            dev.saxpy_conserved_quantities(0.25, 0.75)
+            self.relative_time = t0 + dt * 0.5
+            dev.update_ghosts()
+            substep(2)
+            self._check_negative(dev.update_conserved_quantities(dt))
+            dev.saxpy_conserved_quantities(2.0, 1.0, 3.0)
+        self.relative_time = t0
+
+    def _check_negative(self, n):
+        self._negative_cells = getattr(self, "_negative_cells", 0) + n
+
+    def evolve(self, yieldstep=None, finaltime=None, duration=None, skip_initial_step=False):
+        """Generator with the reference's protocol: yields the model time with the
+        conserved centroid arrays valid on the host (shallow_water_domain.py:2300-2407,
+        generic_domain.py:1715-1912)."""
+        if self.boundary_map is None:
+            raise Exception("Boundary tags must be bound to boundary objects before evolving system, "
+                            "e.g. using the method set_boundary.\nThis system has the boundary tags %s"
+                            % self.get_boundary_tags())
+        if self.evolved_called:
+            skip_initial_step = True
+        self.evolved_called = True
+        if skip_initial_step:
+            self.evolve_starttime = self.relative_time
+        if self.relative_time != self.evolve_starttime:
+            self.relative_time = self.evolve_starttime
+        yieldstep = self.evolve_max_timestep if yieldstep is None else float(yieldstep)
+        self.yieldstep = yieldstep
+        self._order_ = self.default_order
+        if finaltime is not None and duration is not None:
+            raise Exception("Only one of finaltime and duration may be specified")
+        if finaltime is not None:
+            self.finaltime = float(finaltime)
+            self.relative_finaltime = self.finaltime - self.starttime
+        if duration is not None:
+            self.finaltime = float(duration) + self.get_time()
+            self.relative_finaltime = float(duration) + self.relative_time
+        if self.relative_finaltime is not None and self.relative_finaltime < self.relative_time:
+            import warnings
+            warnings.warn("\n finaltime %g is less than current time %g! finaltime set to current time"
+                          % (self.finaltime, self.get_time()))
+            self.finaltime = self.get_time()
+            self.relative_finaltime = self.relative_time
+            return
+
+        dev = self._ensure_device()
+        self._push_quantities(force=not hasattr(self, "_pushed_once"))
+        self._pushed_once = True
+        dev.set_time(self.relative_time)
+        self._push_boundaries(self.get_time())
+        self._push_operators(self.get_time())
+
+        self.relative_yieldtime = self.relative_time + yieldstep
+        self.recorded_min_timestep = self.evolve_max_timestep
+        self.recorded_max_timestep = self.evolve_min_timestep
+        self.number_of_steps = 0
+        self.number_of_first_order_steps = 0
+        dev.reset_yield_statistics()
+        dev.update_ghosts()
+
+        if not skip_initial_step:
+            dev.distribute_to_vertices_and_edges()
+            dev.update_boundary()
+            self._mark_device_newer()
+            self._pull_centroids()
+            yield self.get_time()
+
+        while True:
+            # user code may have touched the arrays during the yield
+            self._push_quantities()
+            if self._boundary_dirty:
+                self._push_boundaries(self.get_time())
+            if self._operators_dirty:
+                self._push_operators(self.get_time())
+            if self._params_dirty:
+                dev.set_params(self._param_dict())
+                self._params_dirty = False
+
+            if self._needs_host_stepping():
+                reason = self._evolve_host_stepped()
+            else:
+                r = dev.evolve(self.relative_yieldtime, self.relative_finaltime, 0)
+                self._absorb(r)
+                reason = r.stop_reason
+            self._mark_device_newer()
+            self._pull_centroids()
+            if getattr(self, "_negative_cells_warned", 0) < self._negative_total():
+                import warnings
+                self._negative_cells_warned = self._negative_total()
+                warnings.warn("Negative cells being set to zero depth, possible loss of conservation. \n"
+                              "Consider using domain.report_water_volume_statistics() to check the extent "
+                              "of the problem")
+            if reason == 2:
+                yield self.get_time()
+                break
+            yield self.get_time()
+            self.relative_yieldtime += yieldstep
+            self.recorded_min_timestep = self.evolve_max_timestep
+            self.recorded_max_timestep = self.evolve_min_timestep
+            self.number_of_steps = 0
+            self.number_of_first_order_steps = 0
+            dev.reset_yield_statistics()
+
+    def _negative_total(self):
+        return getattr(self, "_negative_device", 0) + getattr(self, "_negative_cells", 0)
+
+    def _absorb(self, r):
+        self.relative_time = r.time
+        self.timestep = r.timestep
+        self.flux_timestep = r.flux_timestep
+        self.recorded_min_timestep = r.recorded_min_timestep
+        self.recorded_max_timestep = r.recorded_max_timestep
+        self.number_of_steps = r.number_of_steps
+        self.number_of_first_order_steps = r.number_of_first_order_steps
+        self.boundary_flux_integral = r.boundary_flux_integral
+        self.fractional_step_volume_integral = r.fractional_step_volume_integral
+        self.total_steps = r.total_steps
+        self.mass_error = r.mass_error
+        self._negative_device = r.negative_cells
+        self.kernel_launches += r.kernel_launches
+
+    def _evolve_host_stepped(self):
+        """_evolve_base's while loop with host-evaluated callbacks (time-dependent
+        boundaries, rate functions of time).  One device->host scalar read per step."""
+        dev = self._dev
+        while True:
+            t0 = self.relative_time
+            dev.set_time(t0)
+            self._push_operators(self.get_time())
+            # the whole step on the device when nothing depends on the substep time,
+            # else substep by substep
+            self._host_step()
+            # apply_fractional_steps runs inside swk_evolve's step; here do it explicitly:
+            self._host_fractional_steps()
+            self.relative_time = t0 + self.timestep
+            dev.set_time(self.relative_time)
+            dev.update_ghosts()
+            self.number_of_steps += 1
+            self.total_steps += 1
+            if self.record_timestep_history:
+                self.timestep_history.append(self.timestep)
+            if self._order_ == 1:
+                self.number_of_first_order_steps += 1
+            if self.relative_finaltime is not None and self.relative_time >= self.relative_finaltime - self.epsilon:
+                if self.relative_time > self.relative_finaltime:
+                    raise Exception("WARNING (domain.py): time overshot finaltime. ")
+                self.relative_time = self.relative_finaltime
+                dev.set_time(self.relative_time)
+                dev.distribute_to_vertices_and_edges()
+                self._push_boundaries(self.get_time())
+                dev.update_boundary()
+                return 2
+            if self.relative_time >= self.relative_yieldtime:
+                dev.distribute_to_vertices_and_edges()
+                self._push_boundaries(self.get_time())
+                dev.update_boundary()
+                return 1
+
+    def _host_fractional_steps(self):
+        """apply_fractional_steps (generic_domain.py:2312) for a host-driven step"""
+        self._dev.apply_fractional_steps(self.timestep)
+        r = self._dev.get_statistics()
+        self.boundary_flux_integral = r.boundary_flux_integral
+        self.fractional_step_volume_integral = r.fractional_step_volume_integral
+        self.mass_error = r.mass_error
+
+
+def rectangular_cross_domain(m, n, len1=1.0, len2=1.0, origin=(0.0, 0.0), **kwargs):
+    """anuga/extras.py:13 - rectangular_cross mesh wrapped in a Domain."""
+    points, vertices, boundary = rectangular_cross(int(m), int(n), len1, len2, origin)
+    return Domain(points, vertices, boundary, **kwargs)

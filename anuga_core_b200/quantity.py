@@ -1,0 +1,185 @@
+"""Host-side Quantity: the user-visible numpy arrays of one field.
+
+Mirror of the parts of anuga/abstract_2d_finite_volumes/quantity.py the hot path
+touches: the arrays (quantity.py:63-103), ``set_values`` for constants, arrays,
+callables and other quantities at 'vertices' / 'centroids' (:709-1010,
+:1103-1200), ``interpolate`` (:quantity.c:665-688) and
+``extrapolate_first_order``.  File/geospatial/raster sources are out of scope
+(SURVEY.md section 2, rows 7-9).
+
+Arrays are allocated on first access so that a 16M-triangle domain does not pay
+for (N,3) arrays nobody reads.
+"""
+import numpy as np
+
+_LAZY = {
+    "vertex_values": 3, "edge_values": 3, "explicit_update": 1, "semi_implicit_update": 1,
+    "centroid_backup_values": 1,
+}
+
+
+class Quantity:
+    def __init__(self, domain, name=None):
+        self.domain = domain
+        self.name = name
+        N = domain.number_of_triangles
+        self.N = N
+        self.centroid_values = np.zeros(N, dtype=np.float64)
+        self.boundary_values = np.zeros(domain.boundary_length, dtype=np.float64)
+        self._arrays = {}
+        self.beta = 1.0
+        # host copy is newer than the device copy (set by the setters below)
+        self.host_dirty = True
+
+    def __len__(self):
+        return self.N
+
+    def __getattr__(self, name):
+        if name in _LAZY:
+            arrays = self.__dict__["_arrays"]
+            if name not in arrays:
+                N = self.__dict__["N"]
+                k = _LAZY[name]
+                arrays[name] = np.zeros((N, 3) if k == 3 else N, dtype=np.float64)
+                if k == 3:   # first touch: consistent with the centroid values
+                    arrays[name][:] = self.__dict__["centroid_values"][:, None]
+            fetch = self.__dict__.get("_fetch")
+            if fetch is not None:
+                fetch(self, name, arrays[name])
+            return arrays[name]
+        raise AttributeError(name)
+
+    # ------------------------------------------------------------------
+    def set_values(self, numeric=None, quantity=None, function=None, location="vertices",
+                   indices=None, **unsupported):
+        for k, v in unsupported.items():
+            if v not in (None, False):
+                raise NotImplementedError("set_values(%s=...) is outside the hot-path scope" % k)
+        if location == "edges":
+            raise Exception("edges has been deprecated as valid location")
+        if location not in ("vertices", "centroids", "unique vertices"):
+            raise Exception("Invalid location: %s" % location)
+        if location == "unique vertices":
+            raise NotImplementedError("location='unique vertices' is outside the hot-path scope")
+        given = [x for x in (numeric, quantity, function) if x is not None]
+        if len(given) != 1:
+            raise Exception("Exactly one of the arguments numeric, quantity, function must be present.")
+        if function is not None:
+            assert callable(function), "Argument function must be callable"
+            numeric = function
+        if quantity is not None:
+            numeric = quantity
+
+        if isinstance(numeric, Quantity):
+            self._from_quantity(numeric, location, indices)
+        elif callable(numeric):
+            self._from_function(numeric, location, indices)
+        elif isinstance(numeric, (list, tuple, np.ndarray)):
+            self._from_array(np.asarray(numeric, dtype=np.float64), location, indices)
+        else:
+            self._from_constant(float(numeric), location, indices)
+
+        if location == "vertices":
+            self.interpolate()
+        else:
+            self.extrapolate_first_order()
+        self.host_dirty = True
+
+    def _from_constant(self, X, location, indices):
+        if location == "centroids":
+            if indices is None:
+                self.centroid_values[:] = X
+            else:
+                self.centroid_values[np.asarray(indices, dtype=np.int64)] = X
+        else:
+            if indices is None:
+                self.vertex_values[:] = X
+            else:
+                self.vertex_values[np.asarray(indices, dtype=np.int64)] = X
+
+    def _from_array(self, values, location, indices):
+        N = self.N
+        if location == "centroids":
+            if indices is None:
+                assert values.shape == (N,), "Number of values must match number of elements"
+                self.centroid_values[:] = values
+            else:
+                self.centroid_values[np.asarray(indices, dtype=np.int64)] = values
+        else:
+            if values.ndim == 1:
+                # one value per mesh node (quantity.py set_values_from_array, 1-D branch)
+                assert indices is None
+                assert values.shape[0] == self.domain.number_of_nodes, \
+                    "1-D vertex arrays must hold one value per node"
+                self.vertex_values[:] = values[self.domain.triangles]
+            else:
+                if indices is None:
+                    assert values.shape == (N, 3), "Array must be N x 3"
+                    self.vertex_values[:] = values
+                else:
+                    self.vertex_values[np.asarray(indices, dtype=np.int64)] = values
+
+    def _from_function(self, f, location, indices):
+        if location == "centroids":
+            C = self.domain.centroid_coordinates
+            if indices is not None:
+                C = C[np.asarray(indices, dtype=np.int64)]
+            res = f(C[:, 0], C[:, 1])
+            if np.isscalar(res):
+                self._from_constant(float(res), location, indices)
+            else:
+                self._from_array(np.asarray(res, dtype=np.float64), location, indices)
+        else:
+            V = self.domain.vertex_coordinates
+            values = f(V[:, 0], V[:, 1])
+            if np.isscalar(values):
+                self._from_constant(float(values), location, indices)
+                return
+            values = np.asarray(values, dtype=np.float64).reshape(self.N, 3)
+            if indices is None:
+                self.vertex_values[:] = values
+            else:
+                idx = np.asarray(indices, dtype=np.int64)
+                self.vertex_values[idx] = values[idx]
+
+    def _from_quantity(self, q, location, indices):
+        assert indices is None
+        self.vertex_values[:] = q.vertex_values
+        self.centroid_values[:] = q.centroid_values
+        self.edge_values[:] = q.edge_values
+
+    # ------------------------------------------------------------------
+    def interpolate(self):
+        """centroid = mean of vertices, edges = vertex mid-points (quantity.c:665-688)"""
+        v = self.vertex_values
+        q0, q1, q2 = v[:, 0], v[:, 1], v[:, 2]
+        self.centroid_values[:] = (q0 + q1 + q2) / 3.0
+        e = self.edge_values
+        e[:, 0] = 0.5 * (q1 + q2)
+        e[:, 1] = 0.5 * (q0 + q2)
+        e[:, 2] = 0.5 * (q0 + q1)
+
+    def extrapolate_first_order(self):
+        c = self.centroid_values
+        if "vertex_values" in self._arrays:
+            self._arrays["vertex_values"][:] = c[:, None]
+        if "edge_values" in self._arrays:
+            self._arrays["edge_values"][:] = c[:, None]
+
+    def get_values(self, location="vertices", indices=None):
+        if location == "centroids":
+            a = self.centroid_values
+        elif location == "edges":
+            a = self.edge_values
+        elif location == "vertices":
+            a = self.vertex_values
+        else:
+            raise NotImplementedError(location)
+        return a if indices is None else a[np.asarray(indices, dtype=np.int64)]
+
+    def get_integral(self, full_only=True):
+        areas = self.domain.areas
+        if full_only:
+            m = self.domain.tri_full_flag == 1
+            return float(np.sum(areas[m] * self.centroid_values[m]))
+        return float(np.sum(areas * self.centroid_values))

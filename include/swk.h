@@ -1,0 +1,311 @@
+/* swk.h - C ABI of the B200-native shallow-water kernel library (libswk.so).
+ *
+ * Drop-in boundary for ONE hot path of ANUGA: the per-timestep discontinuous-
+ * elevation (DE0/DE1/DE2) update of anuga.shallow_water.Domain.  Everything is
+ * `extern "C"`, plain pointers and sizes, no Python.h, no torch types.  Host
+ * arrays use the reference's own layouts (C-contiguous numpy: int64 indices,
+ * FP64 values); the library converts them to its device layout (32-byte SoA
+ * records, int32 connectivity, locality-reordered) on upload.
+ *
+ * Two layers:
+ *
+ *  (1) RESIDENT layer  - swk_create / swk_set_* / swk_evolve / swk_get_* ...
+ *      The arrays live in HBM for the life of the handle; the time loop
+ *      (generic_domain.py:1835-1912, evolve_one_{euler,rk2,rk3}_step :1914-2179,
+ *      update_timestep :2349-2415) runs on the device, the host only sees
+ *      scalars until a yield.  This is what the new multiprocessor_mode uses.
+ *
+ *  (2) PER-CALL layer  - swk_call_*  (host arrays in, host arrays out)
+ *      One entry point per function the reference's Cython FFI binds for this
+ *      path (anuga/shallow_water/sw_domain_openmp_ext.pyx:371-459,
+ *      anuga/abstract_2d_finite_volumes/quantity_ext.pyx:38-117), with the same
+ *      argument meaning and in-place update of the same host arrays, so that
+ *      the dispatch sites in shallow_water_domain.py:1855-1874, 1893-1915,
+ *      2022-2039, 2114-2154 and friction.py:40-73 keep working for per-call use
+ *      (differential tests in the style of shallow_water/tests/test_DE_openmp.py).
+ *
+ * Every function returns an int status (SWK_OK = 0, negative = error) and never
+ * throws or aborts.  swk_last_error() returns a thread-local message.
+ * A handle is not thread-safe; different handles are independent.
+ * There is NO CPU fallback: every entry point fails with SWK_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef SWK_H
+#define SWK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWK_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define SWK_OK                 0
+#define SWK_ERR_CUDA          -1   /* no device / CUDA runtime error */
+#define SWK_ERR_ARG           -2   /* bad argument */
+#define SWK_ERR_DENOMINATOR   -3   /* semi-implicit denominator <= 0: the reference's
+                                      _update returns -1 (quantity.c:806-808) */
+#define SWK_ERR_SMALLSTEP     -4   /* "Too small timestep ... even after N steps of 1 order
+                                      scheme" (generic_domain.py:2377-2388) */
+#define SWK_ERR_OVERSHOOT     -5   /* time overshot finaltime (generic_domain.py:1873-1878) */
+#define SWK_ERR_UNSUPPORTED   -6   /* feature outside the hot-path scope */
+#define SWK_ERR_NCCL          -7
+
+typedef struct swk_domain swk_domain;     /* opaque, owns all device memory */
+
+/* ---- scalar parameters -----------------------------------------------------
+ * Same names and meaning as the scalars of the reference's `struct domain`
+ * (shallow_water/sw_domain.h:16-36) plus the time-loop constants the reference
+ * keeps on the Python object (generic_domain.py:2349-2415, config.py).       */
+typedef struct {
+  double epsilon;                 /* config.py:12   1e-12 */
+  double H0;                      /* config.py:186  1e-5  */
+  double g;                       /* config.py:45   9.8   */
+  double minimum_allowed_height;
+  double maximum_allowed_speed;
+  double evolve_max_timestep;     /* config.py:153  1000  */
+  double evolve_min_timestep;     /* config.py:154  1e-6  */
+  double beta_w, beta_w_dry, beta_uh, beta_uh_dry, beta_vh, beta_vh_dry;
+  double CFL;
+  double fixed_flux_timestep;     /* <= 0 : variable timestepping (generic_domain.py:2332-2360) */
+  int64_t extrapolate_velocity_second_order;
+  int64_t low_froude;             /* 0, 1, 2 (sw_domain_openmp.c:178-194) */
+  int64_t timestepping_method;    /* 1 euler, 2 rk2, 3 rk3 = timestep_fluxcalls */
+  int64_t use_sloped_mannings;    /* friction.py:65-73 */
+  int64_t max_smallsteps;         /* config.py: 50 */
+  int64_t default_order;          /* 1 or 2 (only the bookkeeping of update_timestep uses it) */
+  int64_t ghost_layer_width;      /* rk2 skips the mid-step exchange when >= 4 (generic_domain.py:2014) */
+  int64_t centroid_transmissive_bc;
+} swk_params;
+
+/* ---- static mesh description (host pointers, borrowed during swk_create) ---
+ * Field names follow `struct domain` / the Mesh attributes they come from
+ * (neighbour_mesh.py:94-97, general_mesh.py:134-148, generic_domain.py:285).   */
+typedef struct {
+  int64_t number_of_elements;            /* N */
+  int64_t boundary_length;               /* M */
+  const int64_t *neighbours;             /* (N,3)  <0: boundary index -(m+1) */
+  const int64_t *neighbour_edges;        /* (N,3) */
+  const int64_t *surrogate_neighbours;   /* (N,3) */
+  const int64_t *number_of_boundaries;   /* (N,)  */
+  const int64_t *tri_full_flag;          /* (N,)  1 full, 0 ghost */
+  const double *normals;                 /* (N,6) */
+  const double *edgelengths;             /* (N,3) */
+  const double *radii;                   /* (N,)  */
+  const double *areas;                   /* (N,)  */
+  const double *centroid_coordinates;    /* (N,2) */
+  const double *edge_coordinates;        /* (3N,2) edge midpoints */
+  const double *vertex_coordinates;      /* (3N,2) (sloped Manning only; may be NULL) */
+  const int64_t *boundary_cells;         /* (M,) */
+  const int64_t *boundary_edges;         /* (M,) */
+  /* riverwall tables (shallow_water_domain.py:371-399); all NULL/0 when absent */
+  int64_t number_of_riverwall_edges;
+  int64_t ncol_riverwall_hydraulic_properties;
+  const int64_t *edge_flux_type;         /* (3N,) */
+  const int64_t *edge_river_wall_counter;/* (3N,) */
+  const double *riverwall_elevation;
+  const int64_t *riverwall_rowIndex;
+  const double *riverwall_hydraulic_properties;
+  /* optional locality reordering: permutation[new] = old.  NULL = keep order.
+   * All host-facing arrays and ids stay in the caller's ("old") order.        */
+  const int64_t *permutation;
+} swk_mesh;
+
+/* ---- quantity ids for swk_set_quantity / swk_get_quantity ------------------ */
+enum {
+  SWK_Q_STAGE_C = 0, SWK_Q_XMOM_C = 1, SWK_Q_YMOM_C = 2,      /* (N,)   conserved, centroid  */
+  SWK_Q_ELEVATION_C = 3, SWK_Q_FRICTION_C = 4,                /* (N,)   static inputs        */
+  SWK_Q_HEIGHT_C = 5,                                         /* (N,)   get only: max(w-z,0) */
+  SWK_Q_STAGE_E = 10, SWK_Q_XMOM_E = 11, SWK_Q_YMOM_E = 12,   /* (N,3)  edge values          */
+  SWK_Q_HEIGHT_E = 13, SWK_Q_ELEVATION_E = 14,                /*        (14: get only)       */
+  SWK_Q_STAGE_V = 20, SWK_Q_XMOM_V = 21, SWK_Q_YMOM_V = 22,   /* (N,3)  get only: from edges */
+  SWK_Q_HEIGHT_V = 23, SWK_Q_ELEVATION_V = 24,                /*   (24: settable, sloped Manning) */
+  SWK_Q_STAGE_B = 30, SWK_Q_XMOM_B = 31, SWK_Q_YMOM_B = 32,   /* (M,)   boundary values      */
+  SWK_Q_STAGE_EU = 40, SWK_Q_XMOM_EU = 41, SWK_Q_YMOM_EU = 42,/* (N,)   explicit_update      */
+  SWK_Q_MAX_SPEED = 50,                                       /* (N,)   get only             */
+  SWK_Q_STAGE_BACKUP = 60, SWK_Q_XMOM_BACKUP = 61, SWK_Q_YMOM_BACKUP = 62
+};
+
+/* ---- boundary kinds (a4 of SURVEY.md section 8) --------------------------------
+ * Only stage/xmom/ymom boundary values feed the flux (sw_domain_openmp.c:556-560). */
+enum {
+  SWK_BC_NONE = 0,                 /* boundary_map[tag] is None: values left untouched */
+  SWK_BC_REFLECTIVE = 1,           /* boundaries.py:235-288 */
+  SWK_BC_DIRICHLET = 2,            /* generic_boundary_conditions.py:221-264; also Time_boundary
+                                      :370-411 and Time_stage_zero_momentum boundaries.py:616-635
+                                      with host-evaluated values */
+  SWK_BC_TRANSMISSIVE = 3,         /* generic_boundary_conditions.py:173-193 */
+  SWK_BC_TRANSMISSIVE_N_ZERO_T_SET_STAGE = 4,   /* boundaries.py:477-517 */
+  SWK_BC_TRANSMISSIVE_MOMENTUM_SET_STAGE = 5,   /* boundaries.py:344-372 */
+  SWK_BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6   /* boundaries.py:543-551 */
+};
+
+/* ---- evolve result ------------------------------------------------------------ */
+typedef struct {
+  double time;                     /* relative model time reached */
+  double timestep;                 /* last timestep taken */
+  double flux_timestep;            /* last CFL-limiting timestep from the flux kernel */
+  double recorded_min_timestep, recorded_max_timestep;
+  double boundary_flux_integral;   /* boundary_flux_integral_operator.py:44-62 */
+  double fractional_step_volume_integral;   /* rate_operators.py:259 */
+  double mass_error;               /* accumulated return of protect (sw_domain_openmp.c:1149) */
+  double boundary_flux_sum[3];
+  int64_t number_of_steps;         /* since the last yield */
+  int64_t number_of_first_order_steps;
+  int64_t total_steps;             /* since swk_create */
+  int64_t negative_cells;          /* accumulated fix_negative_cells count */
+  int64_t stop_reason;             /* 0 step budget exhausted, 1 yieldtime reached, 2 finaltime reached */
+  int64_t kernel_launches;         /* library kernels launched by this call */
+} swk_evolve_result;
+
+/* =========================== (1) RESIDENT LAYER ================================ */
+
+/* Number of usable sm_100 devices (0 and SWK_ERR_CUDA semantics: *count = 0). */
+int swk_device_count(int *count);
+const char *swk_last_error(void);
+int swk_abi_version(void);
+
+int swk_create(const swk_mesh *mesh, const swk_params *params, int device, swk_domain **out);
+int swk_destroy(swk_domain *d);
+/* Re-read scalars (set_flow_algorithm after creation; SURVEY.md 8(b) "State to mirror"). */
+int swk_set_params(swk_domain *d, const swk_params *params);
+
+/* Host<->device transfer of one quantity in the caller's triangle order.
+ * n must equal the quantity's element count (N, 3N or M).                       */
+int swk_set_quantity(swk_domain *d, int quantity_id, const double *host, int64_t n);
+int swk_get_quantity(swk_domain *d, int quantity_id, double *host, int64_t n);
+
+/* Bind a boundary kind to a list of boundary indices (Generic_Domain.set_boundary
+ * :937-1033 / tag_boundary_cells).  values[0..2]: Dirichlet constants or
+ * values[0] = stage for the set-stage kinds.  segment ids are boundary indices m. */
+int swk_set_boundary_segment(swk_domain *d, int segment, int kind, const int64_t *ids,
+                             int64_t n_ids, const double values[3]);
+int swk_set_boundary_values(swk_domain *d, int segment, const double values[3]);
+
+/* Rate_operator (operators/rate_operators.py:24-269): stage += factor*dt*rate on
+ * `indices` (NULL = all).  rate_array (N,) optional per-centroid rates (NULL: scalar). */
+int swk_add_rate_operator(swk_domain *d, double rate, double factor, const double *rate_array,
+                          const int64_t *indices, int64_t n_indices, int *op_id);
+int swk_set_rate(swk_domain *d, int op_id, double rate, double factor);
+
+/* Single-process ghost copy (Generic_Domain.update_ghosts :2448-2469):
+ * centroid values of full_ids are copied onto ghost_ids after each update.       */
+int swk_set_local_ghost_copy(swk_domain *d, const int64_t *full_ids, const int64_t *ghost_ids,
+                             int64_t n);
+
+/* Time state (relative times, generic_domain.py:1764-1807). */
+int swk_set_time(swk_domain *d, double relative_time);
+
+/* Individual steps of the path, operating on resident data ---------------------- */
+int swk_protect(swk_domain *d, double *mass_error);                 /* sw_domain_openmp.c:1096 */
+int swk_extrapolate_second_order_edge_sw(swk_domain *d);            /* :1336 (incl. loop-1/3 effects) */
+int swk_distribute_to_vertices_and_edges(swk_domain *d);            /* protect + extrapolate */
+int swk_update_boundary(swk_domain *d);                             /* generic_domain.py:2288 */
+int swk_compute_fluxes(swk_domain *d, int substep, double *flux_timestep); /* :456 */
+/* compute_forcing_terms (Manning friction, friction.py:22-73 -> sw_domain_openmp.c:1954, 1988) has no
+ * entry point of its own on resident data: the semi-implicit friction term is evaluated inside
+ * the update kernel, from the same protected centroid values, instead of round-tripping
+ * semi_implicit_update through HBM.  swk_update_conserved_quantities = forcing terms +
+ * Quantity.update x3 (quantity.c:772) + fix_negative_cells (:2037).                             */
+int swk_update_conserved_quantities(swk_domain *d, double timestep, int64_t *num_negative);
+int swk_backup_conserved_quantities(swk_domain *d);                 /* quantity.c:735 */
+int swk_saxpy_conserved_quantities(swk_domain *d, double a, double b, double divide_by); /* quantity.c:752 (+ /3, generic_domain.py:2167-2170) */
+int swk_update_ghosts(swk_domain *d);
+/* apply_fractional_steps (generic_domain.py:2312-2314) for a host-driven step of length
+ * `timestep`: boundary_flux_integral_operator + every registered Rate_operator.      */
+int swk_apply_fractional_steps(swk_domain *d, double timestep);
+/* current clock scalars (time, integrals, counters) without stepping */
+int swk_get_statistics(swk_domain *d, swk_evolve_result *result);
+
+/* Device-resident time loop.  Runs whole timesteps until relative_yieldtime or
+ * relative_finaltime is reached (finaltime < 0: none) or max_steps steps were
+ * taken (max_steps <= 0: unlimited).  Implements _evolve_base's loop body:
+ * evolve_one_*_step, apply_fractional_steps, update_ghosts, step counters.
+ * At a yield the centroid arrays are protected/extrapolated exactly as
+ * distribute_to_vertices_and_edges + update_boundary do (generic_domain.py:1884-1902). */
+int swk_evolve(swk_domain *d, double relative_yieldtime, double relative_finaltime,
+               int64_t max_steps, swk_evolve_result *result);
+/* reset per-yield statistics (generic_domain.py:1906-1912) */
+int swk_reset_yield_statistics(swk_domain *d);
+
+/* Exactly `n_steps` timesteps with a fixed sequence, no host interaction inside:
+ * used by bench.py (CUDA events around the call on swk_stream).                  */
+int swk_stream(swk_domain *d, void **cuda_stream_out);
+int swk_synchronize(swk_domain *d);
+int swk_kernel_launch_count(swk_domain *d, int64_t *count);
+/* Algorithmic HBM bytes per triangle and timestep of the current configuration
+ *  and the bytes this library's layout actually moves.       */
+int swk_bytes_per_triangle_step(swk_domain *d, double *algorithmic, double *layout);
+
+/* ---- multi-GPU (one process per GPU) -----------------------
+ * The caller creates the NCCL unique id on rank 0 (swk_nccl_unique_id), ships the
+ * 128 bytes to every rank by its own means (torch.distributed, MPI, file), then
+ * each rank calls swk_comm_init.  Halo lists are the reference's
+ * full_send_dict[p][0] / ghost_recv_dict[p][0] (distribute_mesh.py:1128-1170).    */
+int swk_nccl_unique_id(void *id128);
+int swk_comm_init(swk_domain *d, const void *id128, int rank, int nranks);
+int swk_set_halo(swk_domain *d, int n_peers, const int *peer_ranks,
+                 const int64_t *send_counts, const int64_t *const *send_ids,
+                 const int64_t *recv_counts, const int64_t *const *recv_ids);
+
+/* ============================ (2) PER-CALL LAYER =================================
+ * Host view of one reference Domain: the pointers that
+ * get_python_domain_pointers (sw_domain_openmp_ext.pyx:138-365) extracts, by the
+ * same names.  Arrays are read and updated IN PLACE like the reference's C code
+ * does, so user code holding numpy aliases keeps seeing the results.           */
+typedef struct {
+  swk_mesh mesh;
+  swk_params params;
+  double *stage_centroid_values, *xmom_centroid_values, *ymom_centroid_values;
+  double *bed_centroid_values, *height_centroid_values, *friction_centroid_values;
+  double *stage_edge_values, *xmom_edge_values, *ymom_edge_values;
+  double *bed_edge_values, *height_edge_values;
+  double *stage_vertex_values, *xmom_vertex_values, *ymom_vertex_values;
+  double *bed_vertex_values, *height_vertex_values;
+  double *stage_boundary_values, *xmom_boundary_values, *ymom_boundary_values;
+  double *stage_explicit_update, *xmom_explicit_update, *ymom_explicit_update;
+  double *stage_semi_implicit_update, *xmom_semi_implicit_update, *ymom_semi_implicit_update;
+  double *max_speed;
+  double *boundary_flux_sum;          /* (timestep_fluxcalls,) */
+} swk_host_view;
+
+/* A per-call context caches the device copy of the static mesh between calls. */
+int swk_call_open(const swk_host_view *v, int device, swk_domain **out);
+int swk_call_close(swk_domain *d);
+
+/* replaces compute_fluxes_ext_central(domain, timestep) -> float
+ * (sw_domain_openmp_ext.pyx:371 -> sw_domain_openmp.c:456).  `substep` replaces the
+ * function-static call counter (:492-505).  Reads edge + boundary values, stage/bed
+ * centroids; writes explicit_update x3, max_speed, boundary_flux_sum[substep].    */
+int swk_call_compute_fluxes_ext_central(swk_domain *d, const swk_host_view *v, double timestep,
+                                        int substep, double *flux_timestep);
+/* replaces extrapolate_second_order_edge_sw(domain) (pyx:384 -> .c:1336) */
+int swk_call_extrapolate_second_order_edge_sw(swk_domain *d, const swk_host_view *v);
+/* replaces protect_new(domain) -> mass_error (pyx:397 -> .c:1096) */
+int swk_call_protect_new(swk_domain *d, const swk_host_view *v, double *mass_error);
+/* replaces fix_negative_cells(domain) -> count (pyx:449 -> .c:2037) */
+int swk_call_fix_negative_cells(swk_domain *d, const swk_host_view *v, int64_t *count);
+/* replaces manning_friction_flat / _sloped (pyx:417-446 -> .c:1954, 1988) */
+int swk_call_manning_friction_flat(int device, double g, double eps, int64_t N, const double *w,
+                                   const double *zv, const double *uh, const double *vh,
+                                   const double *eta, double *xmom_update, double *ymom_update);
+int swk_call_manning_friction_sloped(int device, double g, double eps, int64_t N, const double *x,
+                                     const double *w, const double *zv, const double *uh,
+                                     const double *vh, const double *eta,
+                                     double *xmom_update, double *ymom_update);
+/* replaces quantity_ext.update / backup_centroid_values / saxpy_centroid_values
+ * (quantity_ext.pyx:38-117 -> quantity.c:735-820)                                */
+int swk_call_update(int device, int64_t N, double timestep, double *centroid_values,
+                    const double *explicit_update, double *semi_implicit_update);
+int swk_call_backup_centroid_values(int device, int64_t N, const double *centroid_values,
+                                    double *centroid_backup_values);
+int swk_call_saxpy_centroid_values(int device, int64_t N, double a, double b,
+                                   double *centroid_values, const double *centroid_backup_values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWK_H */
