@@ -131,6 +131,8 @@ SYMBOLS = {
     "swk_get_statistics": (C.c_int, [_H, C.POINTER(SwkEvolveResult)]),
     "swk_evolve": (C.c_int, [_H, _D, _D, _I, C.POINTER(SwkEvolveResult)]),
     "swk_reset_yield_statistics": (C.c_int, [_H]),
+    "swk_run_steps": (C.c_int, [_H, _I, C.c_int, C.POINTER(C.c_float)]),
+    "swk_kernel_timing": (C.c_int, [_H, _PD, _PI]),
     "swk_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "swk_synchronize": (C.c_int, [_H]),
     "swk_kernel_launch_count": (C.c_int, [_H, _PI]),
@@ -384,6 +386,20 @@ class DeviceDomain:
         ft = -1.0 if relative_finaltime is None else float(relative_finaltime)
         _check(self.lib.swk_evolve(self.h, float(relative_yieldtime), ft, int(max_steps), C.byref(r)))
         return r
+
+    def run_steps(self, n_steps, per_kernel=False):
+        """exactly n_steps timesteps, CUDA-event timed on the library stream -> elapsed ms"""
+        ms = C.c_float(0.0)
+        _check(self.lib.swk_run_steps(self.h, int(n_steps), int(bool(per_kernel)), C.byref(ms)))
+        return float(ms.value)
+
+    KERNEL_NAMES = ("extrapolate", "flux", "update", "flux_update")
+
+    def kernel_timing(self):
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        _check(self.lib.swk_kernel_timing(self.h, ms, n))
+        return {name: (ms[i], n[i]) for i, name in enumerate(self.KERNEL_NAMES)}
 
     def reset_yield_statistics(self):
         _check(self.lib.swk_reset_yield_statistics(self.h))

@@ -175,6 +175,33 @@ struct swk_domain {
   double *d_dt_scratch = nullptr;
 
   int64_t launches = 0;
+
+  // optional per-kernel event timing (bench.py roofline)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_kind;
+  size_t ev_used = 0;
+  double k_ms[4] = {0, 0, 0, 0};
+  int64_t k_n[4] = {0, 0, 0, 0};
+};
+
+struct TimedScope {
+  swk_domain *d;
+  bool on = false;
+  size_t slot = 0;
+  TimedScope(swk_domain *d_, int kind) : d(d_)
+  {
+    if (!d->timing || d->ev_used + 2 > d->ev_pool.size()) return;
+    on = true;
+    slot = d->ev_used;
+    d->ev_used += 2;
+    d->ev_kind[slot / 2] = kind;
+    cudaEventRecord(d->ev_pool[slot], d->stream);
+  }
+  ~TimedScope()
+  {
+    if (on) cudaEventRecord(d->ev_pool[slot + 1], d->stream);
+  }
 };
 
 static void make_consts(swk_domain *d)
@@ -811,6 +838,7 @@ extern "C" int swk_reset_yield_statistics(swk_domain *d)
 // ----------------------------------------------------------------------------
 static void launch_extrapolate(swk_domain *d, const Consts &K)
 {
+  TimedScope ts(d, 0);
   LAUNCH(d, k_extrapolate, nblk(d->N), BLOCK, d->D, K);
 }
 
@@ -828,6 +856,7 @@ static int launch_boundary(swk_domain *d)
 
 static void launch_flux(swk_domain *d, int first, int write_speed)
 {
+  TimedScope ts(d, 1);
   if (d->has_riverwalls) LAUNCH(d, k_flux<true>, nblk(d->N), BLOCK, d->D, d->K, first, write_speed);
   else LAUNCH(d, k_flux<false>, nblk(d->N), BLOCK, d->D, d->K, first, write_speed);
 }
@@ -899,7 +928,10 @@ static int launch_first_substep(swk_domain *d, int do_backup)
   launch_bflux(d, 0);
   CKV(launch_dt_allreduce(d));
   LAUNCH(d, k_update_timestep, 1, 1, d->d_clock, d->TP);
-  LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, do_backup, 0, 1.0, 0.0, 1.0), -1.0);
+  {
+    TimedScope ts(d, 2);
+    LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, do_backup, 0, 1.0, 0.0, 1.0), -1.0);
+  }
   return SWK_OK;
 }
 
@@ -911,8 +943,10 @@ static int launch_later_substep(swk_domain *d, int substep, double a, double b, 
   const UpdateArgs U = update_args(d, 0, 1, a, b, divide_by);
   if (d->has_riverwalls) {
     launch_flux(d, 0, 0);
+    TimedScope ts(d, 2);
     LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, U, -1.0);
   } else {
+    TimedScope ts(d, 3);
     LAUNCH(d, k_flux_update, nblk(d->N), BLOCK, d->D, d->K, U);
   }
   launch_bflux(d, substep);
@@ -1021,6 +1055,68 @@ extern "C" int swk_evolve(swk_domain *d, double relative_yieldtime, double relat
   fill_result(d, result, launches0);
   c->stop = 0;
   CKV(push_clock(d));
+  return SWK_OK;
+}
+
+extern "C" int swk_run_steps(swk_domain *d, int64_t n_steps, int per_kernel, float *elapsed_ms)
+{
+  if (!d || n_steps < 0) return fail(SWK_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(d->device));
+  CKV(pull_clock(d));
+  Clock *c = d->h_clock;
+  if (c->stop < 0) return status_from_stop(c->stop);
+  c->yieldtime = 1.0e300;
+  c->finaltime = -1.0;
+  c->step_budget = 0;
+  c->stop = 0;
+  CKV(push_clock(d));
+  d->timing = false;
+  if (per_kernel) {
+    const size_t want = (size_t)std::min<int64_t>(n_steps, 512) * 5 * 2;
+    while (d->ev_pool.size() < want) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      d->ev_pool.push_back(e);
+    }
+    d->ev_kind.assign(d->ev_pool.size() / 2, 0);
+    d->ev_used = 0;
+    for (int i = 0; i < 4; i++) { d->k_ms[i] = 0; d->k_n[i] = 0; }
+    d->timing = true;
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaStreamSynchronize(d->stream));
+  CK(cudaEventRecord(e0, d->stream));
+  int rc = SWK_OK;
+  for (int64_t s = 0; s < n_steps && rc == SWK_OK; s++) rc = launch_step(d);
+  CK(cudaEventRecord(e1, d->stream));
+  d->timing = false;
+  CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (elapsed_ms) *elapsed_ms = ms;
+  if (per_kernel) {
+    for (size_t j = 0; j + 1 < d->ev_used; j += 2) {
+      float kms = 0.f;
+      if (cudaEventElapsedTime(&kms, d->ev_pool[j], d->ev_pool[j + 1]) == cudaSuccess) {
+        d->k_ms[d->ev_kind[j / 2]] += kms;
+        d->k_n[d->ev_kind[j / 2]] += 1;
+      }
+    }
+  }
+  if (rc != SWK_OK) return rc;
+  CKV(pull_clock(d));
+  if (c->stop < 0) return status_from_stop(c->stop);
+  return SWK_OK;
+}
+
+extern "C" int swk_kernel_timing(swk_domain *d, double total_ms[4], int64_t launches[4])
+{
+  if (!d || !total_ms || !launches) return fail(SWK_ERR_ARG, "NULL argument");
+  for (int i = 0; i < 4; i++) { total_ms[i] = d->k_ms[i]; launches[i] = d->k_n[i]; }
   return SWK_OK;
 }
 

@@ -79,6 +79,43 @@ def rectangular_cross(m, n, len1=1.0, len2=1.0, origin=(0.0, 0.0)):
     return points, elements, boundary
 
 
+def rectangular(m, n, len1=1.0, len2=1.0, origin=(0.0, 0.0)):
+    """Rectangular grid, two triangles per cell (mesh_factory.py:64-135): cell (i, j) owns
+    the lower triangle 2(i*n+j) = [i4, i3, i2] and the upper one [i1, i2, i3]."""
+    m = int(m)
+    n = int(n)
+    delta1 = float(len1) / m
+    delta2 = float(len2) / n
+    Np = (m + 1) * (n + 1)
+    points = np.zeros((Np, 2), dtype=np.float64)
+    ii = np.arange(m + 1, dtype=np.float64)
+    jj = np.arange(n + 1, dtype=np.float64)
+    points[:, 0] = np.repeat(ii * delta1 + origin[0], n + 1)
+    points[:, 1] = np.tile(jj * delta2 + origin[1], m + 1)
+    ci = np.repeat(np.arange(m, dtype=np.int64), n)
+    cj = np.tile(np.arange(n, dtype=np.int64), m)
+    i1 = ci * (n + 1) + cj + 1
+    i2 = ci * (n + 1) + cj
+    i3 = (ci + 1) * (n + 1) + cj + 1
+    i4 = (ci + 1) * (n + 1) + cj
+    elements = np.zeros((2 * m * n, 3), dtype=np.int64)
+    elements[0::2] = np.stack([i4, i3, i2], axis=1)
+    elements[1::2] = np.stack([i1, i2, i3], axis=1)
+    boundary = {}
+    for i in range(m):
+        for j in range(n):
+            nt = 2 * (i * n + j)
+            if i == m - 1:
+                boundary[(nt, 2)] = "right"
+            if j == 0:
+                boundary[(nt, 1)] = "bottom"
+            if i == 0:
+                boundary[(nt + 1, 2)] = "left"
+            if j == n - 1:
+                boundary[(nt + 1, 1)] = "top"
+    return points, elements, boundary
+
+
 def build_neighbour_structure(triangles, number_of_nodes):
     """neighbours, neighbour_edges, number_of_boundaries from the triangle table.
 

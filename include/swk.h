@@ -231,8 +231,15 @@ int swk_evolve(swk_domain *d, double relative_yieldtime, double relative_finalti
 /* reset per-yield statistics (generic_domain.py:1906-1912) */
 int swk_reset_yield_statistics(swk_domain *d);
 
-/* Exactly `n_steps` timesteps with a fixed sequence, no host interaction inside:
- * used by bench.py (CUDA events around the call on swk_stream).                  */
+/* Launch exactly n_steps timesteps back to back (no host interaction inside) and time them
+ * with CUDA events recorded on the library's stream; *elapsed_ms covers the whole region.
+ * The clock keeps running (yield/final times are pushed out of the way).  With
+ * per_kernel != 0 every launch of the four hot kernels is additionally bracketed by its
+ * own event pair; read the totals with swk_kernel_timing.                              */
+int swk_run_steps(swk_domain *d, int64_t n_steps, int per_kernel, float *elapsed_ms);
+/* kernel ids: 0 extrapolate (pass A), 1 flux (B1), 2 update (B2), 3 flux_update (fused B).
+ * total_ms[4], launches[4] accumulated by the last swk_run_steps(per_kernel=1).          */
+int swk_kernel_timing(swk_domain *d, double total_ms[4], int64_t launches[4]);
 int swk_stream(swk_domain *d, void **cuda_stream_out);
 int swk_synchronize(swk_domain *d);
 int swk_kernel_launch_count(swk_domain *d, int64_t *count);

@@ -1,0 +1,177 @@
+"""Golden cases, written ONCE against the reference's public API.
+
+Every builder takes ``A`` - either the reference package (``anuga``, scratch build, used by
+make_golden.py in the build container) or this repository's ``anuga_core_b200`` - and uses
+only names both export (Domain, rectangular, rectangular_cross_domain, *_boundary,
+Rate_operator, set_flow_algorithm, set_quantity, set_boundary, evolve ...).  That the same
+script drives both is the drop-in claim of INTEGRATION.md.
+
+CASES maps name -> (builder, evolve kwargs).
+"""
+import numpy as np
+
+
+def _reflective_all(A, d):
+    Br = A.Reflective_boundary(d)
+    d.set_boundary({t: Br for t in d.get_boundary_tags()})
+
+
+def kat_bedslope_more_steps(A):
+    """anuga/shallow_water/tests/test_shallow_water_domain.py:5913-6050
+    (test_bedslope_problem_second_order_more_steps): rectangular(6,6), default DE0,
+    betas 0.9, elevation -x/3, stage = elevation + 0.05."""
+    points, vertices, boundary = A.rectangular(6, 6)
+    d = A.Domain(points, vertices, boundary)
+    d.set_store(False)
+    d.smooth = False
+    d.default_order = 2
+    d.beta_w = 0.9
+    d.beta_w_dry = 0.9
+    d.beta_uh = 0.9
+    d.beta_uh_dry = 0.9
+    d.beta_vh = 0.9
+    d.beta_vh_dry = 0.9
+    d.set_low_froude(0)
+    d.H0 = 0
+    d.set_quantity("elevation", lambda x, y: -x / 3)
+    Br = A.Reflective_boundary(d)
+    d.set_boundary({"left": Br, "right": Br, "top": Br, "bottom": Br})
+    d.set_quantity("stage", d.quantities["elevation"].vertex_values + 0.05)
+    return d
+
+
+def dam_break_de0(A, n=30):
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE0")
+    d.set_store(False)
+    d.set_quantity("elevation", lambda x, y: -x / (n / 2.0))
+    d.set_quantity("stage", lambda x, y: np.where(x < n / 2.0, 1.0, 0.2), location="centroids")
+    d.set_quantity("friction", 0.03)
+    _reflective_all(A, d)
+    return d
+
+
+def dam_break_de0_fixed_dt(A):
+    d = dam_break_de0(A, n=24)
+    d.set_fixed_flux_timestep(0.01)
+    return d
+
+
+def dam_break_de1(A):
+    d = dam_break_de0(A, n=30)
+    d.set_flow_algorithm("DE1")
+    return d
+
+
+def dam_break_de2(A):
+    d = dam_break_de0(A, n=20)
+    d.set_flow_algorithm("DE2")
+    return d
+
+
+def beach_de1(A, n=24):
+    """dam break running up a dry beach: protect, dry-cell zeroing, fix-negative"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: 0.5 * (x - 0.4 * L) / (0.6 * L) * (x > 0.4 * L) + 0.05 * np.sin(y))
+    d.set_quantity("stage", lambda x, y: np.where(x < 0.25 * L, 0.8, -1.0), location="centroids")
+    d.set_quantity("friction", 0.03)
+    _reflective_all(A, d)
+    return d
+
+
+def beach_de0_7(A):
+    d = beach_de1(A, n=20)
+    d.set_flow_algorithm("DE0_7")
+    return d
+
+
+def tsunami_set_stage(A, n=24):
+    """configs[1] style: beach + island, set-stage inflow (time dependent), transmissive outflow"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: -(10 - 9.9 * x / L) + 0.5 * np.exp(-((x - 0.7 * L) ** 2 + (y - 0.5 * L) ** 2) / (0.05 * L) ** 2))
+    d.set_quantity("stage", 0.0)
+    d.set_quantity("friction", 0.025)
+    Br = A.Reflective_boundary(d)
+    Bl = A.Transmissive_n_momentum_zero_t_momentum_set_stage_boundary(d, lambda t: 0.5 * np.sin(2 * np.pi * t / 60.0))
+    d.set_boundary({"left": Bl, "right": A.Transmissive_boundary(d), "top": Br, "bottom": Br})
+    return d
+
+
+def tsunami_dirichlet(A, n=24):
+    d = tsunami_set_stage(A, n)
+    Br = A.Reflective_boundary(d)
+    d.set_boundary({"left": A.Dirichlet_boundary([0.3, 0.0, 0.0]), "right": A.Transmissive_boundary(d),
+                    "top": Br, "bottom": Br})
+    return d
+
+
+def time_boundary_de1(A, n=16):
+    d = tsunami_set_stage(A, n)
+    Br = A.Reflective_boundary(d)
+    d.set_boundary({"left": A.Time_boundary(d, lambda t: [0.2 * np.sin(t / 3.0), 0.0, 0.0]),
+                    "right": A.Transmissive_boundary(d), "top": Br, "bottom": Br})
+    return d
+
+
+def rain_de1(A, n=30):
+    """configs[2] fields at small size with the rain Rate_operator"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    elev = lambda x, y: 0.01 * np.sin(2 * np.pi * x / 200.0) * np.cos(2 * np.pi * y / 200.0)
+    d.set_quantity("elevation", elev)
+    d.set_quantity("stage", lambda x, y: elev(x, y) + 0.5 + 0.1 * np.exp(-((x - L / 2) ** 2 + (y - L / 2) ** 2) / (0.1 * L) ** 2),
+                   location="centroids")
+    d.set_quantity("friction", 0.03)
+    _reflective_all(A, d)
+    A.Rate_operator(d, rate=1.0e-4)
+    return d
+
+
+def drain_de1(A):
+    """negative rate: the clamped branch of Rate_operator (rate_operators.py:213-245)"""
+    d = beach_de1(A, n=16)
+    A.Rate_operator(d, rate=-0.05)
+    return d
+
+
+def sloped_manning_de1(A):
+    d = dam_break_de0(A, n=16)
+    d.set_flow_algorithm("DE1")
+    d.set_sloped_mannings_function(True)
+    return d
+
+
+def low_froude_de1(A):
+    d = dam_break_de0(A, n=16)
+    d.set_flow_algorithm("DE1")
+    d.set_low_froude(1)
+    return d
+
+
+CASES = {
+    "kat_bedslope_more_steps": (kat_bedslope_more_steps, dict(yieldstep=0.05, finaltime=0.5)),
+    "dam_break_de0": (dam_break_de0, dict(yieldstep=1.0, finaltime=6.0)),
+    "dam_break_de0_fixed_dt": (dam_break_de0_fixed_dt, dict(yieldstep=5.0, finaltime=10.0)),
+    "dam_break_de1": (dam_break_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "dam_break_de2": (dam_break_de2, dict(yieldstep=1.0, finaltime=3.0)),
+    "beach_de1": (beach_de1, dict(yieldstep=1.0, finaltime=5.0)),
+    "beach_de0_7": (beach_de0_7, dict(yieldstep=1.0, finaltime=3.0)),
+    "tsunami_set_stage": (tsunami_set_stage, dict(yieldstep=1.0, finaltime=4.0)),
+    "tsunami_dirichlet": (tsunami_dirichlet, dict(yieldstep=1.0, finaltime=4.0)),
+    "time_boundary_de1": (time_boundary_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "rain_de1": (rain_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "drain_de1": (drain_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "sloped_manning_de1": (sloped_manning_de1, dict(yieldstep=0.5, finaltime=2.0)),
+    "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
+}
+
+# 8-digit expected values embedded in the reference's own test (the KAT proper)
+KAT_BEDSLOPE_W_EX_HEAD = [-0.0301883, -0.01127593, -0.02834861, -0.0108968, -0.02806583, -0.01074475]

@@ -5,49 +5,7 @@ import numpy as np
 import anuga_core_b200 as ab
 
 
-def domain_to_scenario(domain):
-    """Plain-array snapshot of a product Domain for oracle.driver.OracleDomain."""
-    q = domain.quantities
-    m = domain.mesh
-    sc = {}
-    for name in ("neighbours", "neighbour_edges", "surrogate_neighbours", "number_of_boundaries",
-                 "normals", "edgelengths", "radii", "areas", "centroid_coordinates",
-                 "vertex_coordinates", "boundary_cells", "boundary_edges"):
-        sc[name] = np.array(getattr(m, name), copy=True)
-    sc["edge_coordinates"] = np.array(m.edge_midpoint_coordinates, copy=True)
-    sc["tri_full_flag"] = np.array(domain.tri_full_flag, copy=True)
-    sc["stage_centroid_values"] = q["stage"].centroid_values.copy()
-    sc["xmom_centroid_values"] = q["xmomentum"].centroid_values.copy()
-    sc["ymom_centroid_values"] = q["ymomentum"].centroid_values.copy()
-    sc["bed_centroid_values"] = q["elevation"].centroid_values.copy()
-    sc["friction_centroid_values"] = q["friction"].centroid_values.copy()
-    sc["bed_vertex_values"] = q["elevation"].vertex_values.copy()
-    sc["params"] = dict(
-        g=domain.g, epsilon=domain.epsilon, H0=domain.H0,
-        minimum_allowed_height=domain.minimum_allowed_height,
-        maximum_allowed_speed=domain.maximum_allowed_speed,
-        evolve_max_timestep=domain.evolve_max_timestep, evolve_min_timestep=domain.evolve_min_timestep,
-        max_smallsteps=domain.max_smallsteps, CFL=domain.CFL,
-        timestepping_method=domain.timestepping_method,
-        beta_w=domain.beta_w, beta_w_dry=domain.beta_w_dry, beta_uh=domain.beta_uh,
-        beta_uh_dry=domain.beta_uh_dry, beta_vh=domain.beta_vh, beta_vh_dry=domain.beta_vh_dry,
-        extrapolate_velocity_second_order=int(domain.extrapolate_velocity_second_order),
-        low_froude=int(domain.low_froude), sloped_mannings=bool(domain.use_sloped_mannings),
-        fixed_flux_timestep=domain.fixed_flux_timestep, ghost_layer_width=domain.ghost_layer_width,
-        centroid_transmissive_bc=bool(domain.centroid_transmissive_bc), default_order=domain.default_order,
-    )
-    if domain.boundary_map is not None:
-        sc["boundary_map"] = {t: (None if B is None else B.oracle_spec()) for t, B in domain.boundary_map.items()}
-    sc["tag_boundary_cells"] = {t: np.array(v, dtype=np.int64) for t, v in domain.tag_boundary_cells.items()}
-    sc["operators"] = [op.oracle_spec() for op in domain.fractional_step_operators]
-    if domain.processor in domain.full_send_dict and domain.processor in domain.ghost_recv_dict:
-        sc["ghost_copy"] = (np.asarray(domain.full_send_dict[domain.processor][0], dtype=np.int64),
-                            np.asarray(domain.ghost_recv_dict[domain.processor][0], dtype=np.int64))
-    for k in ("edge_flux_type", "edge_river_wall_counter", "riverwall_elevation", "riverwall_rowIndex",
-              "riverwall_hydraulic_properties", "ncol_riverwall_hydraulic_properties"):
-        if hasattr(domain, k):
-            sc[k] = getattr(domain, k)
-    return sc
+from anuga_core_b200.workloads import domain_to_scenario  # noqa: E402,F401
 
 
 def dam_break(n=20, alg="DE1", friction=0.03, boundary="reflective", **domain_kw):

@@ -1,0 +1,190 @@
+"""GPU: parity of the CUDA path, called through the C ABI, against
+  (1) the golden fixtures generated from the unmodified Python reference (mode 2),
+  (2) the reference's own C sources (oracle/_ref) / the C port on the same inputs,
+on every boundary kind, flow algorithm and operator of the hot path.
+
+Tolerances (BASELINE.json north_star): stage/xmom/ymom within 1e-12 relative after one
+step and 1e-9 after the whole run; timestep sequences agree.  The kernels are compiled with
+-fmad=false in the reference's operation order, so in practice the results are bit-identical;
+the asserts use the north_star tolerances and the test output reports the measured error.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import anuga_core_b200 as ab
+from anuga_core_b200.workloads import domain_to_scenario
+from golden_util import cases, load, rel_err
+from oracle.driver import LIBS, OracleDomain
+
+pytestmark = pytest.mark.gpu
+
+TOL_1STEP = 1e-12
+TOL_FINAL = 1e-9
+REF = "ref" if os.path.exists(LIBS["ref"]) else "port"
+
+
+def conserved(d):
+    d.sync_to_host()
+    q = d.quantities
+    return q["stage"].centroid_values, q["xmomentum"].centroid_values, q["ymomentum"].centroid_values
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_evolve_matches_python_reference_golden(name):
+    g = load(name)
+    builder, ev = cases.CASES[name]
+    # one step
+    d1 = builder(ab)
+    it = d1.evolve(yieldstep=ev["yieldstep"], finaltime=ev["finaltime"])
+    next(it)
+    d1._push_quantities()
+    if d1._needs_host_stepping():
+        d1.relative_yieldtime = d1.relative_time + ev["yieldstep"]
+        d1._host_step()
+        d1._host_fractional_steps()
+        d1._mark_device_newer()
+        dt1 = d1.timestep
+    else:
+        r = d1._dev.evolve(ev["yieldstep"], ev["finaltime"], 1)
+        d1._mark_device_newer()
+        dt1 = r.timestep
+    w, uh, vh = conserved(d1)
+    assert dt1 == g["dts"][0]
+    e1 = max(rel_err(w, g["step1_stage"]), rel_err(uh, g["step1_xmom"]), rel_err(vh, g["step1_ymom"]))
+    assert e1 <= TOL_1STEP, e1
+
+    # whole run
+    d = builder(ab)
+    d.record_timestep_history = True
+    yields, steps = [], 0
+    for t in d.evolve(**ev):
+        yields.append(t)
+        steps += d.number_of_steps
+    w, uh, vh = conserved(d)
+    assert np.array_equal(np.array(yields), g["yields"])
+    assert d.total_steps == len(g["dts"])
+    assert d.timestep == g["dts"][-1]
+    ef = max(rel_err(w, g["final_stage"]), rel_err(uh, g["final_xmom"]), rel_err(vh, g["final_ymom"]))
+    assert ef <= TOL_FINAL, ef
+    assert rel_err(d.quantities["stage"].edge_values, g["final_stage_edge"]) <= TOL_FINAL
+    assert rel_err(d.quantities["xmomentum"].vertex_values, g["final_xmom_vertex"]) <= TOL_FINAL
+    assert abs(d.boundary_flux_integral - g["bfi"][0]) <= 1e-9 * abs(g["bfi"][0]) + 1e-12
+    assert abs(d.fractional_step_volume_integral - g["fsvi"][0]) <= 1e-12 * abs(g["fsvi"][0]) + 1e-15
+    print("\n[%s] 1-step rel err %.2e, final rel err %.2e, %d steps" % (name, e1, ef, d.total_steps))
+
+
+@pytest.mark.parametrize("alg", ["DE0", "DE1", "DE2"])
+@pytest.mark.parametrize("reorder", [True, False])
+def test_each_pass_matches_reference_c_code(alg, reorder):
+    """differential test in the style of shallow_water/tests/test_DE_openmp.py:32-153:
+    distribute_to_vertices_and_edges(); update_boundary(); compute_fluxes() then compare edge values,
+    boundary values, flux_timestep, explicit_update x3, max_speed."""
+    d = cases.beach_de1(ab, n=14)
+    d.set_flow_algorithm(alg)
+    d.reorder = reorder
+    o = OracleDomain(domain_to_scenario(d), backend=REF)
+    # burn in a few steps on both sides so that the state is not the initial condition
+    for _ in d.evolve(yieldstep=0.3, finaltime=0.3):
+        pass
+    for _ in o.evolve(yieldstep=0.3, finaltime=0.3):
+        pass
+    d.distribute_to_vertices_and_edges()
+    o.distribute_to_vertices_and_edges()
+    q = d.quantities
+    for mine, ref in ((q["stage"].edge_values, o.stage_e), (q["height"].edge_values, o.height_e),
+                      (q["xmomentum"].edge_values, o.xmom_e), (q["ymomentum"].edge_values, o.ymom_e),
+                      (q["elevation"].edge_values, o.bed_e), (q["stage"].vertex_values, o.stage_v),
+                      (q["elevation"].vertex_values, o.bed_v), (q["ymomentum"].vertex_values, o.ymom_v)):
+        assert rel_err(mine, ref) <= TOL_1STEP
+    w, uh, vh = conserved(d)
+    assert rel_err(w, o.stage_c) <= TOL_1STEP and rel_err(uh, o.xmom_c) <= TOL_1STEP and rel_err(vh, o.ymom_c) <= TOL_1STEP
+    d.update_boundary()
+    o.update_boundary()
+    dev = d._dev
+    assert rel_err(dev.get_quantity("STAGE_B"), o.stage_b) <= TOL_1STEP
+    assert rel_err(dev.get_quantity("XMOM_B"), o.xmom_b) <= TOL_1STEP
+    assert rel_err(dev.get_quantity("YMOM_B"), o.ymom_b) <= TOL_1STEP
+    ft = d.compute_fluxes(0)
+    o.compute_fluxes(0)
+    assert ft == o.flux_timestep
+    assert rel_err(q["stage"].explicit_update, o.stage_eu) <= TOL_1STEP
+    assert rel_err(q["xmomentum"].explicit_update, o.xmom_eu) <= TOL_1STEP
+    assert rel_err(q["ymomentum"].explicit_update, o.ymom_eu) <= TOL_1STEP
+    assert rel_err(d.get_max_speed(), o.max_speed) <= TOL_1STEP
+    # later substeps return evolve_max_timestep (sw_domain_openmp.c:768-771)
+    if alg != "DE0":
+        assert d.compute_fluxes(1) == d.evolve_max_timestep
+
+
+def test_config0_40k_dam_break_de0_free_dt_sequence():
+    """BASELINE.json configs[0]: rectangular_cross 100x100 (40k triangles), DE0, Reflective:
+    the free-dt sequence and the state agree with the reference C code over the whole run."""
+    d = cases.dam_break_de0(ab, n=100)
+    o = OracleDomain(domain_to_scenario(d), backend=REF)
+    dts = []
+    for t in d.evolve(yieldstep=0.25, finaltime=4.0):
+        dts.append((d.timestep, d.number_of_steps))
+    odts = []
+    for t in o.evolve(yieldstep=0.25, finaltime=4.0):
+        odts.append((o.timestep, o.number_of_steps))
+    assert dts == odts
+    assert d.total_steps == len(o.timestep_history) and d.total_steps > 200
+    w, uh, vh = conserved(d)
+    e = max(rel_err(w, o.stage_c), rel_err(uh, o.xmom_c), rel_err(vh, o.ymom_c))
+    assert e <= TOL_FINAL, e
+    print("\nconfig0: %d steps, rel err %.2e" % (d.total_steps, e))
+
+
+def test_1000_fixed_dt_steps_de1():
+    """north_star: within 1e-9 after 1000 fixed-dt steps (set_fixed_flux_timestep)"""
+    d = cases.dam_break_de0(ab, n=40)
+    d.set_flow_algorithm("DE1")
+    d.set_fixed_flux_timestep(0.004)
+    o = OracleDomain(domain_to_scenario(d), backend=REF)
+    for _ in d.evolve(yieldstep=2.0, finaltime=4.0):
+        pass
+    for _ in o.evolve(yieldstep=2.0, finaltime=4.0):
+        pass
+    assert d.total_steps == len(o.timestep_history) == 1000
+    w, uh, vh = conserved(d)
+    e = max(rel_err(w, o.stage_c), rel_err(uh, o.xmom_c), rel_err(vh, o.ymom_c))
+    assert e <= TOL_FINAL, e
+    print("\n1000 fixed-dt DE1 steps: rel err %.2e" % e)
+
+
+def test_quantities_round_trip_and_yield_protocol():
+    d = cases.beach_de1(ab, n=10)
+    w0 = d.quantities["stage"].centroid_values.copy()
+    it = d.evolve(yieldstep=0.2, finaltime=0.4)
+    t = next(it)
+    assert t == 0.0
+    # at the initial yield the centroid arrays are protected (stage >= bed) but otherwise unchanged
+    w = d.quantities["stage"].centroid_values
+    z = d.quantities["elevation"].centroid_values
+    assert np.all(w >= z) and np.array_equal(np.maximum(w0, z), w)
+    t = next(it)
+    assert t == 0.2 and d.number_of_steps > 0
+    # user modification between yields is picked up (set_quantity marks the host copy dirty)
+    d.set_quantity("stage", 2.0, location="centroids")
+    t = next(it)
+    assert t == 0.4
+    assert d.quantities["stage"].centroid_values.min() > 1.5
+    with pytest.raises(StopIteration):
+        next(it)
+    # evolve again continues from the current time without the initial yield
+    ts = [t for t in d.evolve(yieldstep=0.2, duration=0.2)]
+    assert ts == [pytest.approx(0.6)]
+
+
+def test_error_paths():
+    d = cases.dam_break_de0(ab, n=6)
+    d.evolve_min_timestep = 1.0e3       # every step is "too small": order drops to 1, then raises
+    d.max_smallsteps = 2
+    with pytest.raises(ab.SwkError) as e:
+        for _ in d.evolve(yieldstep=10.0, finaltime=10.0):
+            pass
+    assert e.value.code == -4
+    with pytest.raises(Exception):
+        ab.rectangular_cross_domain(2, 2).set_store(True)
