@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswk.so")
+LIB_PATH = os.environ.get("SWK_LIB", os.path.join(_HERE, "libswk.so"))   # SWK_LIB: kernel-variant experiments
 
 SWK_OK = 0
 ERRORS = {
@@ -54,7 +54,7 @@ class SwkParams(C.Structure):
         ("beta_vh", _D), ("beta_vh_dry", _D), ("CFL", _D), ("fixed_flux_timestep", _D),
         ("extrapolate_velocity_second_order", _I), ("low_froude", _I), ("timestepping_method", _I),
         ("use_sloped_mannings", _I), ("max_smallsteps", _I), ("default_order", _I),
-        ("ghost_layer_width", _I), ("centroid_transmissive_bc", _I),
+        ("ghost_layer_width", _I), ("centroid_transmissive_bc", _I), ("track_max_speed", _I),
     ]
 
 
@@ -222,6 +222,7 @@ def make_params(p):
     sp.default_order = int(p.get("default_order", 2))
     sp.ghost_layer_width = int(p.get("ghost_layer_width", 2))
     sp.centroid_transmissive_bc = int(bool(p.get("centroid_transmissive_bc", False)))
+    sp.track_max_speed = int(bool(p.get("track_max_speed", False)))
     return sp
 
 

@@ -149,8 +149,10 @@ struct swk_domain {
   Clock *d_clock = nullptr, *h_clock = nullptr;
   double *staging = nullptr;     // 3*N doubles
   size_t staging_n = 0;
-  int *d_acct = nullptr;
-  int n_acct = 0;
+  double *acct_val = nullptr;
+  int *pos_b = nullptr, *acct_keys = nullptr, *acct_keys_pos = nullptr;
+  int n_acct = 0, n_acct_keys = 0;
+  double full_area = 0.0;
 
   // boundary
   int *b_cell = nullptr, *b_edge = nullptr, *b_seg = nullptr;
@@ -304,7 +306,7 @@ extern "C" int swk_destroy(swk_domain *d)
   if (d->stream) cudaStreamSynchronize(d->stream);
   void *ptrs[] = {d->cq, d->eq, d->xg, d->fg, d->bq, d->connA, d->connB, d->eu, d->bk, d->eta, d->max_speed,
                   d->vcoord, d->zflag, d->rw_counter, d->rw_rowIndex, d->rw_elevation, d->rw_hydraulic,
-                  d->d_clock, d->staging, d->d_acct, d->b_cell, d->b_edge, d->b_seg, d->d_seg_kind,
+                  d->d_clock, d->staging, d->acct_val, d->pos_b, d->acct_keys, d->acct_keys_pos, d->b_cell, d->b_edge, d->b_seg, d->d_seg_kind,
                   d->d_seg_val, d->d_new2old, d->d_ghost_full, d->d_ghost_ghost, d->d_dt_scratch, d->d_ident_b};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -371,7 +373,6 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
   // ---- static records, built in device order with the reference's arithmetic ----
   std::vector<i4> connA(NP), connB(NP);
   std::vector<d4> xg(3 * NP), fg(3 * NP);
-  std::vector<int> acct;
   const double *cc = m->centroid_coordinates, *ec = m->edge_coordinates;
   for (int64_t k = 0; k < NP; k++) {
     if (k >= N) {   // padding: self-referencing dry cell, never executed (k >= N guards) but keep it sane
@@ -411,7 +412,8 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
       dy2 = dx2 * dy1;
       dx2 *= dx1;
     }
-    connA[k] = {o2n[s0], o2n[s1], o2n[s2], (nb & 3) | (which << 2)};
+    const int fullbit = (m->tri_full_flag[o] == 1) ? 1 : 0;
+    connA[k] = {o2n[s0], o2n[s1], o2n[s2], (nb & 3) | (which << 2) | (fullbit << 4)};
     xg[k] = {dxv[0], dxv[1], dxv[2], dyv[0]};
     xg[NP + k] = {dyv[1], dyv[2], dx1, dx2};
     xg[2 * NP + k] = {dy1, dy2, inv_area2, m->areas[o]};
@@ -433,24 +435,42 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
         pk[i] = (o2n[n] << 2) | (int)m->neighbour_edges[3 * o + i];
       }
       if (d->has_riverwalls && m->edge_flux_type[3 * o + i] == 1) flags |= (2 << i);
+      if (n >= 0 && m->tri_full_flag[o] == 1 && m->tri_full_flag[n] == 0) flags |= (16 << i);
     }
     connB[k] = {pk[0], pk[1], pk[2], flags};
   }
-  // boundary-flux accounting edges in the reference's (k, i) order (:696)
-  for (int64_t o = 0; o < N; o++) {
-    if (m->tri_full_flag[o] != 1) continue;
-    for (int i = 0; i < 3; i++) {
-      const int64_t n = m->neighbours[3 * o + i];
-      if (n < 0 || m->tri_full_flag[n] == 0) acct.push_back((o2n[o] << 2) | i);
+  // boundary-flux accounting edges in the reference's (k, i) order (:696): one slot each
+  std::vector<int> pos_b(std::max<int64_t>(M, 1), -1);
+  std::vector<std::pair<int, int>> ghost_keys;     // (device key, slot)
+  {
+    int slot = 0;
+    double area_sum = 0.0;
+    for (int64_t o = 0; o < N; o++) {
+      if (m->tri_full_flag[o] != 1) continue;
+      area_sum += m->areas[o];
+      for (int i = 0; i < 3; i++) {
+        const int64_t n = m->neighbours[3 * o + i];
+        if (n < 0) pos_b[-n - 1] = slot++;
+        else if (m->tri_full_flag[n] == 0) ghost_keys.push_back({(o2n[o] << 2) | i, slot++});
+      }
     }
+    d->n_acct = slot;
+    d->full_area = area_sum;
   }
-  d->n_acct = (int)acct.size();
+  std::sort(ghost_keys.begin(), ghost_keys.end());
+  std::vector<int> gk(ghost_keys.size()), gp(ghost_keys.size());
+  for (size_t j = 0; j < ghost_keys.size(); j++) { gk[j] = ghost_keys[j].first; gp[j] = ghost_keys[j].second; }
+  d->n_acct_keys = (int)gk.size();
+  CKV(dalloc(&d->pos_b, pos_b.size())); CKV(upload(d->pos_b, pos_b));
+  CKV(dalloc(&d->acct_keys, gk.size())); CKV(upload(d->acct_keys, gk));
+  CKV(dalloc(&d->acct_keys_pos, gp.size())); CKV(upload(d->acct_keys_pos, gp));
+  CKV(dalloc(&d->acct_val, (size_t)d->n_acct));
+  CK(cudaMemset(d->acct_val, 0, std::max(d->n_acct, 1) * sizeof(double)));
 
   CKV(dalloc(&d->connA, NP)); CKV(upload(d->connA, connA));
   CKV(dalloc(&d->connB, NP)); CKV(upload(d->connB, connB));
   CKV(dalloc(&d->xg, 3 * NP)); CKV(upload(d->xg, xg));
   CKV(dalloc(&d->fg, 3 * NP)); CKV(upload(d->fg, fg));
-  CKV(dalloc(&d->d_acct, acct.size())); CKV(upload(d->d_acct, acct));
   CKV(dalloc(&d->d_new2old, N)); CKV(upload(d->d_new2old, d->new2old));
   {
     std::vector<i4>().swap(connA); std::vector<i4>().swap(connB);
@@ -529,6 +549,8 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
   D.connA = d->connA; D.connB = d->connB;
   D.eu = d->eu; D.bk = d->bk; D.eta = d->eta; D.zflag = d->zflag; D.max_speed = d->max_speed;
   D.bq = d->bq; D.vcoord = d->vcoord; D.clock = d->d_clock;
+  D.acct_val = d->acct_val; D.pos_b = d->pos_b; D.acct_keys = d->acct_keys; D.acct_keys_pos = d->acct_keys_pos;
+  D.n_acct = d->n_acct; D.n_acct_keys = d->n_acct_keys;
   D.rw_counter = d->rw_counter; D.rw_elevation = d->rw_elevation; D.rw_rowIndex = d->rw_rowIndex;
   D.rw_hydraulic = d->rw_hydraulic; D.rw_ncol = (int)m->ncol_riverwall_hydraulic_properties;
   CK(cudaDeviceSynchronize());
@@ -863,17 +885,32 @@ static void launch_flux(swk_domain *d, int first, int write_speed)
 
 static void launch_bflux(swk_domain *d, int substep)
 {
-  if (d->has_riverwalls) LAUNCH(d, k_boundary_flux_sum<true>, 1, 1024, d->D, d->K, d->d_acct, d->n_acct, substep);
-  else LAUNCH(d, k_boundary_flux_sum<false>, 1, 1024, d->D, d->K, d->d_acct, d->n_acct, substep);
+  LAUNCH(d, k_boundary_flux_sum, 1, 1024, d->D, substep);
 }
 
-static UpdateArgs update_args(swk_domain *d, int do_backup, int do_saxpy, double a, double b, double divide_by)
+// A single scalar, non-negative, all-cells Rate_operator is folded into the last update kernel
+// of the step (no extra pass over the centroids); anything else runs as its own kernel.
+static bool rain_is_fusable(const swk_domain *d)
+{
+  if (d->rate_ops.size() != 1) return false;
+  const RateOp &op = d->rate_ops[0];
+  return !op.d_indices && !op.d_rate_array && op.all_nonneg;
+}
+
+static UpdateArgs update_args(swk_domain *d, int do_backup, int do_saxpy, double a, double b, double divide_by,
+                              bool last_of_step = false)
 {
   UpdateArgs U;
   U.a = a; U.b = b; U.divide_by = divide_by;
   U.g = d->P.g;
   U.do_backup = do_backup; U.do_saxpy = do_saxpy;
   U.sloped = d->P.use_sloped_mannings ? 1 : 0;
+  U.do_rain = 0; U.rain_rate = 0.0; U.rain_factor = 0.0;
+  if (last_of_step && rain_is_fusable(d)) {
+    U.do_rain = 1;
+    U.rain_rate = d->rate_ops[0].rate;
+    U.rain_factor = d->rate_ops[0].factor;
+  }
   return U;
 }
 
@@ -920,27 +957,28 @@ static int launch_dt_allreduce(swk_domain *d)
 }
 
 // one substep-0 sequence: A, boundary, B1, boundary-flux sum, dt, B2
-static int launch_first_substep(swk_domain *d, int do_backup)
+static int launch_first_substep(swk_domain *d, int do_backup, bool last_of_step)
 {
   launch_extrapolate(d, d->K);
   CKV(launch_boundary(d));
-  launch_flux(d, 1, 1);
-  launch_bflux(d, 0);
+  launch_flux(d, 1, (int)d->P.track_max_speed);
   CKV(launch_dt_allreduce(d));
-  LAUNCH(d, k_update_timestep, 1, 1, d->d_clock, d->TP);
+  LAUNCH(d, k_update_timestep, 1, 1024, d->D, d->TP, 1);
   {
     TimedScope ts(d, 2);
-    LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, do_backup, 0, 1.0, 0.0, 1.0), -1.0);
+    LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K,
+           update_args(d, do_backup, 0, 1.0, 0.0, 1.0, last_of_step), -1.0);
   }
   return SWK_OK;
 }
 
 // a later RK substep with the RK combination folded in
-static int launch_later_substep(swk_domain *d, int substep, double a, double b, double divide_by)
+static int launch_later_substep(swk_domain *d, int substep, double a, double b, double divide_by,
+                                bool last_of_step)
 {
   launch_extrapolate(d, d->K);
   CKV(launch_boundary(d));
-  const UpdateArgs U = update_args(d, 0, 1, a, b, divide_by);
+  const UpdateArgs U = update_args(d, 0, 1, a, b, divide_by, last_of_step);
   if (d->has_riverwalls) {
     launch_flux(d, 0, 0);
     TimedScope ts(d, 2);
@@ -949,33 +987,39 @@ static int launch_later_substep(swk_domain *d, int substep, double a, double b, 
     TimedScope ts(d, 3);
     LAUNCH(d, k_flux_update, nblk(d->N), BLOCK, d->D, d->K, U);
   }
-  launch_bflux(d, substep);
+  if (!last_of_step) launch_bflux(d, substep);     // the last substep's sum rides in k_finish_step
   return SWK_OK;
 }
 
 // one full timestep = one iteration of _evolve_base's while loop (generic_domain.py:1835-1862)
 static int launch_step(swk_domain *d)
 {
+  // step_start_time / dt_min_bits are (re)set by the previous k_finish_step (or by the host before
+  // the first step of a call), so a step is: [A, bc, B1, dt, B2] [A, bc, B]* finish.
   const int method = (int)d->P.timestepping_method;
-  LAUNCH(d, k_begin_step, 1, 1, d->d_clock);
   if (method == 1) {
-    CKV(launch_first_substep(d, 0));
+    CKV(launch_first_substep(d, 0, true));
   } else if (method == 2) {
-    CKV(launch_first_substep(d, 1));
-    LAUNCH(d, k_set_substep_time, 1, 1, d->d_clock, 1.0);
+    CKV(launch_first_substep(d, 1, false));
     if (d->P.ghost_layer_width < 4) CKV(launch_ghosts(d));
-    CKV(launch_later_substep(d, 1, 0.5, 0.5, 1.0));
+    CKV(launch_later_substep(d, 1, 0.5, 0.5, 1.0, true));
   } else {
-    CKV(launch_first_substep(d, 1));
-    LAUNCH(d, k_set_substep_time, 1, 1, d->d_clock, 1.0);
+    CKV(launch_first_substep(d, 1, false));
     CKV(launch_ghosts(d));
-    CKV(launch_later_substep(d, 1, 0.25, 0.75, 1.0));
-    LAUNCH(d, k_set_substep_time, 1, 1, d->d_clock, 0.5);
+    CKV(launch_later_substep(d, 1, 0.25, 0.75, 1.0, false));
     CKV(launch_ghosts(d));
-    CKV(launch_later_substep(d, 2, 2.0, 1.0, 3.0));
+    CKV(launch_later_substep(d, 2, 2.0, 1.0, 3.0, true));
   }
-  launch_rate_ops(d);                               // apply_fractional_steps (:1849)
-  LAUNCH(d, k_finish_step, 1, 1, d->d_clock, d->TP);
+  FusedRain R;
+  R.on = 0; R.rate = 0.0; R.factor = 0.0; R.full_area = d->full_area;
+  if (rain_is_fusable(d)) {                         // apply_fractional_steps (:1849)
+    R.on = 1;
+    R.rate = d->rate_ops[0].rate;
+    R.factor = d->rate_ops[0].factor;
+  } else {
+    launch_rate_ops(d);
+  }
+  LAUNCH(d, k_finish_step, 1, 1024, d->D, d->TP, method == 1 ? -1 : method - 1, R);
   CKV(launch_ghosts(d));                            // :1857
   return SWK_OK;
 }
@@ -1024,6 +1068,8 @@ extern "C" int swk_evolve(swk_domain *d, double relative_yieldtime, double relat
   c->finaltime = relative_finaltime;
   c->step_budget = (max_steps > 0) ? c->total_steps + max_steps : 0;
   c->stop = 0;
+  c->step_start_time = c->time;
+  c->dt_min_bits = 0x54B249AD2594C37DULL;          // bits of 1.0e+100
   CKV(push_clock(d));
 
   int64_t batch = 1;
@@ -1069,6 +1115,8 @@ extern "C" int swk_run_steps(swk_domain *d, int64_t n_steps, int per_kernel, flo
   c->finaltime = -1.0;
   c->step_budget = 0;
   c->stop = 0;
+  c->step_start_time = c->time;
+  c->dt_min_bits = 0x54B249AD2594C37DULL;          // bits of 1.0e+100
   CKV(push_clock(d));
   d->timing = false;
   if (per_kernel) {

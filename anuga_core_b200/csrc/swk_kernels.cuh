@@ -21,7 +21,16 @@
 
 namespace swk {
 
-constexpr int BLOCK = 256;
+#ifndef SWK_BLOCK
+#define SWK_BLOCK 128
+#endif
+#ifndef SWK_MINB_A          // min resident blocks per SM for pass A (extrapolate)
+#define SWK_MINB_A 6
+#endif
+#ifndef SWK_MINB_F          // ... for the flux kernels
+#define SWK_MINB_F 5
+#endif
+constexpr int BLOCK = SWK_BLOCK;
 
 // ---- device-side clock: the scalars of Generic_Domain's time loop -------------
 struct Clock {
@@ -65,6 +74,12 @@ struct Dev {
   d4 *bq;
   const double *vcoord;          // (6*NP) vertex coordinates x0,y0,x1,y1,x2,y2 planes (sloped Manning), may be null
   Clock *clock;
+  // boundary-flux accounting (sw_domain_openmp.c:696-701): slot per accounting edge, in (k, i) order
+  double *acct_val;              // [n_acct]
+  const int *pos_b;              // [M] slot of boundary edge m, -1 if its cell is a ghost
+  const int *acct_keys;          // sorted (k<<2|i) of full-cell edges facing a ghost cell
+  const int *acct_keys_pos;      // their slots
+  int n_acct, n_acct_keys;
   // riverwalls
   const int *rw_counter;         // [3][NP] edge_river_wall_counter (1-based) or null
   const double *rw_elevation;
@@ -80,7 +95,7 @@ struct Dev {
 // are NOT modified (their protected form is recomputed by the consumers).
 // One thread per triangle.  Reads cq (own + 3 gathered), connA, xg; writes eq, zflag.
 // =============================================================================
-__global__ void __launch_bounds__(BLOCK) k_extrapolate(Dev D, Consts K)
+__global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts K)
 {
   if (D.clock->stop) return;
   const int k = blockIdx.x * BLOCK + threadIdx.x;
@@ -113,7 +128,7 @@ __global__ void __launch_bounds__(BLOCK) k_extrapolate(Dev D, Consts K)
   const bool dry2 = (e2.h < K.mah) | (s.z == k);
   const bool zero_mom = dry0 & dry1 & dry2;
   if (zero_mom) { e.u = 0.0; e.v = 0.0; }
-  D.zflag[k] = zero_mom ? 1 : 0;
+  D.zflag[k] = (zero_mom ? 1 : 0) | ((s.w >> 3) & 2);   // bit0: zeroed momenta, bit1: tri_full_flag
 
   double w0, w1, w2, h0, h1, h2, u0, u1, u2, v0, v1, v2;
   if (nb == 3) {                                   // :1498-1522
@@ -126,11 +141,11 @@ __global__ void __launch_bounds__(BLOCK) k_extrapolate(Dev D, Consts K)
     const double c_tmp = 1.0 / (a_tmp - b_tmp);
     const double d_tmp = 1.0 - (c_tmp * a_tmp);
     const double hc = e.h;
-    const double hmin = fmin(fmin(e0.h, fmin(e1.h, e2.h)), hc);
-    const double hmax = fmax(fmax(e0.h, fmax(e1.h, e2.h)), hc);
-    double hfactor = fmax(0., fmin(c_tmp * fmax(hmin, 0.0) / fmax(hc, 1.0e-06) + d_tmp,
-                                   fmin(c_tmp * fmax(hc, 0.) / fmax(hmax, 1.0e-06) + d_tmp, 1.0)));
-    hfactor = fmin(1.2 * fmax(hmin - K.mah, 0.) / (fmax(hmin, 0.) + 1. * K.mah), hfactor);
+    const double hmin = dmin(dmin(e0.h, dmin(e1.h, e2.h)), hc);
+    const double hmax = dmax(dmax(e0.h, dmax(e1.h, e2.h)), hc);
+    double hfactor = dmax(0., dmin(c_tmp * dmax(hmin, 0.0) / dmax(hc, 1.0e-06) + d_tmp,
+                                   dmin(c_tmp * dmax(hc, 0.) / dmax(hmax, 1.0e-06) + d_tmp, 1.0)));
+    hfactor = dmin(1.2 * dmax(hmin - K.mah, 0.) / (dmax(hmin, 0.) + 1. * K.mah), hfactor);
     double beta = K.beta_w_dry + (K.beta_w - K.beta_w_dry) * hfactor;
     edge_values_3(beta, e.w, e0.w, e1.w, e2.w, G, w0, w1, w2);
     edge_values_3(beta, e.h, e0.h, e1.h, e2.h, G, h0, h1, h2);
@@ -175,7 +190,7 @@ __global__ void __launch_bounds__(BLOCK) k_materialize_centroids(Dev D, Consts K
   } else {
     const Eff e = effective(c, K);
     c.x = e.w; c.y = e.uh; c.z = e.vh;
-    if (D.zflag[k]) { c.y = 0.0; c.z = 0.0; }
+    if (D.zflag[k] & 1) { c.y = 0.0; c.z = 0.0; }
   }
   D.cq[k] = c;
 }
@@ -239,7 +254,7 @@ __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, 
         const d4 c = D.cq[k];                  // centroid arrays as the reference sees them
         const Eff ef = effective(c, K);
         out.x = ef.w; out.y = ef.uh; out.z = ef.vh;
-        if (D.zflag[k]) { out.y = 0.0; out.z = 0.0; }
+        if (D.zflag[k] & 1) { out.y = 0.0; out.z = 0.0; }
       } else {
         out.x = e.x; out.y = e.z; out.z = e.w;
       }
@@ -280,8 +295,20 @@ struct TriFlux {
   double su, xu, yu;      // explicit updates (already scaled by 1/area)
   double dtmin;           // min edge timestep of this triangle (1e100 if none)
   double speed;           // max_speed[k]
-  double bflux[3];        // -flux0*length per edge (boundary-flux accounting)
 };
+
+// slot of an accounting edge that faces a ghost cell (multi-GPU sub-domains only)
+__device__ __noinline__ int acct_slot_lookup(const int *keys, const int *keys_pos, int n, int key)
+{
+  int lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int v = keys[mid];
+    if (v == key) return keys_pos[mid];
+    if (v < key) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
 
 template <bool RW>
 __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, int k, const i4 p,
@@ -323,23 +350,23 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
     if (pn[i] < 0) {                                  // :551-561
       wr = er[i].x; uhr = er[i].y; vhr = er[i].z;
       zr = zl;
-      hre = fmax(wr - zr, 0.0);
+      hre = dmax(wr - zr, 0.0);
     } else {                                          // :562-576
       wr = er[i].x; hre = er[i].y; uhr = er[i].z; vhr = er[i].w;
       zr = wr - hre;
     }
-    double z_half = fmax(zl, zr);
+    double z_half = dmax(zl, zr);
     bool rw_edge = false;
     int rwc = 0;
     if (RW) {
       rw_edge = (p.w >> (1 + i)) & 1;
       if (rw_edge) {                                  // :582-588
         rwc = D.rw_counter[i * NP + k];
-        z_half = fmax(D.rw_elevation[rwc - 1], z_half);
+        z_half = dmax(D.rw_elevation[rwc - 1], z_half);
       }
     }
-    const double h_left = fmax(hle + zl - z_half, 0.);
-    const double h_right = fmax(hre + zr - z_half, 0.);
+    const double h_left = dmax(hle + zl - z_half, 0.);
+    const double h_right = dmax(hre + zr - z_half, 0.);
     EdgeFlux F = edge_flux_central(wl, uhl, vhl, wr, uhr, vhr, h_left, h_right, hle, hre,
                                    nx[i], ny[i], z_half, K);
     if (RW) {
@@ -351,17 +378,17 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
         const double h1 = D.rw_hydraulic[ii + 3];
         const double h2 = D.rw_hydraulic[ii + 4];
         const double rw_elev = D.rw_elevation[rwc - 1];
-        const double weir_height = fmax(rw_elev - fmin(zl, zr), 0.);
-        const double h_left_tmp = fmax(own.w - z_half, 0.);
+        const double weir_height = dmax(rw_elev - dmin(zl, zr), 0.);
+        const double h_left_tmp = dmax(own.w - z_half, 0.);
         double h_right_tmp, zc_n = zc;
         if (pn[i] >= 0) {
           const Eff en = effective(D.cq[pn[i] >> 2], K);
           zc_n = en.z;
-          h_right_tmp = fmax(en.w - z_half, 0.);
+          h_right_tmp = dmax(en.w - z_half, 0.);
         } else {
-          h_right_tmp = fmax(hc + zr - z_half, 0.);
+          h_right_tmp = dmax(hc + zr - z_half, 0.);
         }
-        if (rw_elev > fmax(zc, zc_n))
+        if (rw_elev > dmax(zc, zc_n))
           weir_adjust(F, h_left_tmp, h_right_tmp, K.g, weir_height, Qfactor, s1, s2, h1, h2);
       }
     }
@@ -372,16 +399,22 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
     const double pressuregrad =
         length * (-K.g * 0.5 * (h_left * h_left - hle * hle - (hle + hc) * (zl - zc)) + F.pressure_flux);
     if (first) {                                      // :667-686
-      const double edge_timestep = radius * 1.0 / fmax(F.max_speed, K.epsilon);
+      const double edge_timestep = radius * 1.0 / dmax(F.max_speed, K.epsilon);
       if (full && F.max_speed > K.epsilon) {
-        T.dtmin = fmin(T.dtmin, edge_timestep);
-        T.speed = fmax(T.speed, F.max_speed);
+        T.dtmin = dmin(T.dtmin, edge_timestep);
+        T.speed = dmax(T.speed, F.max_speed);
       }
     }
     T.su += ef0;
     T.xu += ef1;
     T.yu += ef2;
-    T.bflux[i] = ef0;
+    if (pn[i] < 0) {                                  // boundary_flux_sum terms (:696-701)
+      const int slot = D.pos_b[-pn[i] - 1];
+      if (slot >= 0) D.acct_val[slot] = ef0;
+    } else if ((p.w >> (4 + i)) & 1) {
+      const int slot = acct_slot_lookup(D.acct_keys, D.acct_keys_pos, D.n_acct_keys, (k << 2) | i);
+      if (slot >= 0) D.acct_val[slot] = ef0;
+    }
     T.xu -= nx[i] * pressuregrad;
     T.yu -= ny[i] * pressuregrad;
   }
@@ -396,14 +429,14 @@ __device__ __forceinline__ void block_min_to_clock(double v, Clock *clock)
 {
   __shared__ double smin[BLOCK / 32];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, o));
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) smin[wid] = v;
   __syncthreads();
   if (wid == 0) {
     v = (lane < BLOCK / 32) ? smin[lane] : 1.0e+100;
 #pragma unroll
-    for (int o = BLOCK / 64; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = BLOCK / 64; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0 && v < 1.0e+100) atomicMin(&clock->dt_min_bits, d2u(v));
   }
 }
@@ -415,20 +448,23 @@ __device__ __forceinline__ void block_min_to_clock(double v, Clock *clock)
 struct UpdateArgs {
   double a, b, divide_by;     // saxpy coefficients; combine only if do_saxpy
   double g;
-  int do_backup, do_saxpy, sloped;
+  double rain_rate, rain_factor;   // fused scalar Rate_operator (rate >= 0, all cells), see k_finish_step
+  int do_backup, do_saxpy, sloped, do_rain;
 };
 
 __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, const UpdateArgs &U,
-                                                int k, const d4 raw, Eff e, bool full,
+                                                int k, const d4 raw, Eff e,
                                                 double su, double xu, double yu, double dt)
 {
   const int NP = D.NP;
+  const unsigned char zf = D.zflag[k];
+  const bool full = (zf & 2) != 0;
   if (U.do_backup) {                                   // backup holds the RAW start-of-step values
     D.bk[k] = raw.x;
     D.bk[NP + k] = raw.y;
     D.bk[2 * NP + k] = raw.z;
   }
-  if (D.zflag[k]) { e.uh = 0.0; e.vh = 0.0; }
+  if (zf & 1) { e.uh = 0.0; e.vh = 0.0; }
   double zs = 1.0;
   double h = e.w - e.z;
   if (U.sloped) {                                      // :2003-2023 with the dynamic bed vertex values
@@ -466,6 +502,7 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
       vh = vh / U.divide_by;
     }
   }
+  if (U.do_rain) w = w + U.rain_factor * dt * U.rain_rate;   // rate_operators.py:205-208 (all rates >= 0)
   d4 out;
   out.x = w; out.y = uh; out.z = vh; out.w = e.z;
   D.cq[k] = out;
@@ -473,7 +510,7 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
 
 // Pass B1 (substep 0): flux + dt partials.  writes eu, max_speed, dt_min_bits.
 template <bool RW>
-__global__ void __launch_bounds__(BLOCK) k_flux(Dev D, Consts K, int first, int write_speed)
+__global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int first, int write_speed)
 {
   if (D.clock->stop) return;
   const int k = blockIdx.x * BLOCK + threadIdx.x;
@@ -500,14 +537,13 @@ __global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U,
   const double dt = (dt_override >= 0.0) ? dt_override : D.clock->dt;
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
-  const bool full = D.connB[k].w & 1;
-  triangle_update(D, K, U, k, raw, e, full, D.eu[k], D.eu[D.NP + k], D.eu[2 * D.NP + k], dt);
+  triangle_update(D, K, U, k, raw, e, D.eu[k], D.eu[D.NP + k], D.eu[2 * D.NP + k], dt);
 }
 
 // Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
 // dt is already known, so explicit updates never touch HBM.  (Not used with
 // riverwalls: the weir branch reads the neighbour's stage centroid, :635.)
-__global__ void __launch_bounds__(BLOCK) k_flux_update(Dev D, Consts K, UpdateArgs U)
+__global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux_update(Dev D, Consts K, UpdateArgs U)
 {
   if (D.clock->stop) return;
   const int k = blockIdx.x * BLOCK + threadIdx.x;
@@ -517,37 +553,35 @@ __global__ void __launch_bounds__(BLOCK) k_flux_update(Dev D, Consts K, UpdateAr
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
   const TriFlux T = triangle_flux<false>(D, K, k, p, e, false);
-  triangle_update(D, K, U, k, raw, e, p.w & 1, T.su, T.xu, T.yu, dt);
+  triangle_update(D, K, U, k, raw, e, T.su, T.xu, T.yu, dt);
 }
 
 // =============================================================================
-// boundary_flux_sum[substep]: sum of the mass flux through edges of full cells that
-// face a boundary or a ghost cell (:696-701, 765).  The accounting edges are few
-// (O(sqrt N)); their fluxes are re-evaluated here by ONE block that walks the list
-// in the reference's (k, i) order with a fixed reduction tree, so the sum is
-// reproducible run to run.
+// boundary_flux_sum[substep]: sum of the mass flux through edges of full cells that face a
+// boundary or a ghost cell (:696-701, 765).  The flux kernels drop each such term into its
+// slot (slots are in the reference's (k, i) order); one 1024-thread block adds them with a
+// fixed order and tree, so the sum is reproducible run to run.  The reduction rides in the
+// single-block clock kernels below.
 // =============================================================================
-template <bool RW>
-__global__ void __launch_bounds__(1024) k_boundary_flux_sum(Dev D, Consts K, const int *acct, int n_acct, int substep)
+__device__ __forceinline__ double block_sum_acct(const Dev &D)
 {
-  if (D.clock->stop) return;
   __shared__ double part[1024];
   double s = 0.0;
-  for (int j = threadIdx.x; j < n_acct; j += 1024) {
-    const int ki = acct[j];
-    const int k = ki >> 2, i = ki & 3;
-    const i4 p = D.connB[k];
-    const Eff own = effective(D.cq[k], K);
-    const TriFlux T = triangle_flux<RW>(D, K, k, p, own, false);
-    s += T.bflux[i];
-  }
+  for (int j = threadIdx.x; j < D.n_acct; j += 1024) s += D.acct_val[j];
   part[threadIdx.x] = s;
   __syncthreads();
   for (int o = 512; o > 0; o >>= 1) {
     if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) D.clock->boundary_flux_sum[substep] = part[0];
+  return part[0];
+}
+
+__global__ void __launch_bounds__(1024) k_boundary_flux_sum(Dev D, int substep)
+{
+  if (D.clock->stop) return;
+  const double s = block_sum_acct(D);
+  if (threadIdx.x == 0) D.clock->boundary_flux_sum[substep] = s;
 }
 
 // =============================================================================
@@ -561,16 +595,22 @@ __global__ void k_begin_step(Clock *c)
   c->dt_min_bits = d2u(1.0e+100);
 }
 
-__global__ void k_update_timestep(Clock *c, TimeParams P)
+__global__ void __launch_bounds__(1024) k_update_timestep(Dev D, TimeParams P, int reduce_bflux)
 {
+  Clock *c = D.clock;
   if (c->stop) return;
+  if (reduce_bflux) {
+    const double bsum = block_sum_acct(D);
+    if (threadIdx.x == 0) c->boundary_flux_sum[0] = bsum;
+  }
+  if (threadIdx.x != 0) return;
   // compute_fluxes returned the min edge timestep (substep 0) ...
   double flux_dt = u2d(c->dt_min_bits);
   if (P.fixed_flux_timestep > 0.0) flux_dt = P.fixed_flux_timestep;
   c->flux_dt = flux_dt;
-  double timestep = fmin(P.CFL * flux_dt, P.evolve_max_timestep);
-  c->recorded_max_timestep = fmax(timestep, c->recorded_max_timestep);
-  c->recorded_min_timestep = fmin(timestep, c->recorded_min_timestep);
+  double timestep = dmin(P.CFL * flux_dt, P.evolve_max_timestep);
+  c->recorded_max_timestep = dmax(timestep, c->recorded_max_timestep);
+  c->recorded_min_timestep = dmin(timestep, c->recorded_min_timestep);
   if (timestep < P.evolve_min_timestep) {
     c->smallsteps += 1;
     if (c->smallsteps > P.max_smallsteps) {
@@ -594,15 +634,27 @@ __global__ void k_set_substep_time(Clock *c, double fraction)
   c->time = c->step_start_time + c->dt * fraction;
 }
 
-__global__ void k_finish_step(Clock *c, TimeParams P)
+struct FusedRain {
+  double rate, factor, full_area;   // influx = (factor*dt*rate) * sum of full-cell areas
+  int on;
+};
+
+__global__ void __launch_bounds__(1024) k_finish_step(Dev D, TimeParams P, int last_substep, FusedRain R)
 {
+  Clock *c = D.clock;
   if (c->stop) return;
+  if (last_substep >= 0) {
+    const double bsum = block_sum_acct(D);
+    if (threadIdx.x == 0) c->boundary_flux_sum[last_substep] = bsum;
+  }
+  if (threadIdx.x != 0) return;
   // boundary_flux_integral_operator.__call__ (boundary_flux_integral_operator.py:44-62)
   const double dt = c->dt;
   if (P.method == 1) c->boundary_flux_integral += dt * c->boundary_flux_sum[0];
   else if (P.method == 2) c->boundary_flux_integral += 0.5 * dt * (c->boundary_flux_sum[0] + c->boundary_flux_sum[1]);
   else c->boundary_flux_integral += 1.0 / 6.0 * dt * (c->boundary_flux_sum[0] + c->boundary_flux_sum[1] + 4.0 * c->boundary_flux_sum[2]);
   c->boundary_flux_sum[0] = c->boundary_flux_sum[1] = c->boundary_flux_sum[2] = 0.0;
+  if (R.on) c->fractional_step_volume_integral += R.factor * dt * R.rate * R.full_area;   // rate_operators.py:206, 259
   c->time = c->step_start_time + c->dt;                 // :1855
   c->number_of_steps += 1;
   c->total_steps += 1;
@@ -615,7 +667,10 @@ __global__ void k_finish_step(Clock *c, TimeParams P)
     return;
   }
   if (c->time >= c->yieldtime) { c->stop = 1; return; }  // :1891
-  if (c->step_budget > 0 && c->total_steps >= c->step_budget) c->stop = 3;
+  if (c->step_budget > 0 && c->total_steps >= c->step_budget) { c->stop = 3; return; }
+  // begin the next step
+  c->step_start_time = c->time;
+  c->dt_min_bits = d2u(1.0e+100);
 }
 
 // =============================================================================
@@ -640,7 +695,7 @@ __global__ void __launch_bounds__(BLOCK) k_rate_operator(Dev D, double rate, dou
       c.x = c.x + local_rate;
     } else {
       const double height = c.x - c.w;
-      local_rate = fmax(local_rate, -height);
+      local_rate = dmax(local_rate, -height);
       const double f = (local_rate < 0.0) ? (local_rate + height) / (height + 1.0e-10) : 1.0;
       c.x = c.x + local_rate;
       c.y = c.y * f;

@@ -62,6 +62,15 @@ __device__ __forceinline__ double pow_7_3(double h)
 }
 
 // ---------------------------------------------------------------------------
+// min / max without the NaN plumbing of fmin / fmax (DSETP + 2 selects instead of
+// DSETP + 2 selects + NaN quieting + moves).  For non-NaN operands the value is the
+// same as the reference's fmin / fmax; on a +0/-0 tie either zero may be returned by
+// libm as well, and no consumer distinguishes them (no division by these values).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a : b; }
+
+// ---------------------------------------------------------------------------
 // Scalars every kernel needs (copied into kernel parameter space).
 // ---------------------------------------------------------------------------
 struct Consts {
@@ -97,7 +106,7 @@ __device__ __forceinline__ Eff effective(const d4 c, const Consts &K)
     e.mass_added = e.z - e.w;
     e.w = e.z;
   }
-  e.h = fmax(e.w - e.z, 0.0);           // :1376
+  e.h = dmax(e.w - e.z, 0.0);           // :1376
   if (e.h <= K.mah) {                   // :1382-1388 (subsumes protect's xmom-only zeroing :1136-1140)
     e.uh = 0.0;
     e.vh = 0.0;
@@ -120,14 +129,14 @@ __device__ __forceinline__ void limit_gradient(double &d0, double &d1, double &d
   double r = 1000.0, r0 = 1.0;
   if (d0 < -TINY) r0 = qmin / d0;
   if (d0 > TINY) r0 = qmax / d0;
-  r = fmin(r0, r);
+  r = dmin(r0, r);
   if (d1 < -TINY) r0 = qmin / d1;
   if (d1 > TINY) r0 = qmax / d1;
-  r = fmin(r0, r);
+  r = dmin(r0, r);
   if (d2 < -TINY) r0 = qmin / d2;
   if (d2 > TINY) r0 = qmax / d2;
-  r = fmin(r0, r);
-  const double phi = fmin(r * beta, 1.0);
+  r = dmin(r0, r);
+  const double phi = dmin(r * beta, 1.0);
   d0 = d0 * phi;
   d1 = d1 * phi;
   d2 = d2 * phi;
@@ -156,8 +165,8 @@ __device__ __forceinline__ void edge_values_3(double beta, double qc, double q0,
     double d0 = a * G.dxv0 + b * G.dyv0;
     double d1 = a * G.dxv1 + b * G.dyv1;
     double d2 = a * G.dxv2 + b * G.dyv2;
-    const double qmax = fmax(fmax(dq0, fmax(dq0 + dq1, dq0 + dq2)), 0.0);
-    const double qmin = fmin(fmin(dq0, fmin(dq0 + dq1, dq0 + dq2)), 0.0);
+    const double qmax = dmax(dmax(dq0, dmax(dq0 + dq1, dq0 + dq2)), 0.0);
+    const double qmin = dmin(dmin(dq0, dmin(dq0 + dq1, dq0 + dq2)), 0.0);
     limit_gradient(d0, d1, d2, qmin, qmax, beta);
     e0 = qc + d0;
     e1 = qc + d1;
@@ -238,18 +247,18 @@ __device__ __forceinline__ EdgeFlux edge_flux_central(double wl, double uhl_xy, 
 
   double local_fr = 1.0;
   if (K.low_froude == 1) {
-    local_fr = sqrt(fmax(0.001, fmin(1.0,
+    local_fr = sqrt(dmax(0.001, dmin(1.0,
         (u_right * u_right + u_left * u_left + v_right * v_right + v_left * v_left) /
         (c_left * c_left + c_right * c_right + 1.0e-10))));
   } else if (K.low_froude == 2) {
     local_fr = sqrt((u_right * u_right + u_left * u_left + v_right * v_right + v_left * v_left) /
                     (c_left * c_left + c_right * c_right + 1.0e-10));
-    local_fr = sqrt(fmin(1.0, 0.01 + fmax(local_fr - 0.01, 0.0)));
+    local_fr = sqrt(dmin(1.0, 0.01 + dmax(local_fr - 0.01, 0.0)));
   }
 
-  double s_max = fmax(u_left + c_left, u_right + c_right);
+  double s_max = dmax(u_left + c_left, u_right + c_right);
   if (s_max < 0.0) s_max = 0.0;
-  double s_min = fmin(u_left - c_left, u_right - c_right);
+  double s_min = dmin(u_left - c_left, u_right - c_right);
   if (s_min > 0.0) s_min = 0.0;
 
   const double fl0 = u_left * h_left, fl1 = u_left * uh_left, fl2 = u_left * vh_left;
@@ -262,11 +271,11 @@ __device__ __forceinline__ EdgeFlux edge_flux_central(double wl, double uhl_xy, 
     F.pressure_flux = 0.5 * K.g * 0.5 * (h_left * h_left + h_right * h_right);
     return F;
   }
-  F.max_speed = fmax(s_max, -s_min);
-  const double inv_denom = 1.0 / fmax(denom, 1.0e-100);
+  F.max_speed = dmax(s_max, -s_min);
+  const double inv_denom = 1.0 / dmax(denom, 1.0e-100);
   const double smm = s_max * s_min;
   double e0 = s_max * fl0 - s_min * fr0;
-  e0 += smm * (fmax(wr, ze) - fmax(wl, ze));
+  e0 += smm * (dmax(wr, ze) - dmax(wl, ze));
   e0 *= inv_denom;
   double e1 = s_max * fl1 - s_min * fr1;
   e1 += local_fr * smm * (uh_right - uh_left);
@@ -288,26 +297,26 @@ __device__ __noinline__ void weir_adjust(EdgeFlux &F, double h_left, double h_ri
 {
   const double twothirds = (2.0 / 3.0);
   if ((h_left <= 0.0) && (h_right <= 0.0)) return;
-  const double minhd = fmin(h_left, h_right);
-  const double maxhd = fmax(h_left, h_right);
+  const double minhd = dmin(h_left, h_right);
+  const double maxhd = dmax(h_left, h_right);
   double rw = Qfactor * twothirds * maxhd * sqrt(twothirds * g * maxhd);
   const double rw2 = Qfactor * twothirds * minhd * sqrt(twothirds * g * minhd);
-  const double rwRat = rw2 / fmax(rw, 1.0e-100);
-  const double hdRat = minhd / fmax(maxhd, 1.0e-100);
-  const double hdWrRat = minhd / fmax(weir_height, 1.0e-100);
+  const double rwRat = rw2 / dmax(rw, 1.0e-100);
+  const double hdRat = minhd / dmax(maxhd, 1.0e-100);
+  const double hdWrRat = minhd / dmax(weir_height, 1.0e-100);
   rw = rw * pow(1.0 - rwRat, 0.385);
   if (h_right > h_left) rw *= -1.0;
   if ((hdRat < s2) & (hdWrRat < h2)) {
-    const double w1 = fmin(fmax(hdRat - s1, 0.) / (s2 - s1), 1.0);
-    const double w2 = fmin(fmax(hdWrRat - h1, 0.) / (h2 - h1), 1.0);
+    const double w1 = dmin(dmax(hdRat - s1, 0.) / (s2 - s1), 1.0);
+    const double w2 = dmin(dmax(hdWrRat - h1, 0.) / (h2 - h1), 1.0);
     const double newFlux = (rw * (1.0 - w1) + w1 * F.f0) * (1.0 - w2) + w2 * F.f0;
     double scaleFlux;
     if (fabs(F.f0) > 1.0e-100) scaleFlux = newFlux / F.f0;
     else scaleFlux = 0.;
-    scaleFlux = fmax(scaleFlux, 0.);
+    scaleFlux = dmax(scaleFlux, 0.);
     F.f0 = newFlux;
-    F.f1 *= fmin(scaleFlux, 10.);
-    F.f2 *= fmin(scaleFlux, 10.);
+    F.f1 *= dmin(scaleFlux, 10.);
+    F.f2 *= dmin(scaleFlux, 10.);
   }
   if (fabs(F.f0) > 0.)
     F.max_speed = sqrt(g * (maxhd + weir_height)) + fabs(F.f0 / (maxhd + 1.0e-12));

@@ -364,6 +364,7 @@ class Domain:
             use_sloped_mannings=self.use_sloped_mannings, max_smallsteps=self.max_smallsteps,
             default_order=self.default_order, ghost_layer_width=self.ghost_layer_width,
             centroid_transmissive_bc=self.centroid_transmissive_bc,
+            track_max_speed=getattr(self, "track_max_speed", False),
         )
 
     def _mesh_dict(self):
@@ -552,6 +553,12 @@ class Domain:
         self._ensure_device()
         self._dev.update_ghosts()
         self._mark_device_newer()
+
+    def set_track_max_speed(self, flag=True):
+        """max_speed[k] (sw_domain_openmp.c:709-710) is a diagnostic; the device time loop only
+        writes it when asked (8 bytes per triangle and step)."""
+        self.track_max_speed = bool(flag)
+        self._params_dirty = True
 
     def get_max_speed(self):
         self._ensure_device()

@@ -79,6 +79,8 @@ typedef struct {
   int64_t default_order;          /* 1 or 2 (only the bookkeeping of update_timestep uses it) */
   int64_t ghost_layer_width;      /* rk2 skips the mid-step exchange when >= 4 (generic_domain.py:2014) */
   int64_t centroid_transmissive_bc;
+  int64_t track_max_speed;        /* 1: the resident time loop also writes max_speed[k] (:709-710);
+                                     the per-call layer always does */
 } swk_params;
 
 /* ---- static mesh description (host pointers, borrowed during swk_create) ---
