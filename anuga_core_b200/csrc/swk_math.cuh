@@ -113,28 +113,39 @@ __device__ __forceinline__ Eff effective(const d4 c, const Consts &K)
   }
   e.u = e.uh;
   e.v = e.vh;
-  if (K.vel2 && e.h > K.mah) {          // :1390-1401
-    const double inv = 1.0 / e.h;
+  if (K.vel2) {                         // :1390-1401; dry cells have uh = vh = 0, so the product with
+    const double inv = 1.0 / ((e.h > K.mah) ? e.h : 1.0);   // 1/1 is the reference's "untouched" value
     e.u = e.uh * inv;
     e.v = e.vh * inv;
   }
   return e;
 }
 
-// limiter, sw_domain_openmp.c:1195-1231 (r0 carried across the three edges)
+// limiter, sw_domain_openmp.c:1195-1231 (r0 carried across the three edges).
+// The reference's two conditional divisions per edge (qmin/dq when dq < -TINY, qmax/dq when
+// dq > TINY) are evaluated here as ONE branch-free division with a selected numerator and a
+// harmless denominator for the |dq| <= TINY case: the sign of dq differs from thread to
+// thread, so the branching form would execute both divisions in almost every warp.
+__device__ __forceinline__ double limiter_ratio(double dq, double qmin, double qmax, double r0)
+{
+  const double TINY = 1.0e-100;
+  const bool neg = dq < -TINY;
+  const bool valid = neg | (dq > TINY);
+  const double num = neg ? qmin : qmax;
+  const double den = valid ? dq : 1.0;
+  const double q = num / den;
+  return valid ? q : r0;
+}
+
 __device__ __forceinline__ void limit_gradient(double &d0, double &d1, double &d2,
                                                double qmin, double qmax, double beta)
 {
-  const double TINY = 1.0e-100;
   double r = 1000.0, r0 = 1.0;
-  if (d0 < -TINY) r0 = qmin / d0;
-  if (d0 > TINY) r0 = qmax / d0;
+  r0 = limiter_ratio(d0, qmin, qmax, r0);
   r = dmin(r0, r);
-  if (d1 < -TINY) r0 = qmin / d1;
-  if (d1 > TINY) r0 = qmax / d1;
+  r0 = limiter_ratio(d1, qmin, qmax, r0);
   r = dmin(r0, r);
-  if (d2 < -TINY) r0 = qmin / d2;
-  if (d2 > TINY) r0 = qmax / d2;
+  r0 = limiter_ratio(d2, qmin, qmax, r0);
   r = dmin(r0, r);
   const double phi = dmin(r * beta, 1.0);
   d0 = d0 * phi;

@@ -405,14 +405,40 @@ class Domain:
                 q.host_dirty = True
             for op in self.fractional_step_operators:
                 op.op_id = None
-            if self.processor in self.full_send_dict and self.processor in self.ghost_recv_dict \
-                    and self.numproc == 1:
+            if self.processor in self.full_send_dict and self.processor in self.ghost_recv_dict:
                 self._dev.set_local_ghost_copy(self.full_send_dict[self.processor][0],
                                                self.ghost_recv_dict[self.processor][0])
+            if getattr(self, "_comm", None) is not None:
+                self._attach_device_comm()
         if self._params_dirty:
             self._dev.set_params(self._param_dict())
             self._params_dirty = False
         return self._dev
+
+    def attach_communicator(self, comm):
+        """Join a process group (anuga_core_b200.parallel.Communicator): the halo lists of
+        full_send_dict / ghost_recv_dict and the global timestep then run over NCCL inside the
+        device time loop (Parallel_domain.update_ghosts / update_timestep,
+        parallel_shallow_water.py:128-144)."""
+        self._comm = comm
+        if self._dev is not None:
+            self._attach_device_comm()
+
+    def _attach_device_comm(self):
+        import os
+        comm = self._comm
+        if comm.size <= 1:
+            return
+        from .parallel import nccl_library_path
+        lib = nccl_library_path()
+        if lib and "SWK_NCCL_LIB" not in os.environ:
+            os.environ["SWK_NCCL_LIB"] = lib
+        uid = _b.DeviceDomain.nccl_unique_id() if comm.rank == 0 else b""
+        uid = comm.broadcast_bytes(uid, 128)
+        self._dev.comm_init(uid, comm.rank, comm.size)
+        send = {int(q): v[0] for q, v in self.full_send_dict.items() if q != self.processor}
+        recv = {int(q): v[0] for q, v in self.ghost_recv_dict.items() if q != self.processor}
+        self._dev.set_halo(send, recv)
 
     def _locality_permutation(self):
         """Morton order of the centroids; full triangles stay in front of ghosts so that

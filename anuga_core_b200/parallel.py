@@ -1,0 +1,383 @@
+"""Multi-GPU mode: one process per GPU, the reference's partition / ghost-triangle scheme,
+halo exchange and global timestep over NCCL (inside libswk).
+
+Partition indexing restates, for a GIVEN element partition vector ``epart``
+(the reference obtains it from pymetis, which is third-party arithmetic and absent here -
+SURVEY.md 8(c)), the pipeline of anuga/parallel/distribute_mesh.py:
+
+  reorder_by_epart   pmesh_divide_metis_helper :218-255 (stable argsort of epart, contiguous ranges)
+  partition_mesh     submesh_full :318-400, ghost_layer :515-575 (BFS rings over `neighbours`),
+                     ghost_bnd_layer :650-710 ('ghost' tags), ghost_commun_pattern :776,
+                     full_commun_pattern :811, build_local_mesh :1192-1262 (full triangles first,
+                     ghosts after in ascending global id; nodes renumbered full-then-ghost),
+                     build_local_commun :1128-1170 (send/recv lists sorted by global id, so both
+                     sides agree without exchanging ids), extract_l2g_map :1643
+  Parallel_domain    parallel_shallow_water.py:32-107 (tri_full_flag, boundary_map['ghost'] = None)
+
+Evolve-time communication (parallel_generic_communications.py:35-248): the halo pack /
+ncclSend / ncclRecv / unpack and the ncclAllReduce(min) of dt run on the device inside
+swk_evolve; Python only bootstraps the communicator (the NCCL unique id travels through
+torch.distributed, any backend).
+
+Conserved centroid values are distributed exactly (the reference ships vertex values and
+re-interpolates, which perturbs centroids by an ulp); with exact ghosts and an exact min
+the N-GPU state of every full triangle is bit-identical to the 1-GPU state.
+"""
+import os
+
+import numpy as np
+
+from .mesh import Mesh, rectangular_cross
+from .domain import Domain
+from .boundaries import Reflective_boundary
+from .operators import Rate_operator
+from . import workloads
+
+
+# ----------------------------------------------------------------------------------------
+# partition indexing
+# ----------------------------------------------------------------------------------------
+def reorder_by_epart(triangles, boundary, epart, nparts):
+    """Contiguous per-rank triangle ranges by a stable sort of epart.
+    Returns new_triangles, new_boundary, triangles_per_proc, epart_order (new -> old),
+    new_tri_index (old -> (proc, local))."""
+    epart = np.asarray(epart, dtype=np.int64)
+    triangles = np.asarray(triangles, dtype=np.int64)
+    n_tri = len(triangles)
+    triangles_per_proc = np.bincount(epart, minlength=nparts)
+    assert np.all(triangles_per_proc > 0), \
+        "partition where at least one submesh has no triangles"
+    proc_sum = np.zeros(nparts + 1, dtype=np.int64)
+    proc_sum[1:] = np.cumsum(triangles_per_proc)
+    epart_order = np.argsort(epart, kind="mergesort")
+    new_triangles = triangles[epart_order]
+    new_tri_index = np.zeros((n_tri, 2), dtype=np.int64)
+    new_pos = np.empty(n_tri, dtype=np.int64)
+    new_pos[epart_order] = np.arange(n_tri)
+    new_tri_index[:, 0] = epart
+    new_tri_index[:, 1] = new_pos - proc_sum[epart]
+    new_boundary = {}
+    for (t, e), tag in boundary.items():
+        new_boundary[(int(new_pos[t]), int(e))] = tag
+    return new_triangles, new_boundary, triangles_per_proc, epart_order, new_tri_index
+
+
+def _ghost_layer(neighbours, tlower, tupper, layer_width):
+    full_ids = np.arange(tlower, tupper)
+    n0 = np.unique(neighbours[full_ids, :].ravel())
+    n0 = n0[n0 >= 0]
+    n0 = n0[(n0 < tlower) | (tupper <= n0)]
+    layers = [n0]
+    for i in range(layer_width - 1):
+        n0 = np.unique(neighbours[n0, :].ravel())
+        n0 = n0[n0 >= 0]
+        n0 = n0[(n0 < tlower) | (tupper <= n0)]
+        for j in range(i + 1):
+            n0 = np.setdiff1d(n0, layers[j])
+        layers.append(n0)
+    ghosts = layers[0]
+    for i in range(layer_width - 1):
+        ghosts = np.union1d(ghosts, layers[i + 1])
+    return ghosts
+
+
+def _ghost_boundary(neighbours, boundary, ghosts, tlower, tupper):
+    sub = {}
+    for e in range(3):
+        nb = neighbours[ghosts, e]
+        gl = ghosts[(nb < tlower) | (nb >= tupper)]
+        nb = neighbours[gl, e]
+        gl = gl[~np.isin(nb, ghosts)]
+        for g in gl.tolist():
+            sub[(g, e)] = "ghost"
+    for k in list(sub.keys()):
+        if k in boundary:
+            sub[k] = boundary[k]
+    return sub
+
+
+def partition_mesh(nodes, triangles, boundary, triangles_per_proc, ghost_layer_width=2, ranks=None,
+                   mesh=None):
+    """Per-rank local meshes for contiguous triangle ranges (triangles already ordered by rank).
+
+    Returns {p: dict(points, triangles, boundary, full_send_dict, ghost_recv_dict, tri_l2g,
+    node_l2g, number_of_full_triangles, number_of_full_nodes, ghost_layer_width)} with the
+    reference's local numbering."""
+    nodes = np.asarray(nodes, dtype=np.float64)
+    triangles = np.asarray(triangles, dtype=np.int64)
+    if mesh is None:
+        mesh = Mesh(nodes, triangles, boundary)
+    neighbours = mesh.neighbours
+    gboundary = mesh.boundary
+    nproc = len(triangles_per_proc)
+    upper = np.cumsum(triangles_per_proc)
+    lower = upper - np.asarray(triangles_per_proc)
+    ranges = upper - 1
+    if ranks is None:
+        ranks = range(nproc)
+
+    ghosts_of = {}
+    for p in range(nproc):
+        ghosts_of[p] = _ghost_layer(neighbours, lower[p], upper[p], ghost_layer_width)
+
+    out = {}
+    for p in ranks:
+        tl, tu = int(lower[p]), int(upper[p])
+        ghosts = ghosts_of[p]
+        full_tri = triangles[tl:tu]
+        full_node_ids = np.unique(full_tri.ravel())
+        ghost_tri = triangles[ghosts]
+        ghost_node_ids = np.setdiff1d(np.unique(ghost_tri.ravel()), full_node_ids)
+        node_ids = np.concatenate([full_node_ids, ghost_node_ids])
+        node_map = -np.ones(int(node_ids.max()) + 1, dtype=np.int64)
+        node_map[node_ids] = np.arange(len(node_ids))
+        ltri = node_map[np.concatenate([full_tri, ghost_tri])]
+        nglobal = max(tu, int(ghosts.max()) if len(ghosts) else 0)
+        tri_map = -np.ones(nglobal + 1, dtype=np.int64)
+        tri_map[tl:tu] = np.arange(tu - tl)
+        tri_map[ghosts] = np.arange(len(ghosts)) + (tu - tl)
+        lb = {}
+        for (k, e), tag in gboundary.items():
+            if tl <= k < tu:
+                lb[(int(tri_map[k]), int(e))] = tag
+        for (k, e), tag in _ghost_boundary(neighbours, gboundary, ghosts, tl, tu).items():
+            lb[(int(tri_map[k]), int(e))] = tag
+        owner = np.searchsorted(ranges, ghosts)
+        ghost_recv = {}
+        for c in range(nproc):
+            dsel = ghosts[owner == c]
+            if len(dsel) > 0:
+                ghost_recv[c] = [tri_map[dsel], dsel]
+        full_send = {}
+        for q in range(nproc):
+            if q == p:
+                continue
+            gq = ghosts_of[q]
+            mine = gq[(gq >= tl) & (gq < tu)]
+            if len(mine) > 0:
+                mine = np.sort(mine)
+                full_send[q] = [tri_map[mine], mine]
+        tri_l2g = np.concatenate([np.arange(tl, tu), ghosts])
+        out[p] = dict(points=nodes[node_ids], triangles=ltri, boundary=lb, full_send_dict=full_send,
+                      ghost_recv_dict=ghost_recv, tri_l2g=tri_l2g, node_l2g=node_ids,
+                      number_of_full_triangles=tu - tl, number_of_full_nodes=len(full_node_ids),
+                      ghost_layer_width=ghost_layer_width)
+    return out
+
+
+def distribute(domain, nparts, epart=None, ghost_layer_width=2, ranks=None, domain_kw=None):
+    """anuga.distribute (parallel_api.py:71-160) for a given element partition: returns
+    {rank: Domain} with full/ghost bookkeeping, quantities (centroid values) and boundary map
+    carried over.  epart defaults to equal contiguous blocks."""
+    N = domain.number_of_triangles
+    if epart is None:
+        epart = (np.arange(N) * nparts) // N
+    new_tri, new_bnd, tpp, order, _ = reorder_by_epart(domain.triangles, domain.mesh.boundary, epart, nparts)
+    parts = partition_mesh(domain.nodes, new_tri, new_bnd, tpp, ghost_layer_width, ranks)
+    out = {}
+    for p, sub in parts.items():
+        kw = dict(domain_kw or {})
+        d = Domain(sub["points"], sub["triangles"], sub["boundary"], full_send_dict=sub["full_send_dict"],
+                   ghost_recv_dict=sub["ghost_recv_dict"], processor=p, numproc=nparts,
+                   number_of_full_triangles=sub["number_of_full_triangles"],
+                   ghost_layer_width=ghost_layer_width, **kw)
+        d.tri_l2g = sub["tri_l2g"]
+        d.node_l2g = sub["node_l2g"]
+        d.tri_l2s = order[sub["tri_l2g"]]          # local -> sequential (original) triangle id
+        _copy_settings(domain, d)
+        for name in ("stage", "xmomentum", "ymomentum", "elevation", "friction"):
+            src = domain.quantities[name]
+            d.quantities[name].set_values(src.centroid_values[d.tri_l2s], location="centroids")
+            if "vertex_values" in src._arrays:
+                d.quantities[name].vertex_values[:] = src.vertex_values[d.tri_l2s]
+        if domain.boundary_map is not None:
+            bmap = dict(domain.boundary_map)
+            bmap["ghost"] = None                    # parallel_api.py:129
+            d.set_boundary({t: bmap[t] for t in d.get_boundary_tags()})
+        for op in domain.fractional_step_operators:
+            if not isinstance(op, Rate_operator) or op.indices is not None or op.rate_array is not None:
+                raise NotImplementedError("only scalar / f(t) all-cell Rate_operators are distributed")
+            Rate_operator(d, rate=op.rate_callable if op.rate_callable is not None else op.rate, factor=op.factor)
+        out[p] = d
+    return out
+
+
+def _copy_settings(src, dst):
+    for k in ("flow_algorithm", "CFL", "timestepping_method", "minimum_allowed_height", "H0", "g", "epsilon",
+              "beta_w", "beta_w_dry", "beta_uh", "beta_uh_dry", "beta_vh", "beta_vh_dry", "low_froude",
+              "extrapolate_velocity_second_order", "use_sloped_mannings", "evolve_max_timestep",
+              "evolve_min_timestep", "max_smallsteps", "default_order", "fixed_flux_timestep",
+              "centroid_transmissive_bc", "maximum_allowed_speed", "starttime"):
+        setattr(dst, k, getattr(src, k))
+    dst._params_dirty = True
+
+
+# ----------------------------------------------------------------------------------------
+# scalable strip partition of rectangular_cross (benchmark configs 3/4)
+# ----------------------------------------------------------------------------------------
+def strip_slab(m, n, rank, nranks, len1=None, len2=None, ghost_layer_width=2, pad=2):
+    """Local mesh of `rank` for rectangular_cross(m, n) cut in `nranks` strips of cell columns
+    (contiguous global triangle ranges, i.e. epart = equal blocks of columns), built from a slab
+    of the global mesh: the rank's columns plus `pad` columns either side.  Gives exactly what
+    partition_mesh gives on the global mesh (tests/test_partition.py) without ever building it."""
+    len1 = float(m) if len1 is None else float(len1)
+    len2 = float(n) if len2 is None else float(len2)
+    cols = [(m * r) // nranks for r in range(nranks + 1)]
+    i0, i1 = cols[rank], cols[rank + 1]
+    s0, s1 = max(0, i0 - pad), min(m, i1 + pad)
+    ms = s1 - s0
+    delta1 = len1 / m
+    # slab mesh with GLOBAL coordinates: x = i*delta1 for global column index i
+    pts, tri, bnd = rectangular_cross(ms, n, ms * delta1, len2, origin=(0.0, 0.0))
+    ngs = (ms + 1) * (n + 1)
+    # recompute x exactly as the global factory does (i*delta1 + origin), i global
+    gi = np.repeat(np.arange(s0, s1 + 1, dtype=np.float64), n + 1)
+    pts[:ngs, 0] = gi * delta1 + 0.0
+    delta2 = len2 / n
+    pts[:ngs, 1] = np.tile(np.arange(n + 1, dtype=np.float64) * delta2 + 0.0, ms + 1)
+    ci = np.repeat(np.arange(ms, dtype=np.int64), n)
+    cj = np.tile(np.arange(n, dtype=np.int64), ms)
+    v1 = ci * (n + 1) + cj + 1
+    v2 = ci * (n + 1) + cj
+    v3 = (ci + 1) * (n + 1) + cj + 1
+    v4 = (ci + 1) * (n + 1) + cj
+    pts[ngs:, 0] = (pts[v1, 0] + pts[v2, 0] + pts[v3, 0] + pts[v4, 0]) * 0.25
+    pts[ngs:, 1] = (pts[v1, 1] + pts[v2, 1] + pts[v3, 1] + pts[v4, 1]) * 0.25
+    # physical boundary of the slab: drop the artificial left/right cuts
+    if s0 > 0:
+        bnd = {k: v for k, v in bnd.items() if v != "left"}
+    if s1 < m:
+        bnd = {k: v for k, v in bnd.items() if v != "right"}
+    # the slab's own "rank" is the block of columns [i0, i1): triangle range inside the slab
+    tpp = [4 * n * (i0 - s0), 4 * n * (i1 - i0), 4 * n * (s1 - i1)]
+    keep = [k for k, c in enumerate(tpp) if c > 0]
+    me = keep.index(1)
+    tpp_nz = [tpp[k] for k in keep]
+    smesh = Mesh(pts, tri, bnd)
+    # cut edges of the slab are not physical boundaries: they only touch triangles farther than
+    # `pad` columns away from the rank's strip, which never enter a width<=pad ghost layer
+    sub = partition_mesh(pts, tri, smesh.boundary, tpp_nz, ghost_layer_width, ranks=[me], mesh=smesh)[me]
+    # slab ids -> global ids
+    tri_off = 4 * n * s0
+    sub["tri_l2g"] = sub["tri_l2g"] + tri_off
+    ng_glob = (m + 1) * (n + 1)
+    nl = sub["node_l2g"]
+    grid = nl < ngs
+    gnode = np.where(grid, nl + s0 * (n + 1), (nl - ngs) + ng_glob + s0 * n)
+    sub["node_l2g"] = gnode
+    # slab part k (0 = left padding, 1 = me, 2 = right padding) stands for rank-1, rank, rank+1:
+    # a padding of `pad` >= ghost depth columns sees the same cut as the real neighbour strip,
+    # so its ghost layer on this side (hence my send list) and its triangles inside my ghost
+    # layer (my recv list) are the neighbour rank's.
+    for r in range(nranks):
+        assert cols[r + 1] - cols[r] >= pad, "strips must be at least %d cell columns wide" % pad
+
+    def remap(dct):
+        return {rank + (keep[sp] - 1): [lids, gids + tri_off] for sp, (lids, gids) in dct.items()}
+    sub["full_send_dict"] = remap(sub["full_send_dict"])
+    sub["ghost_recv_dict"] = remap(sub["ghost_recv_dict"])
+    sub["columns"] = (i0, i1)
+    return sub
+
+
+def weak_scaling_shape(size, nranks):
+    """Global rectangular_cross shape with 4*size*size triangles per rank: 1 GPU size x size,
+    2 GPUs 2size x size, 4 GPUs 2size x 2size, 8 GPUs 4size x 2size (size = 2000: the
+    8000x4000, 128M-triangle mesh of BASELINE.json configs[3])."""
+    n = size * (2 if nranks >= 4 else 1)
+    m = nranks * size * size // n
+    return m, n
+
+
+def strip_partitioned_sweep_domain(m, n, rank, nranks, device=0, alg="DE1", rain=1.0e-4):
+    """configs[3]/[4] building block: rank's strip of rectangular_cross(m, n) with the
+    roofline-sweep fields of workloads.roofline_sweep_domain."""
+    sub = strip_slab(m, n, rank, nranks)
+    d = Domain(sub["points"], sub["triangles"], sub["boundary"], full_send_dict=sub["full_send_dict"],
+               ghost_recv_dict=sub["ghost_recv_dict"], processor=rank, numproc=nranks,
+               number_of_full_triangles=sub["number_of_full_triangles"], ghost_layer_width=2, device=device)
+    d.tri_l2g = sub["tri_l2g"]
+    d.set_flow_algorithm(alg)
+    d.set_store(False)
+    d.set_quantity("elevation", workloads.sweep_elevation)
+    d.set_quantity("stage", workloads.sweep_stage(float(m), float(n)), location="centroids")
+    d.set_quantity("friction", 0.03)
+    B = Reflective_boundary(d)
+    bmap = {t: B for t in d.get_boundary_tags()}
+    if "ghost" in bmap:
+        bmap["ghost"] = None
+    d.set_boundary(bmap)
+    if rain is not None:
+        Rate_operator(d, rate=rain)
+    return d
+
+
+# ----------------------------------------------------------------------------------------
+# process group plumbing (torch.distributed carries the NCCL id and python scalars)
+# ----------------------------------------------------------------------------------------
+class Communicator:
+    def __init__(self, rank, size, dist=None):
+        self.rank, self.size, self.dist = rank, size, dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _all(self, x, op):
+        if self.dist is None:
+            return x
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        if self.dist.get_backend() == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def allreduce_max(self, x):
+        import torch.distributed as td
+        return self._all(x, td.ReduceOp.MAX) if self.dist is not None else x
+
+    def allreduce_sum(self, x):
+        import torch.distributed as td
+        return self._all(x, td.ReduceOp.SUM) if self.dist is not None else x
+
+    def broadcast_bytes(self, payload, n):
+        """rank 0's `payload` (n bytes) to everyone"""
+        if self.dist is None:
+            return payload
+        import torch
+        buf = torch.zeros(n, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = torch.tensor(list(payload), dtype=torch.uint8)
+        if self.dist.get_backend() == "nccl":
+            buf = buf.cuda()
+        self.dist.broadcast(buf, src=0)
+        return bytes(buf.cpu().tolist())
+
+
+def init_process_group(backend=None):
+    """RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT from the environment (torchrun)."""
+    rank = int(os.environ.get("RANK", "0"))
+    size = int(os.environ.get("WORLD_SIZE", "1"))
+    if size == 1:
+        return Communicator(0, 1, None)
+    import torch
+    import torch.distributed as dist
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if not dist.is_initialized():
+        dist.init_process_group(backend=backend, rank=rank, world_size=size)
+    return Communicator(rank, size, dist)
+
+
+def nccl_library_path():
+    try:
+        import nvidia.nccl
+        p = os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so.2")
+        if os.path.exists(p):
+            return p
+    except Exception:
+        pass
+    return None

@@ -98,7 +98,8 @@ def build_domain(size, rank=0, nranks=1, device=0):
     if nranks == 1:
         return workloads.roofline_sweep_domain(size, size, alg="DE1", rain=1.0e-4, device=device)
     from anuga_core_b200 import parallel
-    return parallel.strip_partitioned_sweep_domain(size, rank, nranks, device=device)
+    m, n = parallel.weak_scaling_shape(size, nranks)
+    return parallel.strip_partitioned_sweep_domain(m, n, rank, nranks, device=device)
 
 
 def cpu_reference_run(size, steps, warmup, kind_pref="reference"):

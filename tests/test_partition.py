@@ -1,0 +1,146 @@
+"""CPU: ghost/partition indexing is bit-exact with the reference's pipeline
+(anuga/parallel/distribute_mesh.py) for a shared element partition, and the host-side
+multi-process plumbing works with world_size 2 over gloo."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import anuga_core_b200 as ab
+from anuga_core_b200 import parallel as P
+from golden_util import load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = ["partition_strips_8x5_p3", "partition_checker_6x6_p4", "partition_strips_10x4_p2_w4"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_partition_indexing_matches_reference(name):
+    g = load(name)
+    m, n, nparts, width = int(g["m"]), int(g["n"]), int(g["nparts"]), int(g["width"])
+    pts, tri, bnd = ab.rectangular_cross(m, n, float(m), float(n))
+    new_tri, new_bnd, tpp, order, _ = P.reorder_by_epart(tri, bnd, g["epart"], nparts)
+    parts = P.partition_mesh(pts, new_tri, new_bnd, tpp, width)
+    for p in range(nparts):
+        pre = "r%d_" % p
+        s = parts[p]
+        assert np.array_equal(s["points"], g[pre + "points"])
+        assert np.array_equal(s["triangles"], g[pre + "triangles"])
+        keys = sorted(s["boundary"].keys())
+        assert np.array_equal(np.array(keys, dtype=np.int64).reshape(-1, 2), g[pre + "boundary_keys"])
+        assert [s["boundary"][k] for k in keys] == [str(t) for t in g[pre + "boundary_tags"]]
+        assert np.array_equal(order[s["tri_l2g"]], g[pre + "tri_l2s"])
+        assert np.array_equal(s["node_l2g"], g[pre + "node_l2g"])
+        assert s["number_of_full_triangles"] == int(g[pre + "nfull"][0])
+        for kind, dct in (("send", s["full_send_dict"]), ("recv", s["ghost_recv_dict"])):
+            expect = sorted(int(k.split("_")[2]) for k in g.files if k.startswith(pre + kind) and k.endswith("_local"))
+            assert sorted(dct.keys()) == expect, (p, kind)
+            for q in expect:
+                assert np.array_equal(dct[q][0], g[pre + "%s_%d_local" % (kind, q)])
+                assert np.array_equal(dct[q][1], g[pre + "%s_%d_global" % (kind, q)])
+
+
+def test_send_and_recv_lists_pair_up():
+    pts, tri, bnd = ab.rectangular_cross(9, 7, 9.0, 7.0)
+    rng = np.random.default_rng(3)
+    c = ab.Mesh(pts, tri, bnd).centroid_coordinates
+    epart = ((c[:, 0] > 4.5).astype(int) + 2 * (c[:, 1] > 3.5 + 0.3 * rng.normal(size=len(c)))).astype(int)
+    new_tri, new_bnd, tpp, order, _ = P.reorder_by_epart(tri, bnd, epart, 4)
+    parts = P.partition_mesh(pts, new_tri, new_bnd, tpp, 2)
+    for p, s in parts.items():
+        for q, (lids, gids) in s["full_send_dict"].items():
+            assert np.array_equal(parts[q]["ghost_recv_dict"][p][1], gids)      # same global ids, same order
+            assert np.all(lids < s["number_of_full_triangles"])
+        for q, (lids, gids) in s["ghost_recv_dict"].items():
+            assert np.all(lids >= s["number_of_full_triangles"])
+
+
+@pytest.mark.parametrize("m,n,R", [(12, 5, 3), (16, 3, 4), (9, 6, 2)])
+def test_strip_slab_equals_global_partition(m, n, R):
+    """the scalable per-rank builder used for the 128M-triangle runs gives exactly the generic result"""
+    pts, tri, bnd = ab.rectangular_cross(m, n, float(m), float(n))
+    cols = [(m * r) // R for r in range(R + 1)]
+    epart = np.zeros(len(tri), dtype=int)
+    for r in range(R):
+        epart[4 * n * cols[r]:4 * n * cols[r + 1]] = r
+    nt, nb, tpp, order, _ = P.reorder_by_epart(tri, bnd, epart, R)
+    gen = P.partition_mesh(pts, nt, nb, tpp, 2)
+    for r in range(R):
+        sl = P.strip_slab(m, n, r, R)
+        g = gen[r]
+        for k in ("tri_l2g", "node_l2g", "points", "triangles"):
+            assert np.array_equal(sl[k], g[k]), (r, k)
+        assert sl["boundary"] == g["boundary"]
+        for k in ("full_send_dict", "ghost_recv_dict"):
+            assert sorted(sl[k]) == sorted(g[k])
+            for q in g[k]:
+                assert np.array_equal(sl[k][q][0], g[k][q][0]) and np.array_equal(sl[k][q][1], g[k][q][1])
+
+
+def test_distribute_carries_quantities_and_flags():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import cases
+    d = cases.beach_de1(ab, n=8)
+    subs = P.distribute(d, 3)
+    total_full = 0
+    for p, s in subs.items():
+        nf = s.number_of_full_triangles
+        total_full += nf
+        assert np.all(s.tri_full_flag[:nf] == 1) and np.all(s.tri_full_flag[nf:] == 0)
+        assert np.array_equal(s.quantities["stage"].centroid_values, d.quantities["stage"].centroid_values[s.tri_l2s])
+        assert np.array_equal(s.quantities["elevation"].centroid_values, d.quantities["elevation"].centroid_values[s.tri_l2s])
+        assert s.boundary_map["ghost"] is None
+        assert s.get_flow_algorithm() == "DE1" and s.timestepping_method == "rk2"
+    assert total_full == d.number_of_triangles
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import torch, torch.distributed as dist
+import anuga_core_b200 as ab
+from anuga_core_b200 import parallel as P
+comm = P.init_process_group(backend="gloo")
+rank, size = comm.rank, comm.size
+sub = P.strip_slab(8, 4, rank, size)
+# every rank ships the GLOBAL ids it sends to each peer; the peer checks them against its recv list
+for q in range(size):
+    if q == rank:
+        continue
+    mine = torch.tensor(sub["full_send_dict"].get(q, [np.zeros(0, int), np.zeros(0, int)])[1], dtype=torch.int64)
+    n = torch.tensor([mine.numel()])
+    theirs_n = torch.zeros(1, dtype=torch.int64)
+    if rank < q:
+        dist.send(n, q); dist.recv(theirs_n, q)
+    else:
+        dist.recv(theirs_n, q); dist.send(n, q)
+    theirs = torch.zeros(int(theirs_n), dtype=torch.int64)
+    if rank < q:
+        dist.send(mine, q); dist.recv(theirs, q)
+    else:
+        dist.recv(theirs, q); dist.send(mine, q)
+    expect = sub["ghost_recv_dict"].get(q, [np.zeros(0, int), np.zeros(0, int)])[1]
+    assert np.array_equal(theirs.numpy(), expect), (rank, q)
+tot = comm.allreduce_sum(sub["number_of_full_triangles"])
+assert tot == 4 * 8 * 4
+assert comm.allreduce_max(rank) == size - 1
+payload = comm.broadcast_bytes(bytes(range(128)) if rank == 0 else b"", 128)
+assert payload == bytes(range(128))
+comm.barrier()
+sys.stdout.write("[rank" + str(rank) + "-ok]"); sys.stdout.flush()
+'''
+
+
+def test_world_size_2_gloo_halo_lists_and_plumbing(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    port = 29500 + (os.getpid() % 500)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "[rank0-ok]" in res.stdout and "[rank1-ok]" in res.stdout
