@@ -733,7 +733,8 @@ __global__ void __launch_bounds__(1024) k_rate_finish(Clock *c, const double *in
 // single-process ghost copy, Generic_Domain.update_ghosts (generic_domain.py:2448-2469)
 __global__ void __launch_bounds__(BLOCK) k_ghost_copy(Dev D, const int *full_ids, const int *ghost_ids, int n)
 {
-  if (D.clock->stop) return;
+  // no stop check: the exchange after the last step of a yield must still run; surplus
+  // (speculative) exchanges after the stop are idempotent copies
   const int j = blockIdx.x * BLOCK + threadIdx.x;
   if (j >= n) return;
   const d4 s = D.cq[full_ids[j]];
@@ -745,7 +746,8 @@ __global__ void __launch_bounds__(BLOCK) k_ghost_copy(Dev D, const int *full_ids
 // halo pack / unpack for the multi-GPU exchange (parallel_generic_communications.py:188-245)
 __global__ void __launch_bounds__(BLOCK) k_halo_pack(Dev D, const int *ids, int n, double *buf)
 {
-  if (D.clock->stop) return;
+  // no stop check: the exchange after the last step of a yield must still run; surplus
+  // (speculative) exchanges after the stop are idempotent copies
   const int j = blockIdx.x * BLOCK + threadIdx.x;
   if (j >= n) return;
   const d4 s = D.cq[ids[j]];
@@ -754,7 +756,8 @@ __global__ void __launch_bounds__(BLOCK) k_halo_pack(Dev D, const int *ids, int 
 
 __global__ void __launch_bounds__(BLOCK) k_halo_unpack(Dev D, const int *ids, int n, const double *buf)
 {
-  if (D.clock->stop) return;
+  // no stop check: the exchange after the last step of a yield must still run; surplus
+  // (speculative) exchanges after the stop are idempotent copies
   const int j = blockIdx.x * BLOCK + threadIdx.x;
   if (j >= n) return;
   d4 t = D.cq[ids[j]];
