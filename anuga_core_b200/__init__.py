@@ -10,5 +10,6 @@ from .boundaries import (Reflective_boundary, Dirichlet_boundary, Transmissive_b
 from .operators import Rate_operator
 from .domain import Domain, rectangular_cross_domain, MODE_B200
 from .backend import SwkError, device_count
+from .attach import set_multiprocessor_mode_b200, B200_interface
 
 __version__ = "0.1.0"

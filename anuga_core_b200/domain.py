@@ -163,6 +163,9 @@ class Domain:
     def get_flow_algorithm(self):
         return self.flow_algorithm
 
+    def get_using_discontinuous_elevation(self):
+        return True
+
     def set_timestepping_method(self, flag):
         m = {1: "euler", 2: "rk2", 3: "rk3", "euler": "euler", "rk2": "rk2", "rk3": "rk3"}
         if flag not in m:

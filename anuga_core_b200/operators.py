@@ -27,12 +27,21 @@ class Rate_operator:
         domain.set_fractional_step_operator(self)
 
     @property
+    def rate_type(self):          # the reference's attribute (rate_operators.py:95-140)
+        if self.rate_callable is not None:
+            return "t"
+        return "centroid_array" if self.rate_array is not None else "scalar"
+
+    rate_spatial = False
+
+    @property
     def time_dependent(self):
         return self.rate_callable is not None or callable(self.factor)
 
     def set_rate(self, rate):
         self.rate_callable = None
         self.rate_array = None
+        self.rate_input = rate
         if callable(rate):
             import inspect
             nargs = len(inspect.signature(rate).parameters)

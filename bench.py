@@ -143,7 +143,7 @@ def cpu_reference_run(size, steps, warmup, kind_pref="reference"):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=2000, help="cells per side per GPU (2000 -> 16M triangles)")

@@ -1,0 +1,63 @@
+"""The drop-in for a reference Domain (anuga_core_b200/attach.py).
+CPU part: needs the scratch build of the Python reference (skipped elsewhere).
+GPU part: the adapter driven through an object with the reference's attribute names."""
+import numpy as np
+import pytest
+
+import anuga_core_b200 as ab
+from golden_util import cases, load, rel_err
+from oracle import pyref
+
+
+@pytest.mark.skipif(not pyref.available(), reason="python reference not built (oracle/build_pyref.py)")
+def test_adapter_snapshots_a_real_reference_domain():
+    anuga = pyref.import_anuga()
+    ref = cases.tsunami_set_stage(anuga, n=8)
+    anuga.Rate_operator(ref, rate=2.0e-4, factor=0.5)
+    iface = ab.B200_interface(ref)
+    d = iface.dev_domain
+    # same buffers, not copies
+    assert d.quantities["stage"].centroid_values is ref.quantities["stage"].centroid_values
+    assert d.quantities["xmomentum"].edge_values is ref.quantities["xmomentum"].edge_values
+    assert d.mesh is ref.mesh
+    # scalars of the DE1 preset are read from the reference object
+    assert (d.CFL, d.timestepping_method, d.minimum_allowed_height, d.beta_w, d.H0) == (1.0, "rk2", 1e-5, 1.0, 1e-5)
+    kinds = {t: (None if B is None else B.device_kind) for t, B in d.boundary_map.items()}
+    assert kinds == {"left": 4, "right": 3, "top": 1, "bottom": 1}
+    assert d._needs_host_stepping()
+    assert len(d.fractional_step_operators) == 1 and d.fractional_step_operators[0].rate == 2.0e-4
+    assert d.fractional_step_operators[0].factor == 0.5
+    # mesh arrays handed to the C ABI are the reference's own
+    m = d._mesh_dict()
+    assert m["neighbours"] is ref.mesh.neighbours and m["normals"] is ref.mesh.normals
+    # a later set_flow_algorithm is picked up at the next evolve (mode 4 of the reference goes stale)
+    ref.set_flow_algorithm("DE0")
+    iface.refresh()
+    assert d.timestepping_method == "euler" and d.CFL == 0.9
+    if ab.device_count() == 0:
+        with pytest.raises(ab.SwkError):
+            ab.set_multiprocessor_mode_b200(ref)
+
+
+@pytest.mark.skipif(not pyref.available(), reason="python reference not built (oracle/build_pyref.py)")
+def test_adapter_rejects_what_it_cannot_run():
+    anuga = pyref.import_anuga()
+    ref = cases.dam_break_de0(anuga, n=4)
+    ref.boundary_map["left"] = type("Flather_external_stage_zero_velocity_boundary", (object,), {})()
+    with pytest.raises(NotImplementedError):
+        ab.B200_interface(ref)
+
+
+@pytest.mark.gpu
+def test_adapter_time_loop_matches_golden():
+    """evolve through the adapter (host arrays updated in place) == the golden reference run"""
+    g = load("beach_de1")
+    builder, ev = cases.CASES["beach_de1"]
+    ref_like = builder(ab)                       # carries the reference's attribute names
+    stage_alias = ref_like.quantities["stage"].centroid_values
+    iface = ab.B200_interface(ref_like)
+    times = [t for t in iface.evolve_base(**ev)]
+    assert np.array_equal(np.array(times), g["yields"])
+    assert rel_err(stage_alias, g["final_stage"]) <= 1e-9          # the alias saw the result
+    assert rel_err(ref_like.quantities["xmomentum"].centroid_values, g["final_xmom"]) <= 1e-9
+    assert ref_like.timestep == g["dts"][-1]
