@@ -135,6 +135,8 @@ SYMBOLS = {
     "swk_kernel_timing": (C.c_int, [_H, _PD, _PI]),
     "swk_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "swk_synchronize": (C.c_int, [_H]),
+    "swk_pin_host_buffer": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
+    "swk_unpin_host_buffer": (C.c_int, [_H, C.c_void_p]),
     "swk_kernel_launch_count": (C.c_int, [_H, _PI]),
     "swk_bytes_per_triangle_step": (C.c_int, [_H, _PD, _PD]),
     "swk_nccl_unique_id": (C.c_int, [C.c_void_p]),
@@ -275,9 +277,11 @@ class DeviceDomain:
         self.device = int(device)
         self._mesh = None      # host mesh arrays are only borrowed during swk_create
         self._segments = {}
+        self._pinned = {}
 
     def close(self):
         if getattr(self, "h", None):
+            self.unpin_all()
             self.lib.swk_destroy(self.h)
             self.h = None
 
@@ -407,6 +411,18 @@ class DeviceDomain:
 
     def synchronize(self):
         _check(self.lib.swk_synchronize(self.h))
+
+    def pin(self, array):
+        """page-lock a long-lived numpy buffer (idempotent)"""
+        key = array.ctypes.data
+        if key not in self._pinned:
+            _check(self.lib.swk_pin_host_buffer(self.h, C.c_void_p(key), array.nbytes))
+            self._pinned[key] = array.nbytes
+
+    def unpin_all(self):
+        for key in list(self._pinned):
+            self.lib.swk_unpin_host_buffer(self.h, C.c_void_p(key))
+        self._pinned = {}
 
     def stream(self):
         s = C.c_void_p()

@@ -1182,6 +1182,25 @@ extern "C" int swk_synchronize(swk_domain *d)
   return sync_check(d);
 }
 
+extern "C" int swk_pin_host_buffer(swk_domain *d, void *host, size_t bytes)
+{
+  if (!d || !host) return fail(SWK_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(d->device));
+  cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return SWK_OK; }
+  if (e != cudaSuccess) return fail(SWK_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  return SWK_OK;
+}
+
+extern "C" int swk_unpin_host_buffer(swk_domain *d, void *host)
+{
+  if (!d || !host) return fail(SWK_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(d->device));
+  cudaError_t e = cudaHostUnregister(host);
+  if (e != cudaSuccess) { cudaGetLastError(); }
+  return SWK_OK;
+}
+
 extern "C" int swk_kernel_launch_count(swk_domain *d, int64_t *count)
 {
   if (!d || !count) return fail(SWK_ERR_ARG, "NULL argument");

@@ -25,7 +25,7 @@ namespace swk {
 #define SWK_BLOCK 128
 #endif
 #ifndef SWK_MINB_A          // min resident blocks per SM for pass A (extrapolate)
-#define SWK_MINB_A 6
+#define SWK_MINB_A 5
 #endif
 #ifndef SWK_MINB_F          // ... for the flux kernels
 #define SWK_MINB_F 5
@@ -95,17 +95,20 @@ struct Dev {
 // are NOT modified (their protected form is recomputed by the consumers).
 // One thread per triangle.  Reads cq (own + 3 gathered), connA, xg; writes eq, zflag.
 // =============================================================================
-__global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts K)
+// Edge records of ONE triangle k from the centroid records `cq` (own + 3 surrogate neighbours).
+// Returns the three {stage, height, xmom, ymom} edge records, the own effective state and the
+// loop-2 "surrounded by dry cells" flag.  count_mass: add protect's mass error to the clock
+// (only for triangles a block owns, not for halo re-evaluations).
+__device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, const d4 *__restrict__ cq,
+                                                int k, bool count_mass, d4 &r0, d4 &r1, d4 &r2,
+                                                Eff &e, bool &zero_mom, int &connA_flags)
 {
-  if (D.clock->stop) return;
-  const int k = blockIdx.x * BLOCK + threadIdx.x;
-  if (k >= D.N) return;
   const int NP = D.NP;
   const i4 s = D.connA[k];
-  const d4 c = D.cq[k];
-  const d4 c0 = D.cq[s.x];
-  const d4 c1 = D.cq[s.y];
-  const d4 c2 = D.cq[s.z];
+  const d4 c = cq[k];
+  const d4 c0 = cq[s.x];
+  const d4 c1 = cq[s.y];
+  const d4 c2 = cq[s.z];
   const d4 g0 = D.xg[k];
   const d4 g1 = D.xg[NP + k];
   const d4 g2 = D.xg[2 * NP + k];
@@ -114,21 +117,21 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts
   G.dyv1 = g1.x; G.dyv2 = g1.y; G.dx1 = g1.z; G.dx2 = g1.w;
   G.dy1 = g2.x; G.dy2 = g2.y; G.inv_area2 = g2.z;
   const double area = g2.w;
+  connA_flags = s.w;
 
-  Eff e = effective(c, K);
+  e = effective(c, K);
   const Eff e0 = effective(c0, K);
   const Eff e1 = effective(c1, K);
   const Eff e2 = effective(c2, K);
-  if (e.mass_added != 0.0) atomicAdd(&D.clock->mass_error, e.mass_added * area);
+  if (count_mass && e.mass_added != 0.0) atomicAdd(&D.clock->mass_error, e.mass_added * area);
 
   const int nb = s.w & 3;
   // loop 2 head (:1486-1495): all neighbours dry (or self) -> no momentum
   const bool dry0 = (e0.h < K.mah) | (s.x == k);
   const bool dry1 = (e1.h < K.mah) | (s.y == k);
   const bool dry2 = (e2.h < K.mah) | (s.z == k);
-  const bool zero_mom = dry0 & dry1 & dry2;
+  zero_mom = dry0 & dry1 & dry2;
   if (zero_mom) { e.u = 0.0; e.v = 0.0; }
-  D.zflag[k] = (zero_mom ? 1 : 0) | ((s.w >> 3) & 2);   // bit0: zeroed momenta, bit1: tri_full_flag
 
   double w0, w1, w2, h0, h1, h2, u0, u1, u2, v0, v1, v2;
   if (nb == 3) {                                   // :1498-1522
@@ -166,10 +169,25 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts
     u1 = u1 * h1; v1 = v1 * h1;
     u2 = u2 * h2; v2 = v2 * h2;
   }
-  d4 r;
-  r.x = w0; r.y = h0; r.z = u0; r.w = v0; D.eq[k] = r;
-  r.x = w1; r.y = h1; r.z = u1; r.w = v1; D.eq[NP + k] = r;
-  r.x = w2; r.y = h2; r.z = u2; r.w = v2; D.eq[2 * NP + k] = r;
+  r0.x = w0; r0.y = h0; r0.z = u0; r0.w = v0;
+  r1.x = w1; r1.y = h1; r1.z = u1; r1.w = v1;
+  r2.x = w2; r2.y = h2; r2.z = u2; r2.w = v2;
+}
+
+__global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts K)
+{
+  if (D.clock->stop) return;
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= D.N) return;
+  d4 r0, r1, r2;
+  Eff e;
+  bool zero_mom;
+  int fl;
+  extrapolate_tri(D, K, D.cq, k, true, r0, r1, r2, e, zero_mom, fl);
+  D.zflag[k] = (zero_mom ? 1 : 0) | ((fl >> 3) & 2);   // bit0: zeroed momenta, bit1: tri_full_flag
+  D.eq[k] = r0;
+  D.eq[D.NP + k] = r1;
+  D.eq[2 * D.NP + k] = r2;
 }
 
 // Write the protected/zeroed centroid values in place: what the reference's centroid
@@ -217,6 +235,47 @@ struct Segments {
   const double *seg_val;   // [nseg][3]
 };
 
+// boundary value of one edge from the triangle's own edge record e = {stage, height, xmom, ymom},
+// its outward normal and (centroid-transmissive only) its protected centroid state
+__device__ __forceinline__ bool boundary_value_core(int kind, double v0, double v1, double v2, const d4 e,
+                                                    double n1, double n2, int centroid_transmissive,
+                                                    double cw, double cuh, double cvh, d4 &out)
+{
+  switch (kind) {
+    case 1: {                                  // Reflective (boundaries.py:262-278)
+      const double q1 = e.z, q2 = e.w;
+      const double r1 = -q1 * n1 - q2 * n2;
+      const double r2 = -q1 * n2 + q2 * n1;
+      out.x = e.x;
+      out.y = n1 * r1 - n2 * r2;
+      out.z = n2 * r1 + n1 * r2;
+    } break;
+    case 2:                                    // Dirichlet / host-evaluated time boundary
+      out.x = v0; out.y = v1; out.z = v2;
+      break;
+    case 3:                                    // Transmissive
+      if (centroid_transmissive) { out.x = cw; out.y = cuh; out.z = cvh; }
+      else { out.x = e.x; out.y = e.z; out.z = e.w; }
+      break;
+    case 4: {                                  // Transmissive_n_momentum_zero_t_momentum_set_stage
+      const double ndotq = n1 * e.z + n2 * e.w;
+      out.x = v0;
+      out.y = ndotq * n1;
+      out.z = ndotq * n2;
+    } break;
+    case 5:                                    // Transmissive_momentum_set_stage
+      out.x = v0; out.y = e.z; out.z = e.w;
+      break;
+    case 6:                                    // Transmissive_stage_zero_momentum
+      out.x = e.x; out.y = 0.0; out.z = 0.0;
+      break;
+    default:
+      return false;
+  }
+  out.w = 0.0;
+  return true;
+}
+
 __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, const Consts &K,
                                                int m, int centroid_transmissive, d4 &out, bool &touched)
 {
@@ -235,46 +294,14 @@ __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, 
     n1 = (i == 0) ? f0.x : ((i == 1) ? f0.z : f1.x);
     n2 = (i == 0) ? f0.y : ((i == 1) ? f0.w : f1.y);
   }
-  const double v0 = S.seg_val[3 * seg], v1 = S.seg_val[3 * seg + 1], v2 = S.seg_val[3 * seg + 2];
-  touched = true;
-  switch (kind) {
-    case 1: {                                  // Reflective (boundaries.py:262-278)
-      const double q1 = e.z, q2 = e.w;
-      const double r1 = -q1 * n1 - q2 * n2;
-      const double r2 = -q1 * n2 + q2 * n1;
-      out.x = e.x;
-      out.y = n1 * r1 - n2 * r2;
-      out.z = n2 * r1 + n1 * r2;
-    } break;
-    case 2:                                    // Dirichlet / host-evaluated time boundary
-      out.x = v0; out.y = v1; out.z = v2;
-      break;
-    case 3:                                    // Transmissive
-      if (centroid_transmissive) {
-        const d4 c = D.cq[k];                  // centroid arrays as the reference sees them
-        const Eff ef = effective(c, K);
-        out.x = ef.w; out.y = ef.uh; out.z = ef.vh;
-        if (D.zflag[k] & 1) { out.y = 0.0; out.z = 0.0; }
-      } else {
-        out.x = e.x; out.y = e.z; out.z = e.w;
-      }
-      break;
-    case 4: {                                  // Transmissive_n_momentum_zero_t_momentum_set_stage
-      const double ndotq = n1 * e.z + n2 * e.w;
-      out.x = v0;
-      out.y = ndotq * n1;
-      out.z = ndotq * n2;
-    } break;
-    case 5:                                    // Transmissive_momentum_set_stage
-      out.x = v0; out.y = e.z; out.z = e.w;
-      break;
-    case 6:                                    // Transmissive_stage_zero_momentum
-      out.x = e.x; out.y = 0.0; out.z = 0.0;
-      break;
-    default:
-      touched = false;
+  double cw = 0.0, cuh = 0.0, cvh = 0.0;
+  if (centroid_transmissive && kind == 3) {   // centroid arrays as the reference sees them
+    const Eff ef = effective(D.cq[k], K);
+    cw = ef.w; cuh = ef.uh; cvh = ef.vh;
+    if (D.zflag[k] & 1) { cuh = 0.0; cvh = 0.0; }
   }
-  out.w = 0.0;
+  touched = boundary_value_core(kind, S.seg_val[3 * seg], S.seg_val[3 * seg + 1], S.seg_val[3 * seg + 2], e,
+                                n1, n2, centroid_transmissive, cw, cuh, cvh, out);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_boundary_values(Dev D, Segments S, Consts K, int centroid_transmissive)
@@ -310,26 +337,16 @@ __device__ __noinline__ int acct_slot_lookup(const int *keys, const int *keys_po
   return -1;
 }
 
+// el[i]: own edge records; er[i]: the neighbour's record of the shared edge, or for a boundary edge
+// (pn[i] < 0) the boundary value {stage, xmom, ymom, -}.
 template <bool RW>
-__device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, int k, const i4 p,
-                                                 const Eff &own, bool first)
+__device__ __forceinline__ TriFlux triangle_flux_core(const Dev &D, const Consts &K, int k, const int (&pn)[3],
+                                                      const int flags, const d4 (&el)[3], const d4 (&er)[3],
+                                                      const d4 f0, const d4 f1, const d4 f2,
+                                                      const Eff &own, bool first)
 {
   const int NP = D.NP;
-  d4 el[3];
-  el[0] = D.eq[k];
-  el[1] = D.eq[NP + k];
-  el[2] = D.eq[2 * NP + k];
-  const d4 f0 = D.fg[k];
-  const d4 f1 = D.fg[NP + k];
-  const d4 f2 = D.fg[2 * NP + k];
-  const int pn[3] = {p.x, p.y, p.z};
-  d4 er[3];
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const int q = pn[i];
-    if (q >= 0) er[i] = D.eq[(q & 3) * NP + (q >> 2)];
-    else er[i] = D.bq[-q - 1];
-  }
+  const i4 p = {pn[0], pn[1], pn[2], flags};
   const double nx[3] = {f0.x, f0.z, f1.x};
   const double ny[3] = {f0.y, f0.w, f1.y};
   const double len[3] = {f1.z, f1.w, f2.x};
@@ -398,12 +415,8 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
     const double ef2 = -F.f2 * length;
     const double pressuregrad =
         length * (-K.g * 0.5 * (h_left * h_left - hle * hle - (hle + hc) * (zl - zc)) + F.pressure_flux);
-    if (first) {                                      // :667-686
-      const double edge_timestep = radius * 1.0 / dmax(F.max_speed, K.epsilon);
-      if (full && F.max_speed > K.epsilon) {
-        T.dtmin = dmin(T.dtmin, edge_timestep);
-        T.speed = dmax(T.speed, F.max_speed);
-      }
+    if (first) {                                      // :667-686, division hoisted out of the loop (below)
+      if (full && F.max_speed > K.epsilon) T.speed = dmax(T.speed, F.max_speed);
     }
     T.su += ef0;
     T.xu += ef1;
@@ -418,28 +431,57 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
     T.xu -= nx[i] * pressuregrad;
     T.yu -= ny[i] * pressuregrad;
   }
+  // min_i fl(radius / speed_i) == fl(radius / max_i speed_i): correctly rounded division is monotone,
+  // so one division per triangle gives the reference's local timestep bit for bit
+  if (first && T.speed > 0.0) T.dtmin = radius * 1.0 / T.speed;
   T.su *= inv_area;
   T.xu *= inv_area;
   T.yu *= inv_area;
   return T;
 }
 
-// block-wide min of positive doubles -> one atomicMin per block
-__device__ __forceinline__ void block_min_to_clock(double v, Clock *clock)
+template <bool RW>
+__device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, int k, const i4 p,
+                                                 const Eff &own, bool first)
 {
-  __shared__ double smin[BLOCK / 32];
+  const int NP = D.NP;
+  d4 el[3];
+  el[0] = D.eq[k];
+  el[1] = D.eq[NP + k];
+  el[2] = D.eq[2 * NP + k];
+  const d4 f0 = D.fg[k];
+  const d4 f1 = D.fg[NP + k];
+  const d4 f2 = D.fg[2 * NP + k];
+  const int pn[3] = {p.x, p.y, p.z};
+  d4 er[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int q = pn[i];
+    if (q >= 0) er[i] = D.eq[(q & 3) * NP + (q >> 2)];
+    else er[i] = D.bq[-q - 1];
+  }
+  return triangle_flux_core<RW>(D, K, k, pn, p.w, el, er, f0, f1, f2, own, first);
+}
+
+// block-wide min of positive doubles -> one atomicMin per block
+template <int NT>
+__device__ __forceinline__ void block_min_to_clock_t(double v, Clock *clock)
+{
+  __shared__ double smin[NT / 32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, o));
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) smin[wid] = v;
   __syncthreads();
   if (wid == 0) {
-    v = (lane < BLOCK / 32) ? smin[lane] : 1.0e+100;
+    v = (lane < NT / 32) ? smin[lane] : 1.0e+100;
 #pragma unroll
-    for (int o = BLOCK / 64; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0 && v < 1.0e+100) atomicMin(&clock->dt_min_bits, d2u(v));
   }
 }
+
+__device__ __forceinline__ void block_min_to_clock(double v, Clock *clock) { block_min_to_clock_t<BLOCK>(v, clock); }
 
 // update of one triangle's conserved quantities from its explicit updates:
 // friction (sw_domain_openmp.c:1954-2034) -> Quantity.update x3 (quantity.c:772-820)
@@ -453,11 +495,11 @@ struct UpdateArgs {
 };
 
 __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, const UpdateArgs &U,
-                                                int k, const d4 raw, Eff e,
-                                                double su, double xu, double yu, double dt)
+                                                int k, const d4 raw, Eff e, const unsigned zf,
+                                                double su, double xu, double yu, double dt,
+                                                d4 *__restrict__ cq_out, const d4 *own_edges)
 {
   const int NP = D.NP;
-  const unsigned char zf = D.zflag[k];
   const bool full = (zf & 2) != 0;
   if (U.do_backup) {                                   // backup holds the RAW start-of-step values
     D.bk[k] = raw.x;
@@ -468,7 +510,9 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
   double zs = 1.0;
   double h = e.w - e.z;
   if (U.sloped) {                                      // :2003-2023 with the dynamic bed vertex values
-    const d4 a0 = D.eq[k], a1 = D.eq[NP + k], a2 = D.eq[2 * NP + k];
+    const d4 a0 = own_edges ? own_edges[0] : D.eq[k];
+    const d4 a1 = own_edges ? own_edges[1] : D.eq[NP + k];
+    const d4 a2 = own_edges ? own_edges[2] : D.eq[2 * NP + k];
     const double b0 = a0.x - a0.y, b1 = a1.x - a1.y, b2 = a2.x - a2.y;
     const double z0 = b1 + b2 - b0, z1 = b0 + b2 - b1, z2 = b0 + b1 - b2;
     const double x0 = D.vcoord[k], y0 = D.vcoord[NP + k], x1 = D.vcoord[2 * NP + k];
@@ -505,7 +549,7 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
   if (U.do_rain) w = w + U.rain_factor * dt * U.rain_rate;   // rate_operators.py:205-208 (all rates >= 0)
   d4 out;
   out.x = w; out.y = uh; out.z = vh; out.w = e.z;
-  D.cq[k] = out;
+  cq_out[k] = out;
 }
 
 // Pass B1 (substep 0): flux + dt partials.  writes eu, max_speed, dt_min_bits.
@@ -537,7 +581,7 @@ __global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U,
   const double dt = (dt_override >= 0.0) ? dt_override : D.clock->dt;
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
-  triangle_update(D, K, U, k, raw, e, D.eu[k], D.eu[D.NP + k], D.eu[2 * D.NP + k], dt);
+  triangle_update(D, K, U, k, raw, e, D.zflag[k], D.eu[k], D.eu[D.NP + k], D.eu[2 * D.NP + k], dt, D.cq, nullptr);
 }
 
 // Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
@@ -553,7 +597,7 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux_update(Dev D, Consts
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
   const TriFlux T = triangle_flux<false>(D, K, k, p, e, false);
-  triangle_update(D, K, U, k, raw, e, T.su, T.xu, T.yu, dt);
+  triangle_update(D, K, U, k, raw, e, D.zflag[k], T.su, T.xu, T.yu, dt, D.cq, nullptr);
 }
 
 // =============================================================================
@@ -941,3 +985,4 @@ __global__ void k_bfi_update(Clock *c, TimeParams P)
   c->boundary_flux_sum[0] = c->boundary_flux_sum[1] = c->boundary_flux_sum[2] = 0.0;
 }
 }  // namespace swk
+

@@ -127,6 +127,7 @@ class Domain:
         self.store = False
         self.name = "domain"
         self._dev = None
+        self.pin_host_arrays = True
         self._stale = set()
         self.timestep_history = []
         self.record_timestep_history = False
@@ -299,6 +300,29 @@ class Domain:
                                  for (v, e) in sorted(self.mesh.boundary.keys())]
         self._boundary_dirty = True
 
+    def set_riverwall_tables(self, edge_flux_type, riverwall_elevation, hydraulic_properties_rowIndex,
+                             hydraulic_properties):
+        """Riverwall edge tables as structures/riverwall.py:406-415 leaves them on the domain:
+        edge_flux_type (3N,) == 1 on wall edges, one elevation / row index per wall edge in (k, i)
+        order, hydraulic_properties rows = [Qfactor, s1, s2, h1, h2].  (Building them from
+        breaklines is mesh set-up, outside the hot path.)"""
+        eft = np.ascontiguousarray(edge_flux_type, dtype=np.int64).reshape(-1)
+        assert eft.size == 3 * self.number_of_triangles
+        self.edge_flux_type = eft
+        counter = np.zeros_like(eft)
+        idx = np.flatnonzero(eft == 1)
+        counter[idx] = np.arange(1, idx.size + 1)
+        self.edge_river_wall_counter = counter
+        self.number_of_riverwall_edges = int(idx.size)
+        self.riverwall_elevation = np.ascontiguousarray(riverwall_elevation, dtype=np.float64)
+        self.riverwall_rowIndex = np.ascontiguousarray(hydraulic_properties_rowIndex, dtype=np.int64)
+        hp = np.ascontiguousarray(hydraulic_properties, dtype=np.float64)
+        self.riverwall_hydraulic_properties = hp.reshape(-1)
+        self.ncol_riverwall_hydraulic_properties = hp.shape[1] if hp.ndim == 2 else 5
+        assert self.riverwall_elevation.size == idx.size == self.riverwall_rowIndex.size
+        if self._dev is not None:
+            self._release_device()
+
     def set_fractional_step_operator(self, operator):
         self.fractional_step_operators.append(operator)
         self._operators_dirty = True
@@ -459,13 +483,15 @@ class Domain:
         for name, qid in (("stage", "STAGE_C"), ("xmomentum", "XMOM_C"), ("ymomentum", "YMOM_C"),
                           ("elevation", "ELEVATION_C"), ("friction", "FRICTION_C")):
             if force or q[name].host_dirty:
+                if self.pin_host_arrays and name in self.conserved_quantities:
+                    dev.pin(q[name].centroid_values)       # moved every yield: page-lock once
                 dev.set_quantity(qid, q[name].centroid_values)
                 q[name].host_dirty = False
                 self._stale.discard(name)
 
-    def sync_from_host(self):
+    def sync_from_host(self, quantities=("stage", "xmomentum", "ymomentum", "elevation", "friction")):
         """Declare that the numpy centroid arrays were modified in place."""
-        for name in ("stage", "xmomentum", "ymomentum", "elevation", "friction"):
+        for name in quantities:
             self.quantities[name].host_dirty = True
         self._push_quantities()
 

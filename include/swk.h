@@ -244,6 +244,10 @@ int swk_run_steps(swk_domain *d, int64_t n_steps, int per_kernel, float *elapsed
 int swk_kernel_timing(swk_domain *d, double total_ms[4], int64_t launches[4]);
 int swk_stream(swk_domain *d, void **cuda_stream_out);
 int swk_synchronize(swk_domain *d);
+/* Page-lock / unlock a host buffer that is used repeatedly with swk_set/get_quantity (the numpy
+ * arrays of Domain.quantities live as long as the domain), so that the copies run at PCIe speed. */
+int swk_pin_host_buffer(swk_domain *d, void *host, size_t bytes);
+int swk_unpin_host_buffer(swk_domain *d, void *host);
 int swk_kernel_launch_count(swk_domain *d, int64_t *count);
 /* Algorithmic HBM bytes per triangle and timestep of the current configuration
  *  and the bytes this library's layout actually moves.       */

@@ -188,3 +188,52 @@ def test_error_paths():
     assert e.value.code == -4
     with pytest.raises(Exception):
         ab.rectangular_cross_domain(2, 2).set_store(True)
+
+
+def riverwall_domain(alg="DE1", n=12):
+    """synthetic riverwall: a weir along x = n/2 (cell boundaries), crest partly overtopped"""
+    d = cases.dam_break_de0(ab, n=n)
+    d.set_flow_algorithm(alg)
+    d.set_quantity("stage", lambda x, y: np.where(x < n / 2.0, 1.0, -0.5), location="centroids")
+    E = d.edge_midpoint_coordinates.reshape(-1, 3, 2)
+    on = np.abs(E[:, :, 0] - n / 2.0) < 1e-9
+    vert = np.abs(d.normals.reshape(-1, 3, 2)[:, :, 1]) < 1e-9          # edges lying on the line x = n/2
+    eft = (on & vert).astype(np.int64).reshape(-1)
+    nrw = int(eft.sum())
+    assert nrw == 2 * n
+    y = E.reshape(-1, 2)[eft == 1, 1]
+    crest = 0.2 + 0.05 * np.sin(y)                                      # stage 1.0 upstream overtops it
+    d.set_riverwall_tables(eft, crest, np.zeros(nrw, dtype=np.int64), np.array([[1.0, 0.9, 0.95, 1.0, 1.5]]))
+    return d
+
+
+@pytest.mark.parametrize("alg", ["DE0", "DE1"])
+def test_riverwall_edges_match_reference_c_code(alg):
+    """edge_flux_type == 1: z_half raised to the crest, Villemonte weir blend, max_speed override
+    (sw_domain_openmp.c:324-426, 582-653) against the reference's own C code."""
+    d = riverwall_domain(alg)
+    o = OracleDomain(domain_to_scenario(d), backend=REF)
+    d.distribute_to_vertices_and_edges()
+    o.distribute_to_vertices_and_edges()
+    d.update_boundary()
+    o.update_boundary()
+    ft = d.compute_fluxes(0)
+    o.compute_fluxes(0)
+    q = d.quantities
+    assert ft == o.flux_timestep
+    assert rel_err(q["stage"].explicit_update, o.stage_eu) <= TOL_1STEP
+    assert rel_err(q["xmomentum"].explicit_update, o.xmom_eu) <= 1e-11      # pow(x, 0.385) in the weir law: CUDA pow, 2 ulp
+    assert rel_err(d.get_max_speed(), o.max_speed) <= 1e-11
+    d2 = riverwall_domain(alg)
+    o2 = OracleDomain(domain_to_scenario(d2), backend=REF)
+    for _ in d2.evolve(yieldstep=0.5, finaltime=2.0):
+        pass
+    for _ in o2.evolve(yieldstep=0.5, finaltime=2.0):
+        pass
+    assert d2.total_steps == len(o2.timestep_history)
+    w, uh, vh = conserved(d2)
+    e = max(rel_err(w, o2.stage_c), rel_err(uh, o2.xmom_c), rel_err(vh, o2.ymom_c))
+    assert e <= 1e-8, e
+    # water did cross the wall
+    assert (w - d2.quantities["elevation"].centroid_values)[d2.centroid_coordinates[:, 0] > 6.5].max() > 1e-3
+    print("\nriverwall %s: %d steps, rel err %.2e" % (alg, d2.total_steps, e))

@@ -94,3 +94,26 @@ def test_protect_and_fix_negative_edge_cases(oracle_libs):
     o.tri_full_flag[0] = 0
     n = o.fn["fix_negative_cells"](__import__("ctypes").byref(o.D))
     assert n == len(o.stage_c) - 1 and o.stage_c[0] == -1.0 and np.all(o.stage_c[1:] == 0.0)
+
+
+@pytest.mark.skipif(not os.path.exists(LIBS["ref"]), reason="oracle/_ref not built")
+def test_riverwall_port_equals_reference_c_code(oracle_libs):
+    """the weir branch (sw_domain_openmp.c:324-426, 582-653) of the port against the reference's
+    own C code on a synthetic wall (real riverwall meshes need meshpy, absent here)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "tgp", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_gpu_parity.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    d = m.riverwall_domain("DE1")
+    res = {}
+    for be in ("port", "ref"):
+        o = OracleDomain(domain_to_scenario(d), backend=be)
+        for _ in o.evolve(yieldstep=0.5, finaltime=2.0):
+            pass
+        res[be] = o
+    assert len(res["port"].timestep_history) == len(res["ref"].timestep_history) > 20
+    for k in ("stage_c", "xmom_c", "ymom_c", "max_speed"):
+        assert np.array_equal(getattr(res["port"], k), getattr(res["ref"], k)), k
+    wet_right = (res["ref"].stage_c - res["ref"].bed_c)[d.centroid_coordinates[:, 0] > 6.5].max()
+    assert wet_right > 1e-3          # the wall was overtopped: the weir law was exercised
