@@ -178,6 +178,14 @@ struct swk_domain {
 
   int64_t launches = 0;
 
+  // one whole timestep captured as a CUDA graph: small meshes are launch-bound (a 40k-triangle
+  // step is ~10 kernels of a few microseconds each)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_valid = false;
+  bool use_graph = true;
+  int64_t launches_per_step = 0;
+
   // optional per-kernel event timing (bench.py roofline)
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -322,6 +330,8 @@ extern "C" int swk_destroy(swk_domain *d)
     if (pe.d_recv_buf) cudaFree(pe.d_recv_buf);
   }
   if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+  if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
+  if (d->graph) cudaGraphDestroy(d->graph);
   if (d->h_clock) cudaFreeHost(d->h_clock);
   if (d->ev_update) cudaEventDestroy(d->ev_update);
   if (d->ev_halo) cudaEventDestroy(d->ev_halo);
@@ -346,6 +356,10 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
       !m->centroid_coordinates || !m->edge_coordinates || (M > 0 && (!m->boundary_cells || !m->boundary_edges)))
     return fail(SWK_ERR_ARG, "mesh has NULL arrays");
   CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  {
+    const char *env = getenv("SWK_NO_GRAPH");
+    d->use_graph = !(env && env[0] == '1');
+  }
 
   // permutation
   d->new2old.resize(N);
@@ -583,6 +597,7 @@ extern "C" int swk_set_params(swk_domain *d, const swk_params *params)
     return fail(SWK_ERR_ARG, "use_sloped_mannings must be chosen at swk_create (vertex coordinates are uploaded there)");
   d->P = *params;
   make_consts(d);
+  d->graph_valid = false;
   return SWK_OK;
 }
 
@@ -735,6 +750,7 @@ extern "C" int swk_set_boundary_segment(swk_domain *d, int segment, int kind, co
     d->h_b_seg[ids[j]] = segment;
   }
   d->seg_dirty = true;
+  d->graph_valid = false;
   return SWK_OK;
 }
 
@@ -743,7 +759,7 @@ extern "C" int swk_set_boundary_values(swk_domain *d, int segment, const double 
   if (!d || !values) return fail(SWK_ERR_ARG, "NULL argument");
   if (segment < 0 || segment >= (int)d->seg_kind.size()) return fail(SWK_ERR_ARG, "unknown segment");
   for (int j = 0; j < 3; j++) d->seg_val[3 * segment + j] = values[j];
-  d->seg_dirty = true;
+  d->seg_dirty = true;                 // values live in device tables: the graph stays valid
   return SWK_OK;
 }
 
@@ -780,6 +796,7 @@ extern "C" int swk_add_rate_operator(swk_domain *d, double rate, double factor, 
   op.nblocks = nblk(op.n);
   CKV(dalloc(&op.d_partial, op.nblocks));
   d->rate_ops.push_back(op);
+  d->graph_valid = false;
   if (op_id) *op_id = (int)d->rate_ops.size() - 1;
   return SWK_OK;
 }
@@ -791,6 +808,7 @@ extern "C" int swk_set_rate(swk_domain *d, int op_id, double rate, double factor
   op.rate = rate;
   op.factor = factor;
   if (!op.d_rate_array) op.all_nonneg = (rate >= 0.0) ? 1 : 0;
+  d->graph_valid = false;
   return SWK_OK;
 }
 
@@ -813,6 +831,7 @@ extern "C" int swk_set_local_ghost_copy(swk_domain *d, const int64_t *full_ids, 
   CKV(dalloc(&d->d_ghost_full, n)); CKV(upload(d->d_ghost_full, f));
   CKV(dalloc(&d->d_ghost_ghost, n)); CKV(upload(d->d_ghost_ghost, g));
   d->n_ghost_copy = (int)n;
+  d->graph_valid = false;
   return SWK_OK;
 }
 
@@ -1024,6 +1043,44 @@ static int launch_step(swk_domain *d)
   return SWK_OK;
 }
 
+// Capture launch_step once; every parameter baked into the kernel nodes (scalars, boundary tables,
+// rain rate, halo lists) invalidates the graph through d->graph_valid = false.
+static int ensure_graph(swk_domain *d)
+{
+  if (d->graph_exec && d->graph_valid) return SWK_OK;
+  if (d->graph_exec) { cudaGraphExecDestroy(d->graph_exec); d->graph_exec = nullptr; }
+  if (d->graph) { cudaGraphDestroy(d->graph); d->graph = nullptr; }
+  CKV(push_segments(d));                       // host->device table copies must not be captured
+  const int64_t l0 = d->launches;
+  CK(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = launch_step(d);
+  cudaError_t e = cudaStreamEndCapture(d->stream, &d->graph);
+  if (rc != SWK_OK) return rc;
+  if (e != cudaSuccess) return fail(SWK_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  d->launches_per_step = d->launches - l0;
+  d->launches = l0;
+  CK(cudaGraphInstantiate(&d->graph_exec, d->graph, 0));
+  d->graph_valid = true;
+  return SWK_OK;
+}
+
+static bool graph_ok(const swk_domain *d)
+{
+  return d->use_graph && !d->comm && !d->timing;
+}
+
+static int run_one_step(swk_domain *d)
+{
+  if (graph_ok(d)) {
+    CKV(ensure_graph(d));
+    CKV(push_segments(d));                     // time-independent kinds only; cheap when clean
+    CK(cudaGraphLaunch(d->graph_exec, d->stream));
+    d->launches += d->launches_per_step;
+    return SWK_OK;
+  }
+  return launch_step(d);
+}
+
 static int status_from_stop(int stop)
 {
   switch (stop) {
@@ -1074,7 +1131,7 @@ extern "C" int swk_evolve(swk_domain *d, double relative_yieldtime, double relat
 
   int64_t batch = 1;
   for (;;) {
-    for (int64_t b = 0; b < batch; b++) CKV(launch_step(d));
+    for (int64_t b = 0; b < batch; b++) CKV(run_one_step(d));
     CKV(pull_clock(d));
     if (c->stop != 0) break;
     // estimate how many more steps fit before the next stop (the device clips dt itself;
@@ -1137,7 +1194,7 @@ extern "C" int swk_run_steps(swk_domain *d, int64_t n_steps, int per_kernel, flo
   CK(cudaStreamSynchronize(d->stream));
   CK(cudaEventRecord(e0, d->stream));
   int rc = SWK_OK;
-  for (int64_t s = 0; s < n_steps && rc == SWK_OK; s++) rc = launch_step(d);
+  for (int64_t s = 0; s < n_steps && rc == SWK_OK; s++) rc = run_one_step(d);
   CK(cudaEventRecord(e1, d->stream));
   d->timing = false;
   CK(cudaEventSynchronize(e1));

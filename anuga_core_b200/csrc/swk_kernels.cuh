@@ -986,3 +986,4 @@ __global__ void k_bfi_update(Clock *c, TimeParams P)
 }
 }  // namespace swk
 
+
