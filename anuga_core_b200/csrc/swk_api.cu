@@ -172,8 +172,11 @@ struct swk_domain {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   std::vector<Peer> peers;
+  int n_full = 0;              // full triangles occupy device ids [0, n_full) (0: not a prefix)
+  int halo_front = 0;          // every halo-source (send) triangle has a device id < halo_front
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_update = nullptr, ev_halo = nullptr;
+  bool overlap = true;         // SWK_NO_OVERLAP=1: halo exchange in-stream
   double *d_dt_scratch = nullptr;
 
   int64_t launches = 0;
@@ -377,6 +380,14 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
     for (int64_t k = 0; k < N; k++) d->new2old[k] = d->old2new[k] = (int)k;
   }
   const std::vector<int> &n2o = d->new2old, &o2n = d->old2new;
+  {   // full triangles first, ghosts after (the reference's local numbering; kept by the reordering)?
+    int64_t nf = 0;
+    while (nf < N && m->tri_full_flag[n2o[nf]] == 1) nf++;
+    bool prefix = true;
+    for (int64_t k = nf; k < N; k++)
+      if (m->tri_full_flag[n2o[k]] == 1) { prefix = false; break; }
+    d->n_full = prefix ? (int)nf : 0;
+  }
 
   // riverwalls?
   d->has_riverwalls = false;
@@ -895,11 +906,19 @@ static int launch_boundary(swk_domain *d)
   return SWK_OK;
 }
 
+// Triangles the flux / update kernels work on: with a communicator the ghosts are refreshed from
+// their owners after every update, so only the full triangles [0, n_full) are evaluated.
+static int n_active(const swk_domain *d)
+{
+  return (d->comm && d->n_full > 0) ? d->n_full : (int)d->N;
+}
+
 static void launch_flux(swk_domain *d, int first, int write_speed)
 {
   TimedScope ts(d, 1);
-  if (d->has_riverwalls) LAUNCH(d, k_flux<true>, nblk(d->N), BLOCK, d->D, d->K, first, write_speed);
-  else LAUNCH(d, k_flux<false>, nblk(d->N), BLOCK, d->D, d->K, first, write_speed);
+  const int n = n_active(d);
+  if (d->has_riverwalls) LAUNCH(d, k_flux<true>, nblk(n), BLOCK, d->D, d->K, first, write_speed, 0, n);
+  else LAUNCH(d, k_flux<false>, nblk(n), BLOCK, d->D, d->K, first, write_speed, 0, n);
 }
 
 static void launch_bflux(swk_domain *d, int substep)
@@ -942,23 +961,63 @@ static void launch_rate_ops(swk_domain *d)
   }
 }
 
-// ghost update: local copy and/or NCCL halo exchange (parallel_generic_communications.py:159-248)
+// NCCL halo exchange on `stream` (parallel_generic_communications.py:159-248): pack the
+// full_send lists, grouped ncclSend/ncclRecv with every peer, unpack into the ghosts
+static int launch_exchange(swk_domain *d, cudaStream_t stream)
+{
+  if (!d->comm || d->peers.empty()) return SWK_OK;
+  for (auto &pe : d->peers)
+    if (pe.n_send > 0) {
+      k_halo_pack<<<nblk(pe.n_send), BLOCK, 0, stream>>>(d->D, pe.d_send_ids, pe.n_send, pe.d_send_buf);
+      d->launches++;
+    }
+  NK(g_nccl.GroupStart());
+  for (auto &pe : d->peers) {
+    if (pe.n_recv > 0) NK(g_nccl.Recv(pe.d_recv_buf, 3 * (size_t)pe.n_recv, ncclFloat64, pe.rank, d->comm, stream));
+    if (pe.n_send > 0) NK(g_nccl.Send(pe.d_send_buf, 3 * (size_t)pe.n_send, ncclFloat64, pe.rank, d->comm, stream));
+  }
+  NK(g_nccl.GroupEnd());
+  for (auto &pe : d->peers)
+    if (pe.n_recv > 0) {
+      k_halo_unpack<<<nblk(pe.n_recv), BLOCK, 0, stream>>>(d->D, pe.d_recv_ids, pe.n_recv, pe.d_recv_buf);
+      d->launches++;
+    }
+  return SWK_OK;
+}
+
+// ghost update in-stream: local copy and/or NCCL halo exchange
 static int launch_ghosts(swk_domain *d)
 {
   if (d->n_ghost_copy > 0)
     LAUNCH(d, k_ghost_copy, nblk(d->n_ghost_copy), BLOCK, d->D, d->d_ghost_full, d->d_ghost_ghost, d->n_ghost_copy);
-  if (d->comm && !d->peers.empty()) {
-    for (auto &pe : d->peers)
-      if (pe.n_send > 0) LAUNCH(d, k_halo_pack, nblk(pe.n_send), BLOCK, d->D, pe.d_send_ids, pe.n_send, pe.d_send_buf);
-    NK(g_nccl.GroupStart());
-    for (auto &pe : d->peers) {
-      if (pe.n_recv > 0) NK(g_nccl.Recv(pe.d_recv_buf, 3 * (size_t)pe.n_recv, ncclFloat64, pe.rank, d->comm, d->stream));
-      if (pe.n_send > 0) NK(g_nccl.Send(pe.d_send_buf, 3 * (size_t)pe.n_send, ncclFloat64, pe.rank, d->comm, d->stream));
-    }
-    NK(g_nccl.GroupEnd());
-    for (auto &pe : d->peers)
-      if (pe.n_recv > 0) LAUNCH(d, k_halo_unpack, nblk(pe.n_recv), BLOCK, d->D, pe.d_recv_ids, pe.n_recv, pe.d_recv_buf);
+  return launch_exchange(d, d->stream);
+}
+
+// Run an update-type kernel f(k0, k1) over the active triangles and, if a ghost update follows it,
+// overlap the halo exchange with the bulk of the kernel: the halo-source triangles [0, halo_front)
+// are updated first, their values travel on the communication stream while [halo_front, n) is
+// still being computed, and the main stream only waits for the unpack before the next
+// extrapolation (north_star: "overlapped with interior flux computation").
+template <typename F>
+static int update_with_exchange(swk_domain *d, bool exchange_after, F f)
+{
+  const int n = n_active(d);
+  const bool overlap = exchange_after && d->comm && !d->peers.empty() && d->n_full > 0 &&
+                       d->halo_front > 0 && d->halo_front < n && d->overlap;
+  if (!overlap) {
+    f(0, n);
+    if (exchange_after) CKV(launch_ghosts(d));
+    return SWK_OK;
   }
+  f(0, d->halo_front);
+  CK(cudaEventRecord(d->ev_update, d->stream));
+  CK(cudaStreamWaitEvent(d->comm_stream, d->ev_update, 0));
+  CKV(launch_exchange(d, d->comm_stream));
+  CK(cudaEventRecord(d->ev_halo, d->comm_stream));
+  f(d->halo_front, n);
+  if (d->n_ghost_copy > 0)
+    LAUNCH(d, k_ghost_copy, nblk(d->n_ghost_copy), BLOCK, d->D, d->d_ghost_full, d->d_ghost_ghost, d->n_ghost_copy);
+  CK(cudaStreamWaitEvent(d->stream, d->ev_halo, 0));
   return SWK_OK;
 }
 
@@ -975,36 +1034,39 @@ static int launch_dt_allreduce(swk_domain *d)
   return SWK_OK;
 }
 
-// one substep-0 sequence: A, boundary, B1, boundary-flux sum, dt, B2
-static int launch_first_substep(swk_domain *d, int do_backup, bool last_of_step)
+// one substep-0 sequence: A, boundary, B1 (+ boundary-flux sum, dt), B2 [+ ghost update]
+static int launch_first_substep(swk_domain *d, int do_backup, bool last_of_step, bool exchange_after)
 {
   launch_extrapolate(d, d->K);
   CKV(launch_boundary(d));
   launch_flux(d, 1, (int)d->P.track_max_speed);
   CKV(launch_dt_allreduce(d));
   LAUNCH(d, k_update_timestep, 1, 1024, d->D, d->TP, 1);
-  {
+  const UpdateArgs U = update_args(d, do_backup, 0, 1.0, 0.0, 1.0, last_of_step);
+  return update_with_exchange(d, exchange_after, [&](int k0, int k1) {
     TimedScope ts(d, 2);
-    LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K,
-           update_args(d, do_backup, 0, 1.0, 0.0, 1.0, last_of_step), -1.0);
-  }
-  return SWK_OK;
+    LAUNCH(d, k_update, nblk(k1 - k0), BLOCK, d->D, d->K, U, -1.0, k0, k1);
+  });
 }
 
-// a later RK substep with the RK combination folded in
+// a later RK substep with the RK combination folded in [+ ghost update]
 static int launch_later_substep(swk_domain *d, int substep, double a, double b, double divide_by,
-                                bool last_of_step)
+                                bool last_of_step, bool exchange_after)
 {
   launch_extrapolate(d, d->K);
   CKV(launch_boundary(d));
   const UpdateArgs U = update_args(d, 0, 1, a, b, divide_by, last_of_step);
   if (d->has_riverwalls) {
     launch_flux(d, 0, 0);
-    TimedScope ts(d, 2);
-    LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, U, -1.0);
+    CKV(update_with_exchange(d, exchange_after, [&](int k0, int k1) {
+      TimedScope ts(d, 2);
+      LAUNCH(d, k_update, nblk(k1 - k0), BLOCK, d->D, d->K, U, -1.0, k0, k1);
+    }));
   } else {
-    TimedScope ts(d, 3);
-    LAUNCH(d, k_flux_update, nblk(d->N), BLOCK, d->D, d->K, U);
+    CKV(update_with_exchange(d, exchange_after, [&](int k0, int k1) {
+      TimedScope ts(d, 3);
+      LAUNCH(d, k_flux_update, nblk(k1 - k0), BLOCK, d->D, d->K, U, k0, k1);
+    }));
   }
   if (!last_of_step) launch_bflux(d, substep);     // the last substep's sum rides in k_finish_step
   return SWK_OK;
@@ -1015,19 +1077,19 @@ static int launch_step(swk_domain *d)
 {
   // step_start_time / dt_min_bits are (re)set by the previous k_finish_step (or by the host before
   // the first step of a call), so a step is: [A, bc, B1, dt, B2] [A, bc, B]* finish.
+  // Ghost updates (:1857, 2013-2015, 2096, 2135) ride with the update kernel that precedes them; the
+  // one after the step can do so only when no separate fractional-step kernel still changes the state.
   const int method = (int)d->P.timestepping_method;
+  const bool ops_fused = d->rate_ops.empty() || rain_is_fusable(d);
   if (method == 1) {
-    CKV(launch_first_substep(d, 0, true));
+    CKV(launch_first_substep(d, 0, true, ops_fused));
   } else if (method == 2) {
-    CKV(launch_first_substep(d, 1, false));
-    if (d->P.ghost_layer_width < 4) CKV(launch_ghosts(d));
-    CKV(launch_later_substep(d, 1, 0.5, 0.5, 1.0, true));
+    CKV(launch_first_substep(d, 1, false, d->P.ghost_layer_width < 4));
+    CKV(launch_later_substep(d, 1, 0.5, 0.5, 1.0, true, ops_fused));
   } else {
-    CKV(launch_first_substep(d, 1, false));
-    CKV(launch_ghosts(d));
-    CKV(launch_later_substep(d, 1, 0.25, 0.75, 1.0, false));
-    CKV(launch_ghosts(d));
-    CKV(launch_later_substep(d, 2, 2.0, 1.0, 3.0, true));
+    CKV(launch_first_substep(d, 1, false, true));
+    CKV(launch_later_substep(d, 1, 0.25, 0.75, 1.0, false, true));
+    CKV(launch_later_substep(d, 2, 2.0, 1.0, 3.0, true, ops_fused));
   }
   FusedRain R;
   R.on = 0; R.rate = 0.0; R.factor = 0.0; R.full_area = d->full_area;
@@ -1039,7 +1101,7 @@ static int launch_step(swk_domain *d)
     launch_rate_ops(d);
   }
   LAUNCH(d, k_finish_step, 1, 1024, d->D, d->TP, method == 1 ? -1 : method - 1, R);
-  CKV(launch_ghosts(d));                            // :1857
+  if (!ops_fused) CKV(launch_ghosts(d));            // :1857
   return SWK_OK;
 }
 
@@ -1348,7 +1410,7 @@ extern "C" int swk_update_conserved_quantities(swk_domain *d, double timestep, i
   CK(cudaSetDevice(d->device));
   CKV(pull_clock(d));
   const long long before = d->h_clock->negative_cells;
-  LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, 0, 0, 1.0, 0.0, 1.0), timestep);
+  LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, 0, 0, 1.0, 0.0, 1.0), timestep, 0, (int)d->N);
   CKV(pull_clock(d));
   if (d->h_clock->stop < 0) {
     const int st = d->h_clock->stop;
@@ -1428,6 +1490,13 @@ extern "C" int swk_comm_init(swk_domain *d, const void *id128, int rank, int nra
   d->rank = rank;
   d->nranks = nranks;
   CKV(dalloc(&d->d_dt_scratch, 1));
+  CK(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&d->ev_update, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
+  {
+    const char *env = getenv("SWK_NO_OVERLAP");
+    d->overlap = !(env && env[0] == '1');
+  }
   return SWK_OK;
 }
 
@@ -1444,6 +1513,7 @@ extern "C" int swk_set_halo(swk_domain *d, int n_peers, const int *peer_ranks, c
     if (pe.d_recv_buf) cudaFree(pe.d_recv_buf);
   }
   d->peers.clear();
+  d->halo_front = 0;
   for (int q = 0; q < n_peers; q++) {
     Peer pe;
     pe.rank = peer_ranks[q];
@@ -1462,8 +1532,10 @@ extern "C" int swk_set_halo(swk_domain *d, int n_peers, const int *peer_ranks, c
     CKV(dalloc(&pe.d_recv_ids, r.size())); CKV(upload(pe.d_recv_ids, r));
     CKV(dalloc(&pe.d_send_buf, 3 * s.size()));
     CKV(dalloc(&pe.d_recv_buf, 3 * r.size()));
+    for (int v : s) d->halo_front = std::max(d->halo_front, v + 1);
     d->peers.push_back(pe);
   }
+  if (d->n_full > 0 && d->halo_front > d->n_full) d->halo_front = 0;   // a send id among the ghosts: no overlap
   return SWK_OK;
 }
 

@@ -554,12 +554,13 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
 
 // Pass B1 (substep 0): flux + dt partials.  writes eu, max_speed, dt_min_bits.
 template <bool RW>
-__global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int first, int write_speed)
+__global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int first, int write_speed,
+                                                            int k0, int k1)
 {
   if (D.clock->stop) return;
-  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
   double dtmin = 1.0e+100;
-  if (k < D.N) {
+  if (k < k1) {
     const i4 p = D.connB[k];
     const Eff own = effective(D.cq[k], K);
     const TriFlux T = triangle_flux<RW>(D, K, k, p, own, first != 0);
@@ -573,11 +574,12 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int
 }
 
 // Pass B2 (substep 0): friction + update + fix-negative (+ RK backup), dt from the clock.
-__global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U, double dt_override)
+__global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U, double dt_override,
+                                                  int k0, int k1)
 {
   if (D.clock->stop) return;
-  const int k = blockIdx.x * BLOCK + threadIdx.x;
-  if (k >= D.N) return;
+  const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= k1) return;
   const double dt = (dt_override >= 0.0) ? dt_override : D.clock->dt;
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
@@ -587,11 +589,11 @@ __global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U,
 // Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
 // dt is already known, so explicit updates never touch HBM.  (Not used with
 // riverwalls: the weir branch reads the neighbour's stage centroid, :635.)
-__global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux_update(Dev D, Consts K, UpdateArgs U)
+__global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux_update(Dev D, Consts K, UpdateArgs U, int k0, int k1)
 {
   if (D.clock->stop) return;
-  const int k = blockIdx.x * BLOCK + threadIdx.x;
-  if (k >= D.N) return;
+  const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
+  if (k >= k1) return;
   const double dt = D.clock->dt;
   const i4 p = D.connB[k];
   const d4 raw = D.cq[k];

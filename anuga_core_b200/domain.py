@@ -472,7 +472,14 @@ class Domain:
         the reference's "full first, ghosts after" numbering invariant survives."""
         perm = morton_order(self.centroid_coordinates)
         full = self.tri_full_flag[perm] == 1
-        return np.concatenate([perm[full], perm[~full]])
+        # halo-source triangles (listed in any full_send_dict) lead the numbering, so that the device
+        # can update them first and ship them while the interior is still being computed
+        send = np.zeros(self.number_of_triangles, dtype=bool)
+        for q, v in self.full_send_dict.items():
+            if q != self.processor:
+                send[np.asarray(v[0], dtype=np.int64)] = True
+        s = send[perm]
+        return np.concatenate([perm[full & s], perm[full & ~s], perm[~full]])
 
     _DEVICE_NAMES = {"stage": "STAGE", "xmomentum": "XMOM", "ymomentum": "YMOM",
                      "elevation": "ELEVATION", "height": "HEIGHT"}
