@@ -107,6 +107,7 @@ SYMBOLS = {
     "swk_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "swk_last_error": (C.c_char_p, []),
     "swk_abi_version": (C.c_int, []),
+    "swk_build_neighbour_structure": (C.c_int, [_I, _I, _PI, _PI, _PI, _PI]),
     "swk_create": (C.c_int, [C.POINTER(SwkMesh), C.POINTER(SwkParams), C.c_int, C.POINTER(_H)]),
     "swk_destroy": (C.c_int, [_H]),
     "swk_set_params": (C.c_int, [_H, C.POINTER(SwkParams)]),
@@ -463,3 +464,21 @@ class DeviceDomain:
         sp = (_PI * max(n, 1))(*[_pi(a) for a in s_arr])
         rp = (_PI * max(n, 1))(*[_pi(a) for a in r_arr])
         _check(self.lib.swk_set_halo(self.h, n, ranks, _pi(sc), sp, _pi(rc), rp))
+
+
+def build_neighbour_structure_native(triangles, number_of_nodes):
+    """neighbours, neighbour_edges, number_of_boundaries through libswk's host-side helper
+    (the reference also does this natively, neighbour_table.cpp); None when the library is absent."""
+    try:
+        lib = load_library()
+    except (SwkError, OSError):
+        return None
+    tri = _i64(triangles)
+    N = tri.shape[0]
+    nb = np.empty((N, 3), dtype=np.int64)
+    ne = np.empty((N, 3), dtype=np.int64)
+    nob = np.empty(N, dtype=np.int64)
+    code = lib.swk_build_neighbour_structure(N, int(number_of_nodes), _pi(tri), _pi(nb), _pi(ne), _pi(nob))
+    if code != SWK_OK:
+        raise Exception(lib.swk_last_error().decode())
+    return nb, ne, nob

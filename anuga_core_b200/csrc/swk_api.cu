@@ -308,6 +308,66 @@ static int select_device(int device)
 }
 
 // ----------------------------------------------------------------------------
+// host-side set-up helper: neighbour structure by sorting the directed edges
+// ----------------------------------------------------------------------------
+struct EdgeKey { uint64_t key; uint32_t idx; uint32_t pad; };
+
+// LSD radix sort of 16-byte (key, idx) records on the low `bits` bits of the key
+static void radix_sort_keys(std::vector<EdgeKey> &a, int bits)
+{
+  std::vector<EdgeKey> b(a.size());
+  const int RB = 11, R = 1 << RB;
+  std::vector<size_t> count(R);
+  for (int shift = 0; shift < bits; shift += RB) {
+    std::fill(count.begin(), count.end(), 0);
+    for (const EdgeKey &x : a) count[(x.key >> shift) & (R - 1)]++;
+    size_t sum = 0;
+    for (int r = 0; r < R; r++) { const size_t c = count[r]; count[r] = sum; sum += c; }
+    for (const EdgeKey &x : a) b[count[(x.key >> shift) & (R - 1)]++] = x;
+    a.swap(b);
+  }
+}
+
+extern "C" int swk_build_neighbour_structure(int64_t N, int64_t nn, const int64_t *tri, int64_t *neighbours,
+                                             int64_t *neighbour_edges, int64_t *number_of_boundaries)
+{
+  if (N < 0 || nn <= 0 || !tri || !neighbours || !neighbour_edges || !number_of_boundaries)
+    return fail(SWK_ERR_ARG, "bad argument");
+  if ((double)nn * (double)nn >= 9.0e18) return fail(SWK_ERR_ARG, "too many nodes");
+  // directed edge (a, b) of triangle k, edge e (opposite vertex e): key a*nn+b; its twin is (b, a)
+  static const int A[3] = {1, 2, 0}, B[3] = {2, 0, 1};
+  std::vector<EdgeKey> fwd((size_t)3 * N), rev((size_t)3 * N);
+  for (int64_t k = 0; k < N; k++)
+    for (int e = 0; e < 3; e++) {
+      const uint64_t a = (uint64_t)tri[3 * k + A[e]], b = (uint64_t)tri[3 * k + B[e]];
+      if (a >= (uint64_t)nn || b >= (uint64_t)nn) return fail(SWK_ERR_ARG, "triangle refers to a node >= number_of_nodes");
+      fwd[3 * k + e] = {a * (uint64_t)nn + b, (uint32_t)(3 * k + e), 0};
+      rev[3 * k + e] = {b * (uint64_t)nn + a, (uint32_t)(3 * k + e), 0};
+    }
+  int bits = 1;
+  while (bits < 63 && ((uint64_t)1 << bits) < (uint64_t)nn * (uint64_t)nn) bits++;
+  radix_sort_keys(fwd, bits);
+  radix_sort_keys(rev, bits);
+  for (size_t j = 1; j < fwd.size(); j++)
+    if (fwd[j].key == fwd[j - 1].key)
+      return fail(SWK_ERR_ARG, "Edge " + std::to_string(fwd[j].idx % 3) + " of triangle " +
+                                   std::to_string(fwd[j].idx / 3) + " is duplicating an edge of another triangle");
+  for (int64_t k = 0; k < N; k++) number_of_boundaries[k] = 3;
+  for (int64_t j = 0; j < 3 * N; j++) { neighbours[j] = -1; neighbour_edges[j] = -1; }
+  size_t f = 0;
+  for (size_t r = 0; r < rev.size(); r++) {          // both sorted: one linear merge
+    while (f < fwd.size() && fwd[f].key < rev[r].key) f++;
+    if (f < fwd.size() && fwd[f].key == rev[r].key) {
+      const uint32_t me = rev[r].idx, other = fwd[f].idx;
+      neighbours[me] = other / 3;
+      neighbour_edges[me] = other % 3;
+      number_of_boundaries[me / 3]--;
+    }
+  }
+  return SWK_OK;
+}
+
+// ----------------------------------------------------------------------------
 // create / destroy
 // ----------------------------------------------------------------------------
 extern "C" int swk_destroy(swk_domain *d)

@@ -125,6 +125,11 @@ def build_neighbour_structure(triangles, number_of_nodes):
     """
     tri = np.ascontiguousarray(triangles, dtype=np.int64)
     N = tri.shape[0]
+    if N >= 200000:          # large meshes: libswk's native helper (same result, ~10x faster)
+        from . import backend
+        res = backend.build_neighbour_structure_native(tri, number_of_nodes)
+        if res is not None:
+            return res
     nn = np.int64(number_of_nodes)
     src = np.empty((N, 3), dtype=np.int64)
     dst = np.empty((N, 3), dtype=np.int64)
@@ -154,7 +159,7 @@ class Mesh:
     """Static mesh data with the reference's attribute names and layouts."""
 
     def __init__(self, coordinates, triangles, boundary=None,
-                 use_inscribed_circle=False):
+                 use_inscribed_circle=False, neighbour_structure=None):
         self.nodes = np.ascontiguousarray(coordinates, dtype=np.float64)
         self.triangles = np.ascontiguousarray(triangles, dtype=np.int64)
         if self.nodes.ndim != 2 or self.nodes.shape[1] != 2:
@@ -220,8 +225,10 @@ class Mesh:
         E[2::3] = 0.5 * (V[0::3] + V[1::3])
         self.edge_midpoint_coordinates = E
 
-        (self.neighbours, self.neighbour_edges,
-         self.number_of_boundaries) = build_neighbour_structure(self.triangles, self.number_of_nodes)
+        if neighbour_structure is None:
+            neighbour_structure = build_neighbour_structure(self.triangles, self.number_of_nodes)
+        # (a sub-mesh cut out of a larger mesh may pass the structure it already knows)
+        self.neighbours, self.neighbour_edges, self.number_of_boundaries = neighbour_structure
         rng = np.arange(N, dtype=np.int64)[:, None]
         self.surrogate_neighbours = np.where(self.neighbours < 0, rng, self.neighbours)
 
@@ -278,6 +285,22 @@ class Mesh:
 
     def get_areas(self):
         return self.areas
+
+
+class Topology:
+    """neighbours + boundary of a triangle table without the geometry (what the partition needs)"""
+
+    def __init__(self, number_of_nodes, triangles, boundary):
+        self.triangles = np.ascontiguousarray(triangles, dtype=np.int64)
+        self.number_of_triangles = len(self.triangles)
+        (self.neighbours, self.neighbour_edges,
+         self.number_of_boundaries) = build_neighbour_structure(self.triangles, number_of_nodes)
+        b = dict(boundary) if boundary else {}
+        vols, edges = np.nonzero(self.neighbours < 0)
+        for v, e in zip(vols.tolist(), edges.tolist()):
+            if (v, e) not in b:
+                b[(v, e)] = DEFAULT_BOUNDARY_TAG
+        self.boundary = b
 
 
 def morton_order(centroid_coordinates, bits=21):

@@ -27,7 +27,7 @@ import os
 
 import numpy as np
 
-from .mesh import Mesh, rectangular_cross
+from .mesh import Mesh, Topology, rectangular_cross
 from .domain import Domain
 from .boundaries import Reflective_boundary
 from .operators import Rate_operator
@@ -106,7 +106,7 @@ def partition_mesh(nodes, triangles, boundary, triangles_per_proc, ghost_layer_w
     nodes = np.asarray(nodes, dtype=np.float64)
     triangles = np.asarray(triangles, dtype=np.int64)
     if mesh is None:
-        mesh = Mesh(nodes, triangles, boundary)
+        mesh = Topology(len(nodes), triangles, boundary)
     neighbours = mesh.neighbours
     gboundary = mesh.boundary
     nproc = len(triangles_per_proc)
@@ -158,7 +158,16 @@ def partition_mesh(nodes, triangles, boundary, triangles_per_proc, ghost_layer_w
                 mine = np.sort(mine)
                 full_send[q] = [tri_map[mine], mine]
         tri_l2g = np.concatenate([np.arange(tl, tu), ghosts])
-        out[p] = dict(points=nodes[node_ids], triangles=ltri, boundary=lb, full_send_dict=full_send,
+        # neighbour structure of the local mesh = the global one restricted to the local triangles
+        gn = neighbours[tri_l2g]
+        inside = gn >= 0
+        inside[inside] = tri_map[np.minimum(gn[inside], nglobal)] >= 0
+        inside &= gn <= nglobal
+        ln = np.where(inside, tri_map[np.clip(gn, 0, nglobal)], -1)
+        lne = np.where(inside, mesh.neighbour_edges[tri_l2g], -1)
+        lnb = 3 - inside.sum(axis=1)
+        out[p] = dict(neighbour_structure=(ln.astype(np.int64), lne.astype(np.int64), lnb.astype(np.int64)),
+                      points=nodes[node_ids], triangles=ltri, boundary=lb, full_send_dict=full_send,
                       ghost_recv_dict=ghost_recv, tri_l2g=tri_l2g, node_l2g=node_ids,
                       number_of_full_triangles=tu - tl, number_of_full_nodes=len(full_node_ids),
                       ghost_layer_width=ghost_layer_width)
@@ -177,7 +186,9 @@ def distribute(domain, nparts, epart=None, ghost_layer_width=2, ranks=None, doma
     out = {}
     for p, sub in parts.items():
         kw = dict(domain_kw or {})
-        d = Domain(sub["points"], sub["triangles"], sub["boundary"], full_send_dict=sub["full_send_dict"],
+        d = Domain(mesh=Mesh(sub["points"], sub["triangles"], sub["boundary"],
+                             neighbour_structure=sub["neighbour_structure"]),
+                   full_send_dict=sub["full_send_dict"],
                    ghost_recv_dict=sub["ghost_recv_dict"], processor=p, numproc=nparts,
                    number_of_full_triangles=sub["number_of_full_triangles"],
                    ghost_layer_width=ghost_layer_width, **kw)
@@ -253,7 +264,7 @@ def strip_slab(m, n, rank, nranks, len1=None, len2=None, ghost_layer_width=2, pa
     keep = [k for k, c in enumerate(tpp) if c > 0]
     me = keep.index(1)
     tpp_nz = [tpp[k] for k in keep]
-    smesh = Mesh(pts, tri, bnd)
+    smesh = Topology(len(pts), tri, bnd)
     # cut edges of the slab are not physical boundaries: they only touch triangles farther than
     # `pad` columns away from the rank's strip, which never enter a width<=pad ghost layer
     sub = partition_mesh(pts, tri, smesh.boundary, tpp_nz, ghost_layer_width, ranks=[me], mesh=smesh)[me]
@@ -293,7 +304,9 @@ def strip_partitioned_sweep_domain(m, n, rank, nranks, device=0, alg="DE1", rain
     """configs[3]/[4] building block: rank's strip of rectangular_cross(m, n) with the
     roofline-sweep fields of workloads.roofline_sweep_domain."""
     sub = strip_slab(m, n, rank, nranks)
-    d = Domain(sub["points"], sub["triangles"], sub["boundary"], full_send_dict=sub["full_send_dict"],
+    d = Domain(mesh=Mesh(sub["points"], sub["triangles"], sub["boundary"],
+                         neighbour_structure=sub["neighbour_structure"]),
+               full_send_dict=sub["full_send_dict"],
                ghost_recv_dict=sub["ghost_recv_dict"], processor=rank, numproc=nranks,
                number_of_full_triangles=sub["number_of_full_triangles"], ghost_layer_width=2, device=device)
     d.tri_l2g = sub["tri_l2g"]

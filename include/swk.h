@@ -163,6 +163,15 @@ typedef struct {
   int64_t kernel_launches;         /* library kernels launched by this call */
 } swk_evolve_result;
 
+/* ---- host-side set-up helper (no GPU needed) --------------------------------------------------
+ * Neighbour structure of a triangle table, the job of the reference's native
+ * neighbour_table.cpp (build_neighbour_structure, semantics of neighbour_mesh.py:234-294):
+ * neighbours / neighbour_edges (N,3) filled with -1 where there is no neighbour,
+ * number_of_boundaries (N,).  Returns SWK_ERR_ARG when two triangles own the same directed edge. */
+int swk_build_neighbour_structure(int64_t number_of_triangles, int64_t number_of_nodes,
+                                  const int64_t *triangles, int64_t *neighbours,
+                                  int64_t *neighbour_edges, int64_t *number_of_boundaries);
+
 /* =========================== (1) RESIDENT LAYER ================================ */
 
 /* Number of usable sm_100 devices (0 and SWK_ERR_CUDA semantics: *count = 0). */

@@ -73,6 +73,11 @@ def test_strip_slab_equals_global_partition(m, n, R):
         for k in ("tri_l2g", "node_l2g", "points", "triangles"):
             assert np.array_equal(sl[k], g[k]), (r, k)
         assert sl["boundary"] == g["boundary"]
+        # the neighbour structure handed over from the slab == the one rebuilt from the local triangles
+        rebuilt = ab.Mesh(sl["points"], sl["triangles"], sl["boundary"])
+        given = ab.Mesh(sl["points"], sl["triangles"], sl["boundary"], neighbour_structure=sl["neighbour_structure"])
+        for k in ("neighbours", "neighbour_edges", "number_of_boundaries", "surrogate_neighbours", "boundary_cells"):
+            assert np.array_equal(getattr(rebuilt, k), getattr(given, k)), (r, k)
         for k in ("full_send_dict", "ghost_recv_dict"):
             assert sorted(sl[k]) == sorted(g[k])
             for q in g[k]:
