@@ -117,6 +117,9 @@ SYMBOLS = {
     "swk_set_boundary_values": (C.c_int, [_H, C.c_int, _PD]),
     "swk_add_rate_operator": (C.c_int, [_H, _D, _D, _PD, _PI, _I, C.POINTER(C.c_int)]),
     "swk_set_rate": (C.c_int, [_H, C.c_int, _D, _D]),
+    "swk_gather_centroids": (C.c_int, [_H, _PI, _I, _PD]),
+    "swk_scatter_centroids": (C.c_int, [_H, _PI, _I, _PD]),
+    "swk_add_fractional_step_volume": (C.c_int, [_H, _D]),
     "swk_set_local_ghost_copy": (C.c_int, [_H, _PI, _PI, _I]),
     "swk_set_time": (C.c_int, [_H, _D]),
     "swk_protect": (C.c_int, [_H, _PD]),
@@ -336,6 +339,21 @@ class DeviceDomain:
 
     def set_rate(self, op_id, rate, factor=1.0):
         _check(self.lib.swk_set_rate(self.h, int(op_id), float(rate), float(factor)))
+
+    def gather_centroids(self, ids):
+        """(n,4) {stage, xmomentum, ymomentum, elevation} of the listed triangles"""
+        ids = _i64(ids)
+        out = np.empty((ids.size, 4), dtype=np.float64)
+        _check(self.lib.swk_gather_centroids(self.h, _pi(ids), ids.size, _pd(out)))
+        return out
+
+    def scatter_centroids(self, ids, values):
+        ids = _i64(ids)
+        v = _f64(values).reshape(ids.size, 3)
+        _check(self.lib.swk_scatter_centroids(self.h, _pi(ids), ids.size, _pd(v)))
+
+    def add_fractional_step_volume(self, volume):
+        _check(self.lib.swk_add_fractional_step_volume(self.h, float(volume)))
 
     def set_local_ghost_copy(self, full_ids, ghost_ids):
         f, g = _i64(full_ids), _i64(ghost_ids)

@@ -692,6 +692,9 @@ static int ensure_staging(swk_domain *d, size_t n)
     (d)->launches++;                                                 \
   } while (0)
 
+static int pull_clock(swk_domain *d);
+static int push_clock(swk_domain *d);
+
 static int sync_check(swk_domain *d)
 {
   CK(cudaStreamSynchronize(d->stream));
@@ -881,6 +884,56 @@ extern "C" int swk_set_rate(swk_domain *d, int op_id, double rate, double factor
   if (!op.d_rate_array) op.all_nonneg = (rate >= 0.0) ? 1 : 0;
   d->graph_valid = false;
   return SWK_OK;
+}
+
+static int cell_ids_to_device(swk_domain *d, const int64_t *ids, int64_t n, int **d_ids)
+{
+  std::vector<int> v(n);
+  for (int64_t j = 0; j < n; j++) {
+    if (ids[j] < 0 || ids[j] >= d->N) return fail(SWK_ERR_ARG, "triangle id out of range");
+    v[j] = d->old2new[ids[j]];
+  }
+  CKV(dalloc(d_ids, (size_t)n));
+  return upload(*d_ids, v);
+}
+
+extern "C" int swk_gather_centroids(swk_domain *d, const int64_t *ids, int64_t n, double *out)
+{
+  if (!d || !ids || !out || n < 0) return fail(SWK_ERR_ARG, "bad argument");
+  if (n == 0) return SWK_OK;
+  CK(cudaSetDevice(d->device));
+  int *d_ids = nullptr;
+  CKV(cell_ids_to_device(d, ids, n, &d_ids));
+  CKV(ensure_staging(d, (size_t)std::max<int64_t>(4 * n, 3LL * d->N)));
+  LAUNCH(d, k_gather_cells, nblk(n), BLOCK, d->D, d_ids, (int)n, d->staging);
+  cudaError_t e = cudaMemcpyAsync(out, d->staging, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, d->stream);
+  int rc = (e == cudaSuccess) ? sync_check(d) : fail(SWK_ERR_CUDA, cudaGetErrorString(e));
+  cudaFree(d_ids);
+  return rc;
+}
+
+extern "C" int swk_scatter_centroids(swk_domain *d, const int64_t *ids, int64_t n, const double *in)
+{
+  if (!d || !ids || !in || n < 0) return fail(SWK_ERR_ARG, "bad argument");
+  if (n == 0) return SWK_OK;
+  CK(cudaSetDevice(d->device));
+  int *d_ids = nullptr;
+  CKV(cell_ids_to_device(d, ids, n, &d_ids));
+  CKV(ensure_staging(d, (size_t)std::max<int64_t>(4 * n, 3LL * d->N)));
+  cudaError_t e = cudaMemcpyAsync(d->staging, in, 3 * n * sizeof(double), cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) LAUNCH(d, k_scatter_cells, nblk(n), BLOCK, d->D, d_ids, (int)n, d->staging);
+  int rc = (e == cudaSuccess) ? sync_check(d) : fail(SWK_ERR_CUDA, cudaGetErrorString(e));
+  cudaFree(d_ids);
+  return rc;
+}
+
+extern "C" int swk_add_fractional_step_volume(swk_domain *d, double volume)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(pull_clock(d));
+  d->h_clock->fractional_step_volume_integral += volume;
+  return push_clock(d);
 }
 
 extern "C" int swk_set_local_ghost_copy(swk_domain *d, const int64_t *full_ids, const int64_t *ghost_ids, int64_t n)

@@ -989,3 +989,22 @@ __global__ void k_bfi_update(Clock *c, TimeParams P)
 }  // namespace swk
 
 
+
+namespace swk {
+__global__ void __launch_bounds__(BLOCK) k_gather_cells(Dev D, const int *ids, int n, double *out)
+{
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= n) return;
+  const d4 c = D.cq[ids[j]];
+  out[4 * j] = c.x; out[4 * j + 1] = c.y; out[4 * j + 2] = c.z; out[4 * j + 3] = c.w;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_scatter_cells(Dev D, const int *ids, int n, const double *in)
+{
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= n) return;
+  d4 c = D.cq[ids[j]];
+  c.x = in[3 * j]; c.y = in[3 * j + 1]; c.z = in[3 * j + 2];
+  D.cq[ids[j]] = c;
+}
+}  // namespace swk

@@ -431,7 +431,8 @@ class Domain:
             for q in self.quantities.values():
                 q.host_dirty = True
             for op in self.fractional_step_operators:
-                op.op_id = None
+                if not getattr(op, "host_side", False):
+                    op.op_id = None
             if self.processor in self.full_send_dict and self.processor in self.ghost_recv_dict:
                 self._dev.set_local_ghost_copy(self.full_send_dict[self.processor][0],
                                                self.ghost_recv_dict[self.processor][0])
@@ -554,6 +555,8 @@ class Domain:
     def _push_operators(self, t):
         dev = self._dev
         for op in self.fractional_step_operators:
+            if getattr(op, "host_side", False):
+                continue
             if op.op_id is None:
                 op.op_id = dev.add_rate_operator(op.current_rate(t), op.current_factor(t),
                                                  op.rate_array, op.indices)
@@ -849,8 +852,15 @@ class Domain:
                 return 1
 
     def _host_fractional_steps(self):
-        """apply_fractional_steps (generic_domain.py:2312) for a host-driven step"""
+        """apply_fractional_steps (generic_domain.py:2312) for a host-driven step: the device
+        operators (boundary-flux integral, Rate_operators) first, then host-side operators in
+        registration order on gathered cells.  (Mixed orders are not supported.)"""
         self._dev.apply_fractional_steps(self.timestep)
+        for op in self.fractional_step_operators:
+            if getattr(op, "host_side", False):
+                added = op()
+                if added != 0.0:
+                    self._dev.add_fractional_step_volume(added)
         r = self._dev.get_statistics()
         self.boundary_flux_integral = r.boundary_flux_integral
         self.fractional_step_volume_integral = r.fractional_step_volume_integral

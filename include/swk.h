@@ -202,6 +202,15 @@ int swk_add_rate_operator(swk_domain *d, double rate, double factor, const doubl
                           const int64_t *indices, int64_t n_indices, int *op_id);
 int swk_set_rate(swk_domain *d, int op_id, double rate, double factor);
 
+/* Small index sets (inlets, structures, gauges): read / write the centroid records of `n` triangles
+ * without moving whole arrays.  out: (n,4) row-major {stage, xmomentum, ymomentum, elevation};
+ * in: (n,3) {stage, xmomentum, ymomentum}.  Used by host-side operators that do scalar hydraulics on a
+ * handful of cells per step (structures/inlet.py:69-190, inlet_operator.py:78-157).              */
+int swk_gather_centroids(swk_domain *d, const int64_t *ids, int64_t n, double *out);
+int swk_scatter_centroids(swk_domain *d, const int64_t *ids, int64_t n, const double *in);
+/* fractional_step_volume_integral += volume (host-side operators account their own water) */
+int swk_add_fractional_step_volume(swk_domain *d, double volume);
+
 /* Single-process ghost copy (Generic_Domain.update_ghosts :2448-2469):
  * centroid values of full_ids are copied onto ghost_ids after each update.       */
 int swk_set_local_ghost_copy(swk_domain *d, const int64_t *full_ids, const int64_t *ghost_ids,

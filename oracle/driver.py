@@ -469,6 +469,8 @@ class OracleDomain:
         for op in self.operators:
             if op[0] == "rate":
                 self._rate_operator(op[1])
+            elif op[0] == "inlet":
+                self._inlet_operator(op[1])
             else:
                 raise ValueError("unknown operator %r" % (op[0],))
 
@@ -501,6 +503,55 @@ class OracleDomain:
         areas = self.areas[sl]
         fsel = full[sl]
         self.fractional_step_volume_integral += float(np.sum((local_rates * areas)[fsel]))
+
+    def _inlet_operator(self, o):
+        """structures/inlet_operator.py:78-157 with structures/inlet.py:107-227"""
+        idx = np.asarray(o["indices"], dtype=np.int64)
+        dt = self.timestep
+        t = self.get_time()
+        Qf = o["Q"]
+        q = (lambda tt: float(Qf(tt))) if callable(Qf) else (lambda tt: float(Qf))
+        areas = self.areas[idx]
+        total_area = np.sum(areas)
+        stages = self.stage_c[idx]
+        elev = self.bed_c[idx]
+        depths = stages - elev
+        current_volume = np.sum(depths * areas)
+        Q = 0.5 * (q(t) + q(t + dt))
+        volume = Q * dt
+        u = self.xmom_c[idx] * depths / (depths * depths + 1.0e-6)
+        v = self.ymom_c[idx] * depths / (depths * depths + 1.0e-6)
+
+        def set_momenta():
+            d2 = self.stage_c[idx] - elev
+            if o.get("velocity") is not None:
+                self.xmom_c[idx] = d2 * o["velocity"][0]
+                self.ymom_c[idx] = d2 * o["velocity"][1]
+            else:
+                self.xmom_c[idx] = d2 * u
+                self.ymom_c[idx] = d2 * v
+            if o.get("zero_velocity"):
+                self.xmom_c[idx] = 0.0
+                self.ymom_c[idx] = 0.0
+        if volume >= 0.0:
+            order = stages.argsort()
+            summed_areas = np.cumsum(areas[order])
+            summed_volume = np.zeros_like(areas)
+            summed_volume[1:] = np.cumsum(summed_areas[:-1] * np.diff(stages[order]))
+            index = np.nonzero(summed_volume <= volume)[0][-1]
+            depth = (volume - summed_volume[index]) / summed_areas[index]
+            new = stages.copy()
+            new[order[0:index + 1]] = stages[order[index]] + depth
+            self.stage_c[idx] = new
+            self.fractional_step_volume_integral += volume
+            set_momenta()
+        elif current_volume + volume >= 0.0:
+            self.stage_c[idx] = elev + (current_volume + volume) / total_area
+            self.fractional_step_volume_integral += volume
+            set_momenta()
+        else:
+            self.stage_c[idx] = elev + 0.0
+            self.fractional_step_volume_integral -= current_volume
 
     # -- evolve ------------------------------------------------------------------
     def evolve(self, yieldstep=None, finaltime=None, duration=None, skip_initial_step=False):

@@ -156,6 +156,22 @@ def low_froude_de1(A):
     return d
 
 
+def _inlet_indices(d, x0, x1, y0, y1):
+    c = d.centroid_coordinates
+    return np.flatnonzero((c[:, 0] > x0) & (c[:, 0] < x1) & (c[:, 1] > y0) & (c[:, 1] < y1))
+
+
+def inlet_de1(A, n=16):
+    """config[4] building block: Inlet_operator with a discharge hydrograph on a sloping, partly dry
+    bed (structures/inlet_operator.py), plus a second inlet that extracts water"""
+    d = beach_de1(A, n=n)
+    L = float(n)
+    A.Inlet_operator(d, A.Region(d, indices=_inlet_indices(d, 0.55 * L, 0.7 * L, 0.3 * L, 0.6 * L)),
+                     Q=lambda t: 2.0 + 1.5 * np.sin(t))
+    A.Inlet_operator(d, A.Region(d, indices=_inlet_indices(d, 0.0, 0.15 * L, 0.0, 0.3 * L)), Q=-1.0)
+    return d
+
+
 CASES = {
     "kat_bedslope_more_steps": (kat_bedslope_more_steps, dict(yieldstep=0.05, finaltime=0.5)),
     "dam_break_de0": (dam_break_de0, dict(yieldstep=1.0, finaltime=6.0)),
@@ -171,6 +187,7 @@ CASES = {
     "drain_de1": (drain_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "sloped_manning_de1": (sloped_manning_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
+    "inlet_de1": (inlet_de1, dict(yieldstep=1.0, finaltime=3.0)),
 }
 
 # 8-digit expected values embedded in the reference's own test (the KAT proper)
