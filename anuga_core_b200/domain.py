@@ -699,7 +699,17 @@ class Domain:
             substep(2)
             self._check_negative(dev.update_conserved_quantities(dt))
             dev.saxpy_conserved_quantities(2.0, 1.0, 3.0)
-        self.relative_time = t0
+            self.relative_time = t0 + dt
+        # NB the reference leaves relative_time advanced by dt after an rk2 / rk3 step (set_relative_time,
+        # generic_domain.py:2011, 2176) and only _evolve_base resets it after apply_fractional_steps
+        # (:1849-1855): fractional-step operators therefore see t0 + dt (euler: t0).  Kept.
+
+    def _host_step_with_operators(self):
+        """evolve_one_*_step + apply_fractional_steps; time-dependent rates are evaluated at the
+        time the reference's operators see (see _host_step)"""
+        self._host_step()
+        self._push_operators(self.get_time())
+        self._host_fractional_steps()
 
     def _check_negative(self, n):
         self._negative_cells = getattr(self, "_negative_cells", 0) + n
@@ -824,9 +834,7 @@ class Domain:
             self._push_operators(self.get_time())
             # the whole step on the device when nothing depends on the substep time,
             # else substep by substep
-            self._host_step()
-            # apply_fractional_steps runs inside swk_evolve's step; here do it explicitly:
-            self._host_fractional_steps()
+            self._host_step_with_operators()
             self.relative_time = t0 + self.timestep
             dev.set_time(self.relative_time)
             dev.update_ghosts()

@@ -135,6 +135,13 @@ def rain_de1(A, n=30):
     return d
 
 
+def rain_time_de1(A):
+    """rate as a function of time: evaluated at the time the operators see after an rk2 step"""
+    d = beach_de1(A, n=16)
+    A.Rate_operator(d, rate=lambda t: 2.0e-3 * (1.0 + np.sin(3.0 * t)), factor=0.75)
+    return d
+
+
 def drain_de1(A):
     """negative rate: the clamped branch of Rate_operator (rate_operators.py:213-245)"""
     d = beach_de1(A, n=16)
@@ -188,6 +195,7 @@ CASES = {
     "sloped_manning_de1": (sloped_manning_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "inlet_de1": (inlet_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "rain_time_de1": (rain_time_de1, dict(yieldstep=1.0, finaltime=3.0)),
 }
 
 # 8-digit expected values embedded in the reference's own test (the KAT proper)

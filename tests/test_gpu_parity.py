@@ -42,8 +42,7 @@ def test_evolve_matches_python_reference_golden(name):
     d1._push_quantities()
     if d1._needs_host_stepping():
         d1.relative_yieldtime = d1.relative_time + ev["yieldstep"]
-        d1._host_step()
-        d1._host_fractional_steps()
+        d1._host_step_with_operators()
         d1._mark_device_newer()
         dt1 = d1.timestep
     else:
