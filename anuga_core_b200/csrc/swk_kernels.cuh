@@ -1008,3 +1008,4 @@ __global__ void __launch_bounds__(BLOCK) k_scatter_cells(Dev D, const int *ids, 
   D.cq[ids[j]] = c;
 }
 }  // namespace swk
+
