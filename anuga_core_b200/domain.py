@@ -245,6 +245,33 @@ class Domain:
     def get_multiprocessor_mode(self):
         return self.multiprocessor_mode
 
+    def compute_flux_update_frequency(self, *a, **k):
+        """local time-stepping is a no-op in the reference's modes 2-4 as well
+        (sw_domain_openmp_ext.pyx:413-415)"""
+        return None
+
+    # checkpointing (shallow_water_domain.py:2376-2397 pickles the whole Domain): bring the state to
+    # the host and drop the device handle; it is rebuilt on the next evolve()
+    def __getstate__(self):
+        self.sync_to_host()
+        state = dict(self.__dict__)
+        state["_dev"] = None
+        state["_comm"] = None
+        state["_segments"] = {}
+        state.pop("_pushed_once", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        for q in self.quantities.values():
+            q.host_dirty = True
+            q._fetch = self._fetch_lazy
+        self._stale = set()
+        self._lazy_stale = set()
+        for op in self.fractional_step_operators:
+            if hasattr(op, "op_id"):
+                op.op_id = None
+
     # accepted for script compatibility; SWW output is out of scope (SURVEY.md 2, row 7)
     def set_store(self, flag=True):
         if flag:

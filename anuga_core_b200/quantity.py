@@ -34,6 +34,14 @@ class Quantity:
     def __len__(self):
         return self.N
 
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_fetch", None)          # bound method of the owning Domain: restored by Domain.__setstate__
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
     def __getattr__(self, name):
         if name in _LAZY:
             arrays = self.__dict__["_arrays"]

@@ -236,3 +236,66 @@ def test_riverwall_edges_match_reference_c_code(alg):
     # water did cross the wall
     assert (w - d2.quantities["elevation"].centroid_values)[d2.centroid_coordinates[:, 0] > 6.5].max() > 1e-3
     print("\nriverwall %s: %d steps, rel err %.2e" % (alg, d2.total_steps, e))
+
+
+def test_checkpoint_pickle_round_trip():
+    """set_checkpointing pickles the Domain (shallow_water_domain.py:2376-2397): a device-backed
+    domain must survive pickle.dumps / loads and continue bit-identically"""
+    import pickle
+    d = cases.beach_de1(ab, n=12)
+    it = d.evolve(yieldstep=0.5, finaltime=2.0)
+    next(it)
+    next(it)
+    blob = pickle.dumps(d)
+    rest = [t for t in it]
+    d2 = pickle.loads(blob)
+    assert d2._dev is None and d2.get_time() == 0.5
+    rest2 = [t for t in d2.evolve(yieldstep=0.5, finaltime=2.0)]
+    assert rest == rest2 == [1.0, 1.5, 2.0]
+    for name in ("stage", "xmomentum", "ymomentum"):
+        assert np.array_equal(d.quantities[name].centroid_values, d2.quantities[name].centroid_values)
+
+
+@pytest.mark.parametrize("size", [2000])
+def test_full_size_16M_properties_and_reference_parity(size):
+    """BASELINE.json configs[2] at full size (16,000,000 triangles, DE1 + rain):
+    (1) two timesteps agree with the reference's own C code (all host cores) to 1e-12,
+    (2) size-independent properties over more steps: volume balance
+        d(volume) == rain volume added (closed Reflective basin), stage >= bed everywhere,
+        the dt sequence is positive and below the CFL bound of the initial state."""
+    from anuga_core_b200 import workloads
+    d = workloads.roofline_sweep_domain(size, size, alg="DE1", rain=1.0e-4)
+    o = OracleDomain(domain_to_scenario(d), backend=REF)
+    it = d.evolve(yieldstep=1.0e9, finaltime=None)
+    next(it)
+    v0 = d.compute_total_volume()
+    dev = d._dev
+    r = dev.evolve(1.0e9, None, 2)
+    d._absorb(r)
+    d._mark_device_newer()
+    o.relative_finaltime = None
+    o.relative_yieldtime = 1.0e300
+    o.distribute_to_vertices_and_edges()
+    dts = []
+    for _ in range(2):
+        t0 = o.relative_time
+        o.evolve_one_rk2_step(None, None)
+        o.apply_fractional_steps()
+        o.relative_time = t0 + o.timestep
+        dts.append(o.timestep)
+    w, uh, vh = conserved(d)
+    assert r.timestep == dts[-1] and r.total_steps == 2
+    e = max(rel_err(w, o.stage_c), rel_err(uh, o.xmom_c), rel_err(vh, o.ymom_c))
+    assert e <= TOL_1STEP, e
+    del o
+    r = dev.evolve(1.0e9, None, 30)
+    d._absorb(r)
+    d._mark_device_newer()
+    v1 = d.compute_total_volume()
+    added = d.fractional_step_volume_integral
+    assert added > 0
+    assert abs((v1 - v0) - added) <= 1e-9 * v0
+    q = d.quantities
+    assert np.all(q["stage"].centroid_values >= q["elevation"].centroid_values)
+    assert 0.0 < r.timestep < 1.0
+    print("\n16M: 2-step rel err vs reference C %.2e; volume balance residual %.3e of %.3e" % (e, (v1 - v0) - added, v0))
