@@ -6,23 +6,37 @@ The hydraulics are scalar / O(inlet triangles) numpy on the HOST, on values gath
 device (swk_gather_centroids) and scattered back (swk_scatter_centroids); the big arrays stay
 resident.  SURVEY.md section 8(f) row 1.
 
-Region resolution from polygons / lines is mesh set-up geometry (anuga/geometry), outside the hot
-path: a Region here is a list of triangle indices, a circle or a polygon tested on centroids.
+Structure_operator / Boyd_box_operator (structures/structure_operator.py:13-330,
+structures/boyd_box_operator.py:8-460, structures/inlet_enquiry.py): a culvert moving water between
+two such exchange regions, driven by the energy difference at two enquiry triangles.  Same split:
+gather (inlet triangles + enquiry triangle), scalar hydraulics on the host, scatter.
+
+Region resolution is mesh set-up geometry (anuga/geometry), outside the hot path: a Region here is
+a list of triangle indices, a circle, a polygon (centroids inside, optionally plus every triangle
+cut by the outline: the reference's expand_polygon) or a line (triangles it cuts).
 """
+import math
+
 import numpy as np
 
 velocity_protection = 1.0e-6        # anuga/config.py:18
+g = 9.8                             # anuga/config.py
 
 
 class Region:
     """abstract_2d_finite_volumes/region.py:24-150, for indices / center+radius / polygon (centroids)"""
 
-    def __init__(self, domain, indices=None, polygon=None, center=None, radius=None, **unsupported):
-        for k, v in unsupported.items():
-            if v not in (None, False):
-                raise NotImplementedError("Region(%s=...) is set-up geometry outside the hot path" % k)
+    def __init__(self, domain, indices=None, polygon=None, center=None, radius=None, line=None, poly=None,
+                 expand_polygon=False, verbose=False):
         self.domain = domain
         c = domain.centroid_coordinates
+        if poly is not None:                      # region.py:118-131: 2 points = line, more = polygon
+            assert indices is None and polygon is None and line is None and center is None
+            poly = np.asarray(poly, dtype=np.float64)
+            if len(poly) > 2:
+                polygon = poly
+            else:
+                line = poly
         if indices is not None:
             self.indices = np.asarray(indices, dtype=np.int64)
             self.type = "user_defined"
@@ -31,8 +45,18 @@ class Region:
             self.indices = np.flatnonzero(d2 < radius ** 2).astype(np.int64)
             self.type = "circle"
         elif polygon is not None:
-            self.indices = np.flatnonzero(_inside_polygon(c, np.asarray(polygon, dtype=np.float64))).astype(np.int64)
+            polygon = np.asarray(polygon, dtype=np.float64)
+            ids = np.flatnonzero(_inside_polygon(c, polygon)).astype(np.int64)
+            if expand_polygon:                    # region.py:252-257
+                n = len(polygon)
+                for j in range(n):
+                    ids = np.union1d(ids, triangles_cut_by_segment(domain, polygon[j], polygon[(j + 1) % n]))
+            self.indices = ids.astype(np.int64)
             self.type = "polygon"
+        elif line is not None:
+            line = np.asarray(line, dtype=np.float64)
+            self.indices = triangles_cut_by_segment(domain, line[0], line[1])
+            self.type = "line"
         else:
             self.indices = None
             self.type = "all"
@@ -57,6 +81,51 @@ def _inside_polygon(points, poly):
         inside ^= cross
         j = i
     return inside
+
+
+def triangles_cut_by_segment(domain, p0, p1):
+    """ids (ascending) of the triangles a segment touches: one of their sides meets the segment
+    (closed ends), or the segment lies strictly inside.  Same predicate as the reference's
+    geometry/polygon.c:446-523, evaluated for all triangles at once."""
+    V = np.asarray(domain.vertex_coordinates, dtype=np.float64).reshape(-1, 3, 2)
+    p0 = np.asarray(p0, dtype=np.float64)
+    p1 = np.asarray(p1, dtype=np.float64)
+    u = p1 - p0
+    perp_u = np.array([-u[1], u[0]])
+    hit = np.zeros(len(V), dtype=bool)
+    beyond = np.zeros(len(V), dtype=np.int64)      # sides crossed by the supporting line past p1
+    before = np.zeros(len(V), dtype=np.int64)      # ... and ahead of p0
+    for j in range(3):
+        t0 = V[:, j]
+        w = V[:, (j + 1) % 3] - t0
+        perp_w = np.stack([-w[:, 1], w[:, 0]], axis=1)
+        den = u[0] * perp_w[:, 0] + u[1] * perp_w[:, 1]
+        ok = den != 0.0                           # parallel sides never count
+        v = t0 - p0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a = (v[:, 0] * perp_w[:, 0] + v[:, 1] * perp_w[:, 1]) / den
+            b = -(v[:, 0] * perp_u[0] + v[:, 1] * perp_u[1]) / (w[:, 0] * perp_u[0] + w[:, 1] * perp_u[1])
+        on_side = ok & (b >= 0.0) & (b <= 1.0)
+        hit |= on_side & (a >= 0.0) & (a <= 1.0)
+        beyond += on_side & (a > 1.0)
+        before += on_side & (a < 0.0)
+    hit |= (beyond >= 1) & (before >= 1)
+    return np.flatnonzero(hit).astype(np.int64)
+
+
+def triangle_containing_point(domain, point):
+    """lowest id of a triangle whose closed hull holds the point (neighbour_mesh.py:1057-1080)"""
+    V = np.asarray(domain.vertex_coordinates, dtype=np.float64).reshape(-1, 3, 2)
+    x, y = float(point[0]), float(point[1])
+    inside = np.ones(len(V), dtype=bool)
+    for j in range(3):
+        a, b = V[:, j], V[:, (j + 1) % 3]
+        cross = (b[:, 0] - a[:, 0]) * (y - a[:, 1]) - (b[:, 1] - a[:, 1]) * (x - a[:, 0])
+        inside &= cross >= -1.0e-12
+    ids = np.flatnonzero(inside)
+    if len(ids) == 0:
+        raise Exception("Point %s not found within a triangle" % str(point))
+    return int(ids[0])
 
 
 class Inlet:
@@ -108,6 +177,18 @@ class Inlet:
 
     def get_average_depth(self):
         return self.get_total_water_volume() / self.area
+
+    def get_average_stage(self):
+        return np.sum(self.get_stages() * self.get_areas()) / self.area
+
+    def get_average_xmom(self):
+        return np.sum(self.get_xmoms() * self.get_areas()) / self.area
+
+    def get_average_ymom(self):
+        return np.sum(self.get_ymoms() * self.get_areas()) / self.area
+
+    def get_average_elevation(self):
+        return np.sum(self.get_elevations() * self.get_areas()) / self.area
 
     def get_velocities(self):
         depths = self.get_depths()
@@ -231,3 +312,479 @@ class Inlet_operator:
     def oracle_spec(self):
         return ("inlet", dict(indices=self.inlet.triangle_indices.copy(), Q=self.Q, velocity=self.velocity,
                               zero_velocity=self.zero_velocity, default=self.default))
+
+
+# ======================================================================================
+# culverts: Inlet_enquiry, Structure_operator, Boyd_box_operator
+# ======================================================================================
+class Inlet_enquiry(Inlet):
+    """An exchange region plus the triangle whose state drives the structure
+    (structures/inlet_enquiry.py:10-161)."""
+
+    def __init__(self, domain, region, enquiry_pt, invert_elevation=None, outward_culvert_vector=None,
+                 verbose=False):
+        if not isinstance(region, Region):
+            region = Region(domain, poly=region, expand_polygon=True)      # inlet.py:26-29
+        Inlet.__init__(self, domain, region, verbose)
+        self.enquiry_pt = enquiry_pt
+        self.invert_elevation = invert_elevation
+        self.outward_culvert_vector = outward_culvert_vector
+        self.enquiry_index = triangle_containing_point(domain, enquiry_pt)
+        self.enquiry = None         # (4,) stage, xmom, ymom, elevation of the enquiry triangle
+        self._gather_ids = np.append(self.triangle_indices, self.enquiry_index).astype(np.int64)
+
+    def fetch(self):
+        both = self.domain._dev.gather_centroids(self._gather_ids)
+        self.values = both[:-1]
+        self.enquiry = both[-1]
+
+    def _write_through(self):
+        """an inlet write is visible to a later enquiry read when the enquiry triangle is an inlet
+        triangle (the reference reads and writes the same arrays)"""
+        k = np.flatnonzero(self.triangle_indices == self.enquiry_index)
+        if len(k):
+            self.enquiry[:3] = self.values[k[0], :3]
+
+    def get_enquiry_stage(self):
+        return self.enquiry[0]
+
+    def get_enquiry_xmom(self):
+        return self.enquiry[1]
+
+    def get_enquiry_ymom(self):
+        return self.enquiry[2]
+
+    def get_enquiry_elevation(self):
+        return self.enquiry[3]
+
+    def get_enquiry_invert_elevation(self):
+        return self.get_enquiry_elevation() if self.invert_elevation is None else self.invert_elevation
+
+    def get_enquiry_depth(self):
+        return max(self.get_enquiry_stage() - self.get_enquiry_invert_elevation(), 0.0)
+
+    def get_enquiry_water_depth(self):
+        return self.get_enquiry_stage() - self.get_enquiry_elevation()
+
+    def get_enquiry_velocity(self):
+        depth = self.get_enquiry_water_depth()
+        u = depth * self.get_enquiry_xmom() / (depth ** 2 + velocity_protection)
+        v = depth * self.get_enquiry_ymom() / (depth ** 2 + velocity_protection)
+        return u, v
+
+    def get_enquiry_speed(self):
+        u, v = self.get_enquiry_velocity()
+        return math.sqrt(u ** 2 + v ** 2)
+
+    def get_enquiry_velocity_head(self):
+        if getattr(self.domain, "use_new_velocity_head", False):
+            u, v = self.get_enquiry_velocity()
+            n1, n2 = self.outward_culvert_vector
+            normal_speed = min(u * n1 + v * n2, 0.0)     # only flow INTO the culvert counts
+            return 0.5 * normal_speed ** 2 / g
+        return 0.5 * self.get_enquiry_speed() ** 2 / g
+
+    def get_enquiry_total_energy(self):
+        return self.get_enquiry_velocity_head() + self.get_enquiry_stage()
+
+    def get_enquiry_specific_energy(self):
+        return self.get_enquiry_velocity_head() + self.get_enquiry_depth()
+
+
+def _unit(v, what):
+    length = math.sqrt(float(np.sum(v ** 2)))
+    assert length > 0.0, "The length of %s is less than 0" % what
+    return v / length, length
+
+
+class Structure_operator:
+    """Base of the culvert family: geometry of the two exchange regions and the semi-implicit
+    transfer of `Q` from the inflow to the outflow region (structure_operator.py:13-330).
+    Subclasses provide discharge_routine() -> (Q, barrel_speed, outlet_depth) and set
+    self.inflow / self.outflow."""
+    time_dependent = True
+    host_side = True
+    counter = 0
+
+    def __init__(self, domain, end_points=None, exchange_lines=None, enquiry_points=None,
+                 invert_elevations=None, width=None, height=None, diameter=None, z1=None, z2=None,
+                 blockage=None, barrels=None, apron=None, manning=None, enquiry_gap=None,
+                 use_momentum_jet=False, zero_outflow_momentum=True, use_old_momentum_method=True,
+                 always_use_Q_wetdry_adjustment=True, force_constant_inlet_elevations=False,
+                 description=None, label=None, structure_type=None, logging=None, verbose=None):
+        self.domain = domain
+        as_array = lambda a: None if a is None else np.array(a, dtype=np.float64)
+        self.end_points = as_array(end_points)
+        self.exchange_lines = as_array(exchange_lines)
+        self.enquiry_points = as_array(enquiry_points)
+        self.invert_elevations = as_array(invert_elevations)
+        assert self.end_points is None or self.exchange_lines is None
+        if force_constant_inlet_elevations:
+            raise NotImplementedError("force_constant_inlet_elevations edits the bed: outside the hot path")
+        if height is None:
+            height = width
+        if width is None:
+            width = diameter
+        if apron is None:
+            apron = width
+        assert width is not None
+        self.width, self.height, self.diameter = width, height, diameter
+        self.z1, self.z2, self.blockage, self.barrels = z1, z2, blockage, barrels
+        self.apron, self.manning, self.enquiry_gap = apron, manning, enquiry_gap
+        if use_momentum_jet and zero_outflow_momentum:
+            raise Exception("Can't have use_momentum_jet and zero_outflow_momentum both True")
+        self.use_momentum_jet = use_momentum_jet
+        self.zero_outflow_momentum = zero_outflow_momentum
+        self.use_old_momentum_method = use_old_momentum_method
+        self.always_use_Q_wetdry_adjustment = always_use_Q_wetdry_adjustment
+        self.description = " " if description is None else description
+        self.label = ("structure" if label is None else label) + "_%g" % Structure_operator.counter
+        self.structure_type = "generic structure" if structure_type is None else structure_type
+        self.verbose = verbose
+        Structure_operator.counter += 1
+
+        self.accumulated_flow = 0.0
+        self.discharge = 0.0
+        self.discharge_abs_timemean = 0.0
+        self.velocity = 0.0
+        self.outlet_depth = 0.0
+        self.delta_total_energy = 0.0
+        self.driving_energy = 0.0
+
+        if self.exchange_lines is not None:
+            self._skew_geometry()
+        elif self.end_points is not None:
+            self._straight_geometry()
+        else:
+            raise Exception("Define either exchange_lines or end_points")
+
+        self.inlets = []
+        for k, outward in ((0, self.outward_vector_0), (1, self.outward_vector_1)):
+            line = self.exchange_lines[k]
+            if self.apron is None:
+                poly = line
+            else:                      # the exchange region: the line swept `apron` away from the culvert
+                offset = -self.apron * outward
+                poly = np.array([line[0], line[1], line[1] + offset, line[0] + offset])
+            invert = None if self.invert_elevations is None else self.invert_elevations[k]
+            self.inlets.append(Inlet_enquiry(domain, poly, self.enquiry_points[k], invert_elevation=invert,
+                                             outward_culvert_vector=outward, verbose=verbose))
+        self.inflow, self.outflow = self.inlets
+        domain.set_fractional_step_operator(self)
+
+    # -- geometry (structure_operator.py:396-480) -----------------------------------------
+    def _straight_geometry(self):
+        self.culvert_vector, self.culvert_length = _unit(self.end_points[1] - self.end_points[0], "culvert")
+        self.outward_vector_0 = self.culvert_vector
+        self.outward_vector_1 = -self.culvert_vector
+        normal = np.array([-self.culvert_vector[1], self.culvert_vector[0]])
+        half = 0.5 * self.width * normal
+        self.exchange_lines = [np.array([self.end_points[i] + half, self.end_points[i] - half]) for i in (0, 1)]
+        if self.enquiry_points is None:
+            gap = (self.apron + self.enquiry_gap) * self.culvert_vector
+            self.enquiry_points = [self.end_points[i] + (2 * i - 1) * gap for i in (0, 1)]
+
+    def _skew_geometry(self):
+        lines = self.exchange_lines
+        centre0 = 0.5 * (lines[0][0] + lines[0][1])
+        centre1 = 0.5 * (lines[1][0] + lines[1][1])
+        n0, n1 = len(lines[0]), len(lines[1])
+        assert n0 == n1, "There should be the same number of points in both exchange_lines"
+        if n0 == 2:
+            vec = centre1 - centre0 if self.end_points is None else self.end_points[1] - self.end_points[0]
+            out0, out1 = vec, -vec
+        elif n0 == 4:
+            out0 = lines[0][3] - lines[0][2]
+            out1 = lines[1][3] - lines[1][2]
+            vec = centre1 - centre0
+        else:
+            raise Exception("n_exchange_0 != 2 or 4")
+        self.culvert_vector, self.culvert_length = _unit(np.array(vec, dtype=np.float64), "culvert")
+        self.outward_vector_0, _ = _unit(np.array(out0, dtype=np.float64), "outlet_vector_0")
+        self.outward_vector_1, _ = _unit(np.array(out1, dtype=np.float64), "outlet_vector_1")
+        if self.enquiry_points is None:
+            raise Exception("enquiry_points are required with exchange_lines")
+
+    # -- accessors ---------------------------------------------------------------------
+    def get_culvert_length(self):
+        return self.culvert_length
+
+    def get_culvert_width(self):
+        return self.width
+
+    def get_culvert_height(self):
+        return self.height
+
+    def get_culvert_blockage(self):
+        return self.blockage
+
+    def get_culvert_barrels(self):
+        return self.barrels
+
+    def get_inlets(self):
+        return self.inlets
+
+    def get_enquiry_depths(self):
+        return [i.get_enquiry_depth() for i in self.inlets]
+
+    def discharge_routine(self):
+        raise NotImplementedError
+
+    def _fetch(self):
+        for inlet in self.inlets:
+            inlet.fetch()
+
+    # -- the transfer (structure_operator.py:215-372) --------------------------------------
+    def __call__(self):
+        timestep = self.domain.get_timestep()
+        self._fetch()
+        Q, barrel_speed, outlet_depth = self.discharge_routine()
+        inflow, outflow = self.inflow, self.outflow
+        area_in, area_out = inflow.get_area(), outflow.get_area()
+
+        depth0 = inflow.get_average_depth()
+        xmom0 = inflow.get_average_xmom()
+        ymom0 = inflow.get_average_ymom()
+
+        dt_Q_on_d = timestep * Q / depth0 if depth0 > 0.0 else 0.0
+        rescale = self.always_use_Q_wetdry_adjustment or (depth0 * area_in <= Q * timestep)
+        factor = 1.0 / (1.0 + dt_Q_on_d / area_in)
+        if rescale:           # Q scaled by new/old depth: the inflow region can never be over-drawn
+            depth1 = depth0 * factor
+            timestep_star = timestep * depth1 / depth0 if depth0 > 0.0 else 0.0
+        else:
+            depth1 = depth0 - timestep * Q / area_in
+            timestep_star = timestep
+
+        if self.use_old_momentum_method:
+            mom_factor = factor
+        elif depth0 > 0.0:
+            if rescale:
+                mom_factor = 1.0 / (1.0 + dt_Q_on_d * depth1 / (depth0 * area_in))
+            else:
+                mom_factor = 1.0 / (1.0 + timestep * Q / (depth0 * area_in))
+        else:
+            mom_factor = 0.0
+        xmom1 = xmom0 * mom_factor
+        ymom1 = ymom0 * mom_factor
+
+        inflow.set_depths(depth1)
+        inflow.set_xmoms(xmom1)
+        inflow.set_ymoms(ymom1)
+
+        loss = (depth0 - depth1) * area_in
+        xmom_loss = (xmom0 - xmom1) * area_in
+        ymom_loss = (ymom0 - ymom1) * area_in
+
+        extra_depth = Q * timestep_star / area_out
+        direction = -outflow.outward_culvert_vector
+        gain = extra_depth * area_out
+        assert np.allclose(gain - loss, 0.0)
+
+        self.accumulated_flow += gain
+        self.discharge = Q * timestep_star / timestep
+        self.discharge_abs_timemean += gain / self.domain.yieldstep
+        self.velocity = barrel_speed
+        self.outlet_depth = outlet_depth
+
+        out_depth = outflow.get_average_depth() + extra_depth
+        outflow.set_depths(out_depth)
+        if self.use_momentum_jet:
+            out_xmom = barrel_speed * out_depth * direction[0]
+            out_ymom = barrel_speed * out_depth * direction[1]
+        elif self.zero_outflow_momentum:
+            out_xmom = out_ymom = 0.0
+        else:
+            out_xmom = outflow.get_average_xmom() + xmom_loss / area_out
+            out_ymom = outflow.get_average_ymom() + ymom_loss / area_out
+        outflow.set_xmoms(out_xmom)
+        outflow.set_ymoms(out_ymom)
+
+        inflow.commit()
+        outflow.commit()
+        return 0.0                    # water is moved, not created: nothing for the volume integral
+
+
+def boyd_box_function(width, depth, blockage, barrels, flow_width, length, driving_energy,
+                      delta_total_energy, outlet_enquiry_depth, sum_loss, manning):
+    """Boyd's box-culvert rating: inlet control (weir / orifice), then outlet control when the
+    tailwater matters.  Returns Q, barrel velocity, outlet depth, flow area, case
+    (boyd_box_operator.py:265-400; constants are Boyd's)."""
+    open_fraction = 1 - blockage
+    if blockage >= 1.0:
+        return 0.0, 0.0, 0.0, 0.00001, "100 blocked culvert"
+    span = open_fraction * width * barrels                  # total clear width of all barrels
+    Q_weir = 0.544 * g ** 0.5 * open_fraction * width * barrels * driving_energy ** 1.50
+    Q_orifice = 0.702 * g ** 0.5 * open_fraction * width * barrels * depth ** 0.89 * driving_energy ** 0.61
+    if Q_weir < Q_orifice:
+        Q = Q_weir
+    else:
+        Q = Q_orifice
+
+    def section(Q):
+        """flow depth (critical, capped by the barrel), wetted area and perimeter"""
+        d = (Q ** 2 / g / span ** 2) ** 0.333333
+        if d > depth:
+            return depth, span * depth, 2 * (span + depth), True
+        return d, span * d, span + 2 * d, False
+
+    outlet_culvert_depth, flow_area, perimeter, full = section(Q)
+    case = "Inlet CTRL Outlet unsubmerged PIPE PART FULL" if full else \
+        "INLET CTRL Culvert is open channel flow we will for now assume critical depth"
+
+    if delta_total_energy < driving_energy:                 # outlet control can govern
+        if outlet_enquiry_depth > depth:
+            outlet_culvert_depth = depth
+            flow_area = span * depth
+            perimeter = 2.0 * (span + depth)
+            case = "Outlet submerged"
+        else:
+            outlet_culvert_depth, flow_area, perimeter, full = section(Q)
+            if full:
+                perimeter = 2.0 * (span + depth)
+            else:
+                perimeter = span + 2.0 * outlet_culvert_depth
+            case = "Outlet is Flowing Full" if full else "Outlet is open channel flow"
+        hyd_rad = flow_area / perimeter
+        culvert_velocity = math.sqrt(delta_total_energy /
+                                     ((sum_loss / 2 / g) + (manning ** 2 * length) / hyd_rad ** 1.33333))
+        Q = min(Q, flow_area * culvert_velocity)
+
+    barrel_velocity = Q / (flow_area + velocity_protection / flow_area)
+    return Q, barrel_velocity, outlet_culvert_depth, flow_area, case
+
+
+def total_energy(smooth_delta_total_energy, delta_total_energy, timestep, smoothing_timescale,
+                 forward_Euler_smooth=True):
+    """exponential smoothing of the head difference (boyd_box_operator.py:402-418)"""
+    if forward_Euler_smooth:
+        ts = timestep / max(timestep, smoothing_timescale, 1.0e-06) if timestep > 0.0 else 1.0
+        smoothed = smooth_delta_total_energy + ts * (delta_total_energy - smooth_delta_total_energy)
+    else:
+        ts = timestep / max(smoothing_timescale, 1.0e-06)
+        smoothed = (smooth_delta_total_energy + ts * delta_total_energy) / (1.0 + ts)
+    return smoothed, ts
+
+
+def smooth_discharge(smooth_delta_total_energy, smooth_Q, Q, flow_area, ts, forward_Euler_smooth=True):
+    """signed, smoothed discharge; a sign flip shuts the culvert for the step
+    (boyd_box_operator.py:420-441)"""
+    sign = np.sign(smooth_delta_total_energy)
+    if forward_Euler_smooth:
+        smooth_Q = smooth_Q + ts * (Q * sign - smooth_Q)
+    else:
+        smooth_Q = (smooth_Q + ts * (Q * sign)) / (1.0 + ts)
+    Q = 0.0 if np.sign(smooth_Q) != sign else min(abs(smooth_Q), Q)
+    barrel_velocity = 0.0 if flow_area == 0 else Q / flow_area
+    return smooth_Q, Q, barrel_velocity
+
+
+class Boyd_box_operator(Structure_operator):
+    """anuga.Boyd_box_operator(domain, losses, width, height=None, barrels=1.0, blockage=0.0, ...,
+    end_points | exchange_lines, enquiry_points, invert_elevations, apron, manning, enquiry_gap,
+    smoothing_timescale, use_momentum_jet, use_velocity_head)  (boyd_box_operator.py:8-262)"""
+
+    def __init__(self, domain, losses, width, height=None, barrels=1.0, blockage=0.0, z1=0.0, z2=0.0,
+                 end_points=None, exchange_lines=None, enquiry_points=None, invert_elevations=None,
+                 apron=0.1, manning=0.013, enquiry_gap=0.0, smoothing_timescale=0.0,
+                 use_momentum_jet=True, use_velocity_head=True, description=None, label=None,
+                 structure_type="boyd_box", logging=False, verbose=False):
+        Structure_operator.__init__(self, domain, end_points=end_points, exchange_lines=exchange_lines,
+                                    enquiry_points=enquiry_points, invert_elevations=invert_elevations,
+                                    width=width, height=height, blockage=blockage, barrels=barrels,
+                                    diameter=None, apron=apron, manning=manning, enquiry_gap=enquiry_gap,
+                                    description=description, label=label, structure_type=structure_type,
+                                    logging=logging, verbose=verbose)
+        if isinstance(losses, dict):
+            self.sum_loss = sum(losses.values())
+        elif isinstance(losses, list):
+            self.sum_loss = sum(losses)
+        else:
+            self.sum_loss = losses
+        self.use_momentum_jet = use_momentum_jet
+        self.zero_outflow_momentum = not use_momentum_jet
+        self.use_velocity_head = use_velocity_head
+        self.culvert_length = self.get_culvert_length()
+        self.culvert_width = self.get_culvert_width()
+        self.culvert_height = self.get_culvert_height()
+        self.culvert_blockage = self.get_culvert_blockage()
+        self.culvert_barrels = self.get_culvert_barrels()
+        self.max_velocity = 10.0
+        self.case = "N/A"
+        # one evaluation on the initial state primes the smoothing memory (:118-126)
+        self.smoothing_timescale = 0.0
+        self.smooth_delta_total_energy = 0.0
+        self.smooth_Q = 0.0
+        self._fetch_initial()
+        Qvd = self.discharge_routine()
+        self.smooth_delta_total_energy = 1.0 * self.delta_total_energy
+        self.smooth_Q = Qvd[0]
+        self.smoothing_timescale = smoothing_timescale
+
+    def _fetch_initial(self):
+        """the constructor runs before the device handle exists: read the host arrays"""
+        q = self.domain.quantities
+        for inlet in self.inlets:
+            ids = inlet._gather_ids
+            both = np.stack([q["stage"].centroid_values[ids], q["xmomentum"].centroid_values[ids],
+                             q["ymomentum"].centroid_values[ids], q["elevation"].centroid_values[ids]], axis=1)
+            inlet.values, inlet.enquiry = both[:-1], both[-1]
+
+    def discharge_routine(self):
+        if self.culvert_height <= 0.0:
+            self.case = "Culvert blocked"
+            self.inflow, self.outflow = self.inlets
+            return 0.0, 0.0, 0.0
+        a, b = self.inlets
+        if self.use_velocity_head:
+            self.delta_total_energy = a.get_enquiry_total_energy() - b.get_enquiry_total_energy()
+        else:
+            self.delta_total_energy = a.get_enquiry_stage() - b.get_enquiry_stage()
+        self.smooth_delta_total_energy, ts = total_energy(self.smooth_delta_total_energy, self.delta_total_energy,
+                                                          self.domain.timestep, self.smoothing_timescale, True)
+        if self.smooth_delta_total_energy >= 0.0:
+            self.inflow, self.outflow = a, b
+            self.delta_total_energy = self.smooth_delta_total_energy
+        else:
+            self.inflow, self.outflow = b, a
+            self.delta_total_energy = -self.smooth_delta_total_energy
+
+        flow_area = None
+        if self.inflow.get_enquiry_depth() > 0.01:
+            assert self.inflow.get_enquiry_specific_energy() >= 0.0, "Specific energy at inlet is negative"
+            if self.use_velocity_head:
+                self.driving_energy = self.inflow.get_enquiry_specific_energy()
+            else:
+                self.driving_energy = self.inflow.get_enquiry_depth()
+            Q, barrel_velocity, outlet_culvert_depth, flow_area, case = boyd_box_function(
+                width=self.culvert_width, depth=self.culvert_height, blockage=self.culvert_blockage,
+                barrels=self.culvert_barrels, flow_width=self.culvert_width, length=self.culvert_length,
+                driving_energy=self.driving_energy, delta_total_energy=self.delta_total_energy,
+                outlet_enquiry_depth=self.outflow.get_enquiry_depth(), sum_loss=self.sum_loss,
+                manning=self.manning)
+            self.smooth_Q, Q, barrel_velocity = smooth_discharge(self.smooth_delta_total_energy, self.smooth_Q,
+                                                                 Q, flow_area, ts, True)
+        else:
+            Q = barrel_velocity = outlet_culvert_depth = 0.0
+            case = "Inlet dry"
+        self.case = case
+        if barrel_velocity > self.max_velocity:
+            barrel_velocity = self.max_velocity
+            Q = flow_area * barrel_velocity
+        return Q, barrel_velocity, outlet_culvert_depth
+
+    def oracle_spec(self):
+        return ("boyd_box", dict(
+            inlet_indices=[i.triangle_indices.copy() for i in self.inlets],
+            enquiry_indices=[i.enquiry_index for i in self.inlets],
+            invert_elevations=[i.invert_elevation for i in self.inlets],
+            outward_vectors=[np.array(i.outward_culvert_vector) for i in self.inlets],
+            width=self.culvert_width, height=self.culvert_height, blockage=self.culvert_blockage,
+            barrels=self.culvert_barrels, length=self.culvert_length, sum_loss=self.sum_loss,
+            manning=self.manning, use_velocity_head=self.use_velocity_head,
+            use_momentum_jet=self.use_momentum_jet, zero_outflow_momentum=self.zero_outflow_momentum,
+            use_old_momentum_method=self.use_old_momentum_method,
+            always_use_Q_wetdry_adjustment=self.always_use_Q_wetdry_adjustment,
+            smoothing_timescale=self.smoothing_timescale, max_velocity=self.max_velocity,
+            smooth_delta_total_energy=self.smooth_delta_total_energy, smooth_Q=self.smooth_Q,
+            use_new_velocity_head=getattr(self.domain, "use_new_velocity_head", False)))

@@ -24,6 +24,8 @@ The input is a *scenario*: a plain dict of numpy arrays and scalars (see
 import ctypes as C
 import os
 
+import math
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -471,6 +473,8 @@ class OracleDomain:
                 self._rate_operator(op[1])
             elif op[0] == "inlet":
                 self._inlet_operator(op[1])
+            elif op[0] == "boyd_box":
+                self._boyd_box_operator(op[1])
             else:
                 raise ValueError("unknown operator %r" % (op[0],))
 
@@ -552,6 +556,143 @@ class OracleDomain:
         else:
             self.stage_c[idx] = elev + 0.0
             self.fractional_step_volume_integral -= current_volume
+
+    def _boyd_box_operator(self, o):
+        """structures/structure_operator.py:215-372 (the transfer) around
+        structures/boyd_box_operator.py:150-441 (the rating) with the enquiry formulas of
+        structures/inlet_enquiry.py:86-158.  `o` carries the resolved geometry (inlet triangle
+        ids, enquiry triangle ids, outward unit vectors, barrel length) and the smoothing memory
+        (smooth_delta_total_energy, smooth_Q), which this function updates in place."""
+        G, VP = 9.8, 1.0e-6                       # anuga/config.py:45, :18
+        dt = self.timestep
+        stage, bed, xm, ym = self.stage_c, self.bed_c, self.xmom_c, self.ymom_c
+
+        def enquiry(k):
+            e = o["enquiry_indices"][k]
+            inv = o["invert_elevations"][k]
+            inv = bed[e] if inv is None else inv
+            depth = max(stage[e] - inv, 0.0)
+            wd = stage[e] - bed[e]
+            u = wd * xm[e] / (wd ** 2 + VP)
+            v = wd * ym[e] / (wd ** 2 + VP)
+            if o.get("use_new_velocity_head"):
+                n1, n2 = o["outward_vectors"][k]
+                head = 0.5 * min(u * n1 + v * n2, 0.0) ** 2 / G
+            else:
+                head = 0.5 * math.sqrt(u ** 2 + v ** 2) ** 2 / G
+            return dict(stage=stage[e], depth=depth, total=head + stage[e], specific=head + depth)
+
+        # ---- discharge_routine ----
+        height, width = o["height"], o["width"]
+        flow_area = None
+        if height <= 0.0:
+            Q = speed = outlet_depth = 0.0
+            i_in, i_out = 0, 1
+        else:
+            E = [enquiry(0), enquiry(1)]
+            key = "total" if o["use_velocity_head"] else "stage"
+            delta = E[0][key] - E[1][key]
+            if dt > 0.0:
+                ts = dt / max(dt, o["smoothing_timescale"], 1.0e-06)
+            else:
+                ts = 1.0
+            o["smooth_delta_total_energy"] = o["smooth_delta_total_energy"] + ts * (delta - o["smooth_delta_total_energy"])
+            sm = o["smooth_delta_total_energy"]
+            if sm >= 0.0:
+                i_in, i_out, delta = 0, 1, sm
+            else:
+                i_in, i_out, delta = 1, 0, -sm
+            if E[i_in]["depth"] > 0.01:
+                assert E[i_in]["specific"] >= 0.0
+                drive = E[i_in]["specific"] if o["use_velocity_head"] else E[i_in]["depth"]
+                Q, speed, outlet_depth, flow_area = self._boyd_box_rating(o, drive, delta, E[i_out]["depth"])
+                sign = np.sign(sm)
+                o["smooth_Q"] = o["smooth_Q"] + ts * (Q * sign - o["smooth_Q"])
+                if np.sign(o["smooth_Q"]) != sign:
+                    Q = 0.0
+                else:
+                    Q = min(abs(o["smooth_Q"]), Q)
+                speed = 0.0 if flow_area == 0 else Q / flow_area
+            else:
+                Q = speed = outlet_depth = 0.0
+        if speed > o["max_velocity"]:
+            speed = o["max_velocity"]
+            Q = flow_area * speed
+
+        # ---- Structure_operator.__call__ ----
+        iin = np.asarray(o["inlet_indices"][i_in], dtype=np.int64)
+        iout = np.asarray(o["inlet_indices"][i_out], dtype=np.int64)
+        a_in, a_out = self.areas[iin], self.areas[iout]
+        A_in, A_out = np.sum(a_in), np.sum(a_out)
+        d_old = np.sum((stage[iin] - bed[iin]) * a_in) / A_in
+        x_old = np.sum(xm[iin] * a_in) / A_in
+        y_old = np.sum(ym[iin] * a_in) / A_in
+        dtQd = dt * Q / d_old if d_old > 0.0 else 0.0
+        adjust = o["always_use_Q_wetdry_adjustment"] or (d_old * A_in <= Q * dt)
+        factor = 1.0 / (1.0 + dtQd / A_in)
+        if adjust:
+            d_new = d_old * factor
+            dt_star = dt * d_new / d_old if d_old > 0.0 else 0.0
+        else:
+            d_new = d_old - dt * Q / A_in
+            dt_star = dt
+        if o["use_old_momentum_method"]:
+            x_new, y_new = x_old * factor, y_old * factor
+        else:
+            if d_old > 0.0:
+                if adjust:
+                    f2 = 1.0 / (1.0 + dtQd * d_new / (d_old * A_in))
+                else:
+                    f2 = 1.0 / (1.0 + dt * Q / (d_old * A_in))
+            else:
+                f2 = 0.0
+            x_new, y_new = x_old * f2, y_old * f2
+        stage[iin] = bed[iin] + d_new
+        xm[iin] = x_new
+        ym[iin] = y_new
+        x_loss = (x_old - x_new) * A_in
+        y_loss = (y_old - y_new) * A_in
+        extra = Q * dt_star / A_out
+        out_dir = -np.asarray(o["outward_vectors"][i_out])
+        d_out = np.sum((stage[iout] - bed[iout]) * a_out) / A_out + extra
+        if o["use_momentum_jet"]:
+            x_out = speed * d_out * out_dir[0]
+            y_out = speed * d_out * out_dir[1]
+        elif o["zero_outflow_momentum"]:
+            x_out = y_out = 0.0
+        else:
+            x_out = np.sum(xm[iout] * a_out) / A_out + x_loss / A_out
+            y_out = np.sum(ym[iout] * a_out) / A_out + y_loss / A_out
+        stage[iout] = bed[iout] + d_out
+        xm[iout] = x_out
+        ym[iout] = y_out
+
+    @staticmethod
+    def _boyd_box_rating(o, drive, delta, tail_depth):
+        """boyd_box_function (boyd_box_operator.py:265-400): inlet control = the smaller of the
+        unsubmerged (weir, E^1.5) and submerged (orifice, D^0.89 E^0.61) ratings; outlet control
+        (energy loss over the barrel) caps it when delta < drive."""
+        G, VP = 9.8, 1.0e-6
+        width, depth, barrels = o["width"], o["height"], o["barrels"]
+        bf = 1 - o["blockage"]
+        if o["blockage"] >= 1.0:
+            return 0.0, 0.0, 0.0, 0.00001
+        Qu = 0.544 * G ** 0.5 * bf * width * barrels * drive ** 1.50
+        Qs = 0.702 * G ** 0.5 * bf * width * barrels * depth ** 0.89 * drive ** 0.61
+        Q = Qu if Qu < Qs else Qs
+        clear = bf * width * barrels
+        dcrit = (Q ** 2 / G / clear ** 2) ** 0.333333
+        if dcrit > depth:
+            out_d, area, perim = depth, clear * depth, 2 * (clear + depth)
+        else:
+            out_d, area, perim = dcrit, clear * dcrit, clear + 2 * dcrit
+        if delta < drive:
+            if tail_depth > depth:
+                out_d, area, perim = depth, clear * depth, 2.0 * (clear + depth)
+            rh = area / perim
+            vel = math.sqrt(delta / ((o["sum_loss"] / 2 / G) + (o["manning"] ** 2 * o["length"]) / rh ** 1.33333))
+            Q = min(Q, area * vel)
+        return Q, Q / (area + VP / area), out_d, area
 
     # -- evolve ------------------------------------------------------------------
     def evolve(self, yieldstep=None, finaltime=None, duration=None, skip_initial_step=False):

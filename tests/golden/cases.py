@@ -179,6 +179,43 @@ def inlet_de1(A, n=16):
     return d
 
 
+def _embankment(A, n=16):
+    """two ponds separated by a dry embankment; only a culvert connects them"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: 1.0 * np.exp(-((x - 0.5 * L) / 1.0) ** 2) + 0.02 * np.cos(y))
+    d.set_quantity("stage", lambda x, y: np.where(x < 0.5 * L, 0.8, 0.25), location="centroids")
+    d.set_quantity("friction", 0.03)
+    _reflective_all(A, d)
+    return d
+
+
+def culvert_de1(A):
+    """config[5] building block: Boyd_box_operator given end points (structures/boyd_box_operator.py,
+    structure_operator.py), default momentum jet + velocity head"""
+    d = _embankment(A)
+    A.Boyd_box_operator(d, losses=1.5, width=1.5, height=0.6, end_points=[[6.1, 8.3], [9.9, 8.3]],
+                        apron=0.55, enquiry_gap=0.4, manning=0.013, use_momentum_jet=True,
+                        use_velocity_head=True, verbose=False)
+    return d
+
+
+def culvert_skew_de1(A):
+    """skew culvert from exchange lines, explicit enquiry points and inverts, smoothed discharge,
+    two partly blocked barrels, no jet, stage-driven; the head difference reverses the flow"""
+    d = _embankment(A)
+    d.set_quantity("stage", lambda x, y: np.where(x < 8.0, 0.3, 0.9), location="centroids")
+    A.Boyd_box_operator(d, losses={"inlet": 0.5, "outlet": 1.0, "bend": 0.0}, width=1.2, height=0.5,
+                        barrels=2.0, blockage=0.2,
+                        exchange_lines=[[[6.15, 5.1], [6.4, 3.7]], [[9.8, 6.3], [10.05, 4.9]]],
+                        enquiry_points=[[5.1, 4.2], [11.1, 5.8]], invert_elevations=[0.1, 0.05],
+                        apron=0.45, manning=0.02, smoothing_timescale=1.5, use_momentum_jet=False,
+                        use_velocity_head=False, verbose=False)
+    return d
+
+
 CASES = {
     "kat_bedslope_more_steps": (kat_bedslope_more_steps, dict(yieldstep=0.05, finaltime=0.5)),
     "dam_break_de0": (dam_break_de0, dict(yieldstep=1.0, finaltime=6.0)),
@@ -196,6 +233,8 @@ CASES = {
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "inlet_de1": (inlet_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "rain_time_de1": (rain_time_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "culvert_de1": (culvert_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "culvert_skew_de1": (culvert_skew_de1, dict(yieldstep=1.0, finaltime=4.0)),
 }
 
 # 8-digit expected values embedded in the reference's own test (the KAT proper)

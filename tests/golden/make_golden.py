@@ -64,6 +64,15 @@ def run_case(name):
     out["yields"] = np.array(yields)
     out["bfi"] = np.array([d.get_boundary_flux_integral()])
     out["fsvi"] = np.array([d.get_fractional_step_volume_integral()])
+    k = 0
+    for op in d.fractional_step_operators:      # culverts: resolved geometry + accumulated transfer
+        if hasattr(op, "inlets"):
+            for j, inlet in enumerate(op.inlets):
+                out["struct%d_inlet%d_ids" % (k, j)] = np.asarray(inlet.triangle_indices, dtype=np.int64)
+            out["struct%d_enquiry" % k] = np.array([i.enquiry_index for i in op.inlets], dtype=np.int64)
+            out["struct%d_length" % k] = np.array([op.culvert_length])
+            out["struct%d_accumulated_flow" % k] = np.array([op.accumulated_flow])
+            k += 1
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print("%-28s N=%6d steps=%5d t=%.3f  max|stage|=%.6f" % (name, len(d), len(dts), yields[-1],
                                                             np.abs(out["final_stage"]).max()))
@@ -71,6 +80,11 @@ def run_case(name):
 
 
 def main():
+    only = sys.argv[1:]
+    if only:                                    # regenerate just the named cases
+        for name in only:
+            run_case(name)
+        return
     for name in cases.CASES:
         d, out = run_case(name)
         if name == "kat_bedslope_more_steps":
