@@ -206,6 +206,9 @@ def distribute(domain, nparts, epart=None, ghost_layer_width=2, ranks=None, doma
             bmap["ghost"] = None                    # parallel_api.py:129
             d.set_boundary({t: bmap[t] for t in d.get_boundary_tags()})
         for op in domain.fractional_step_operators:
+            if hasattr(op, "localise"):             # inlets, culverts: host-side hydraulics on merged rows
+                op.localise(d)
+                continue
             if not isinstance(op, Rate_operator) or op.indices is not None or op.rate_array is not None:
                 raise NotImplementedError("only scalar / f(t) all-cell Rate_operators are distributed")
             Rate_operator(d, rate=op.rate_callable if op.rate_callable is not None else op.rate, factor=op.factor)
@@ -353,6 +356,20 @@ class Communicator:
     def allreduce_sum(self, x):
         import torch.distributed as td
         return self._all(x, td.ReduceOp.SUM) if self.dist is not None else x
+
+    def merge_disjoint(self, a):
+        """Every element of the float64 array `a` is owned (filled) by exactly one rank and is +0.0
+        elsewhere: returns the array with all owners' values, bit for bit (an integer sum of the
+        bit patterns, so no rounding and no -0.0 -> +0.0)."""
+        if self.dist is None:
+            return a
+        import torch
+        import torch.distributed as td
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).view(np.int64).copy())
+        if self.dist.get_backend() == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, op=td.ReduceOp.SUM)
+        return t.cpu().numpy().view(np.float64).reshape(a.shape)
 
     def broadcast_bytes(self, payload, n):
         """rank 0's `payload` (n bytes) to everyone"""

@@ -128,6 +128,19 @@ def triangle_containing_point(domain, point):
     return int(ids[0])
 
 
+def _owned(sub, global_ids):
+    """rows of `global_ids` (ids in the undistributed numbering) that are FULL triangles of
+    sub-domain `sub`, and their local ids"""
+    nf = sub.number_of_full_triangles
+    l2s = np.asarray(sub.tri_l2s[:nf], dtype=np.int64)
+    order = np.argsort(l2s, kind="stable")
+    sorted_ids = l2s[order]
+    gid = np.asarray(global_ids, dtype=np.int64).reshape(-1)
+    pos = np.clip(np.searchsorted(sorted_ids, gid), 0, max(nf - 1, 0))
+    hit = sorted_ids[pos] == gid if nf else np.zeros(len(gid), dtype=bool)
+    return np.flatnonzero(hit).astype(np.int64), order[pos[hit]].astype(np.int64)
+
+
 class Inlet:
     """The exchange region: views of the inlet triangles' centroid values, held on the host for the
     duration of one operator call (structures/inlet.py:11-237)."""
@@ -142,13 +155,52 @@ class Inlet:
         self.area = float(np.sum(self.areas))
         assert self.area > 0.0
         self.values = None          # (n,4) stage, xmom, ymom, elevation; loaded by fetch()
+        self.local_rows = None      # distributed: rows of `values` whose triangle is full on this rank
+        self._extra_ids = np.zeros(0, dtype=np.int64)      # further triangles fetched with the inlet
+        self._extra_rows = np.zeros(0, dtype=np.int64)
+
+    # -- multi-GPU ---------------------------------------------------------------------
+    def localise(self, sub):
+        """The same inlet seen from sub-domain `sub` of a distributed run (parallel/parallel_inlet.py
+        restated): `values` / `areas` keep the layout of the undistributed inlet (rows in ascending
+        global id), every rank fills the rows of the triangles it owns, one exact merge makes all
+        rows visible everywhere and every rank evaluates the same scalar hydraulics; only owned rows
+        are written back.  Ghost copies follow at the update_ghosts that ends the step."""
+        import copy
+        new = copy.copy(self)
+        new.domain = sub
+        new.local_rows, new.triangle_indices = _owned(sub, self.triangle_indices)
+        new.values = None
+        return new
+
+    def _n_rows(self):
+        return len(self.areas)
 
     # -- device exchange ---------------------------------------------------------------
     def fetch(self):
-        self.values = self.domain._dev.gather_centroids(self.triangle_indices)
+        dev = self.domain._dev
+        ids = np.concatenate([self.triangle_indices, self._extra_ids]).astype(np.int64)
+        if self.local_rows is None:
+            got = dev.gather_centroids(ids)
+        else:
+            got = np.zeros((self._n_rows() + self._n_extra, 4), dtype=np.float64)
+            if len(ids):
+                got[np.concatenate([self.local_rows, self._extra_rows])] = dev.gather_centroids(ids)
+            comm = getattr(self.domain, "_comm", None)
+            if comm is None:
+                raise RuntimeError("a distributed inlet needs domain.attach_communicator(comm) before evolve")
+            got = comm.merge_disjoint(got)
+        self._take(got)
+
+    def _take(self, got):
+        self.values = got
 
     def commit(self):
-        self.domain._dev.scatter_centroids(self.triangle_indices, self.values[:, :3])
+        if self.local_rows is None:
+            self.domain._dev.scatter_centroids(self.triangle_indices, self.values[:, :3])
+        elif len(self.triangle_indices):
+            self.domain._dev.scatter_centroids(self.triangle_indices, self.values[self.local_rows, :3])
+    _n_extra = 0
 
     # -- the reference's accessors ----------------------------------------------------
     def get_area(self):
@@ -309,6 +361,15 @@ class Inlet_operator:
             inlet.set_xmoms(0.0)
             inlet.set_ymoms(0.0)
 
+    def localise(self, sub):
+        """this operator on sub-domain `sub` of a distributed run (called by parallel.distribute)"""
+        import copy
+        new = copy.copy(self)
+        new.domain = sub
+        new.inlet = self.inlet.localise(sub)
+        sub.set_fractional_step_operator(new)
+        return new
+
     def oracle_spec(self):
         return ("inlet", dict(indices=self.inlet.triangle_indices.copy(), Q=self.Q, velocity=self.velocity,
                               zero_velocity=self.zero_velocity, default=self.default))
@@ -331,19 +392,20 @@ class Inlet_enquiry(Inlet):
         self.outward_culvert_vector = outward_culvert_vector
         self.enquiry_index = triangle_containing_point(domain, enquiry_pt)
         self.enquiry = None         # (4,) stage, xmom, ymom, elevation of the enquiry triangle
-        self._gather_ids = np.append(self.triangle_indices, self.enquiry_index).astype(np.int64)
+        self._extra_ids = np.array([self.enquiry_index], dtype=np.int64)
+        self._extra_rows = np.array([len(self.triangle_indices)], dtype=np.int64)
+    _n_extra = 1
 
-    def fetch(self):
-        both = self.domain._dev.gather_centroids(self._gather_ids)
-        self.values = both[:-1]
-        self.enquiry = both[-1]
+    def localise(self, sub):
+        new = Inlet.localise(self, sub)
+        hit, local = _owned(sub, [self.enquiry_index])
+        new._extra_ids = local
+        new._extra_rows = np.array([self._n_rows()], dtype=np.int64)[:len(local)]
+        return new
 
-    def _write_through(self):
-        """an inlet write is visible to a later enquiry read when the enquiry triangle is an inlet
-        triangle (the reference reads and writes the same arrays)"""
-        k = np.flatnonzero(self.triangle_indices == self.enquiry_index)
-        if len(k):
-            self.enquiry[:3] = self.values[k[0], :3]
+    def _take(self, got):
+        self.values = got[:-1]
+        self.enquiry = got[-1]
 
     def get_enquiry_stage(self):
         return self.enquiry[0]
@@ -533,6 +595,17 @@ class Structure_operator:
     def _fetch(self):
         for inlet in self.inlets:
             inlet.fetch()
+
+    def localise(self, sub):
+        """this structure on sub-domain `sub` of a distributed run (parallel_structure_operator.py
+        restated: see Inlet.localise); the smoothing memory primed on the whole domain is kept"""
+        import copy
+        new = copy.copy(self)
+        new.domain = sub
+        new.inlets = [i.localise(sub) for i in self.inlets]
+        new.inflow, new.outflow = new.inlets
+        sub.set_fractional_step_operator(new)
+        return new
 
     # -- the transfer (structure_operator.py:215-372) --------------------------------------
     def __call__(self):
@@ -725,7 +798,7 @@ class Boyd_box_operator(Structure_operator):
         """the constructor runs before the device handle exists: read the host arrays"""
         q = self.domain.quantities
         for inlet in self.inlets:
-            ids = inlet._gather_ids
+            ids = np.append(inlet.triangle_indices, inlet.enquiry_index).astype(np.int64)
             both = np.stack([q["stage"].centroid_values[ids], q["xmomentum"].centroid_values[ids],
                              q["ymomentum"].centroid_values[ids], q["elevation"].centroid_values[ids]], axis=1)
             inlet.values, inlet.enquiry = both[:-1], both[-1]

@@ -27,7 +27,9 @@ def run_distributed(case, nranks, tmp_path, rule):
 
 
 @pytest.mark.parametrize("case,rule", [("beach_de1", "blocks"), ("dam_break_de0", "quadrants"),
-                                       ("dam_break_de2", "blocks"), ("rain_de1", "quadrants")])
+                                       ("dam_break_de2", "blocks"), ("rain_de1", "quadrants"),
+                                       ("time_boundary_de1", "blocks"), ("inlet_de1", "quadrants"),
+                                       ("culvert_de1", "blocks"), ("culvert_skew_de1", "quadrants")])
 def test_multi_gpu_equals_single_gpu_bitwise(case, rule, tmp_path):
     ndev = ab.device_count()
     if ndev < 2:
