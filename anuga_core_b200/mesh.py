@@ -79,6 +79,33 @@ def rectangular_cross(m, n, len1=1.0, len2=1.0, origin=(0.0, 0.0)):
     return points, elements, boundary
 
 
+def rectangular_cross_neighbours(m, n):
+    """Closed form of build_neighbour_structure for rectangular_cross(m, n) (same arrays, -1 where
+    there is no neighbour): inside a cell, edge 0 of triangle k meets edge 2 of triangle k-1 and
+    edge 2 meets edge 0 of triangle k+1 (mod 4); edge 1 is the cell side and meets edge 1 of the
+    facing triangle of the adjacent cell (left<->right, bottom<->top)."""
+    m = int(m)
+    n = int(n)
+    N = 4 * m * n
+    nb = np.empty((N, 3), dtype=np.int64)
+    ne = np.empty((N, 3), dtype=np.int64)
+    base = 4 * np.arange(m * n, dtype=np.int64)
+    ci = np.repeat(np.arange(m, dtype=np.int64), n)
+    cj = np.tile(np.arange(n, dtype=np.int64), m)
+    outer = ((base - 4 * n + 2, ci > 0), (base - 4 + 3, cj > 0), (base + 4 * n + 0, ci < m - 1),
+             (base + 4 + 1, cj < n - 1))
+    for k in range(4):
+        nb[k::4, 0] = base + (k + 3) % 4
+        nb[k::4, 2] = base + (k + 1) % 4
+        target, exists = outer[k]
+        nb[k::4, 1] = np.where(exists, target, -1)
+        ne[k::4, 1] = np.where(exists, 1, -1)
+    ne[:, 0] = 2
+    ne[:, 2] = 0
+    nbnd = (nb[:, 1] < 0).astype(np.int64)
+    return nb, ne, nbnd
+
+
 def rectangular(m, n, len1=1.0, len2=1.0, origin=(0.0, 0.0)):
     """Rectangular grid, two triangles per cell (mesh_factory.py:64-135): cell (i, j) owns
     the lower triangle 2(i*n+j) = [i4, i3, i2] and the upper one [i1, i2, i3]."""
@@ -290,11 +317,12 @@ class Mesh:
 class Topology:
     """neighbours + boundary of a triangle table without the geometry (what the partition needs)"""
 
-    def __init__(self, number_of_nodes, triangles, boundary):
+    def __init__(self, number_of_nodes, triangles, boundary, neighbour_structure=None):
         self.triangles = np.ascontiguousarray(triangles, dtype=np.int64)
         self.number_of_triangles = len(self.triangles)
-        (self.neighbours, self.neighbour_edges,
-         self.number_of_boundaries) = build_neighbour_structure(self.triangles, number_of_nodes)
+        if neighbour_structure is None:
+            neighbour_structure = build_neighbour_structure(self.triangles, number_of_nodes)
+        self.neighbours, self.neighbour_edges, self.number_of_boundaries = neighbour_structure
         b = dict(boundary) if boundary else {}
         vols, edges = np.nonzero(self.neighbours < 0)
         for v, e in zip(vols.tolist(), edges.tolist()):

@@ -27,7 +27,7 @@ import os
 
 import numpy as np
 
-from .mesh import Mesh, Topology, rectangular_cross
+from .mesh import Mesh, Topology, rectangular_cross, rectangular_cross_neighbours
 from .domain import Domain
 from .boundaries import Reflective_boundary
 from .operators import Rate_operator
@@ -63,10 +63,9 @@ def reorder_by_epart(triangles, boundary, epart, nparts):
 
 
 def _ghost_layer(neighbours, tlower, tupper, layer_width):
-    full_ids = np.arange(tlower, tupper)
-    n0 = np.unique(neighbours[full_ids, :].ravel())
-    n0 = n0[n0 >= 0]
-    n0 = n0[(n0 < tlower) | (tupper <= n0)]
+    n0 = neighbours[tlower:tupper].ravel()
+    n0 = n0[(n0 >= 0) & ((n0 < tlower) | (tupper <= n0))]      # filter first: the unique is then small
+    n0 = np.unique(n0)
     layers = [n0]
     for i in range(layer_width - 1):
         n0 = np.unique(neighbours[n0, :].ravel())
@@ -125,9 +124,14 @@ def partition_mesh(nodes, triangles, boundary, triangles_per_proc, ghost_layer_w
         tl, tu = int(lower[p]), int(upper[p])
         ghosts = ghosts_of[p]
         full_tri = triangles[tl:tu]
-        full_node_ids = np.unique(full_tri.ravel())
+        used = np.zeros(len(nodes), dtype=bool)             # sorted unique node ids via a mask
+        used[full_tri.ravel()] = True
+        full_node_ids = np.flatnonzero(used)
         ghost_tri = triangles[ghosts]
-        ghost_node_ids = np.setdiff1d(np.unique(ghost_tri.ravel()), full_node_ids)
+        gused = np.zeros(len(nodes), dtype=bool)
+        gused[ghost_tri.ravel()] = True
+        gused &= ~used
+        ghost_node_ids = np.flatnonzero(gused)
         node_ids = np.concatenate([full_node_ids, ghost_node_ids])
         node_map = -np.ones(int(node_ids.max()) + 1, dtype=np.int64)
         node_map[node_ids] = np.arange(len(node_ids))
@@ -267,7 +271,7 @@ def strip_slab(m, n, rank, nranks, len1=None, len2=None, ghost_layer_width=2, pa
     keep = [k for k, c in enumerate(tpp) if c > 0]
     me = keep.index(1)
     tpp_nz = [tpp[k] for k in keep]
-    smesh = Topology(len(pts), tri, bnd)
+    smesh = Topology(len(pts), tri, bnd, neighbour_structure=rectangular_cross_neighbours(ms, n))
     # cut edges of the slab are not physical boundaries: they only touch triangles farther than
     # `pad` columns away from the rank's strip, which never enter a width<=pad ghost layer
     sub = partition_mesh(pts, tri, smesh.boundary, tpp_nz, ghost_layer_width, ranks=[me], mesh=smesh)[me]
