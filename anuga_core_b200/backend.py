@@ -108,6 +108,7 @@ SYMBOLS = {
     "swk_last_error": (C.c_char_p, []),
     "swk_abi_version": (C.c_int, []),
     "swk_build_neighbour_structure": (C.c_int, [_I, _I, _PI, _PI, _PI, _PI]),
+    "swk_mesh_geometry": (C.c_int, [_I, _I, _PD, _PI, _I, _PD, _PD, _PD, _PD, _PD, _PD, _PD, _PI]),
     "swk_create": (C.c_int, [C.POINTER(SwkMesh), C.POINTER(SwkParams), C.c_int, C.POINTER(_H)]),
     "swk_destroy": (C.c_int, [_H]),
     "swk_set_params": (C.c_int, [_H, C.POINTER(SwkParams)]),
@@ -500,3 +501,24 @@ def build_neighbour_structure_native(triangles, number_of_nodes):
     if code != SWK_OK:
         raise Exception(lib.swk_last_error().decode())
     return nb, ne, nob
+
+
+def mesh_geometry_native(nodes, triangles, use_inscribed_circle=False):
+    """(vertex_coordinates, areas, normals, edgelengths, centroid_coordinates, radii,
+    edge_midpoint_coordinates, first_degenerate) through libswk's host-side helper; None when the
+    library is absent (the numpy formulation in mesh.py gives the same bits)."""
+    try:
+        lib = load_library()
+    except (SwkError, OSError):
+        return None
+    nodes = _f64(nodes)
+    tri = _i64(triangles)
+    N = tri.shape[0]
+    V = np.empty((3 * N, 2)); areas = np.empty(N); normals = np.empty((N, 6)); el = np.empty((N, 3))
+    cc = np.empty((N, 2)); radii = np.empty(N); E = np.empty((3 * N, 2))
+    bad = np.full(1, -1, dtype=np.int64)
+    code = lib.swk_mesh_geometry(N, nodes.shape[0], _pd(nodes), _pi(tri), int(bool(use_inscribed_circle)),
+                                 _pd(V), _pd(areas), _pd(normals), _pd(el), _pd(cc), _pd(radii), _pd(E), _pi(bad))
+    if code != SWK_OK:
+        raise Exception(lib.swk_last_error().decode())
+    return V, areas, normals, el, cc, radii, E, int(bad[0])

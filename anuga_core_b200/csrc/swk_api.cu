@@ -328,6 +328,66 @@ static void radix_sort_keys(std::vector<EdgeKey> &a, int bits)
   }
 }
 
+extern "C" int swk_mesh_geometry(int64_t N, int64_t nn, const double *nodes, const int64_t *tri, int64_t inscribed,
+                                 double *V, double *areas, double *normals, double *edgelengths, double *centroids,
+                                 double *radii, double *E, int64_t *first_degenerate)
+{
+  if (N < 0 || nn <= 0 || !nodes || !tri || !V || !areas || !normals || !edgelengths || !centroids || !radii || !E)
+    return fail(SWK_ERR_ARG, "bad argument");
+  int64_t bad = -1;
+  for (int64_t k = 0; k < N; k++) {
+    double x[3], y[3];
+    for (int v = 0; v < 3; v++) {
+      const int64_t p = tri[3 * k + v];
+      if (p < 0 || p >= nn) return fail(SWK_ERR_ARG, "triangle refers to a node >= number_of_nodes");
+      x[v] = nodes[2 * p];
+      y[v] = nodes[2 * p + 1];
+      V[6 * k + 2 * v] = x[v];
+      V[6 * k + 2 * v + 1] = y[v];
+    }
+    const double a = -((x[1] * y[0] - x[0] * y[1]) + (x[2] * y[1] - x[1] * y[2]) + (x[0] * y[2] - x[2] * y[0])) / 2.0;
+    areas[k] = a;
+    if (!(a > 0.0) && bad < 0) bad = k;
+    double len[3];
+    for (int e = 0; e < 3; e++) {           // edge e runs from vertex e+1 to vertex e+2
+      const int p = (e + 1) % 3, q = (e + 2) % 3;
+      double xn = x[q] - x[p], yn = y[q] - y[p];
+      const double l = sqrt(xn * xn + yn * yn);
+      xn = xn / l;
+      yn = yn / l;
+      normals[6 * k + 2 * e] = yn;
+      normals[6 * k + 2 * e + 1] = -xn;
+      edgelengths[3 * k + e] = l;
+      len[e] = l;
+      E[6 * k + 2 * e] = 0.5 * (x[p] + x[q]);
+      E[6 * k + 2 * e + 1] = 0.5 * (y[p] + y[q]);
+    }
+    const double cx = (x[0] + x[1] + x[2]) / 3, cy = (y[0] + y[1] + y[2]) / 3;
+    centroids[2 * k] = cx;
+    centroids[2 * k + 1] = cy;
+    if (!inscribed) {
+      double d[3];
+      for (int e = 0; e < 3; e++) {
+        const int p = (e + 1) % 3, q = (e + 2) % 3;
+        const double xm = (x[p] + x[q]) / 2, ym = (y[p] + y[q]) / 2;
+        const double dx = cx - xm, dy = cy - ym;
+        d[e] = sqrt(dx * dx + dy * dy);
+      }
+      const double d01 = d[0] < d[1] ? d[0] : d[1];
+      radii[k] = d01 < d[2] ? d01 : d[2];
+    } else {
+      // perimeter from the vertex distances in the order |v0v1| + |v1v2| + |v2v0|
+      const double s0 = sqrt((x[0] - x[1]) * (x[0] - x[1]) + (y[0] - y[1]) * (y[0] - y[1]));
+      const double s1 = sqrt((x[1] - x[2]) * (x[1] - x[2]) + (y[1] - y[2]) * (y[1] - y[2]));
+      const double s2 = sqrt((x[2] - x[0]) * (x[2] - x[0]) + (y[2] - y[0]) * (y[2] - y[0]));
+      radii[k] = 2.0 * a / (s0 + s1 + s2);
+    }
+    (void)len;
+  }
+  if (first_degenerate) *first_degenerate = bad;
+  return SWK_OK;
+}
+
 extern "C" int swk_build_neighbour_structure(int64_t N, int64_t nn, const int64_t *tri, int64_t *neighbours,
                                              int64_t *neighbour_edges, int64_t *number_of_boundaries)
 {

@@ -20,7 +20,7 @@ device ``evolve`` raises.
 import numpy as np
 
 from . import backend as _b
-from .mesh import Mesh, rectangular_cross, morton_order
+from .mesh import Mesh, rectangular_cross, rectangular_cross_neighbours, morton_order
 from .quantity import Quantity
 
 # multiprocessor_mode of the B200 backend.  The reference uses 0 (orig C), 1 (simd),
@@ -905,4 +905,6 @@ class Domain:
 def rectangular_cross_domain(m, n, len1=1.0, len2=1.0, origin=(0.0, 0.0), **kwargs):
     """anuga/extras.py:13 - rectangular_cross mesh wrapped in a Domain."""
     points, vertices, boundary = rectangular_cross(int(m), int(n), len1, len2, origin)
-    return Domain(points, vertices, boundary, **kwargs)
+    mesh = Mesh(points, vertices, boundary, use_inscribed_circle=kwargs.pop("use_inscribed_circle", False),
+                neighbour_structure=rectangular_cross_neighbours(int(m), int(n)))
+    return Domain(mesh=mesh, **kwargs)

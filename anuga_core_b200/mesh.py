@@ -197,6 +197,29 @@ class Mesh:
         N = self.number_of_triangles = self.triangles.shape[0]
         self.use_inscribed_circle = use_inscribed_circle
 
+        native = None
+        if N >= 200000:          # large meshes: one pass in libswk's host helper (same bits)
+            from . import backend
+            native = backend.mesh_geometry_native(self.nodes, self.triangles, use_inscribed_circle)
+        if native is not None:
+            (self.vertex_coordinates, self.areas, self.normals, self.edgelengths, self.centroid_coordinates,
+             self.radii, self.edge_midpoint_coordinates, bad) = native
+            if bad >= 0:
+                raise AssertionError("Degenerate Triangle(s) " + str(np.where(self.areas <= 0.0)[0]))
+        else:
+            self._geometry_numpy(use_inscribed_circle)
+
+        if neighbour_structure is None:
+            neighbour_structure = build_neighbour_structure(self.triangles, self.number_of_nodes)
+        # (a sub-mesh cut out of a larger mesh may pass the structure it already knows)
+        self.neighbours, self.neighbour_edges, self.number_of_boundaries = neighbour_structure
+        rng = np.arange(N, dtype=np.int64)[:, None]
+        self.surrogate_neighbours = np.where(self.neighbours < 0, rng, self.neighbours)
+
+        self._build_boundary(boundary)
+
+    def _geometry_numpy(self, use_inscribed_circle):
+        N = self.number_of_triangles
         i0 = self.triangles[:, 0]
         i1 = self.triangles[:, 1]
         i2 = self.triangles[:, 2]
@@ -251,15 +274,6 @@ class Mesh:
         E[1::3] = 0.5 * (V[2::3] + V[0::3])
         E[2::3] = 0.5 * (V[0::3] + V[1::3])
         self.edge_midpoint_coordinates = E
-
-        if neighbour_structure is None:
-            neighbour_structure = build_neighbour_structure(self.triangles, self.number_of_nodes)
-        # (a sub-mesh cut out of a larger mesh may pass the structure it already knows)
-        self.neighbours, self.neighbour_edges, self.number_of_boundaries = neighbour_structure
-        rng = np.arange(N, dtype=np.int64)[:, None]
-        self.surrogate_neighbours = np.where(self.neighbours < 0, rng, self.neighbours)
-
-        self._build_boundary(boundary)
 
     def __len__(self):
         return self.number_of_triangles

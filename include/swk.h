@@ -172,6 +172,16 @@ int swk_build_neighbour_structure(int64_t number_of_triangles, int64_t number_of
                                   const int64_t *triangles, int64_t *neighbours,
                                   int64_t *neighbour_edges, int64_t *number_of_boundaries);
 
+/* Triangle geometry of a mesh, the job of General_mesh.__init__ (general_mesh.py:156-277): per
+ * triangle the vertex coordinates (3N,2), area, outward unit normals of the three edges (N,6),
+ * edge lengths (N,3), centroid (N,2), radius (min distance centroid -> edge midpoint, or the
+ * inscribed-circle radius) and edge midpoints (3N,2), with the reference's operation order.
+ * *first_degenerate receives the first triangle with area <= 0, or -1. */
+int swk_mesh_geometry(int64_t number_of_triangles, int64_t number_of_nodes, const double *nodes,
+                      const int64_t *triangles, int64_t use_inscribed_circle, double *vertex_coordinates,
+                      double *areas, double *normals, double *edgelengths, double *centroid_coordinates,
+                      double *radii, double *edge_midpoint_coordinates, int64_t *first_degenerate);
+
 /* =========================== (1) RESIDENT LAYER ================================ */
 
 /* Number of usable sm_100 devices (0 and SWK_ERR_CUDA semantics: *count = 0). */
