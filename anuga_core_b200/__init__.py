@@ -3,7 +3,7 @@ shallow-water timestep (DE0/DE1/DE2): hand-written sm_100a CUDA behind the
 reference's shallow_water.Domain API.  See DESIGN.md and INTEGRATION.md."""
 from .mesh import Mesh, rectangular_cross, rectangular, morton_order
 from .quantity import Quantity
-from .boundaries import (Reflective_boundary, Dirichlet_boundary, Transmissive_boundary, Time_boundary,
+from .boundaries import (Flather_external_stage_zero_velocity_boundary, Reflective_boundary, Dirichlet_boundary, Transmissive_boundary, Time_boundary,
                          Transmissive_n_momentum_zero_t_momentum_set_stage_boundary,
                          Transmissive_momentum_set_stage_boundary,
                          Transmissive_stage_zero_momentum_boundary, Time_stage_zero_momentum_boundary)

@@ -38,6 +38,8 @@ _BOUNDARY_BY_NAME = {
     "Transmissive_stage_zero_momentum_boundary":
         lambda B, d: _bnd.Transmissive_stage_zero_momentum_boundary(d),
     "Time_stage_zero_momentum_boundary": lambda B, d: _bnd.Time_stage_zero_momentum_boundary(d, B.f),
+    "Flather_external_stage_zero_velocity_boundary":
+        lambda B, d: _bnd.Flather_external_stage_zero_velocity_boundary(d, B.function),
 }
 
 _SCALARS = ("epsilon", "H0", "g", "minimum_allowed_height", "maximum_allowed_speed", "evolve_max_timestep",

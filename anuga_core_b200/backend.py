@@ -33,6 +33,7 @@ Q = dict(
 BC_NONE, BC_REFLECTIVE, BC_DIRICHLET, BC_TRANSMISSIVE = 0, 1, 2, 3
 BC_TRANSMISSIVE_N_ZERO_T_SET_STAGE, BC_TRANSMISSIVE_MOMENTUM_SET_STAGE = 4, 5
 BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6
+BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY = 7
 
 _I = C.c_int64
 _D = C.c_double

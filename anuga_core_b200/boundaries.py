@@ -10,6 +10,7 @@ k_boundary_values (csrc/swk_kernels.cuh) and follows evaluate_segment of
   Transmissive_n_momentum_zero_t_momentum_set_stage_boundary       :477-517
   Transmissive_stage_zero_momentum_boundary                        :543-551
   Time_stage_zero_momentum_boundary                                :616-635
+  Flather_external_stage_zero_velocity_boundary                    :1096-1266
   Transmissive_boundary    anuga/abstract_2d_finite_volumes/generic_boundary_conditions.py:173-193
   Dirichlet_boundary                                               :221-264
   Time_boundary                                                    :370-411
@@ -150,6 +151,16 @@ class Transmissive_momentum_set_stage_boundary(_Set_stage):
 class Time_stage_zero_momentum_boundary(_Set_stage):
     device_kind = _b.BC_DIRICHLET
     _oracle_kind = "time_stage_zero_momentum"
+
+
+class Flather_external_stage_zero_velocity_boundary(_Set_stage):
+    """weakly reflecting open boundary: external stage f(t), zero external velocity, combined with the
+    interior state through characteristic variables (vectorised form, boundaries.py:1207-1266)"""
+    device_kind = _b.BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY
+    _oracle_kind = "flather_external_stage_zero_velocity"
+
+    def __init__(self, domain=None, function=None):
+        _Set_stage.__init__(self, domain, function)
 
 
 class Transmissive_stage_zero_momentum_boundary(Boundary):

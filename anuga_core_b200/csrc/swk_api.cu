@@ -358,7 +358,6 @@ extern "C" int swk_mesh_geometry(int64_t N, int64_t nn, const double *nodes, con
       normals[6 * k + 2 * e] = yn;
       normals[6 * k + 2 * e + 1] = -xn;
       edgelengths[3 * k + e] = l;
-      len[e] = l;
       E[6 * k + 2 * e] = 0.5 * (x[p] + x[q]);
       E[6 * k + 2 * e + 1] = 0.5 * (y[p] + y[q]);
     }
@@ -382,7 +381,6 @@ extern "C" int swk_mesh_geometry(int64_t N, int64_t nn, const double *nodes, con
       const double s2 = sqrt((x[2] - x[0]) * (x[2] - x[0]) + (y[2] - y[0]) * (y[2] - y[0]));
       radii[k] = 2.0 * a / (s0 + s1 + s2);
     }
-    (void)len;
   }
   if (first_degenerate) *first_degenerate = bad;
   return SWK_OK;
@@ -872,7 +870,7 @@ extern "C" int swk_set_boundary_segment(swk_domain *d, int segment, int kind, co
 {
   if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
   if (segment < 0 || segment > 4096) return fail(SWK_ERR_ARG, "segment id out of range");
-  if (kind < SWK_BC_NONE || kind > SWK_BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM) return fail(SWK_ERR_ARG, "unknown boundary kind");
+  if (kind < SWK_BC_NONE || kind > SWK_BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY) return fail(SWK_ERR_ARG, "unknown boundary kind");
   if ((int)d->seg_kind.size() <= segment) {
     d->seg_kind.resize(segment + 1, 0);
     d->seg_val.resize(3 * (segment + 1), 0.0);

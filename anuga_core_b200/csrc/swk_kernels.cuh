@@ -146,9 +146,9 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
     const double hc = e.h;
     const double hmin = dmin(dmin(e0.h, dmin(e1.h, e2.h)), hc);
     const double hmax = dmax(dmax(e0.h, dmax(e1.h, e2.h)), hc);
-    double hfactor = dmax(0., dmin(c_tmp * dmax(hmin, 0.0) / dmax(hc, 1.0e-06) + d_tmp,
-                                   dmin(c_tmp * dmax(hc, 0.) / dmax(hmax, 1.0e-06) + d_tmp, 1.0)));
-    hfactor = dmin(1.2 * dmax(hmin - K.mah, 0.) / (dmax(hmin, 0.) + 1. * K.mah), hfactor);
+    double hfactor = dmax0(dmin(c_tmp * dmax0(hmin) / dmax(hc, 1.0e-06) + d_tmp,
+                                dmin(c_tmp * dmax0(hc) / dmax(hmax, 1.0e-06) + d_tmp, 1.0)));
+    hfactor = dmin(1.2 * dmax0(hmin - K.mah) / (dmax0(hmin) + 1. * K.mah), hfactor);
     double beta = K.beta_w_dry + (K.beta_w - K.beta_w_dry) * hfactor;
     edge_values_3(beta, e.w, e0.w, e1.w, e2.w, G, w0, w1, w2);
     edge_values_3(beta, e.h, e0.h, e1.h, e2.h, G, h0, h1, h2);
@@ -239,7 +239,8 @@ struct Segments {
 // its outward normal and (centroid-transmissive only) its protected centroid state
 __device__ __forceinline__ bool boundary_value_core(int kind, double v0, double v1, double v2, const d4 e,
                                                     double n1, double n2, int centroid_transmissive,
-                                                    double cw, double cuh, double cvh, d4 &out)
+                                                    double cw, double cuh, double cvh, d4 &out,
+                                                    double bed_c = 0.0, double g = 0.0)
 {
   switch (kind) {
     case 1: {                                  // Reflective (boundaries.py:262-278)
@@ -269,6 +270,28 @@ __device__ __forceinline__ bool boundary_value_core(int kind, double v0, double 
     case 6:                                    // Transmissive_stage_zero_momentum
       out.x = e.x; out.y = 0.0; out.z = 0.0;
       break;
+    case 7: {                                  // Flather_external_stage_zero_velocity (boundaries.py:1207-1266)
+      const double sb = e.x, xb = e.z, yb = e.w, eb = e.x - e.y;
+      const double depth = dmax0(sb - bed_c);
+      const double so = 0.0 * sb + v0;
+      // "dry" also whenever the external stage is above the cell's bed (:1255) - kept as is
+      if (depth == 0.0 || so > bed_c) {
+        out.x = (bed_c <= so) ? so : eb;
+        out.y = 0.0 * xb;
+        out.z = 0.0 * yb;
+      } else {
+        const double s = sqrt(g / depth);
+        const double ndotq = n1 * xb + n2 * yb;
+        const double w1 = 0.0 - s * so;
+        const double w2 = (ndotq > 0.0) ? (n2 * xb - n1 * yb) / depth : 0.0 * ndotq;
+        const double w3 = ndotq / depth + s * sb;
+        const double qperp = (w3 + w1) / 2.0 * depth;
+        const double qpar = w2 * depth;
+        out.x = (w3 - w1) / (2.0 * s);
+        out.y = qperp * n1 + qpar * n2;
+        out.z = qperp * n2 - qpar * n1;
+      }
+    } break;
     default:
       return false;
   }
@@ -300,8 +323,9 @@ __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, 
     cw = ef.w; cuh = ef.uh; cvh = ef.vh;
     if (D.zflag[k] & 1) { cuh = 0.0; cvh = 0.0; }
   }
+  const double bed_c = (kind == 7) ? D.cq[k].w : 0.0;
   touched = boundary_value_core(kind, S.seg_val[3 * seg], S.seg_val[3 * seg + 1], S.seg_val[3 * seg + 2], e,
-                                n1, n2, centroid_transmissive, cw, cuh, cvh, out);
+                                n1, n2, centroid_transmissive, cw, cuh, cvh, out, bed_c, K.g);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_boundary_values(Dev D, Segments S, Consts K, int centroid_transmissive)
@@ -367,7 +391,7 @@ __device__ __forceinline__ TriFlux triangle_flux_core(const Dev &D, const Consts
     if (pn[i] < 0) {                                  // :551-561
       wr = er[i].x; uhr = er[i].y; vhr = er[i].z;
       zr = zl;
-      hre = dmax(wr - zr, 0.0);
+      hre = dmax0(wr - zr);
     } else {                                          // :562-576
       wr = er[i].x; hre = er[i].y; uhr = er[i].z; vhr = er[i].w;
       zr = wr - hre;
@@ -382,8 +406,8 @@ __device__ __forceinline__ TriFlux triangle_flux_core(const Dev &D, const Consts
         z_half = dmax(D.rw_elevation[rwc - 1], z_half);
       }
     }
-    const double h_left = dmax(hle + zl - z_half, 0.);
-    const double h_right = dmax(hre + zr - z_half, 0.);
+    const double h_left = dmax0(hle + zl - z_half);
+    const double h_right = dmax0(hre + zr - z_half);
     EdgeFlux F = edge_flux_central(wl, uhl, vhl, wr, uhr, vhr, h_left, h_right, hle, hre,
                                    nx[i], ny[i], z_half, K);
     if (RW) {
@@ -395,15 +419,15 @@ __device__ __forceinline__ TriFlux triangle_flux_core(const Dev &D, const Consts
         const double h1 = D.rw_hydraulic[ii + 3];
         const double h2 = D.rw_hydraulic[ii + 4];
         const double rw_elev = D.rw_elevation[rwc - 1];
-        const double weir_height = dmax(rw_elev - dmin(zl, zr), 0.);
-        const double h_left_tmp = dmax(own.w - z_half, 0.);
+        const double weir_height = dmax0(rw_elev - dmin(zl, zr));
+        const double h_left_tmp = dmax0(own.w - z_half);
         double h_right_tmp, zc_n = zc;
         if (pn[i] >= 0) {
           const Eff en = effective(D.cq[pn[i] >> 2], K);
           zc_n = en.z;
-          h_right_tmp = dmax(en.w - z_half, 0.);
+          h_right_tmp = dmax0(en.w - z_half);
         } else {
-          h_right_tmp = dmax(hc + zr - z_half, 0.);
+          h_right_tmp = dmax0(hc + zr - z_half);
         }
         if (rw_elev > dmax(zc, zc_n))
           weir_adjust(F, h_left_tmp, h_right_tmp, K.g, weir_height, Qfactor, s1, s2, h1, h2);

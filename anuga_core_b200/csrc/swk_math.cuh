@@ -67,8 +67,29 @@ __device__ __forceinline__ double pow_7_3(double h)
 // same as the reference's fmin / fmax; on a +0/-0 tie either zero may be returned by
 // libm as well, and no consumer distinguishes them (no division by these values).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
-__device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a : b; }
+// Written as PTX setp + selp: with a constant operand the compiler would otherwise recognise
+// "(a > C) ? a : C" as fmax(a, C) and emit the NaN-aware form again (DSETP.MAX + SEL + FSEL +
+// LOP3 + moves instead of DSETP + 2 FSEL).
+__device__ __forceinline__ double dmax(double a, double b)
+{
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+__device__ __forceinline__ double dmin(double a, double b)
+{
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+}
+// max(a, 0.0) = (a > 0) ? a : +0.0 on the integer pipe: clear all bits when the sign bit is set
+// (negative numbers and -0.0 give +0.0, exactly as the comparison form does).
+__device__ __forceinline__ double dmax0(double a)
+{
+  const int hi = __double2hiint(a), lo = __double2loint(a);
+  const int keep = ~(hi >> 31);
+  return __hiloint2double(hi & keep, lo & keep);
+}
 
 // ---------------------------------------------------------------------------
 // Scalars every kernel needs (copied into kernel parameter space).
@@ -106,7 +127,7 @@ __device__ __forceinline__ Eff effective(const d4 c, const Consts &K)
     e.mass_added = e.z - e.w;
     e.w = e.z;
   }
-  e.h = dmax(e.w - e.z, 0.0);           // :1376
+  e.h = dmax0(e.w - e.z);           // :1376
   if (e.h <= K.mah) {                   // :1382-1388 (subsumes protect's xmom-only zeroing :1136-1140)
     e.uh = 0.0;
     e.vh = 0.0;
@@ -176,7 +197,7 @@ __device__ __forceinline__ void edge_values_3(double beta, double qc, double q0,
     double d0 = a * G.dxv0 + b * G.dyv0;
     double d1 = a * G.dxv1 + b * G.dyv1;
     double d2 = a * G.dxv2 + b * G.dyv2;
-    const double qmax = dmax(dmax(dq0, dmax(dq0 + dq1, dq0 + dq2)), 0.0);
+    const double qmax = dmax0(dmax(dq0, dmax(dq0 + dq1, dq0 + dq2)));
     const double qmin = dmin(dmin(dq0, dmin(dq0 + dq1, dq0 + dq2)), 0.0);
     limit_gradient(d0, d1, d2, qmin, qmax, beta);
     e0 = qc + d0;
@@ -264,7 +285,7 @@ __device__ __forceinline__ EdgeFlux edge_flux_central(double wl, double uhl_xy, 
   } else if (K.low_froude == 2) {
     local_fr = sqrt((u_right * u_right + u_left * u_left + v_right * v_right + v_left * v_left) /
                     (c_left * c_left + c_right * c_right + 1.0e-10));
-    local_fr = sqrt(dmin(1.0, 0.01 + dmax(local_fr - 0.01, 0.0)));
+    local_fr = sqrt(dmin(1.0, 0.01 + dmax0(local_fr - 0.01)));
   }
 
   double s_max = dmax(u_left + c_left, u_right + c_right);
@@ -318,13 +339,13 @@ __device__ __noinline__ void weir_adjust(EdgeFlux &F, double h_left, double h_ri
   rw = rw * pow(1.0 - rwRat, 0.385);
   if (h_right > h_left) rw *= -1.0;
   if ((hdRat < s2) & (hdWrRat < h2)) {
-    const double w1 = dmin(dmax(hdRat - s1, 0.) / (s2 - s1), 1.0);
-    const double w2 = dmin(dmax(hdWrRat - h1, 0.) / (h2 - h1), 1.0);
+    const double w1 = dmin(dmax0(hdRat - s1) / (s2 - s1), 1.0);
+    const double w2 = dmin(dmax0(hdWrRat - h1) / (h2 - h1), 1.0);
     const double newFlux = (rw * (1.0 - w1) + w1 * F.f0) * (1.0 - w2) + w2 * F.f0;
     double scaleFlux;
     if (fabs(F.f0) > 1.0e-100) scaleFlux = newFlux / F.f0;
     else scaleFlux = 0.;
-    scaleFlux = dmax(scaleFlux, 0.);
+    scaleFlux = dmax0(scaleFlux);
     F.f0 = newFlux;
     F.f1 *= dmin(scaleFlux, 10.);
     F.f2 *= dmin(scaleFlux, 10.);

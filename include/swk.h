@@ -142,7 +142,8 @@ enum {
   SWK_BC_TRANSMISSIVE = 3,         /* generic_boundary_conditions.py:173-193 */
   SWK_BC_TRANSMISSIVE_N_ZERO_T_SET_STAGE = 4,   /* boundaries.py:477-517 */
   SWK_BC_TRANSMISSIVE_MOMENTUM_SET_STAGE = 5,   /* boundaries.py:344-372 */
-  SWK_BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6   /* boundaries.py:543-551 */
+  SWK_BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6,  /* boundaries.py:543-551 */
+  SWK_BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY = 7 /* boundaries.py:1096-1266 (evaluate_segment); v0 = external stage */
 };
 
 /* ---- evolve result ------------------------------------------------------------ */

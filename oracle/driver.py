@@ -360,6 +360,36 @@ class OracleDomain:
                 self.stage_b[ids] = self.stage_e[vol, edge]
                 self.xmom_b[ids] = 0.0
                 self.ymom_b[ids] = 0.0
+            elif kind == "flather_external_stage_zero_velocity":
+                # boundaries.py:1207-1266 (evaluate_segment), gravity = anuga.config.g
+                value = spec[1](t)
+                try:
+                    so = float(value)
+                except Exception:
+                    so = float(value[0])
+                sb = self.stage_e[vol, edge]
+                xb = self.xmom_e[vol, edge]
+                yb = self.ymom_e[vol, edge]
+                eb = self.bed_e[vol, edge]
+                bed = self.bed_c[vol]
+                depth = np.maximum(sb - bed, 0.0)
+                so = 0.0 * sb + so
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    q0_dry = np.where(bed <= so, so, eb)
+                    s = (9.8 / depth) ** 0.5
+                    ndotq = n1 * xb + n2 * yb
+                    w1 = 0.0 - s * so
+                    w2 = np.where(ndotq > 0.0, (n2 * xb - n1 * yb) / depth, 0.0 * ndotq)
+                    w3 = ndotq / depth + s * sb
+                    q0_wet = (w3 - w1) / (2.0 * s)
+                    qperp = (w3 + w1) / 2.0 * depth
+                    qpar = w2 * depth
+                    q1_wet = qperp * n1 + qpar * n2
+                    q2_wet = qperp * n2 - qpar * n1
+                dry = np.logical_or(depth == 0.0, so > bed)
+                self.stage_b[ids] = np.where(dry, q0_dry, q0_wet)
+                self.xmom_b[ids] = np.where(dry, 0.0 * xb, q1_wet)
+                self.ymom_b[ids] = np.where(dry, 0.0 * yb, q2_wet)
             elif kind == "time_stage_zero_momentum":
                 self.stage_b[ids] = float(spec[1](t))
                 self.xmom_b[ids] = 0.0

@@ -179,6 +179,23 @@ def inlet_de1(A, n=16):
     return d
 
 
+def flather_de1(A, n=16):
+    """open-ocean style boundary: Flather_external_stage_zero_velocity_boundary on two sides; the left
+    one sits on a beach whose bed rises above the external stage, so both branches are taken"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: -0.6 + 1.0 * (y / L) ** 2 + 0.05 * np.sin(x))
+    d.set_quantity("stage", lambda x, y: 0.1 + 0.3 * np.exp(-((x - 0.5 * L) ** 2 + (y - 0.3 * L) ** 2) / 4.0),
+                   location="centroids")
+    d.set_quantity("friction", 0.02)
+    Br = A.Reflective_boundary(d)
+    Bf = A.Flather_external_stage_zero_velocity_boundary(d, lambda t: 0.1 + 0.05 * np.sin(t))
+    d.set_boundary({"left": Bf, "right": Bf, "top": Br, "bottom": Bf})
+    return d
+
+
 def _embankment(A, n=16):
     """two ponds separated by a dry embankment; only a culvert connects them"""
     d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
@@ -233,6 +250,7 @@ CASES = {
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "inlet_de1": (inlet_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "rain_time_de1": (rain_time_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "flather_de1": (flather_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "culvert_de1": (culvert_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_skew_de1": (culvert_skew_de1, dict(yieldstep=1.0, finaltime=4.0)),
 }
