@@ -348,7 +348,6 @@ extern "C" int swk_mesh_geometry(int64_t N, int64_t nn, const double *nodes, con
     const double a = -((x[1] * y[0] - x[0] * y[1]) + (x[2] * y[1] - x[1] * y[2]) + (x[0] * y[2] - x[2] * y[0])) / 2.0;
     areas[k] = a;
     if (!(a > 0.0) && bad < 0) bad = k;
-    double len[3];
     for (int e = 0; e < 3; e++) {           // edge e runs from vertex e+1 to vertex e+2
       const int p = (e + 1) % 3, q = (e + 2) % 3;
       double xn = x[q] - x[p], yn = y[q] - y[p];

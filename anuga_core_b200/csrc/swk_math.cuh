@@ -142,32 +142,27 @@ __device__ __forceinline__ Eff effective(const d4 c, const Consts &K)
   return e;
 }
 
-// limiter, sw_domain_openmp.c:1195-1231 (r0 carried across the three edges).
-// The reference's two conditional divisions per edge (qmin/dq when dq < -TINY, qmax/dq when
-// dq > TINY) are evaluated here as ONE branch-free division with a selected numerator and a
-// harmless denominator for the |dq| <= TINY case: the sign of dq differs from thread to
-// thread, so the branching form would execute both divisions in almost every warp.
-__device__ __forceinline__ double limiter_ratio(double dq, double qmin, double qmax, double r0)
-{
-  const double TINY = 1.0e-100;
-  const bool neg = dq < -TINY;
-  const bool valid = neg | (dq > TINY);
-  const double num = neg ? qmin : qmax;
-  const double den = valid ? dq : 1.0;
-  const double q = num / den;
-  return valid ? q : r0;
-}
-
+// limiter, sw_domain_openmp.c:1195-1231:
+//     r = 1000; r0 = 1;  for each edge i: { if (dq_i < -TINY) r0 = qmin/dq_i; else if (dq_i > TINY) r0 = qmax/dq_i;
+//     r = min(r0, r); }   phi = min(r*beta, 1)
+// i.e. r = min(1000, ratios of the valid edges, and 1.0 when edge 0 is not valid (the carried r0)).
+// qmax >= 0 is divided by positive dq only and qmin <= 0 by negative dq only, and a correctly rounded
+// quotient is monotone in its denominator, so
+//     min_i fl(qmax/dq_i) = fl(qmax / max_i dq_i),   min_i fl(qmin/dq_i) = fl(qmin / min_i dq_i):
+// two branch-free divisions per quantity instead of the reference's three (the sign of dq differs from
+// thread to thread, so a branching form would execute every division in almost every warp anyway).
 __device__ __forceinline__ void limit_gradient(double &d0, double &d1, double &d2,
                                                double qmin, double qmax, double beta)
 {
-  double r = 1000.0, r0 = 1.0;
-  r0 = limiter_ratio(d0, qmin, qmax, r0);
-  r = dmin(r0, r);
-  r0 = limiter_ratio(d1, qmin, qmax, r0);
-  r = dmin(r0, r);
-  r0 = limiter_ratio(d2, qmin, qmax, r0);
-  r = dmin(r0, r);
+  const double TINY = 1.0e-100;
+  const double dhi = dmax(d0, dmax(d1, d2));
+  const double dlo = dmin(d0, dmin(d1, d2));
+  const bool pos = dhi > TINY, neg = dlo < -TINY;
+  const double rp = (pos ? qmax : 1000.0) / (pos ? dhi : 1.0);
+  const double rn = (neg ? qmin : 1000.0) / (neg ? dlo : 1.0);
+  double r = dmin(dmin(rp, rn), 1000.0);
+  const bool valid0 = (d0 < -TINY) | (d0 > TINY);
+  r = valid0 ? r : dmin(r, 1.0);
   const double phi = dmin(r * beta, 1.0);
   d0 = d0 * phi;
   d1 = d1 * phi;
