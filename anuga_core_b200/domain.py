@@ -809,7 +809,10 @@ class Domain:
                 self._params_dirty = False
 
             if self._needs_host_stepping():
-                reason = self._evolve_host_stepped()
+                if self._only_host_side_operators_need_the_host():
+                    reason = self._evolve_device_steps_host_operators()
+                else:
+                    reason = self._evolve_host_stepped()
             else:
                 r = dev.evolve(self.relative_yieldtime, self.relative_finaltime, 0)
                 self._absorb(r)
@@ -850,6 +853,44 @@ class Domain:
         self.mass_error = r.mass_error
         self._negative_device = r.negative_cells
         self.kernel_launches += r.kernel_launches
+
+    def _only_host_side_operators_need_the_host(self):
+        """static boundaries and rates: the step itself can stay in the device time loop and only the
+        host-side operators (inlets, culverts) run between steps"""
+        if self.boundary_map:
+            for B in self.boundary_map.values():
+                if B is not None and B.time_dependent:
+                    return False
+        return all(getattr(op, "host_side", False) or not op.time_dependent
+                   for op in self.fractional_step_operators)
+
+    def _evolve_device_steps_host_operators(self):
+        """_evolve_base's loop with one device-resident step (fused kernels, device clock, device-side
+        operators) per iteration, followed by the host-side operators on their gathered cells."""
+        dev = self._dev
+        host_ops = [op for op in self.fractional_step_operators if getattr(op, "host_side", False)]
+        while True:
+            t0 = self.relative_time
+            r = dev.evolve(self.relative_yieldtime, self.relative_finaltime, 1)
+            self._absorb(r)
+            if self.record_timestep_history:
+                self.timestep_history.append(self.timestep)
+            # operators see t0 after an euler step and t0 + dt after rk2 / rk3 (see _host_step)
+            self.relative_time = t0 if self.timestepping_method == "euler" else t0 + self.timestep
+            for op in host_ops:
+                added = op()
+                if added != 0.0:
+                    dev.add_fractional_step_volume(added)
+            self.relative_time = r.time
+            dev.update_ghosts()
+            if host_ops:
+                st = dev.get_statistics()
+                self.fractional_step_volume_integral = st.fractional_step_volume_integral
+            if r.stop_reason in (1, 2):
+                # the device extrapolated for the yield before the operators ran: redo it
+                dev.distribute_to_vertices_and_edges()
+                dev.update_boundary()
+                return r.stop_reason
 
     def _evolve_host_stepped(self):
         """_evolve_base's while loop with host-evaluated callbacks (time-dependent

@@ -46,7 +46,8 @@ class Region:
             self.type = "circle"
         elif polygon is not None:
             polygon = np.asarray(polygon, dtype=np.float64)
-            ids = np.flatnonzero(_inside_polygon(c, polygon)).astype(np.int64)
+            cand = _near(domain, polygon)
+            ids = cand[_inside_polygon(c[cand], polygon)].astype(np.int64)
             if expand_polygon:                    # region.py:252-257
                 n = len(polygon)
                 for j in range(n):
@@ -83,13 +84,25 @@ def _inside_polygon(points, poly):
     return inside
 
 
+def _near(domain, pts):
+    """ids of the triangles that can touch the bounding box of `pts`: centroid within the box grown
+    by the longest edge of the mesh (keeps the exact predicates below off the other millions)"""
+    pts = np.asarray(pts, dtype=np.float64).reshape(-1, 2)
+    c = domain.centroid_coordinates
+    pad = float(np.max(domain.edgelengths))
+    lo = pts.min(axis=0) - pad
+    hi = pts.max(axis=0) + pad
+    return np.flatnonzero((c[:, 0] >= lo[0]) & (c[:, 0] <= hi[0]) & (c[:, 1] >= lo[1]) & (c[:, 1] <= hi[1]))
+
+
 def triangles_cut_by_segment(domain, p0, p1):
     """ids (ascending) of the triangles a segment touches: one of their sides meets the segment
     (closed ends), or the segment lies strictly inside.  Same predicate as the reference's
-    geometry/polygon.c:446-523, evaluated for all triangles at once."""
-    V = np.asarray(domain.vertex_coordinates, dtype=np.float64).reshape(-1, 3, 2)
+    geometry/polygon.c:446-523, evaluated for all candidate triangles at once."""
     p0 = np.asarray(p0, dtype=np.float64)
     p1 = np.asarray(p1, dtype=np.float64)
+    cand = _near(domain, [p0, p1])
+    V = np.asarray(domain.vertex_coordinates, dtype=np.float64).reshape(-1, 3, 2)[cand]
     u = p1 - p0
     perp_u = np.array([-u[1], u[0]])
     hit = np.zeros(len(V), dtype=bool)
@@ -110,19 +123,20 @@ def triangles_cut_by_segment(domain, p0, p1):
         beyond += on_side & (a > 1.0)
         before += on_side & (a < 0.0)
     hit |= (beyond >= 1) & (before >= 1)
-    return np.flatnonzero(hit).astype(np.int64)
+    return cand[hit].astype(np.int64)
 
 
 def triangle_containing_point(domain, point):
     """lowest id of a triangle whose closed hull holds the point (neighbour_mesh.py:1057-1080)"""
-    V = np.asarray(domain.vertex_coordinates, dtype=np.float64).reshape(-1, 3, 2)
+    cand = _near(domain, [point])
+    V = np.asarray(domain.vertex_coordinates, dtype=np.float64).reshape(-1, 3, 2)[cand]
     x, y = float(point[0]), float(point[1])
     inside = np.ones(len(V), dtype=bool)
     for j in range(3):
         a, b = V[:, j], V[:, (j + 1) % 3]
         cross = (b[:, 0] - a[:, 0]) * (y - a[:, 1]) - (b[:, 1] - a[:, 1]) * (x - a[:, 0])
         inside &= cross >= -1.0e-12
-    ids = np.flatnonzero(inside)
+    ids = cand[inside]
     if len(ids) == 0:
         raise Exception("Point %s not found within a triangle" % str(point))
     return int(ids[0])
