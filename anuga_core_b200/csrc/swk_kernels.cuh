@@ -157,12 +157,16 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
     beta = K.beta_vh_dry + (K.beta_vh - K.beta_vh_dry) * hfactor;
     edge_values_3(beta, e.v, e0.v, e1.v, e2.v, G, v0, v1, v2);
   } else {                                         // two boundary edges :1646-1842
-    const int which = (s.w >> 2) & 3;
-    const Eff &en = (which == 0) ? e0 : ((which == 1) ? e1 : e2);
-    edge_values_1(K.beta_w, e.w, en.w, G, w0, w1, w2);
-    edge_values_1(K.beta_w, e.h, en.h, G, h0, h1, h2);
-    edge_values_1(K.beta_w, e.u, en.u, G, u0, u1, u2);
-    edge_values_1(K.beta_w, e.v, en.v, G, v0, v1, v2);
+    const int which = (s.w >> 2) & 3;             // value selects: a reference would put e0..e2 in local memory
+    const bool is0 = which == 0, is1 = which == 1;
+    const double nw = is0 ? e0.w : (is1 ? e1.w : e2.w);
+    const double nh = is0 ? e0.h : (is1 ? e1.h : e2.h);
+    const double nu = is0 ? e0.u : (is1 ? e1.u : e2.u);
+    const double nv = is0 ? e0.v : (is1 ? e1.v : e2.v);
+    edge_values_1(K.beta_w, e.w, nw, G, w0, w1, w2);
+    edge_values_1(K.beta_w, e.h, nh, G, h0, h1, h2);
+    edge_values_1(K.beta_w, e.u, nu, G, u0, u1, u2);
+    edge_values_1(K.beta_w, e.v, nv, G, v0, v1, v2);
   }
   if (K.vel2) {                                    // :1851-1860
     u0 = u0 * h0; v0 = v0 * h0;
