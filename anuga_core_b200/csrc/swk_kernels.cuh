@@ -27,8 +27,14 @@ namespace swk {
 #ifndef SWK_MINB_A          // min resident blocks per SM for pass A (extrapolate)
 #define SWK_MINB_A 5
 #endif
-#ifndef SWK_MINB_F          // ... for the flux kernels
+#ifndef SWK_MINB_F          // ... for the flux kernel of substep 0
 #define SWK_MINB_F 5
+#endif
+#ifndef SWK_MINB_FU         // ... for the fused flux + update kernel
+#define SWK_MINB_FU 7
+#endif
+#ifndef SWK_FU_ROLLED       // fused kernel: one edge per trip of a rolled loop (see triangle_flux)
+#define SWK_FU_ROLLED true
 #endif
 constexpr int BLOCK = SWK_BLOCK;
 
@@ -367,119 +373,127 @@ __device__ __noinline__ int acct_slot_lookup(const int *keys, const int *keys_po
 
 // el[i]: own edge records; er[i]: the neighbour's record of the shared edge, or for a boundary edge
 // (pn[i] < 0) the boundary value {stage, xmom, ymom, -}.
+// contribution of edge i of triangle k: el = own edge record, er = the neighbour's record of the shared
+// edge or, for a boundary edge (q < 0), the boundary value {stage, xmom, ymom, -}
 template <bool RW>
-__device__ __forceinline__ TriFlux triangle_flux_core(const Dev &D, const Consts &K, int k, const int (&pn)[3],
-                                                      const int flags, const d4 (&el)[3], const d4 (&er)[3],
-                                                      const d4 f0, const d4 f1, const d4 f2,
-                                                      const Eff &own, bool first)
+__device__ __forceinline__ void edge_contribution(const Dev &D, const Consts &K, int k, int i, int q, int flags,
+                                                  const d4 el, const d4 er, double nx, double ny, double length,
+                                                  const Eff &own, bool first, TriFlux &T)
 {
   const int NP = D.NP;
-  const i4 p = {pn[0], pn[1], pn[2], flags};
-  const double nx[3] = {f0.x, f0.z, f1.x};
-  const double ny[3] = {f0.y, f0.w, f1.y};
-  const double len[3] = {f1.z, f1.w, f2.x};
-  const double inv_area = f2.y;
-  const double radius = f2.z;
-  const bool full = p.w & 1;
+  const bool full = flags & 1;
   const double hc = own.h, zc = own.z;
-
-  TriFlux T;
-  T.su = 0.0; T.xu = 0.0; T.yu = 0.0;
-  T.dtmin = 1.0e+100;
-  T.speed = 0.0;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const double wl = el[i].x, hle = el[i].y, uhl = el[i].z, vhl = el[i].w;
-    const double zl = wl - hle;                       // bed_edge = stage_edge - height_edge (:1863)
-    double wr, uhr, vhr, zr, hre;
-    if (pn[i] < 0) {                                  // :551-561
-      wr = er[i].x; uhr = er[i].y; vhr = er[i].z;
-      zr = zl;
-      hre = dmax0(wr - zr);
-    } else {                                          // :562-576
-      wr = er[i].x; hre = er[i].y; uhr = er[i].z; vhr = er[i].w;
-      zr = wr - hre;
-    }
-    double z_half = dmax(zl, zr);
-    bool rw_edge = false;
-    int rwc = 0;
-    if (RW) {
-      rw_edge = (p.w >> (1 + i)) & 1;
-      if (rw_edge) {                                  // :582-588
-        rwc = D.rw_counter[i * NP + k];
-        z_half = dmax(D.rw_elevation[rwc - 1], z_half);
-      }
-    }
-    const double h_left = dmax0(hle + zl - z_half);
-    const double h_right = dmax0(hre + zr - z_half);
-    EdgeFlux F = edge_flux_central(wl, uhl, vhl, wr, uhr, vhr, h_left, h_right, hle, hre,
-                                   nx[i], ny[i], z_half, K);
-    if (RW) {
-      if (rw_edge) {                                  // :607-653
-        const int ii = D.rw_rowIndex[rwc - 1] * D.rw_ncol;
-        const double Qfactor = D.rw_hydraulic[ii];
-        const double s1 = D.rw_hydraulic[ii + 1];
-        const double s2 = D.rw_hydraulic[ii + 2];
-        const double h1 = D.rw_hydraulic[ii + 3];
-        const double h2 = D.rw_hydraulic[ii + 4];
-        const double rw_elev = D.rw_elevation[rwc - 1];
-        const double weir_height = dmax0(rw_elev - dmin(zl, zr));
-        const double h_left_tmp = dmax0(own.w - z_half);
-        double h_right_tmp, zc_n = zc;
-        if (pn[i] >= 0) {
-          const Eff en = effective(D.cq[pn[i] >> 2], K);
-          zc_n = en.z;
-          h_right_tmp = dmax0(en.w - z_half);
-        } else {
-          h_right_tmp = dmax0(hc + zr - z_half);
-        }
-        if (rw_elev > dmax(zc, zc_n))
-          weir_adjust(F, h_left_tmp, h_right_tmp, K.g, weir_height, Qfactor, s1, s2, h1, h2);
-      }
-    }
-    const double length = len[i];
-    const double ef0 = -F.f0 * length;
-    const double ef1 = -F.f1 * length;
-    const double ef2 = -F.f2 * length;
-    const double pressuregrad =
-        length * (-K.g * 0.5 * (h_left * h_left - hle * hle - (hle + hc) * (zl - zc)) + F.pressure_flux);
-    if (first) {                                      // :667-686, division hoisted out of the loop (below)
-      if (full && F.max_speed > K.epsilon) T.speed = dmax(T.speed, F.max_speed);
-    }
-    T.su += ef0;
-    T.xu += ef1;
-    T.yu += ef2;
-    if (pn[i] < 0) {                                  // boundary_flux_sum terms (:696-701)
-      const int slot = D.pos_b[-pn[i] - 1];
-      if (slot >= 0) D.acct_val[slot] = ef0;
-    } else if ((p.w >> (4 + i)) & 1) {
-      const int slot = acct_slot_lookup(D.acct_keys, D.acct_keys_pos, D.n_acct_keys, (k << 2) | i);
-      if (slot >= 0) D.acct_val[slot] = ef0;
-    }
-    T.xu -= nx[i] * pressuregrad;
-    T.yu -= ny[i] * pressuregrad;
+  const double wl = el.x, hle = el.y, uhl = el.z, vhl = el.w;
+  const double zl = wl - hle;                         // bed_edge = stage_edge - height_edge (:1863)
+  double wr, uhr, vhr, zr, hre;
+  if (q < 0) {                                        // :551-561
+    wr = er.x; uhr = er.y; vhr = er.z;
+    zr = zl;
+    hre = dmax0(wr - zr);
+  } else {                                            // :562-576
+    wr = er.x; hre = er.y; uhr = er.z; vhr = er.w;
+    zr = wr - hre;
   }
+  double z_half = dmax(zl, zr);
+  bool rw_edge = false;
+  int rwc = 0;
+  if (RW) {
+    rw_edge = (flags >> (1 + i)) & 1;
+    if (rw_edge) {                                    // :582-588
+      rwc = D.rw_counter[i * NP + k];
+      z_half = dmax(D.rw_elevation[rwc - 1], z_half);
+    }
+  }
+  const double h_left = dmax0(hle + zl - z_half);
+  const double h_right = dmax0(hre + zr - z_half);
+  EdgeFlux F = edge_flux_central(wl, uhl, vhl, wr, uhr, vhr, h_left, h_right, hle, hre, nx, ny, z_half, K);
+  if (RW) {
+    if (rw_edge) {                                    // :607-653
+      const int ii = D.rw_rowIndex[rwc - 1] * D.rw_ncol;
+      const double Qfactor = D.rw_hydraulic[ii];
+      const double s1 = D.rw_hydraulic[ii + 1];
+      const double s2 = D.rw_hydraulic[ii + 2];
+      const double h1 = D.rw_hydraulic[ii + 3];
+      const double h2 = D.rw_hydraulic[ii + 4];
+      const double rw_elev = D.rw_elevation[rwc - 1];
+      const double weir_height = dmax0(rw_elev - dmin(zl, zr));
+      const double h_left_tmp = dmax0(own.w - z_half);
+      double h_right_tmp, zc_n = zc;
+      if (q >= 0) {
+        const Eff en = effective(D.cq[q >> 2], K);
+        zc_n = en.z;
+        h_right_tmp = dmax0(en.w - z_half);
+      } else {
+        h_right_tmp = dmax0(hc + zr - z_half);
+      }
+      if (rw_elev > dmax(zc, zc_n))
+        weir_adjust(F, h_left_tmp, h_right_tmp, K.g, weir_height, Qfactor, s1, s2, h1, h2);
+    }
+  }
+  const double ef0 = -F.f0 * length;
+  const double ef1 = -F.f1 * length;
+  const double ef2 = -F.f2 * length;
+  const double pressuregrad =
+      length * (-K.g * 0.5 * (h_left * h_left - hle * hle - (hle + hc) * (zl - zc)) + F.pressure_flux);
+  if (first) {                                        // :667-686, division hoisted out of the loop
+    if (full && F.max_speed > K.epsilon) T.speed = dmax(T.speed, F.max_speed);
+  }
+  T.su += ef0;
+  T.xu += ef1;
+  T.yu += ef2;
+  if (q < 0) {                                        // boundary_flux_sum terms (:696-701)
+    const int slot = D.pos_b[-q - 1];
+    if (slot >= 0) D.acct_val[slot] = ef0;
+  } else if ((flags >> (4 + i)) & 1) {
+    const int slot = acct_slot_lookup(D.acct_keys, D.acct_keys_pos, D.n_acct_keys, (k << 2) | i);
+    if (slot >= 0) D.acct_val[slot] = ef0;
+  }
+  T.xu -= nx * pressuregrad;
+  T.yu -= ny * pressuregrad;
+}
+
+__device__ __forceinline__ void finish_flux(TriFlux &T, double radius, double inv_area, bool first)
+{
   // min_i fl(radius / speed_i) == fl(radius / max_i speed_i): correctly rounded division is monotone,
   // so one division per triangle gives the reference's local timestep bit for bit
   if (first && T.speed > 0.0) T.dtmin = radius * 1.0 / T.speed;
   T.su *= inv_area;
   T.xu *= inv_area;
   T.yu *= inv_area;
-  return T;
 }
 
-template <bool RW>
+template <bool RW, bool ROLLED = false>
 __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, int k, const i4 p,
                                                  const Eff &own, bool first)
 {
   const int NP = D.NP;
+  TriFlux T;
+  T.su = 0.0; T.xu = 0.0; T.yu = 0.0;
+  T.dtmin = 1.0e+100;
+  T.speed = 0.0;
+  const d4 f0 = D.fg[k];
+  const d4 f1 = D.fg[NP + k];
+  const d4 f2 = D.fg[2 * NP + k];
+  if (ROLLED) {
+  // one edge per trip of a rolled loop: operands are loaded inside the trip, so only one edge's
+  // records are live at a time (fewer registers, smaller code) at the price of three load phases
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) {
+    const int q = (i == 0) ? p.x : ((i == 1) ? p.y : p.z);
+    const d4 el = D.eq[i * NP + k];
+    d4 er;
+    if (q >= 0) er = D.eq[(q & 3) * NP + (q >> 2)];
+    else er = D.bq[-q - 1];
+    const double nx = (i == 0) ? f0.x : ((i == 1) ? f0.z : f1.x);
+    const double ny = (i == 0) ? f0.y : ((i == 1) ? f0.w : f1.y);
+    const double len = (i == 0) ? f1.z : ((i == 1) ? f1.w : f2.x);
+    edge_contribution<RW>(D, K, k, i, q, p.w, el, er, nx, ny, len, own, first, T);
+  }
+  } else {
   d4 el[3];
   el[0] = D.eq[k];
   el[1] = D.eq[NP + k];
   el[2] = D.eq[2 * NP + k];
-  const d4 f0 = D.fg[k];
-  const d4 f1 = D.fg[NP + k];
-  const d4 f2 = D.fg[2 * NP + k];
   const int pn[3] = {p.x, p.y, p.z};
   d4 er[3];
 #pragma unroll
@@ -488,7 +502,15 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
     if (q >= 0) er[i] = D.eq[(q & 3) * NP + (q >> 2)];
     else er[i] = D.bq[-q - 1];
   }
-  return triangle_flux_core<RW>(D, K, k, pn, p.w, el, er, f0, f1, f2, own, first);
+  const double nx[3] = {f0.x, f0.z, f1.x};
+  const double ny[3] = {f0.y, f0.w, f1.y};
+  const double len[3] = {f1.z, f1.w, f2.x};
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    edge_contribution<RW>(D, K, k, i, pn[i], p.w, el[i], er[i], nx[i], ny[i], len[i], own, first, T);
+  }
+  finish_flux(T, f2.z, f2.y, first);
+  return T;
 }
 
 // block-wide min of positive doubles -> one atomicMin per block
@@ -617,7 +639,7 @@ __global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U,
 // Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
 // dt is already known, so explicit updates never touch HBM.  (Not used with
 // riverwalls: the weir branch reads the neighbour's stage centroid, :635.)
-__global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux_update(Dev D, Consts K, UpdateArgs U, int k0, int k1)
+__global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Consts K, UpdateArgs U, int k0, int k1)
 {
   if (D.clock->stop) return;
   const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
@@ -626,7 +648,7 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux_update(Dev D, Consts
   const i4 p = D.connB[k];
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
-  const TriFlux T = triangle_flux<false>(D, K, k, p, e, false);
+  const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, e, false);
   triangle_update(D, K, U, k, raw, e, D.zflag[k], T.su, T.xu, T.yu, dt, D.cq, nullptr);
 }
 
