@@ -124,8 +124,17 @@ class Domain:
         self.fractional_step_volume_integral = 0.0
         self.total_steps = 0
         self.kernel_launches = 0
-        self.store = False
+        self.store = False                        # the reference defaults to True; SWW output is opt-in here
         self.name = "domain"
+        self.datadir = "."
+        self.smooth = True                        # set_store_vertices_uniquely(False), :341
+        self.store_centroids = True               # _set_DE*_defaults
+        self.using_centroid_averaging = True      # _set_DE*_defaults (shallow_water_domain.py:596)
+        self.minimum_storable_height = 1.0e-3     # anuga/config.py:189
+        self.quantities_to_be_stored = {"elevation": 1, "friction": 1, "stage": 2, "xmomentum": 2, "ymomentum": 2}
+        self.yieldstep_counter = 0
+        self.output_frequency = 1
+        self.writer = None
         self._dev = None
         self.pin_host_arrays = True
         self._stale = set()
@@ -272,13 +281,23 @@ class Domain:
             if hasattr(op, "op_id"):
                 op.op_id = None
 
-    # accepted for script compatibility; SWW output is out of scope
+    # -- yield-time SWW output (anuga_core_b200/sww.py) ------------------------------------
     def set_store(self, flag=True):
-        if flag:
-            raise NotImplementedError("SWW output is outside the hot-path scope; use set_store(False)")
-        self.store = False
+        if flag and self.numproc > 1:
+            raise NotImplementedError("SWW output of a distributed domain (per-rank files + sww_merge) is not built")
+        self.store = bool(flag)
 
-    def set_name(self, name):
+    def get_store(self):
+        return self.store
+
+    def set_name(self, name=None, timestamp=False):
+        if name is None:
+            name = "domain"
+        if name.endswith(".sww"):
+            name = name[:-4]
+        if timestamp:
+            from time import localtime, strftime
+            name = name + "_" + strftime("%Y%m%d_%H%M%S", localtime())
         self.name = name
 
     def get_name(self):
@@ -286,6 +305,36 @@ class Domain:
 
     def set_datadir(self, path):
         self.datadir = path
+
+    def get_datadir(self):
+        return self.datadir
+
+    def set_store_centroids(self, flag=True):
+        self.store_centroids = flag
+
+    def set_store_vertices_uniquely(self, flag=True, reduction=None):
+        self.smooth = not flag
+
+    def set_store_vertices_smoothly(self, flag=True, reduction=None):
+        self.smooth = flag
+
+    def set_using_centroid_averaging(self, flag=True):
+        self.using_centroid_averaging = bool(flag)
+
+    def get_using_centroid_averaging(self):
+        return self.using_centroid_averaging
+
+    def set_minimum_storable_height(self, h):
+        self.minimum_storable_height = h
+
+    def initialise_storage(self):
+        """shallow_water_domain.py:2410-2423"""
+        from .sww import SWW_file
+        self.writer = SWW_file(self)
+        self.writer.store_connectivity()
+
+    def store_timestep(self):
+        self.writer.store_timestep()
 
     def set_quantities_to_be_stored(self, q):
         self.quantities_to_be_stored = q
@@ -741,10 +790,41 @@ class Domain:
     def _check_negative(self, n):
         self._negative_cells = getattr(self, "_negative_cells", 0) + n
 
-    def evolve(self, yieldstep=None, finaltime=None, duration=None, skip_initial_step=False):
+    def evolve(self, yieldstep=None, outputstep=None, finaltime=None, duration=None, skip_initial_step=False):
+        """Domain.evolve (shallow_water_domain.py:2300-2407): the time loop below plus, with
+        set_store(True), the SWW file: created before the first yield, one frame every `outputstep`."""
+        if outputstep is None or yieldstep is None:
+            self.output_frequency = 1
+        else:
+            freq = outputstep / yieldstep
+            assert float(freq).is_integer(), \
+                "outputstep (%s) should be an integer multiple of yieldstep (%s)" % (outputstep, yieldstep)
+            self.output_frequency = int(freq)
+        new_file = self.store and (self.relative_time == 0.0 or not self.evolved_called)
+        if new_file and (skip_initial_step or self.evolved_called):
+            # no initial yield to hang the file creation on: extrapolate once now (as the reference does)
+            dev = self._ensure_device()
+            self._push_quantities(force=not hasattr(self, "_pushed_once"))
+            self._pushed_once = True
+            dev.distribute_to_vertices_and_edges()
+            self._mark_device_newer()
+            self._pull_centroids()
+            self.initialise_storage()
+            new_file = False
+        for t in self._evolve_base(yieldstep=yieldstep, finaltime=finaltime, duration=duration,
+                                   skip_initial_step=skip_initial_step):
+            if self.store:
+                if new_file:
+                    self.initialise_storage()
+                    new_file = False
+                if self.yieldstep_counter % self.output_frequency == 0:
+                    self.store_timestep()
+            yield t
+            self.yieldstep_counter += 1
+
+    def _evolve_base(self, yieldstep=None, finaltime=None, duration=None, skip_initial_step=False):
         """Generator with the reference's protocol: yields the model time with the
-        conserved centroid arrays valid on the host (shallow_water_domain.py:2300-2407,
-        generic_domain.py:1715-1912)."""
+        conserved centroid arrays valid on the host (generic_domain.py:1715-1912)."""
         if self.boundary_map is None:
             raise Exception("Boundary tags must be bound to boundary objects before evolving system, "
                             "e.g. using the method set_boundary.\nThis system has the boundary tags %s"

@@ -216,6 +216,7 @@ class Mesh:
         rng = np.arange(N, dtype=np.int64)[:, None]
         self.surrogate_neighbours = np.where(self.neighbours < 0, rng, self.neighbours)
 
+        self.vertex_value_indices = None
         self._build_boundary(boundary)
 
     def _geometry_numpy(self, use_inscribed_circle):
@@ -307,6 +308,19 @@ class Mesh:
             self.tag_boundary_cells[tag] = []
         for j, tag in enumerate(self.boundary_tags_by_index):
             self.tag_boundary_cells[tag].append(j)
+
+    def build_inverted_triangle_structure(self):
+        """number_of_triangles_per_node and vertex_value_indices: the vertex slots 3*triangle+vertex
+        grouped by node, in the order the reference uses (general_mesh.py:740-850: an argsort of the
+        flattened triangle table with numpy's default sort)."""
+        if getattr(self, "vertex_value_indices", None) is None:
+            flat = self.triangles.reshape(-1)
+            count = np.bincount(flat, minlength=self.number_of_nodes).astype(np.int64)
+            if np.any(count == 0):
+                raise NotImplementedError("nodes that belong to no triangle are not supported")
+            self.number_of_triangles_per_node = count
+            self.vertex_value_indices = np.argsort(flat).astype(np.int64)
+        return self.number_of_triangles_per_node, self.vertex_value_indices
 
     def get_boundary_tags(self):
         tags = {}

@@ -185,6 +185,40 @@ class Quantity:
             raise NotImplementedError(location)
         return a if indices is None else a[np.asarray(indices, dtype=np.int64)]
 
+    def get_vertex_values(self, xy=True, smooth=None, centroid_averaging=None, precision=None):
+        """One value per mesh node (smooth: mean over the triangles sharing the node of their vertex
+        values or - centroid_averaging, the DE algorithms' setting - of their centroid values, summed
+        in the reference's order) or per triangle vertex, optionally with coordinates and
+        connectivity (quantity.py:2158-2228, quantity.c:823-910)."""
+        d = self.domain
+        if smooth is None:
+            smooth = bool(getattr(d, "smooth", False))
+        if centroid_averaging is None:
+            centroid_averaging = bool(getattr(d, "using_centroid_averaging", False))
+        if precision is None:
+            precision = np.float64
+        if smooth:
+            count, order = d.mesh.build_inverted_triangle_structure()
+            V = d.triangles
+            if centroid_averaging:
+                vals = self.centroid_values[order // 3]
+            else:
+                vals = self.vertex_values.reshape(-1)[order]
+            start = np.concatenate([[0], np.cumsum(count)[:-1]])
+            A = np.zeros(d.number_of_nodes, dtype=np.float64)
+            for j in range(int(count.max())):           # sequential sums, like the C loop
+                m = count > j
+                A[m] += vals[start[m] + j]
+            A = (A / count).astype(precision)
+            points = d.nodes
+        else:
+            V = np.arange(3 * self.N, dtype=np.int64).reshape(-1, 3)
+            points = d.vertex_coordinates
+            A = self.vertex_values.flatten().astype(precision)
+        if xy:
+            return points[:, 0].astype(precision), points[:, 1].astype(precision), A, V
+        return A, V
+
     def get_integral(self, full_only=True):
         areas = self.domain.areas
         if full_only:

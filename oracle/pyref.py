@@ -35,6 +35,29 @@ class _Stub(types.ModuleType):
         raise RuntimeError("stubbed third-party module %s was called" % self.__name__)
 
 
+def _netcdf3_dataset():
+    """netCDF4.Dataset stand-in for the reference's SWW writer (anuga/file/netcdf.py:41-47 asks for
+    format NETCDF3_64BIT, which scipy.io.netcdf_file reads and writes): enough of the netCDF4 API for
+    anuga/file/sww.py to run unmodified in this container, so that SWW files written by the reference
+    can be compared with the ones this repository writes."""
+    from scipy.io import netcdf_file
+    from scipy.io import _netcdf
+    if not hasattr(_netcdf.netcdf_variable, "__len__"):     # netCDF4 variables have a length
+        _netcdf.netcdf_variable.__len__ = lambda self: int(self.shape[0])
+
+    class Dataset(netcdf_file):
+        def __init__(self, filename, mode="r", format=None, **kw):
+            netcdf_file.__init__(self, filename, mode if mode != "wl" else "w", mmap=False, version=2)
+
+        def createDimension(self, name, length):
+            if length in (0, None):                 # netCDF4: size 0 / None = the record dimension
+                self.dimensions[name] = None
+                self._dims.insert(0, name)          # scipy wants it first in the header
+            else:
+                netcdf_file.createDimension(self, name, int(length))
+    return Dataset
+
+
 def available():
     return os.path.isdir(os.path.join(PYREF_DIR, "anuga"))
 
@@ -54,6 +77,8 @@ def import_anuga(epart_fn=None):
                 __import__(name)
             except Exception:
                 sys.modules[name] = _Stub(name)
+    if isinstance(sys.modules.get("netCDF4"), _Stub):
+        sys.modules["netCDF4"].Dataset = _netcdf3_dataset()
     if epart_fn is not None:
         def part_graph(nparts, adjacency=None, **kw):
             return 0, list(epart_fn(nparts, adjacency))

@@ -1,0 +1,82 @@
+"""Yield-time SWW output (anuga_core_b200/sww.py) against files written by the reference's own
+writer (tests/golden/make_golden_sww.py): same dimensions, variables, types and attribute values;
+float32 payloads equal except where the 1e-10-level differences of a long run cross a float32
+rounding boundary."""
+import os
+
+import numpy as np
+import pytest
+
+import anuga_core_b200 as ab
+from golden_util import cases, load
+import sww_cases
+
+
+def read_sww(path):
+    from scipy.io import netcdf_file
+    f = netcdf_file(path, "r", mmap=False)
+    out = {"vars": {k: (np.array(v[:]), tuple(v.dimensions)) for k, v in f.variables.items()},
+           "dims": {k: (-1 if n is None else n) for k, n in f.dimensions.items()},
+           "atts": {k: getattr(f, k) for k in f._attributes}}
+    f.close()
+    return out
+
+
+def compare(mine, g, tol):
+    gvars = sorted(k[4:] for k in g.files if k.startswith("var_"))
+    assert sorted(mine["vars"]) == gvars
+    for k in g.files:
+        if k.startswith("dim_"):
+            assert mine["dims"][k[4:]] == int(g[k][0]), k
+    worst = 0.0
+    for name in gvars:
+        a, dims = mine["vars"][name]
+        b = g["var_" + name]
+        assert dims == tuple(str(x) for x in g["dims_" + name]), name
+        assert a.dtype == b.dtype, (name, a.dtype, b.dtype)
+        assert a.shape == b.shape, (name, a.shape, b.shape)
+        if np.issubdtype(a.dtype, np.integer):
+            assert np.array_equal(a, b), name
+        else:
+            scale = max(float(np.max(np.abs(b))), 1e-30)
+            err = float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) / scale
+            worst = max(worst, err)
+            assert err <= tol, (name, err)
+    for k in ("smoothing", "vertices_are_stored_uniquely", "order", "starttime", "timezone", "institution",
+              "description", "xllcorner", "yllcorner", "zone", "hemisphere", "false_easting", "false_northing",
+              "datum", "projection", "units"):
+        a = mine["atts"][k]
+        a = a.decode() if isinstance(a, bytes) else a
+        b = g["att_" + k][()]
+        assert str(a) == str(b) or float(a) == float(b), (k, a, b)
+    return worst
+
+
+def test_static_frames_equal_reference_writer(tmp_path):
+    """no evolve: header, triangulation, smoothed static and dynamic quantities, dry-point masking,
+    ranges, centroid variables, a second frame - host arrays only"""
+    d = sww_cases.static_domain(ab, str(tmp_path), "mine_static")
+    sww_cases.store_two_frames(d)
+    worst = compare(read_sww(os.path.join(str(tmp_path), "mine_static.sww")), load("sww_static"), 0.0)
+    assert worst == 0.0
+
+
+def test_get_vertex_values_unsmoothed_layout():
+    d = ab.rectangular_cross_domain(3, 2)
+    d.set_quantity("stage", lambda x, y: x + 2 * y)
+    X, Y, A, V = d.quantities["stage"].get_vertex_values(xy=True, smooth=False)
+    assert np.array_equal(V, np.arange(3 * len(d)).reshape(-1, 3))
+    assert np.allclose(A, X + 2 * Y)
+    A2, V2 = d.quantities["stage"].get_vertex_values(xy=False, smooth=True, centroid_averaging=False)
+    assert len(A2) == d.number_of_nodes and np.array_equal(V2, d.triangles)
+    assert np.allclose(A2, d.nodes[:, 0] + 2 * d.nodes[:, 1])
+
+
+@pytest.mark.gpu
+def test_evolve_with_store_writes_the_reference_sww(tmp_path):
+    d = sww_cases.evolve_domain(ab, cases, str(tmp_path), "mine_evolve")
+    times = [t for t in d.evolve(**sww_cases.EVOLVE)]
+    g = load("sww_evolve")
+    assert np.array_equal(np.array(times), g["var_time"])
+    worst = compare(read_sww(os.path.join(str(tmp_path), "mine_evolve.sww")), g, 2.0e-7)
+    print("\n[sww] worst scaled difference %.2e (float32 payload)" % worst)
