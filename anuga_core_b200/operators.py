@@ -14,8 +14,11 @@ class Rate_operator:
                  center=None, radius=None, default_rate=0.0, description=None, label=None,
                  logging=False, verbose=False, monitor=False):
         if region is not None or polygon is not None or center is not None or radius is not None:
-            raise NotImplementedError("Region/polygon selection is set-up geometry outside the hot path; "
-                                      "pass triangle `indices` instead")
+            # base_operator.py:36-50: the region's triangles (centroid inside the polygon / circle)
+            from .structures import Region
+            if region is None:
+                region = Region(domain, indices=indices, polygon=polygon, center=center, radius=radius)
+            indices = region.indices
         self.domain = domain
         self.factor = factor
         self.indices = None if indices is None else np.asarray(indices, dtype=np.int64)

@@ -766,22 +766,12 @@ def smooth_discharge(smooth_delta_total_energy, smooth_Q, Q, flow_area, ts, forw
     return smooth_Q, Q, barrel_velocity
 
 
-class Boyd_box_operator(Structure_operator):
-    """anuga.Boyd_box_operator(domain, losses, width, height=None, barrels=1.0, blockage=0.0, ...,
-    end_points | exchange_lines, enquiry_points, invert_elevations, apron, manning, enquiry_gap,
-    smoothing_timescale, use_momentum_jet, use_velocity_head)  (boyd_box_operator.py:8-262)"""
+class _Boyd_operator(Structure_operator):
+    """What Boyd_box_operator and Boyd_pipe_operator share (boyd_box_operator.py:96-262,
+    boyd_pipe_operator.py:78-196): losses, the smoothed head difference that decides the flow
+    direction, the rating of the barrel (`_rating`, per subclass) and the smoothed discharge."""
 
-    def __init__(self, domain, losses, width, height=None, barrels=1.0, blockage=0.0, z1=0.0, z2=0.0,
-                 end_points=None, exchange_lines=None, enquiry_points=None, invert_elevations=None,
-                 apron=0.1, manning=0.013, enquiry_gap=0.0, smoothing_timescale=0.0,
-                 use_momentum_jet=True, use_velocity_head=True, description=None, label=None,
-                 structure_type="boyd_box", logging=False, verbose=False):
-        Structure_operator.__init__(self, domain, end_points=end_points, exchange_lines=exchange_lines,
-                                    enquiry_points=enquiry_points, invert_elevations=invert_elevations,
-                                    width=width, height=height, blockage=blockage, barrels=barrels,
-                                    diameter=None, apron=apron, manning=manning, enquiry_gap=enquiry_gap,
-                                    description=description, label=label, structure_type=structure_type,
-                                    logging=logging, verbose=verbose)
+    def _init_boyd(self, losses, use_momentum_jet, use_velocity_head, smoothing_timescale):
         if isinstance(losses, dict):
             self.sum_loss = sum(losses.values())
         elif isinstance(losses, list):
@@ -794,6 +784,7 @@ class Boyd_box_operator(Structure_operator):
         self.culvert_length = self.get_culvert_length()
         self.culvert_width = self.get_culvert_width()
         self.culvert_height = self.get_culvert_height()
+        self.culvert_diameter = self.diameter
         self.culvert_blockage = self.get_culvert_blockage()
         self.culvert_barrels = self.get_culvert_barrels()
         self.max_velocity = 10.0
@@ -817,8 +808,16 @@ class Boyd_box_operator(Structure_operator):
                              q["ymomentum"].centroid_values[ids], q["elevation"].centroid_values[ids]], axis=1)
             inlet.values, inlet.enquiry = both[:-1], both[-1]
 
+    def _blocked(self):
+        raise NotImplementedError
+
+    def _rating(self):
+        """-> Q, barrel velocity, outlet depth, flow area, case for the current driving_energy,
+        delta_total_energy and outflow enquiry depth"""
+        raise NotImplementedError
+
     def discharge_routine(self):
-        if self.culvert_height <= 0.0:
+        if self._blocked():
             self.case = "Culvert blocked"
             self.inflow, self.outflow = self.inlets
             return 0.0, 0.0, 0.0
@@ -843,12 +842,7 @@ class Boyd_box_operator(Structure_operator):
                 self.driving_energy = self.inflow.get_enquiry_specific_energy()
             else:
                 self.driving_energy = self.inflow.get_enquiry_depth()
-            Q, barrel_velocity, outlet_culvert_depth, flow_area, case = boyd_box_function(
-                width=self.culvert_width, depth=self.culvert_height, blockage=self.culvert_blockage,
-                barrels=self.culvert_barrels, flow_width=self.culvert_width, length=self.culvert_length,
-                driving_energy=self.driving_energy, delta_total_energy=self.delta_total_energy,
-                outlet_enquiry_depth=self.outflow.get_enquiry_depth(), sum_loss=self.sum_loss,
-                manning=self.manning)
+            Q, barrel_velocity, outlet_culvert_depth, flow_area, case = self._rating()
             self.smooth_Q, Q, barrel_velocity = smooth_discharge(self.smooth_delta_total_energy, self.smooth_Q,
                                                                  Q, flow_area, ts, True)
         else:
@@ -860,13 +854,16 @@ class Boyd_box_operator(Structure_operator):
             Q = flow_area * barrel_velocity
         return Q, barrel_velocity, outlet_culvert_depth
 
+    _oracle_kind = None
+
     def oracle_spec(self):
-        return ("boyd_box", dict(
+        return (self._oracle_kind, dict(
             inlet_indices=[i.triangle_indices.copy() for i in self.inlets],
             enquiry_indices=[i.enquiry_index for i in self.inlets],
             invert_elevations=[i.invert_elevation for i in self.inlets],
             outward_vectors=[np.array(i.outward_culvert_vector) for i in self.inlets],
-            width=self.culvert_width, height=self.culvert_height, blockage=self.culvert_blockage,
+            width=self.culvert_width, height=self.culvert_height, diameter=self.culvert_diameter,
+            blockage=self.culvert_blockage,
             barrels=self.culvert_barrels, length=self.culvert_length, sum_loss=self.sum_loss,
             manning=self.manning, use_velocity_head=self.use_velocity_head,
             use_momentum_jet=self.use_momentum_jet, zero_outflow_momentum=self.zero_outflow_momentum,
@@ -875,3 +872,127 @@ class Boyd_box_operator(Structure_operator):
             smoothing_timescale=self.smoothing_timescale, max_velocity=self.max_velocity,
             smooth_delta_total_energy=self.smooth_delta_total_energy, smooth_Q=self.smooth_Q,
             use_new_velocity_head=getattr(self.domain, "use_new_velocity_head", False)))
+
+
+class Boyd_box_operator(_Boyd_operator):
+    """anuga.Boyd_box_operator(domain, losses, width, height=None, barrels=1.0, blockage=0.0, ...,
+    end_points | exchange_lines, enquiry_points, invert_elevations, apron, manning, enquiry_gap,
+    smoothing_timescale, use_momentum_jet, use_velocity_head)  (boyd_box_operator.py:8-262)"""
+    _oracle_kind = "boyd_box"
+
+    def __init__(self, domain, losses, width, height=None, barrels=1.0, blockage=0.0, z1=0.0, z2=0.0,
+                 end_points=None, exchange_lines=None, enquiry_points=None, invert_elevations=None,
+                 apron=0.1, manning=0.013, enquiry_gap=0.0, smoothing_timescale=0.0,
+                 use_momentum_jet=True, use_velocity_head=True, description=None, label=None,
+                 structure_type="boyd_box", logging=False, verbose=False):
+        Structure_operator.__init__(self, domain, end_points=end_points, exchange_lines=exchange_lines,
+                                    enquiry_points=enquiry_points, invert_elevations=invert_elevations,
+                                    width=width, height=height, blockage=blockage, barrels=barrels,
+                                    diameter=None, apron=apron, manning=manning, enquiry_gap=enquiry_gap,
+                                    description=description, label=label, structure_type=structure_type,
+                                    logging=logging, verbose=verbose)
+        self._init_boyd(losses, use_momentum_jet, use_velocity_head, smoothing_timescale)
+
+    def _blocked(self):
+        return self.culvert_height <= 0.0
+
+    def _rating(self):
+        return boyd_box_function(
+            width=self.culvert_width, depth=self.culvert_height, blockage=self.culvert_blockage,
+            barrels=self.culvert_barrels, flow_width=self.culvert_width, length=self.culvert_length,
+            driving_energy=self.driving_energy, delta_total_energy=self.delta_total_energy,
+            outlet_enquiry_depth=self.outflow.get_enquiry_depth(), sum_loss=self.sum_loss,
+            manning=self.manning)
+
+
+def boyd_pipe_function(depth, diameter, blockage, barrels, length, driving_energy, delta_total_energy,
+                       outlet_enquiry_depth, sum_loss, manning):
+    """Boyd's circular-culvert rating (boyd_pipe_operator.py:199-372): inlet control (unsubmerged /
+    submerged), section properties of a part-full circle, then the barrel's energy loss caps the
+    discharge.  Returns Q, barrel velocity, outlet depth, flow area, case."""
+    if blockage >= 1.0:
+        return 0.0, 0.0, 0.0, 0.00001, "100 blocked culvert"
+    if blockage > 0.9:
+        bf = 3.333 - 3.333 * blockage
+    else:
+        bf = 1.0 - 0.4012316798 * blockage - 0.3768350138 * (blockage ** 2)
+    D = bf * diameter                                       # clear diameter
+    Q_unsub = barrels * (0.421 * g ** 0.5 * (D ** 0.87) * driving_energy ** 1.63)
+    Q_sub = barrels * (0.530 * g ** 0.5 * (D ** 1.87) * driving_energy ** 0.63)
+    Q = min(Q_unsub, Q_sub)
+
+    def critical_depth(Q):
+        d1 = D / 1.26 * (Q / g ** 0.5 * (D ** 2.5)) ** (1 / 3.75)
+        d2 = D / 0.95 * (Q / g ** 0.5 * (D ** 2.5)) ** (1 / 1.95)
+        return d2 if d1 / D > 0.85 else d1
+
+    def full():
+        return D, barrels * (D / 2) ** 2 * math.pi, barrels * bf * diameter * math.pi, barrels * bf * diameter
+
+    def part_full(d):
+        alpha = math.acos(1 - 2 * d / D) * 2
+        return (d, barrels * D ** 2 / 8 * (alpha - math.sin(alpha)), barrels * (alpha * bf * diameter / 2.0),
+                barrels * bf * diameter * math.sin(alpha / 2.0))
+
+    d = critical_depth(Q)
+    if d >= D:
+        outlet_culvert_depth, flow_area, perimeter, flow_width = full()
+        case = "Inlet CTRL Outlet submerged Circular PIPE FULL"
+    else:
+        outlet_culvert_depth, flow_area, perimeter, flow_width = part_full(d)
+        case = "INLET CTRL Culvert is open channel flow we will for now assume critical depth"
+
+    if delta_total_energy < driving_energy:                 # outlet control
+        if outlet_enquiry_depth > D:
+            outlet_culvert_depth, flow_area, perimeter, flow_width = full()
+            case = "Outlet submerged"
+        else:
+            d = critical_depth(Q)
+            if d > D:
+                outlet_culvert_depth, flow_area, perimeter, flow_width = full()
+                case = "Outlet unsubmerged PIPE FULL"
+            else:
+                outlet_culvert_depth, flow_area, perimeter, flow_width = part_full(d)
+                perimeter = barrels * alpha_of(d, D) * bf * diameter / 2.0
+                case = "Outlet is open channel flow we will for now assume critical depth"
+    hyd_rad = flow_area / perimeter
+    culvert_velocity = math.sqrt(delta_total_energy /
+                                 ((sum_loss / 2 / g) + (manning ** 2 * length) / hyd_rad ** 1.33333))
+    Q = min(Q, flow_area * culvert_velocity)
+    barrel_velocity = Q / (flow_area + velocity_protection / flow_area)
+    return Q, barrel_velocity, outlet_culvert_depth, flow_area, case
+
+
+def alpha_of(d, D):
+    """angle subtended by the free surface of depth d in a circle of diameter D"""
+    return math.acos(1 - 2 * d / D) * 2
+
+
+class Boyd_pipe_operator(_Boyd_operator):
+    """anuga.Boyd_pipe_operator(domain, losses, diameter=None, barrels=1.0, blockage=0.0, ...)
+    (boyd_pipe_operator.py:7-196)"""
+    _oracle_kind = "boyd_pipe"
+
+    def __init__(self, domain, losses, diameter=None, barrels=1.0, blockage=0.0, z1=0.0, z2=0.0,
+                 end_points=None, exchange_lines=None, enquiry_points=None, invert_elevations=None,
+                 apron=0.1, manning=0.013, enquiry_gap=0.2, smoothing_timescale=0.0,
+                 use_momentum_jet=True, use_velocity_head=True, description=None, label=None,
+                 structure_type="boyd_pipe", logging=False, verbose=False):
+        Structure_operator.__init__(self, domain, end_points=end_points, exchange_lines=exchange_lines,
+                                    enquiry_points=enquiry_points, invert_elevations=invert_elevations,
+                                    width=None, height=None, diameter=diameter, blockage=blockage,
+                                    barrels=barrels, apron=apron, manning=manning, enquiry_gap=enquiry_gap,
+                                    description=description, label=label, structure_type=structure_type,
+                                    logging=logging, verbose=verbose)
+        self._init_boyd(losses, use_momentum_jet, use_velocity_head, smoothing_timescale)
+
+    def _blocked(self):
+        return self.culvert_diameter <= 0.0
+
+    def _rating(self):
+        return boyd_pipe_function(
+            depth=self.inflow.get_enquiry_depth(), diameter=self.culvert_diameter,
+            blockage=self.culvert_blockage, barrels=self.culvert_barrels, length=self.culvert_length,
+            driving_energy=self.driving_energy, delta_total_energy=self.delta_total_energy,
+            outlet_enquiry_depth=self.outflow.get_enquiry_depth(), sum_loss=self.sum_loss,
+            manning=self.manning)

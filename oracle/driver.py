@@ -505,6 +505,8 @@ class OracleDomain:
                 self._inlet_operator(op[1])
             elif op[0] == "boyd_box":
                 self._boyd_box_operator(op[1])
+            elif op[0] == "boyd_pipe":
+                self._boyd_box_operator(op[1], pipe=True)
             else:
                 raise ValueError("unknown operator %r" % (op[0],))
 
@@ -587,7 +589,7 @@ class OracleDomain:
             self.stage_c[idx] = elev + 0.0
             self.fractional_step_volume_integral -= current_volume
 
-    def _boyd_box_operator(self, o):
+    def _boyd_box_operator(self, o, pipe=False):
         """structures/structure_operator.py:215-372 (the transfer) around
         structures/boyd_box_operator.py:150-441 (the rating) with the enquiry formulas of
         structures/inlet_enquiry.py:86-158.  `o` carries the resolved geometry (inlet triangle
@@ -613,9 +615,8 @@ class OracleDomain:
             return dict(stage=stage[e], depth=depth, total=head + stage[e], specific=head + depth)
 
         # ---- discharge_routine ----
-        height, width = o["height"], o["width"]
         flow_area = None
-        if height <= 0.0:
+        if (o["diameter"] if pipe else o["height"]) <= 0.0:
             Q = speed = outlet_depth = 0.0
             i_in, i_out = 0, 1
         else:
@@ -635,7 +636,8 @@ class OracleDomain:
             if E[i_in]["depth"] > 0.01:
                 assert E[i_in]["specific"] >= 0.0
                 drive = E[i_in]["specific"] if o["use_velocity_head"] else E[i_in]["depth"]
-                Q, speed, outlet_depth, flow_area = self._boyd_box_rating(o, drive, delta, E[i_out]["depth"])
+                rating = self._boyd_pipe_rating if pipe else self._boyd_box_rating
+                Q, speed, outlet_depth, flow_area = rating(o, drive, delta, E[i_out]["depth"])
                 sign = np.sign(sm)
                 o["smooth_Q"] = o["smooth_Q"] + ts * (Q * sign - o["smooth_Q"])
                 if np.sign(o["smooth_Q"]) != sign:
@@ -722,6 +724,52 @@ class OracleDomain:
             rh = area / perim
             vel = math.sqrt(delta / ((o["sum_loss"] / 2 / G) + (o["manning"] ** 2 * o["length"]) / rh ** 1.33333))
             Q = min(Q, area * vel)
+        return Q, Q / (area + VP / area), out_d, area
+
+    @staticmethod
+    def _boyd_pipe_rating(o, drive, delta, tail_depth):
+        """boyd_pipe_function (boyd_pipe_operator.py:199-372): circular barrel; the energy-loss cap
+        is applied in every case"""
+        G, VP = 9.8, 1.0e-6
+        diameter, barrels, blockage = o["diameter"], o["barrels"], o["blockage"]
+        if blockage >= 1.0:
+            return 0.0, 0.0, 0.0, 0.00001
+        if blockage > 0.9:
+            bf = 3.333 - 3.333 * blockage
+        else:
+            bf = 1.0 - 0.4012316798 * blockage - 0.3768350138 * (blockage ** 2)
+        Qu = barrels * (0.421 * G ** 0.5 * ((bf * diameter) ** 0.87) * drive ** 1.63)
+        Qs = barrels * (0.530 * G ** 0.5 * ((bf * diameter) ** 1.87) * drive ** 0.63)
+        Q = min(Qu, Qs)
+        dc1 = (bf * diameter) / 1.26 * (Q / G ** 0.5 * ((bf * diameter) ** 2.5)) ** (1 / 3.75)
+        dc2 = (bf * diameter) / 0.95 * (Q / G ** 0.5 * (bf * diameter) ** 2.5) ** (1 / 1.95)
+        out_d = dc2 if dc1 / (bf * diameter) > 0.85 else dc1
+        if out_d >= (bf * diameter):
+            out_d = bf * diameter
+            area = barrels * (bf * diameter / 2) ** 2 * math.pi
+            perim = barrels * bf * diameter * math.pi
+        else:
+            alpha = math.acos(1 - 2 * out_d / (bf * diameter)) * 2
+            area = barrels * (bf * diameter) ** 2 / 8 * (alpha - math.sin(alpha))
+            perim = barrels * (alpha * bf * diameter / 2.0)
+        if delta < drive:
+            if tail_depth > bf * diameter:
+                out_d = bf * diameter
+                area = barrels * (bf * diameter / 2) ** 2 * math.pi
+                perim = barrels * bf * diameter * math.pi
+            else:
+                out_d = dc2 if dc1 / (bf * diameter) > 0.85 else dc1
+                if out_d > bf * diameter:
+                    out_d = bf * diameter
+                    area = barrels * (bf * diameter / 2) ** 2 * math.pi
+                    perim = barrels * bf * diameter * math.pi
+                else:
+                    alpha = math.acos(1 - 2 * out_d / (bf * diameter)) * 2
+                    area = barrels * (bf * diameter) ** 2 / 8 * (alpha - math.sin(alpha))
+                    perim = barrels * alpha * bf * diameter / 2.0
+        rh = area / perim
+        vel = math.sqrt(delta / ((o["sum_loss"] / 2 / G) + (o["manning"] ** 2 * o["length"]) / rh ** 1.33333))
+        Q = min(Q, area * vel)
         return Q, Q / (area + VP / area), out_d, area
 
     # -- evolve ------------------------------------------------------------------

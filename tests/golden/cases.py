@@ -142,6 +142,14 @@ def rain_time_de1(A):
     return d
 
 
+def rain_regions_de1(A):
+    """rain over a polygon, extraction over a circle (operators resolve their Region)"""
+    d = beach_de1(A, n=16)
+    A.Rate_operator(d, rate=0.02, polygon=[[1.3, 2.2], [9.7, 1.1], [11.2, 8.4], [3.1, 12.6]])
+    A.Rate_operator(d, rate=lambda t: -0.01 * (1.0 + t), center=[4.2, 5.1], radius=2.3)
+    return d
+
+
 def drain_de1(A):
     """negative rate: the clamped branch of Rate_operator (rate_operators.py:213-245)"""
     d = beach_de1(A, n=16)
@@ -233,6 +241,16 @@ def culvert_skew_de1(A):
     return d
 
 
+def culvert_pipe_de1(A):
+    """Boyd_pipe_operator: two partly blocked circular barrels, smoothed discharge, skew exchange lines"""
+    d = _embankment(A)
+    A.Boyd_pipe_operator(d, losses=[0.5, 1.0], diameter=0.7, barrels=2.0, blockage=0.15,
+                         end_points=[[6.1, 10.3], [9.9, 10.3]], apron=0.55, enquiry_gap=0.45,
+                         manning=0.013, smoothing_timescale=0.5, use_momentum_jet=True,
+                         use_velocity_head=True, verbose=False)
+    return d
+
+
 CASES = {
     "kat_bedslope_more_steps": (kat_bedslope_more_steps, dict(yieldstep=0.05, finaltime=0.5)),
     "dam_break_de0": (dam_break_de0, dict(yieldstep=1.0, finaltime=6.0)),
@@ -245,6 +263,7 @@ CASES = {
     "tsunami_dirichlet": (tsunami_dirichlet, dict(yieldstep=1.0, finaltime=4.0)),
     "time_boundary_de1": (time_boundary_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "rain_de1": (rain_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "rain_regions_de1": (rain_regions_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "drain_de1": (drain_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "sloped_manning_de1": (sloped_manning_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
@@ -252,6 +271,7 @@ CASES = {
     "rain_time_de1": (rain_time_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "flather_de1": (flather_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "culvert_de1": (culvert_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "culvert_pipe_de1": (culvert_pipe_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_skew_de1": (culvert_skew_de1, dict(yieldstep=1.0, finaltime=4.0)),
 }
 
