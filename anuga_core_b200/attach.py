@@ -23,6 +23,7 @@ What it does:
 import numpy as np
 
 from . import boundaries as _bnd
+from . import structures as _st
 from .domain import Domain, MODE_B200
 from .operators import Rate_operator
 
@@ -108,6 +109,15 @@ class B200_interface:
             name = type(op).__name__
             if name == "boundary_flux_integral_operator":
                 continue                      # built into the device step
+            if name == "Inlet_operator":          # host-side hydraulics on gathered cells (structures.py)
+                new = _st.Inlet_operator(d, _st.Region(d, indices=op.inlet.triangle_indices), Q=op.Q,
+                                         velocity=op.velocity, zero_velocity=op.zero_velocity,
+                                         default=getattr(op, "default", 0.0))
+                new._mirror = op
+                continue
+            if name in ("Boyd_box_operator", "Boyd_pipe_operator"):
+                getattr(_st, name).adopt(d, op)
+                continue
             if name != "Rate_operator":
                 raise NotImplementedError("operator %s has no device implementation (SURVEY.md 8(f))" % name)
             if getattr(op, "rate_type", None) not in ("scalar", "t", "centroid_array", "quantity") \

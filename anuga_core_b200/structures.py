@@ -360,6 +360,10 @@ class Inlet_operator:
             self.applied_Q = -current_volume / timestep
             added = -current_volume
         inlet.commit()
+        ref_op = getattr(self, "_mirror", None)      # attach.py: statistics the reference's reporting reads
+        if ref_op is not None:
+            ref_op.applied_Q = self.applied_Q
+            ref_op.total_requested_volume = self.total_requested_volume
         return added
 
     def _set_momenta(self, u, v):
@@ -409,6 +413,21 @@ class Inlet_enquiry(Inlet):
         self._extra_ids = np.array([self.enquiry_index], dtype=np.int64)
         self._extra_rows = np.array([len(self.triangle_indices)], dtype=np.int64)
     _n_extra = 1
+
+    @classmethod
+    def from_indices(cls, domain, triangle_indices, enquiry_index, invert_elevation=None,
+                     outward_culvert_vector=None):
+        """an inlet whose geometry was resolved elsewhere (e.g. by the reference package)"""
+        self = cls.__new__(cls)
+        Inlet.__init__(self, domain, Region(domain, indices=np.asarray(triangle_indices, dtype=np.int64)))
+        self.enquiry_pt = None
+        self.invert_elevation = invert_elevation
+        self.outward_culvert_vector = None if outward_culvert_vector is None else np.array(outward_culvert_vector)
+        self.enquiry_index = int(enquiry_index)
+        self.enquiry = None
+        self._extra_ids = np.array([self.enquiry_index], dtype=np.int64)
+        self._extra_rows = np.array([len(self.triangle_indices)], dtype=np.int64)
+        return self
 
     def localise(self, sub):
         new = Inlet.localise(self, sub)
@@ -853,6 +872,39 @@ class _Boyd_operator(Structure_operator):
             barrel_velocity = self.max_velocity
             Q = flow_area * barrel_velocity
         return Q, barrel_velocity, outlet_culvert_depth
+
+    _MIRRORED = ("accumulated_flow", "discharge", "discharge_abs_timemean", "velocity", "outlet_depth",
+                 "delta_total_energy", "driving_energy", "case", "smooth_delta_total_energy", "smooth_Q")
+
+    @classmethod
+    def adopt(cls, domain, ref_op):
+        """This structure for a Boyd operator object of the reference package (attach.py): its resolved
+        geometry, parameters and smoothing memory are taken over, and the statistics the reference's
+        reporting reads are written back to it after every call."""
+        self = cls.__new__(cls)
+        self.domain = domain
+        for k in ("width", "height", "diameter", "blockage", "barrels", "apron", "manning", "enquiry_gap",
+                  "use_momentum_jet", "zero_outflow_momentum", "use_old_momentum_method",
+                  "always_use_Q_wetdry_adjustment", "use_velocity_head", "sum_loss", "culvert_length",
+                  "max_velocity", "smoothing_timescale", "description", "label", "structure_type") + cls._MIRRORED:
+            setattr(self, k, getattr(ref_op, k, None))
+        self.culvert_width, self.culvert_height = self.width, self.height
+        self.culvert_diameter = self.diameter
+        self.culvert_blockage, self.culvert_barrels = self.blockage, self.barrels
+        self.inlets = [Inlet_enquiry.from_indices(domain, i.triangle_indices, i.enquiry_index, i.invert_elevation,
+                                                  i.outward_culvert_vector) for i in ref_op.inlets]
+        self.inflow, self.outflow = self.inlets
+        self._mirror = ref_op
+        domain.set_fractional_step_operator(self)
+        return self
+
+    def __call__(self):
+        out = Structure_operator.__call__(self)
+        ref_op = getattr(self, "_mirror", None)
+        if ref_op is not None:
+            for k in self._MIRRORED:
+                setattr(ref_op, k, getattr(self, k))
+        return out
 
     _oracle_kind = None
 

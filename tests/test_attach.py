@@ -48,11 +48,34 @@ def test_adapter_rejects_what_it_cannot_run():
         ab.B200_interface(ref)
 
 
+@pytest.mark.skipif(not pyref.available(), reason="python reference not built (oracle/build_pyref.py)")
+@pytest.mark.parametrize("name", ["inlet_de1", "culvert_de1", "culvert_pipe_de1"])
+def test_adapter_adopts_reference_structures(name):
+    """Inlet_operator / Boyd operators of a real reference domain are taken over with their resolved
+    geometry, parameters and smoothing memory"""
+    anuga = pyref.import_anuga()
+    ref = cases.CASES[name][0](anuga)
+    iface = ab.B200_interface(ref)
+    mine = [op for op in iface.dev_domain.fractional_step_operators if getattr(op, "host_side", False)]
+    theirs = [op for op in ref.fractional_step_operators if type(op).__name__ != "boundary_flux_integral_operator"]
+    assert len(mine) == len(theirs) > 0
+    for a, b in zip(mine, theirs):
+        assert type(a).__name__ == type(b).__name__
+        if hasattr(b, "inlets"):
+            for ia, ib in zip(a.inlets, b.inlets):
+                assert np.array_equal(ia.triangle_indices, ib.triangle_indices)
+                assert ia.enquiry_index == ib.enquiry_index
+            assert a.smooth_Q == b.smooth_Q and a.culvert_length == b.culvert_length
+        else:
+            assert np.array_equal(a.inlet.triangle_indices, b.inlet.triangle_indices)
+
+
 @pytest.mark.gpu
-def test_adapter_time_loop_matches_golden():
+@pytest.mark.parametrize("name", ["beach_de1", "inlet_de1", "culvert_de1", "culvert_pipe_de1"])
+def test_adapter_time_loop_matches_golden(name):
     """evolve through the adapter (host arrays updated in place) == the golden reference run"""
-    g = load("beach_de1")
-    builder, ev = cases.CASES["beach_de1"]
+    g = load(name)
+    builder, ev = cases.CASES[name]
     ref_like = builder(ab)                       # carries the reference's attribute names
     stage_alias = ref_like.quantities["stage"].centroid_values
     iface = ab.B200_interface(ref_like)
