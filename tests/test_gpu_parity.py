@@ -188,8 +188,9 @@ def test_error_paths():
         for _ in d.evolve(yieldstep=10.0, finaltime=10.0):
             pass
     assert e.value.code == -4
-    with pytest.raises(Exception):
-        ab.rectangular_cross_domain(2, 2).set_store(True)
+    with pytest.raises(Exception):          # no boundary objects bound to the tags
+        for _ in ab.rectangular_cross_domain(2, 2).evolve(yieldstep=1.0, finaltime=1.0):
+            pass
 
 
 def riverwall_domain(alg="DE1", n=12):
