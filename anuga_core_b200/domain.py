@@ -438,6 +438,55 @@ class Domain:
 
     get_water_volume = compute_total_volume
 
+    def report_water_volume_statistics(self, verbose=True, returnStats=False):
+        """volume, boundary-flux integral, fractional-step volume integral and their balance
+        (shallow_water_domain.py:2749-2781)"""
+        vol = self.get_water_volume()
+        if not hasattr(self, "_initial_volume"):
+            self._initial_volume = vol
+        bf, fs = self.get_boundary_flux_integral(), self.get_fractional_step_volume_integral()
+        if verbose and self.processor == 0:
+            print(" ")
+            print("    Volume V is:", vol)
+            print("    Boundary Flux integral BF: ", bf)
+            print("    (rate + inlet) Fractional Step volume integral FS: ", fs)
+            print("    V - BF - FS - InitialVolume :", vol - bf - fs - self._initial_volume)
+            print(" ")
+        if returnStats:
+            return [vol, bf, fs]
+
+    def get_nodes(self, absolute=False):
+        return self.nodes
+
+    def get_triangles(self, indices=None):
+        return self.triangles if indices is None else self.triangles[np.asarray(indices, dtype=np.int64)]
+
+    def get_number_of_triangles(self):
+        return self.number_of_triangles
+
+    def get_number_of_nodes(self):
+        return self.number_of_nodes
+
+    def get_normal(self, i, j):
+        return self.normals[i, 2 * j:2 * j + 2]
+
+    def get_conserved_quantities(self, vol_id, vertex=None, edge=None):
+        """stage, xmomentum, ymomentum of one triangle at its centroid, a vertex or an edge
+        (generic_domain.py:585-620)"""
+        assert vertex is None or edge is None, "Values for both vertex and edge was specified."
+        if vertex is None and edge is None:
+            self._pull_centroids()
+        out = np.zeros(3)
+        for k, name in enumerate(self.conserved_quantities):
+            q = self.quantities[name]
+            if vertex is not None:
+                out[k] = q.vertex_values[vol_id, vertex]
+            elif edge is not None:
+                out[k] = q.edge_values[vol_id, edge]
+            else:
+                out[k] = q.centroid_values[vol_id]
+        return out
+
     def timestepping_statistics(self, *a, **k):
         msg = "Time = %.4f (sec), " % self.get_time()
         if self.recorded_min_timestep == self.recorded_max_timestep:
@@ -831,6 +880,8 @@ class Domain:
                             % self.get_boundary_tags())
         if self.evolved_called:
             skip_initial_step = True
+        elif not hasattr(self, "_initial_volume"):
+            self._initial_volume = self.compute_total_volume()      # volume_history[0] of the reference
         self.evolved_called = True
         if skip_initial_step:
             self.evolve_starttime = self.relative_time
