@@ -283,8 +283,6 @@ class Domain:
 
     # -- yield-time SWW output (anuga_core_b200/sww.py) ------------------------------------
     def set_store(self, flag=True):
-        if flag and self.numproc > 1:
-            raise NotImplementedError("SWW output of a distributed domain (per-rank files + sww_merge) is not built")
         self.store = bool(flag)
 
     def get_store(self):
@@ -298,10 +296,30 @@ class Domain:
         if timestamp:
             from time import localtime, strftime
             name = name + "_" + strftime("%Y%m%d_%H%M%S", localtime())
+        self.global_name = name
+        if self.numproc > 1:          # Parallel_domain.set_name (parallel_shallow_water.py:110-120)
+            name = name + "_P%d_%d" % (self.numproc, self.processor)
         self.name = name
 
     def get_name(self):
         return self.name
+
+    def get_global_name(self):
+        return getattr(self, "global_name", self.name)
+
+    def sww_merge(self, verbose=False, delete_old=False):
+        """one global SWW file from the per-rank files of a distributed run
+        (parallel_shallow_water.py:158-182); a no-op for a sequential domain"""
+        comm = getattr(self, "_comm", None)
+        if comm is not None:
+            comm.barrier()
+        if self.processor == 0 and self.numproc > 1 and self.store:
+            import os
+            from .sww_merge import sww_merge_parallel
+            sww_merge_parallel(os.path.join(self.get_datadir(), self.get_global_name()), self.numproc,
+                               verbose, delete_old)
+        if comm is not None:
+            comm.barrier()
 
     def set_datadir(self, path):
         self.datadir = path

@@ -199,6 +199,13 @@ def distribute(domain, nparts, epart=None, ghost_layer_width=2, ranks=None, doma
         d.tri_l2g = sub["tri_l2g"]
         d.node_l2g = sub["node_l2g"]
         d.tri_l2s = order[sub["tri_l2g"]]          # local -> sequential (original) triangle id
+        d.number_of_global_triangles = N
+        d.number_of_global_nodes = domain.number_of_nodes
+        d.set_name(domain.get_global_name())
+        d.set_datadir(domain.get_datadir())
+        for k in ("store", "smooth", "store_centroids", "minimum_storable_height", "using_centroid_averaging"):
+            setattr(d, k, getattr(domain, k))
+        d.quantities_to_be_stored = dict(domain.quantities_to_be_stored)
         _copy_settings(domain, d)
         for name in ("stage", "xmomentum", "ymomentum", "elevation", "friction"):
             src = domain.quantities[name]
@@ -317,6 +324,9 @@ def strip_partitioned_sweep_domain(m, n, rank, nranks, device=0, alg="DE1", rain
                ghost_recv_dict=sub["ghost_recv_dict"], processor=rank, numproc=nranks,
                number_of_full_triangles=sub["number_of_full_triangles"], ghost_layer_width=2, device=device)
     d.tri_l2g = sub["tri_l2g"]
+    d.node_l2g = sub["node_l2g"]
+    d.number_of_global_triangles = 4 * m * n
+    d.number_of_global_nodes = (m + 1) * (n + 1) + m * n
     d.set_flow_algorithm(alg)
     d.set_store(False)
     d.set_quantity("elevation", workloads.sweep_elevation)

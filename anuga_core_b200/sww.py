@@ -9,8 +9,8 @@ the reference's own writer produced in the build container).
 
 The reference writes through netCDF4 with format NETCDF3_64BIT (anuga/file/netcdf.py:41-47); that
 package is not in this image, scipy.io.netcdf_file writes the same on-disk format.  SURVEY.md
-section 8(f) row 3.  Sequential domains only (a distributed run writes one file per rank in the
-reference and merges them afterwards; not done here).
+section 8(f) row 3.  A distributed run writes one file per rank (name_P<n>_<rank>.sww, with the
+local-to-global maps) and merges them afterwards: anuga_core_b200/sww_merge.py.
 """
 import os
 
@@ -28,6 +28,61 @@ def _open(filename, mode):
     except ImportError as e:                                    # pragma: no cover
         raise RuntimeError("set_store(True) needs scipy (scipy.io.netcdf_file) to write SWW files") from e
     return netcdf_file(filename, mode, mmap=False, version=2)
+
+
+def write_header(fid, starttime, number_of_volumes, number_of_nodes, smoothing, order, static_quantities,
+                 dynamic_quantities, static_c_quantities, dynamic_c_quantities,
+                 description="Output from anuga.file.sww suitable for plotting",
+                 institution=default_institution, timezone="UTC", precision="f"):
+    """Write_sww.store_header + write_dynamic_quantities (sww.py:563-693, 776-803)"""
+    npoints = number_of_nodes if smoothing else 3 * number_of_volumes
+    fid.institution = institution
+    fid.description = description
+    fid.smoothing = "Yes" if smoothing else "No"
+    fid.vertices_are_stored_uniquely = "False" if smoothing else "True"
+    fid.order = np.int32(order)
+    fid.revision_number = "anuga_core_b200"
+    fid.revision_date = "None"
+    fid.anuga_version = "anuga_core_b200"
+    fid.starttime = starttime
+    fid.timezone = timezone
+    fid.createDimension("number_of_timesteps", None)         # the record dimension (first for scipy)
+    fid.createDimension("number_of_volumes", number_of_volumes)
+    fid.createDimension("number_of_triangle_vertices", number_of_nodes)
+    fid.createDimension("number_of_vertices", 3)
+    fid.createDimension("numbers_in_range", 2)
+    fid.createDimension("number_of_points", npoints)
+    fid.createVariable("x", precision, ("number_of_points",))
+    fid.createVariable("y", precision, ("number_of_points",))
+    fid.createVariable("volumes", "i", ("number_of_volumes", "number_of_vertices"))
+    for q in static_quantities:
+        fid.createVariable(q, precision, ("number_of_points",))
+        r = fid.createVariable(q + RANGE, precision, ("numbers_in_range",))
+        r[0] = max_float
+        r[1] = -max_float
+    for q in static_c_quantities:
+        fid.createVariable(q, precision, ("number_of_volumes",))
+    for q in dynamic_quantities:
+        fid.createVariable(q, precision, ("number_of_timesteps", "number_of_points"))
+        r = fid.createVariable(q + RANGE, precision, ("numbers_in_range",))
+        r[0] = max_float
+        r[1] = -max_float
+    for q in dynamic_c_quantities:
+        fid.createVariable(q, precision, ("number_of_timesteps", "number_of_volumes"))
+    fid.createVariable("time", "d", ("number_of_timesteps",))
+
+
+def write_georeference(fid, geo=None):
+    """Geo_reference.write_NetCDF (geo_reference.py:169-185) with the defaults of Geo_reference()"""
+    fid.xllcorner = float(getattr(geo, "xllcorner", 0.0))
+    fid.yllcorner = float(getattr(geo, "yllcorner", 0.0))
+    fid.zone = np.int32(getattr(geo, "zone", -1))
+    fid.hemisphere = str(getattr(geo, "hemisphere", "undefined"))
+    fid.false_easting = np.int32(getattr(geo, "false_easting", 500000))
+    fid.false_northing = np.int32(getattr(geo, "false_northing", 10000000))
+    fid.datum = str(getattr(geo, "datum", "wgs84"))
+    fid.projection = str(getattr(geo, "projection", "UTM"))
+    fid.units = str(getattr(geo, "units", "m"))
 
 
 class SWW_file:
@@ -53,42 +108,10 @@ class SWW_file:
     # -- Write_sww.store_header ------------------------------------------------------------
     def _header(self, fid):
         d = self.domain
-        smoothing = bool(d.smooth)
-        npoints = d.number_of_nodes if smoothing else 3 * d.number_of_triangles
-        fid.institution = getattr(d, "institution", default_institution)
-        fid.description = "Output from anuga.file.sww suitable for plotting"
-        fid.smoothing = "Yes" if smoothing else "No"
-        fid.vertices_are_stored_uniquely = "False" if smoothing else "True"
-        fid.order = np.int32(d.default_order)
-        fid.revision_number = "anuga_core_b200"
-        fid.revision_date = "None"
-        fid.anuga_version = "anuga_core_b200"
-        fid.starttime = d.starttime
-        fid.timezone = str(getattr(d, "timezone", "UTC"))
-        fid.createDimension("number_of_timesteps", None)         # the record dimension (first for scipy)
-        fid.createDimension("number_of_volumes", d.number_of_triangles)
-        fid.createDimension("number_of_triangle_vertices", d.number_of_nodes)
-        fid.createDimension("number_of_vertices", 3)
-        fid.createDimension("numbers_in_range", 2)
-        fid.createDimension("number_of_points", npoints)
-        fid.createVariable("x", self.precision, ("number_of_points",))
-        fid.createVariable("y", self.precision, ("number_of_points",))
-        fid.createVariable("volumes", "i", ("number_of_volumes", "number_of_vertices"))
-        for q in self.static_quantities:
-            fid.createVariable(q, self.precision, ("number_of_points",))
-            r = fid.createVariable(q + RANGE, self.precision, ("numbers_in_range",))
-            r[0] = max_float
-            r[1] = -max_float
-        for q in self.static_c_quantities:
-            fid.createVariable(q, self.precision, ("number_of_volumes",))
-        for q in self.dynamic_quantities:
-            fid.createVariable(q, self.precision, ("number_of_timesteps", "number_of_points"))
-            r = fid.createVariable(q + RANGE, self.precision, ("numbers_in_range",))
-            r[0] = max_float
-            r[1] = -max_float
-        for q in self.dynamic_c_quantities:
-            fid.createVariable(q, self.precision, ("number_of_timesteps", "number_of_volumes"))
-        fid.createVariable("time", "d", ("number_of_timesteps",))
+        write_header(fid, d.starttime, d.number_of_triangles, d.number_of_nodes, bool(d.smooth), d.default_order,
+                     self.static_quantities, self.dynamic_quantities, self.static_c_quantities,
+                     self.dynamic_c_quantities, institution=getattr(d, "institution", default_institution),
+                     timezone=str(getattr(d, "timezone", "UTC")))
 
     # -- SWW_file.store_connectivity -------------------------------------------------------
     def store_connectivity(self):
@@ -96,20 +119,18 @@ class SWW_file:
         fid = _open(self.filename, "a")
         Q = d.quantities["stage"]
         X, Y, _, V = Q.get_vertex_values(xy=True, precision=np.float32)
-        # georeference attributes (Geo_reference defaults: no zone, origin 0,0)
-        geo = getattr(d, "geo_reference", None)
-        fid.xllcorner = float(getattr(geo, "xllcorner", 0.0))
-        fid.yllcorner = float(getattr(geo, "yllcorner", 0.0))
-        fid.zone = np.int32(getattr(geo, "zone", -1))
-        fid.hemisphere = str(getattr(geo, "hemisphere", "undefined"))
-        fid.false_easting = np.int32(getattr(geo, "false_easting", 500000))
-        fid.false_northing = np.int32(getattr(geo, "false_northing", 10000000))
-        fid.datum = str(getattr(geo, "datum", "wgs84"))
-        fid.projection = str(getattr(geo, "projection", "UTM"))
-        fid.units = str(getattr(geo, "units", "m"))
+        write_georeference(fid, getattr(d, "geo_reference", None))
         fid.variables["x"][:] = X
         fid.variables["y"][:] = Y
         fid.variables["volumes"][:] = np.asarray(V, dtype=np.int32).reshape(-1, 3)
+        if d.numproc > 1:            # Write_sww.store_parallel_data (:831-873): what sww_merge needs
+            fid.number_of_global_triangles = np.int32(d.number_of_global_triangles)
+            fid.number_of_global_nodes = np.int32(d.number_of_global_nodes)
+            for vname, dim, values in (("tri_l2g", "number_of_volumes", d.tri_l2g),
+                                       ("node_l2g", "number_of_triangle_vertices", d.node_l2g),
+                                       ("tri_full_flag", "number_of_volumes", d.tri_full_flag)):
+                fid.createVariable(vname, "i", (dim,))
+                fid.variables[vname][:] = np.asarray(values).astype(np.int32)
         for name in self.static_quantities:
             A, _ = d.quantities[name].get_vertex_values(xy=False, precision=np.float32)
             x = A.astype(np.float32)

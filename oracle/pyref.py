@@ -48,6 +48,9 @@ def _netcdf3_dataset():
     class Dataset(netcdf_file):
         def __init__(self, filename, mode="r", format=None, **kw):
             netcdf_file.__init__(self, filename, mode if mode != "wl" else "w", mmap=False, version=2)
+            for k, v in list(self._attributes.items()):     # netCDF4 hands out str, scipy bytes
+                if isinstance(v, bytes):
+                    self.__dict__[k] = v.decode()
 
         def createDimension(self, name, length):
             if length in (0, None):                 # netCDF4: size 0 / None = the record dimension

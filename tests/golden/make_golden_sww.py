@@ -5,6 +5,8 @@ the format the reference asks for).  Stores every variable, dimension and attrib
 tests/golden/sww_*.npz:
     sww_static   a domain that is stored without evolving (two frames; host arrays only)
     sww_evolve   cases.beach_de1 (n=10) evolved with set_store(True): the yield-time output path
+    sww_merged   the reference's sww_merge_parallel applied to three per-rank files (written by this
+                 repository's writer for a distributed copy of sww_static)
 usage: python oracle/build_pyref.py && python tests/golden/make_golden_sww.py
 """
 import os
@@ -47,6 +49,14 @@ def main():
     d = sww_cases.static_domain(anuga, tmp, "ref_static")
     sww_cases.store_two_frames(d)
     dump(os.path.join(tmp, "ref_static.sww"), "sww_static")
+
+    # merge: per-rank files written by THIS repository's writer, merged by the reference's sww_merge
+    import anuga_core_b200 as ab
+    from anuga_core_b200 import parallel as P
+    from anuga.utilities.sww_merge import sww_merge_parallel
+    sww_cases.distributed_static_files(ab, P, tmp, "dist_static", nparts=3)
+    sww_merge_parallel(os.path.join(tmp, "dist_static"), 3, verbose=False, delete_old=False)
+    dump(os.path.join(tmp, "dist_static.sww"), "sww_merged")
 
     d = sww_cases.evolve_domain(anuga, cases, tmp, "ref_evolve")
     for t in d.evolve(**sww_cases.EVOLVE):

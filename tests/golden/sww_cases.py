@@ -35,3 +35,15 @@ def evolve_domain(A, cases, datadir, name):
     d.set_name(name)
     d.set_datadir(datadir)
     return d
+
+
+def distributed_static_files(ab, P, datadir, name, nparts=3):
+    """per-rank SWW files (two frames, no evolve) of static_domain cut in `nparts` by an interleaved
+    element partition; returns the global domain"""
+    g = static_domain(ab, datadir, name)
+    c = g.centroid_coordinates
+    epart = ((np.floor(c[:, 0]) + 2 * np.floor(c[:, 1])) % nparts).astype(int)
+    subs = P.distribute(g, nparts, epart=epart)
+    for p in sorted(subs):
+        store_two_frames(subs[p])
+    return g, subs

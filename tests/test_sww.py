@@ -61,6 +61,40 @@ def test_static_frames_equal_reference_writer(tmp_path):
     assert worst == 0.0
 
 
+def test_merge_of_per_rank_files_equals_reference_merge_and_sequential_file(tmp_path):
+    """distributed output: per-rank files (local-to-global maps, full flags) merged by
+    anuga_core_b200.sww_merge == the reference's sww_merge_parallel on the same files; and, triangle
+    order aside, == the file a sequential domain writes"""
+    from anuga_core_b200 import parallel as P
+    from anuga_core_b200.sww_merge import sww_merge_parallel
+    g, subs = sww_cases.distributed_static_files(ab, P, str(tmp_path), "dist_static", nparts=3)
+    for p, d in subs.items():
+        assert d.get_name() == "dist_static_P3_%d" % p and d.get_global_name() == "dist_static"
+    out = sww_merge_parallel(os.path.join(str(tmp_path), "dist_static"), 3, delete_old=True)
+    assert not os.path.exists(os.path.join(str(tmp_path), "dist_static_P3_0.sww"))
+    mine = read_sww(out)
+    ref = load("sww_merged")
+    for name in sorted(k[4:] for k in ref.files if k.startswith("var_")):
+        a, b = mine["vars"][name][0], ref["var_" + name]
+        assert a.dtype == b.dtype and np.array_equal(a, b), name
+    desc = mine["atts"]["description"]
+    assert (desc.decode() if isinstance(desc, bytes) else desc) == str(ref["att_description"][()])
+    # against the sequential file: mesh and centroid variables identical up to the triangle reordering
+    # (node values are means over the triangles a rank holds, so nodes on a ragged partition
+    # boundary may differ from the sequential mean - in the reference as well)
+    seq = load("sww_static")
+    for name in ("x", "y", "friction", "time"):
+        assert np.array_equal(mine["vars"][name][0], seq["var_" + name]), name
+    same = mine["vars"]["elevation"][0] == seq["var_elevation"]
+    assert same.mean() > 0.8
+    order = np.empty(len(g), dtype=np.int64)
+    for d in subs.values():
+        nf = d.number_of_full_triangles
+        order[d.tri_l2g[:nf]] = d.tri_l2s[:nf]
+    assert np.array_equal(mine["vars"]["volumes"][0], seq["var_volumes"][order])
+    assert np.array_equal(mine["vars"]["stage_c"][0], seq["var_stage_c"][:, order])
+
+
 def test_get_vertex_values_unsmoothed_layout():
     d = ab.rectangular_cross_domain(3, 2)
     d.set_quantity("stage", lambda x, y: x + 2 * y)
