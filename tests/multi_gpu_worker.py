@@ -20,6 +20,11 @@ comm = P.init_process_group()
 rank, size = comm.rank, comm.size
 builder, ev = cases.CASES[case]
 g = builder(ab)
+store = len(sys.argv) > 4 and sys.argv[4] == "store"
+if store:
+    g.set_store(True)
+    g.set_name("multi_" + case)
+    g.set_datadir(outdir)
 N = g.number_of_triangles
 if rule == "blocks":
     epart = (np.arange(N) * size) // N
@@ -33,9 +38,11 @@ times, steps = [], 0
 for t in d.evolve(**ev):
     times.append(t)
     steps += d.number_of_steps
+if store:
+    d.sww_merge(delete_old=True)
 nf = d.number_of_full_triangles
 q = d.quantities
-np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=d.tri_l2s[:nf], stage=q["stage"].centroid_values[:nf],
+np.savez(os.path.join(outdir, "rank%d.npz" % rank), ids=d.tri_l2s[:nf], gids=d.tri_l2g[:nf], stage=q["stage"].centroid_values[:nf],
          xmom=q["xmomentum"].centroid_values[:nf], ymom=q["ymomentum"].centroid_values[:nf],
          times=np.array(times), steps=np.array([steps]), dt=np.array([d.timestep]))
 comm.barrier()
