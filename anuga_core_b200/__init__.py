@@ -7,11 +7,14 @@ from .boundaries import (Flather_external_stage_zero_velocity_boundary, Reflecti
                          Transmissive_n_momentum_zero_t_momentum_set_stage_boundary,
                          Transmissive_momentum_set_stage_boundary,
                          Transmissive_stage_zero_momentum_boundary, Time_stage_zero_momentum_boundary)
-from .operators import Rate_operator
+from .operators import (Rate_operator, Set_quantity, Set_stage, Set_quantity_operator,
+                        Set_stage_operator)
 from .structures import (Region, Inlet, Inlet_operator, Inlet_enquiry, Structure_operator,
                          Boyd_box_operator, Boyd_pipe_operator)
 from .domain import Domain, rectangular_cross_domain, MODE_B200
 from .backend import SwkError, device_count
 from .attach import set_multiprocessor_mode_b200, B200_interface
+# the reference's script-level parallel API (anuga.distribute, myid, numprocs, barrier, finalize)
+from .parallel import distribute_collective as distribute, myid, numprocs, barrier, finalize
 
 __version__ = "0.1.0"

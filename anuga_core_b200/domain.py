@@ -381,10 +381,12 @@ class Domain:
     def set_boundary(self, boundary_map):
         """generic_domain.py:937-1033: every tag of the mesh must be bound."""
         if self.boundary_map is None:
-            self.boundary_map = boundary_map
+            self.boundary_map = dict(boundary_map)
         else:
             for key in boundary_map:
                 self.boundary_map[key] = boundary_map[key]
+        if self.numproc > 1 and "ghost" not in self.boundary_map:
+            self.boundary_map["ghost"] = None       # outer edges of the ghost layer (parallel_api.py:129)
         for tag in self.get_boundary_tags():
             if tag not in self.boundary_map:
                 raise Exception("Tag \"%s\" has not been bound to a boundary object.\n"

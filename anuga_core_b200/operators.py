@@ -83,3 +83,124 @@ class Rate_operator:
             (self.rate_array if self.rate_array is not None else self.rate)
         assert not callable(self.factor)
         return ("rate", dict(rate=rate, factor=float(self.factor), indices=self.indices))
+
+
+# ----------------------------------------------------------------------------------------
+# Set_quantity / Set_stage: assign values over a region (anuga/operators/set_quantity.py:24-140,
+# set_stage.py:24-120).  Called by hand they edit the host arrays (uploaded before the next step);
+# the *_operator forms run once per timestep on the region's cells gathered from the device.
+# ----------------------------------------------------------------------------------------
+def _function_type(value):
+    if not callable(value):
+        return "scalar"
+    import inspect
+    n = len(inspect.signature(value).parameters)
+    return {1: "t", 2: "x,y", 3: "x,y,t"}[n]
+
+
+class Set_quantity:
+    def __init__(self, domain, quantity, value=None, region=None, indices=None, polygon=None, center=None,
+                 radius=None, line=None, verbose=False, test_elevation=True, test_stage=True):
+        from .structures import Region
+        self.domain = domain
+        self.region = region if isinstance(region, Region) else \
+            Region(domain, indices=indices, polygon=polygon, center=center, radius=radius, line=line)
+        self.indices = self.region.indices
+        self.quantity = quantity
+        assert quantity in domain.quantities, "quantity not found in domain"
+        if test_elevation:
+            assert quantity != "elevation", "Use Set_elevation to maintain mass continuity"
+        if test_stage:
+            assert quantity != "stage", "Use Set_stage to maintain non-negative water depth"
+        self.set_value(value)
+        self.coord_c = domain.centroid_coordinates
+
+    def set_value(self, value=None):
+        self.value = value
+        self.value_type = _function_type(value)
+
+    def get_value(self, x=None, y=None, t=None):
+        if t is None:
+            t = self.domain.get_time()
+        if self.value_type == "t":
+            return self.value(t)
+        if self.value_type == "x,y":
+            return self.value(x, y)
+        if self.value_type == "x,y,t":
+            return self.value(x, y, t)
+        return float(self.value)
+
+    def _ids(self):
+        return slice(None) if self.indices is None else np.asarray(self.indices, dtype=np.int64)
+
+    def _new_values(self, ids):
+        return self.get_value(x=self.coord_c[ids, 0], y=self.coord_c[ids, 1])
+
+    def __call__(self):
+        if self.indices is not None and len(self.indices) == 0:
+            return
+        d = self.domain
+        d.sync_to_host()
+        ids = self._ids()
+        q = d.quantities[self.quantity]
+        q.centroid_values[ids] = self._new_values(ids)
+        q.host_dirty = True
+
+
+class Set_stage(Set_quantity):
+    """stage over a region, never below the bed (set_stage.py:24-120)"""
+
+    def __init__(self, domain, stage=None, indices=None, polygon=None, center=None, radius=None, line=None,
+                 verbose=False):
+        Set_quantity.__init__(self, domain, "stage", value=stage, indices=indices, polygon=polygon,
+                              center=center, radius=radius, line=line, verbose=verbose, test_stage=False)
+
+    def _new_values(self, ids):
+        value = Set_quantity._new_values(self, ids)
+        return np.maximum(self.domain.quantities["elevation"].centroid_values[ids], value)
+
+
+class Set_quantity_operator(Set_quantity):
+    """Set_quantity applied every timestep (set_quantity_operator.py:12-60): a host-side
+    fractional-step operator on the region's cells.  Conserved quantities only."""
+    time_dependent = True
+    host_side = True
+    _COLUMN = {"stage": 0, "xmomentum": 1, "ymomentum": 2}
+
+    def __init__(self, domain, quantity, value=None, region=None, indices=None, polygon=None, center=None,
+                 radius=None, line=None, description=None, label=None, logging=False, verbose=False,
+                 test_stage=True, test_elevation=True):
+        Set_quantity.__init__(self, domain, quantity, value, region=region, indices=indices, polygon=polygon,
+                              center=center, radius=radius, line=line, test_stage=test_stage,
+                              test_elevation=test_elevation)
+        if quantity not in self._COLUMN:
+            raise NotImplementedError("Set_quantity_operator on %s: only the conserved quantities live on the device"
+                                      % quantity)
+        domain.set_fractional_step_operator(self)
+
+    def __call__(self):
+        if self.indices is not None and len(self.indices) == 0:
+            return 0.0
+        d = self.domain
+        ids = np.arange(d.number_of_triangles, dtype=np.int64) if self.indices is None \
+            else np.asarray(self.indices, dtype=np.int64)
+        rows = d._dev.gather_centroids(ids)              # stage, xmom, ymom, elevation
+        rows[:, self._COLUMN[self.quantity]] = self.get_value(x=self.coord_c[ids, 0], y=self.coord_c[ids, 1])
+        d._dev.scatter_centroids(ids, rows[:, :3])
+        return 0.0
+
+    def oracle_spec(self):
+        return ("set_quantity", dict(indices=None if self.indices is None else np.asarray(self.indices).copy(),
+                                     quantity=self.quantity, value=self.value, value_type=self.value_type))
+
+
+class Set_stage_operator(Set_quantity_operator):
+    """anuga.Set_stage_operator (set_stage_operator.py:20-50): the stage assigned as given"""
+
+    def __init__(self, domain, stage=None, region=None, indices=None, polygon=None, center=None, radius=None,
+                 line=None, description=None, label=None, logging=False, verbose=False):
+        Set_quantity_operator.__init__(self, domain, "stage", value=stage, region=region, indices=indices,
+                                       polygon=polygon, center=center, radius=radius, line=line,
+                                       test_stage=False)
+    get_stage = Set_quantity.get_value
+    set_stage = Set_quantity.set_value

@@ -178,10 +178,51 @@ def partition_mesh(nodes, triangles, boundary, triangles_per_proc, ghost_layer_w
     return out
 
 
+_QUANTITY_NAMES = ("stage", "xmomentum", "ymomentum", "elevation", "friction")
+_STORE_KEYS = ("store", "smooth", "store_centroids", "minimum_storable_height", "using_centroid_averaging")
+
+
+def _subdomain(sub, order, nparts, p, ghost_layer_width, settings, centroid_values, vertex_values, names, domain_kw):
+    """the Domain of rank p from its local mesh `sub` and the global domain's settings / values"""
+    kw = dict(domain_kw or {})
+    d = Domain(mesh=Mesh(sub["points"], sub["triangles"], sub["boundary"],
+                         neighbour_structure=sub["neighbour_structure"]),
+               full_send_dict=sub["full_send_dict"],
+               ghost_recv_dict=sub["ghost_recv_dict"], processor=p, numproc=nparts,
+               number_of_full_triangles=sub["number_of_full_triangles"],
+               ghost_layer_width=ghost_layer_width, **kw)
+    d.tri_l2g = sub["tri_l2g"]
+    d.node_l2g = sub["node_l2g"]
+    d.tri_l2s = order[sub["tri_l2g"]]          # local -> sequential (original) triangle id
+    d.number_of_global_triangles = names["number_of_global_triangles"]
+    d.number_of_global_nodes = names["number_of_global_nodes"]
+    for k, v in settings.items():
+        setattr(d, k, v)
+    d._params_dirty = True
+    d.set_name(names["global_name"])
+    d.set_datadir(names["datadir"])
+    d.quantities_to_be_stored = dict(names["quantities_to_be_stored"])
+    for name in _QUANTITY_NAMES:
+        d.quantities[name].set_values(centroid_values[name], location="centroids")
+        if name in vertex_values:
+            d.quantities[name].vertex_values[:] = vertex_values[name]
+    return d
+
+
+def _settings_of(domain):
+    return {k: getattr(domain, k) for k in _SETTING_KEYS + _STORE_KEYS}
+
+
+def _names_of(domain):
+    return dict(number_of_global_triangles=domain.number_of_triangles,
+                number_of_global_nodes=domain.number_of_nodes, global_name=domain.get_global_name(),
+                datadir=domain.get_datadir(), quantities_to_be_stored=dict(domain.quantities_to_be_stored))
+
+
 def distribute(domain, nparts, epart=None, ghost_layer_width=2, ranks=None, domain_kw=None):
-    """anuga.distribute (parallel_api.py:71-160) for a given element partition: returns
-    {rank: Domain} with full/ghost bookkeeping, quantities (centroid values) and boundary map
-    carried over.  epart defaults to equal contiguous blocks."""
+    """anuga.distribute (parallel_api.py:71-160) for a given element partition, every process holding
+    the whole domain: returns {rank: Domain} with full/ghost bookkeeping, quantities (centroid values),
+    boundary map and operators carried over.  epart defaults to equal contiguous blocks."""
     N = domain.number_of_triangles
     if epart is None:
         epart = (np.arange(N) * nparts) // N
@@ -189,29 +230,12 @@ def distribute(domain, nparts, epart=None, ghost_layer_width=2, ranks=None, doma
     parts = partition_mesh(domain.nodes, new_tri, new_bnd, tpp, ghost_layer_width, ranks)
     out = {}
     for p, sub in parts.items():
-        kw = dict(domain_kw or {})
-        d = Domain(mesh=Mesh(sub["points"], sub["triangles"], sub["boundary"],
-                             neighbour_structure=sub["neighbour_structure"]),
-                   full_send_dict=sub["full_send_dict"],
-                   ghost_recv_dict=sub["ghost_recv_dict"], processor=p, numproc=nparts,
-                   number_of_full_triangles=sub["number_of_full_triangles"],
-                   ghost_layer_width=ghost_layer_width, **kw)
-        d.tri_l2g = sub["tri_l2g"]
-        d.node_l2g = sub["node_l2g"]
-        d.tri_l2s = order[sub["tri_l2g"]]          # local -> sequential (original) triangle id
-        d.number_of_global_triangles = N
-        d.number_of_global_nodes = domain.number_of_nodes
-        d.set_name(domain.get_global_name())
-        d.set_datadir(domain.get_datadir())
-        for k in ("store", "smooth", "store_centroids", "minimum_storable_height", "using_centroid_averaging"):
-            setattr(d, k, getattr(domain, k))
-        d.quantities_to_be_stored = dict(domain.quantities_to_be_stored)
-        _copy_settings(domain, d)
-        for name in ("stage", "xmomentum", "ymomentum", "elevation", "friction"):
-            src = domain.quantities[name]
-            d.quantities[name].set_values(src.centroid_values[d.tri_l2s], location="centroids")
-            if "vertex_values" in src._arrays:
-                d.quantities[name].vertex_values[:] = src.vertex_values[d.tri_l2s]
+        l2s = order[sub["tri_l2g"]]
+        cv = {name: domain.quantities[name].centroid_values[l2s] for name in _QUANTITY_NAMES}
+        vv = {name: domain.quantities[name].vertex_values[l2s] for name in _QUANTITY_NAMES
+              if "vertex_values" in domain.quantities[name]._arrays}
+        d = _subdomain(sub, order, nparts, p, ghost_layer_width, _settings_of(domain), cv, vv, _names_of(domain),
+                       domain_kw)
         if domain.boundary_map is not None:
             bmap = dict(domain.boundary_map)
             bmap["ghost"] = None                    # parallel_api.py:129
@@ -227,14 +251,73 @@ def distribute(domain, nparts, epart=None, ghost_layer_width=2, ranks=None, doma
     return out
 
 
-def _copy_settings(src, dst):
-    for k in ("flow_algorithm", "CFL", "timestepping_method", "minimum_allowed_height", "H0", "g", "epsilon",
+# ----------------------------------------------------------------------------------------
+# the reference's script-level parallel API (anuga/parallel/parallel_api.py): rank 0 builds the
+# sequential domain, distribute() hands every rank its sub-domain
+# ----------------------------------------------------------------------------------------
+myid = int(os.environ.get("RANK", "0"))
+numprocs = int(os.environ.get("WORLD_SIZE", "1"))
+_COMM = None
+
+
+def communicator():
+    global _COMM
+    if _COMM is None:
+        _COMM = init_process_group()
+    return _COMM
+
+
+def barrier():
+    communicator().barrier()
+
+
+def finalize():
+    c = _COMM
+    if c is not None and c.dist is not None and c.dist.is_initialized():
+        c.dist.barrier()
+        c.dist.destroy_process_group()
+
+
+def distribute_collective(domain=None, verbose=False, debug=False, parameters=None, device=None):
+    """anuga.distribute(domain, verbose, debug, parameters) as the reference's parallel scripts call
+    it: `domain` is the sequential domain on rank 0 (None elsewhere); every rank gets its sub-domain
+    with the communicator attached.  The element partition is equal contiguous blocks of the
+    sequential numbering (pymetis is not used).  Boundaries and operators are set on the returned
+    domain, as those scripts do."""
+    comm = communicator()
+    if comm.size == 1:
+        return domain
+    width = int((parameters or {}).get("ghost_layer_width", 2))
+    payload = [None] * comm.size
+    if comm.rank == 0:
+        if domain.fractional_step_operators:
+            raise NotImplementedError("create operators on the distributed domain (after distribute)")
+        N = domain.number_of_triangles
+        epart = (np.arange(N) * comm.size) // N
+        new_tri, new_bnd, tpp, order, _ = reorder_by_epart(domain.triangles, domain.mesh.boundary, epart, comm.size)
+        parts = partition_mesh(domain.nodes, new_tri, new_bnd, tpp, width)
+        for p, sub in parts.items():
+            l2s = order[sub["tri_l2g"]]
+            payload[p] = dict(sub=sub, l2s=l2s, settings=_settings_of(domain), names=_names_of(domain),
+                              cv={n: domain.quantities[n].centroid_values[l2s] for n in _QUANTITY_NAMES})
+    mine = [None]
+    comm.dist.scatter_object_list(mine, payload if comm.rank == 0 else None, src=0)
+    m = mine[0]
+    order = np.zeros(int(m["sub"]["tri_l2g"].max()) + 1, dtype=np.int64)
+    order[m["sub"]["tri_l2g"]] = m["l2s"]
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    d = _subdomain(m["sub"], order, comm.size, comm.rank, width, m["settings"], m["cv"], {}, m["names"],
+                   dict(device=device))
+    d.attach_communicator(comm)
+    return d
+
+
+_SETTING_KEYS = ("flow_algorithm", "CFL", "timestepping_method", "minimum_allowed_height", "H0", "g", "epsilon",
               "beta_w", "beta_w_dry", "beta_uh", "beta_uh_dry", "beta_vh", "beta_vh_dry", "low_froude",
               "extrapolate_velocity_second_order", "use_sloped_mannings", "evolve_max_timestep",
               "evolve_min_timestep", "max_smallsteps", "default_order", "fixed_flux_timestep",
-              "centroid_transmissive_bc", "maximum_allowed_speed", "starttime"):
-        setattr(dst, k, getattr(src, k))
-    dst._params_dirty = True
+              "centroid_transmissive_bc", "maximum_allowed_speed", "starttime")
 
 
 # ----------------------------------------------------------------------------------------

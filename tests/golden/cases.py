@@ -150,6 +150,14 @@ def rain_regions_de1(A):
     return d
 
 
+def gate_de1(A):
+    """Set_stage_operator with a level that varies in time over a circle, after a one-off Set_stage"""
+    d = beach_de1(A, n=16)
+    A.Set_stage(d, stage=0.9, center=[11.0, 4.0], radius=1.6)()
+    A.Set_stage_operator(d, stage=lambda t: 0.7 + 0.2 * np.sin(2.0 * t), center=[3.2, 8.1], radius=1.7)
+    return d
+
+
 def drain_de1(A):
     """negative rate: the clamped branch of Rate_operator (rate_operators.py:213-245)"""
     d = beach_de1(A, n=16)
@@ -264,6 +272,7 @@ CASES = {
     "time_boundary_de1": (time_boundary_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "rain_de1": (rain_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "rain_regions_de1": (rain_regions_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "gate_de1": (gate_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "drain_de1": (drain_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "sloped_manning_de1": (sloped_manning_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),

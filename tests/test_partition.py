@@ -182,6 +182,29 @@ for k in ("stage", "xmomentum", "ymomentum"):
     assert np.array_equal(sub.quantities[k].centroid_values[:nf], g.quantities[k].centroid_values[ids]), k
     changed += int(np.sum(ref.quantities[k].centroid_values[ids] != g.quantities[k].centroid_values[ids]))
 assert comm.allreduce_sum(changed) > 20
+
+# anuga.distribute as the reference's parallel scripts use it: rank 0 holds the sequential domain
+def plain():
+    d = ab.rectangular_cross_domain(10, 6, len1=10.0, len2=6.0)
+    d.set_flow_algorithm("DE1")
+    d.set_name("collective")
+    d.set_quantity("elevation", lambda x, y: -x / 7.0)
+    d.set_quantity("stage", lambda x, y: 0.2 + 0.01 * x * y, location="centroids")
+    return d
+mine = ab.distribute(plain() if rank == 0 else None, parameters=dict(ghost_layer_width=2))
+ref = P.distribute(plain(), size, ranks=[rank])[rank]
+assert ab.myid == rank and ab.numprocs == size
+assert mine.get_name() == "collective_P" + str(size) + "_" + str(rank) and mine.numproc == size
+assert np.array_equal(mine.triangles, ref.triangles) and np.array_equal(mine.nodes, ref.nodes)
+assert np.array_equal(mine.tri_l2g, ref.tri_l2g) and np.array_equal(mine.tri_l2s, ref.tri_l2s)
+assert mine.flow_algorithm == "DE1" and mine.get_timestepping_method() == "rk2"
+for k in ("stage", "elevation", "friction"):
+    assert np.array_equal(mine.quantities[k].centroid_values, ref.quantities[k].centroid_values), k
+assert sorted(mine.full_send_dict) == sorted(ref.full_send_dict)
+for q in mine.full_send_dict:
+    assert np.array_equal(mine.full_send_dict[q][0], ref.full_send_dict[q][0])
+mine.set_boundary({t: ab.Reflective_boundary(mine) for t in ("left", "right", "top", "bottom") if t in mine.get_boundary_tags()})
+assert mine.boundary_map.get("ghost", 0) is None
 comm.barrier()
 sys.stdout.write("[rank" + str(rank) + "-ok]"); sys.stdout.flush()
 '''
