@@ -62,6 +62,28 @@ def test_reference_unit_test_expected_values(oracle_libs):
     assert np.allclose(o.stage_c[:6], cases.KAT_BEDSLOPE_W_EX_HEAD)
 
 
+@pytest.mark.parametrize("backend", ["port", "ref"])
+@pytest.mark.parametrize("key", ["one_step", "two_steps", "more_steps"])
+def test_known_answers_embedded_in_the_reference_tests(oracle_libs, key, backend):
+    """the expected arrays of test_bedslope_problem_second_order_{one_step,two_steps,more_steps}
+    (test_shallow_water_domain.py:5626, 5717, 5913; tests/golden/make_golden_kat.py), with the
+    tolerance of the num.allclose those tests use"""
+    if backend == "ref" and not os.path.exists(LIBS["ref"]):
+        pytest.skip("oracle/_ref not built")
+    k = load("kat_reference_tests")
+    d = cases.kat_bedslope_more_steps(ab)
+    o = OracleDomain(domain_to_scenario(d), backend=backend)
+    ys, ft = k[key + "_evolve"]
+    for _ in o.evolve(yieldstep=float(ys), finaltime=float(ft)):
+        pass
+    assert np.allclose(o.stage_c, k[key + "_W_EX"])
+    if key + "_UH_EX" in k.files:
+        assert np.allclose(o.xmom_c, k[key + "_UH_EX"]) and np.allclose(o.ymom_c, k[key + "_VH_EX"])
+    if key + "_recorded_min_timestep" in k.files:
+        assert np.allclose(o.recorded_min_timestep, k[key + "_recorded_min_timestep"][0])
+        assert np.allclose(o.recorded_max_timestep, k[key + "_recorded_max_timestep"][0])
+
+
 @pytest.mark.skipif(not os.path.exists(LIBS["ref_fma"]), reason="oracle/_ref not built")
 def test_fma_build_of_the_reference_is_only_close(oracle_libs):
     """The reference's timing build (FMA contraction) differs from its own parity build at
