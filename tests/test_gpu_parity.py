@@ -113,7 +113,7 @@ def test_volume_balance(name):
     assert d.total_steps > 10
     assert abs(vol - v0 - bf - fs) <= 1e-10 * max(abs(v0), 1.0), (vol, v0, bf, fs)
     if name in ("dam_break_de1", "beach_de1", "culvert_de1"):
-        assert bf == 0.0 and fs == 0.0          # closed basin
+        assert abs(bf) <= 1e-15 * abs(v0) and fs == 0.0          # closed basin (wall fluxes cancel to rounding)
     if name in ("rain_de1", "inlet_de1"):
         assert fs != 0.0
 
