@@ -106,9 +106,10 @@ def test_volume_balance(name):
     fractional-step volume integral (rain, inlets; a culvert only moves water)"""
     builder, ev = cases.CASES[name]
     d = builder(ab)
-    v0 = d.get_water_volume()
+    v0 = None
     for _ in d.evolve(**ev):
-        pass
+        if v0 is None:                          # first yield: stage already lifted to the bed where it was below
+            v0 = d.get_water_volume()
     vol, bf, fs = d.report_water_volume_statistics(verbose=False, returnStats=True)
     assert d.total_steps > 10
     assert abs(vol - v0 - bf - fs) <= 1e-10 * max(abs(v0), 1.0), (vol, v0, bf, fs)
