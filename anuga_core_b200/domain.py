@@ -369,6 +369,12 @@ class Domain:
         self.quantities[name].set_values(*args, **kwargs)
         self._stale.discard(name)
 
+    def create_quantity_from_expression(self, expression):
+        """new Quantity from an arithmetic expression over the domain's quantities, e.g.
+        'stage - elevation' (generic_domain.py:916-935; only names of quantities and numbers are
+        visible to the expression)"""
+        return eval(expression, {"__builtins__": {}}, dict(self.quantities))
+
     def get_quantity(self, name):
         return self.quantities[name]
 

@@ -59,10 +59,24 @@ class Quantity:
 
     # ------------------------------------------------------------------
     def set_values(self, numeric=None, quantity=None, function=None, location="vertices",
-                   indices=None, **unsupported):
+                   indices=None, expression=None, polygon=None, **unsupported):
         for k, v in unsupported.items():
             if v not in (None, False):
                 raise NotImplementedError("set_values(%s=...) is outside the hot-path scope" % k)
+        if expression is not None:                  # quantity.py:860-864
+            assert numeric is None and quantity is None and function is None
+            quantity = self.domain.create_quantity_from_expression(expression)
+        if polygon is not None:
+            # quantity.py:778-800: a constant over the triangles whose centroid lies in the polygon;
+            # always applied at centroids, after which ALL vertex / edge values are first order
+            if indices is not None:
+                raise Exception("Only one of polygon and indices can be specified")
+            if numeric is None or not isinstance(numeric, (float, int)):
+                raise Exception("With polygon selected, set_quantity must provide the keyword numeric "
+                                "and it must (currently) be a constant.")
+            from .structures import Region
+            indices = Region(self.domain, polygon=polygon).indices
+            location = "centroids"
         if location == "edges":
             raise Exception("edges has been deprecated as valid location")
         if location not in ("vertices", "centroids", "unique vertices"):
@@ -79,7 +93,9 @@ class Quantity:
             numeric = quantity
 
         if isinstance(numeric, Quantity):
-            self._from_quantity(numeric, location, indices)
+            # set_values_from_quantity (quantity.py:1103-1117): always through the vertex values
+            location = "vertices"
+            self._from_array(np.array(numeric.vertex_values), location, indices)
         elif callable(numeric):
             self._from_function(numeric, location, indices)
         elif isinstance(numeric, (list, tuple, np.ndarray)):
@@ -150,11 +166,73 @@ class Quantity:
                 idx = np.asarray(indices, dtype=np.int64)
                 self.vertex_values[idx] = values[idx]
 
-    def _from_quantity(self, q, location, indices):
-        assert indices is None
-        self.vertex_values[:] = q.vertex_values
-        self.centroid_values[:] = q.centroid_values
-        self.edge_values[:] = q.edge_values
+    # -- arithmetic (quantity.py:230-420): what expressions such as 'elevation + 0.05' evaluate with --
+    def _as_quantity(self, other):
+        if isinstance(other, Quantity):
+            return other
+        Q = Quantity(self.domain)
+        Q.set_values(other)
+        return Q
+
+    def _triple(self, op, Q):
+        result = Quantity(self.domain)
+        result.vertex_values[:] = op(self.vertex_values, Q.vertex_values)
+        result.edge_values[:] = op(self.edge_values, Q.edge_values)
+        result.centroid_values[:] = op(self.centroid_values, Q.centroid_values)
+        return result
+
+    def __neg__(self):
+        Q = Quantity(self.domain)
+        Q.set_values(-self.vertex_values)
+        return Q
+
+    def __add__(self, other):
+        Q = Quantity(self.domain)
+        Q.set_values(other)
+        result = Quantity(self.domain)
+        result.set_values(self.vertex_values + Q.vertex_values)
+        return result
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self + -other
+
+    def __rsub__(self, other):
+        return -self + other
+
+    def __mul__(self, other):
+        return self._triple(lambda a, b: a * b, self._as_quantity(other))
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        eps = 1.0e-12                               # anuga/config.py:12 (safe division)
+        return self._triple(lambda a, b: a / (b + eps), self._as_quantity(other))
+
+    def __pow__(self, other):
+        assert not isinstance(other, Quantity)
+        result = Quantity(self.domain)
+        result.vertex_values[:] = self.vertex_values ** other
+        result.edge_values[:] = self.edge_values ** other
+        result.centroid_values[:] = self.centroid_values ** other
+        return result
+
+    def maximum(self, other):
+        Q = self._as_quantity(other)
+        self.vertex_values[:] = np.maximum(self.vertex_values, Q.vertex_values)
+        self.edge_values[:] = np.maximum(self.edge_values, Q.edge_values)
+        self.centroid_values[:] = np.maximum(self.centroid_values, Q.centroid_values)
+        self.host_dirty = True
+        return self
+
+    def minimum(self, other):
+        Q = self._as_quantity(other)
+        self.vertex_values[:] = np.minimum(self.vertex_values, Q.vertex_values)
+        self.edge_values[:] = np.minimum(self.edge_values, Q.edge_values)
+        self.centroid_values[:] = np.minimum(self.centroid_values, Q.centroid_values)
+        self.host_dirty = True
+        return self
 
     # ------------------------------------------------------------------
     def interpolate(self):

@@ -212,6 +212,22 @@ def flather_de1(A, n=16):
     return d
 
 
+def expression_de0(A, n=12):
+    """quantities set from expressions over other quantities and over a polygon, as the reference's
+    example scripts do (Quantity arithmetic, set_values(expression=...), set_values(polygon=...))"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE0")
+    d.set_store(False)
+    d.set_quantity("elevation", lambda x, y: -0.1 * x + 0.02 * x * y / n)
+    d.set_quantity("stage", expression="elevation + 0.35")
+    d.set_quantity("stage", 0.8, polygon=[[1.2, 1.1], [5.3, 1.4], [4.8, 6.2], [0.9, 5.1]])
+    d.set_quantity("xmomentum", expression="0.1*(stage - elevation)")
+    d.set_quantity("ymomentum", expression="(stage - elevation)**2 / (2.0 + elevation*elevation)")
+    d.set_quantity("friction", 0.03)
+    _reflective_all(A, d)
+    return d
+
+
 def _embankment(A, n=16):
     """two ponds separated by a dry embankment; only a culvert connects them"""
     d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
@@ -278,6 +294,7 @@ CASES = {
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "inlet_de1": (inlet_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "rain_time_de1": (rain_time_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "expression_de0": (expression_de0, dict(yieldstep=0.5, finaltime=1.5)),
     "flather_de1": (flather_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "culvert_de1": (culvert_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_pipe_de1": (culvert_pipe_de1, dict(yieldstep=1.0, finaltime=4.0)),
