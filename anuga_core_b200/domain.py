@@ -369,6 +369,12 @@ class Domain:
         self.quantities[name].set_values(*args, **kwargs)
         self._stale.discard(name)
 
+    def add_quantity(self, name, *args, **kwargs):
+        """name += whatever set_quantity accepts (generic_domain.py:880-905)"""
+        Q = Quantity(self)
+        Q.set_values(*args, **kwargs)
+        self.set_quantity(name, self.quantities[name] + Q)
+
     def create_quantity_from_expression(self, expression):
         """new Quantity from an arithmetic expression over the domain's quantities, e.g.
         'stage - elevation' (generic_domain.py:916-935; only names of quantities and numbers are
@@ -480,6 +486,28 @@ class Domain:
             print(" ")
         if returnStats:
             return [vol, bf, fs]
+
+    def statistics(self, *args, **kwargs):
+        """mesh summary in the spirit of Mesh.statistics (neighbour_mesh.py:820-920)"""
+        a = self.areas
+        x, y = self.nodes[:, 0], self.nodes[:, 1]
+        lines = ["------------------------------------------------",
+                 "Mesh statistics:",
+                 "  Number of triangles = %d" % self.number_of_triangles,
+                 "  Extent [m]:",
+                 "    x in [%e, %e]" % (x.min(), x.max()),
+                 "    y in [%e, %e]" % (y.min(), y.max()),
+                 "  Areas [m^2]:",
+                 "    A in [%e, %e]" % (a.min(), a.max()),
+                 "    number of distinct areas: %d" % len(np.unique(a)),
+                 "  Boundary:",
+                 "    Number of boundary segments == %d" % self.boundary_length,
+                 "    Boundary tags == %s" % self.get_boundary_tags(),
+                 "------------------------------------------------"]
+        return "\n".join(lines)
+
+    def print_statistics(self, *args, **kwargs):
+        print(self.statistics())
 
     def get_nodes(self, absolute=False):
         return self.nodes
