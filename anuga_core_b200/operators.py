@@ -36,14 +36,46 @@ class Rate_operator:
         return "centroid_array" if self.rate_array is not None else "scalar"
 
     rate_spatial = False
+    rate_xyt = None
+
+    @property
+    def host_side(self):
+        return self.rate_xyt is not None
 
     @property
     def time_dependent(self):
-        return self.rate_callable is not None or callable(self.factor)
+        return self.rate_callable is not None or callable(self.factor) or self.rate_xyt is not None
+
+    def __call__(self):
+        """host-side application (spatial-temporal rates only): rate_operators.py:149-269 on gathered rows;
+        returns the volume added to full cells"""
+        d = self.domain
+        t, dt = d.get_time(), d.get_timestep()
+        factor = self.current_factor(t)
+        ids = np.arange(d.number_of_triangles, dtype=np.int64) if self.indices is None else self.indices
+        if len(ids) == 0:
+            return 0.0
+        rows = d._dev.gather_centroids(ids)              # stage, xmom, ymom, elevation
+        c = d.centroid_coordinates
+        rate = np.asarray(self.rate_xyt(c[ids, 0], c[ids, 1], t), dtype=np.float64) * np.ones(len(ids))
+        if np.all(rate >= 0.0):
+            local_rates = factor * dt * rate
+            rows[:, 0] = rows[:, 0] + local_rates
+        else:
+            heights = rows[:, 0] - rows[:, 3]
+            local_rates = np.maximum(factor * dt * rate, -heights)
+            f = np.where(local_rates < 0.0, (local_rates + heights) / (heights + 1.0e-10), 1.0)
+            rows[:, 0] = rows[:, 0] + local_rates
+            rows[:, 1] = rows[:, 1] * f
+            rows[:, 2] = rows[:, 2] * f
+        d._dev.scatter_centroids(ids, rows[:, :3])
+        full = d.tri_full_flag[ids] == 1
+        return float(np.sum((local_rates * d.areas[ids])[full]))
 
     def set_rate(self, rate):
         self.rate_callable = None
         self.rate_array = None
+        self.rate_xyt = None
         self.rate_input = rate
         if callable(rate):
             import inspect
@@ -54,8 +86,9 @@ class Rate_operator:
                 C = self.domain.centroid_coordinates
                 self.rate_array = np.asarray(rate(C[:, 0], C[:, 1]), dtype=np.float64) * np.ones(len(C))
             else:
-                raise NotImplementedError("rate(x, y, t) needs a host evaluation over all centroids every "
-                                          "step; outside the hot-path scope")
+                # rate(x, y, t): evaluated on the host every step over the operator's cells, which are
+                # gathered from / scattered to the device (rate_operators.py:165-172, 276-300)
+                self.rate_xyt = rate
         elif isinstance(rate, (list, tuple, np.ndarray)):
             self.rate_array = np.asarray(rate, dtype=np.float64)
             assert self.rate_array.shape == (self.domain.number_of_triangles,)
@@ -79,6 +112,9 @@ class Rate_operator:
         return float(self.factor(t)) if callable(self.factor) else float(self.factor)
 
     def oracle_spec(self):
+        if self.rate_xyt is not None:
+            assert not callable(self.factor)
+            return ("rate", dict(rate_xyt=self.rate_xyt, rate=None, factor=float(self.factor), indices=self.indices))
         rate = self.rate_callable if self.rate_callable is not None else \
             (self.rate_array if self.rate_array is not None else self.rate)
         assert not callable(self.factor)

@@ -527,6 +527,9 @@ class OracleDomain:
         if callable(rate):
             rate = rate(self.get_time())
         idx = o.get("indices")
+        if o.get("rate_xyt") is not None:          # spatial-temporal rate: rate(x, y, t) at the centroids
+            c = self.centroid_coordinates.reshape(-1, 2)
+            rate = np.asarray(o["rate_xyt"](c[:, 0], c[:, 1], self.get_time()), dtype=np.float64) * np.ones(self.N)
         full = self.tri_full_flag == 1
         if idx is None:
             local_rates = factor * dt * rate * np.ones(self.N) if np.isscalar(rate) else factor * dt * np.asarray(rate)

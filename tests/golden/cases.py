@@ -158,6 +158,15 @@ def gate_de1(A):
     return d
 
 
+def rain_xyt_de1(A):
+    """a rain cell that moves across the domain: rate(x, y, t), positive and (over a polygon) negative"""
+    d = beach_de1(A, n=16)
+    A.Rate_operator(d, rate=lambda x, y, t: 0.02 * np.exp(-((x - 2.0 - 3.0 * t) ** 2 + (y - 8.0) ** 2) / 6.0))
+    A.Rate_operator(d, rate=lambda x, y, t: -0.01 * (1.0 + np.sin(x + t)), factor=0.5,
+                    polygon=[[1.3, 2.2], [6.7, 1.1], [7.2, 6.4], [2.1, 7.6]])
+    return d
+
+
 def drain_de1(A):
     """negative rate: the clamped branch of Rate_operator (rate_operators.py:213-245)"""
     d = beach_de1(A, n=16)
@@ -289,6 +298,7 @@ CASES = {
     "rain_de1": (rain_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "rain_regions_de1": (rain_regions_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "gate_de1": (gate_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "rain_xyt_de1": (rain_xyt_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "drain_de1": (drain_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "sloped_manning_de1": (sloped_manning_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
