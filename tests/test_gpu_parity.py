@@ -80,8 +80,9 @@ def test_evolve_matches_python_reference_golden(name):
     assert ef <= tol, ef
     assert rel_err(d.quantities["stage"].edge_values, g["final_stage_edge"]) <= tol
     assert rel_err(d.quantities["xmomentum"].vertex_values, g["final_xmom_vertex"]) <= tol
-    assert abs(d.boundary_flux_integral - g["bfi"][0]) <= 1e-9 * abs(g["bfi"][0]) + 1e-12
-    assert abs(d.fractional_step_volume_integral - g["fsvi"][0]) <= 1e-12 * abs(g["fsvi"][0]) + 1e-15
+    assert abs(d.boundary_flux_integral - g["bfi"][0]) <= max(1e-9, tol) * abs(g["bfi"][0]) + 1e-12
+    assert abs(d.fractional_step_volume_integral - g["fsvi"][0]) <= \
+        (1e-12 if loose is None else loose) * abs(g["fsvi"][0]) + 1e-15
     if "struct0_accumulated_flow" in g.files:       # culvert: total volume moved through the barrel
         op = [o for o in d.fractional_step_operators if hasattr(o, "inlets")][0]
         assert abs(op.accumulated_flow - g["struct0_accumulated_flow"][0]) <= 1e-9 * abs(g["struct0_accumulated_flow"][0])
