@@ -34,7 +34,7 @@ def conserved(d):
 # cases whose user callbacks evaluate numpy transcendentals on ARRAYS: numpy picks its SIMD code path by
 # host CPU, the last bit of exp / sin then differs between the machine that made the fixture and the GPU
 # box's host, and the runs drift apart at the 1e-9 level (scalar callbacks go through libm and do not)
-HOST_LIBM_SENSITIVE = {"rain_xyt_de1": 1.0e-6}
+HOST_LIBM_SENSITIVE = {}
 
 
 @pytest.mark.parametrize("name", sorted(cases.CASES))
