@@ -160,6 +160,38 @@ class B200_interface:
         d.sync_to_host()
         return 0
 
+    # friction.py:133-147 calls these in mode 4 (manning_friction_implicit_gpu): the semi-implicit updates
+    # of the reference domain's own momentum quantities through the per-call C ABI entry points
+    def _friction(self, sloped):
+        from . import backend as B
+        lib = B.load_library()
+        ref = self.ref
+        q = ref.quantities
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        w, uh, vh = f64(q["stage"].centroid_values), f64(q["xmomentum"].centroid_values), f64(q["ymomentum"].centroid_values)
+        eta = f64(q["friction"].centroid_values)
+        xu, yu = q["xmomentum"].semi_implicit_update, q["ymomentum"].semi_implicit_update
+        assert xu.flags.c_contiguous and yu.flags.c_contiguous
+        N = len(w)
+        dev = self.dev_domain.device
+        if sloped:
+            x = f64(ref.get_vertex_coordinates())
+            zv = f64(q["elevation"].vertex_values)
+            B._check(lib.swk_call_manning_friction_sloped(dev, float(ref.g), float(ref.minimum_allowed_height), N,
+                                                          B._pd(x), B._pd(w), B._pd(zv), B._pd(uh), B._pd(vh),
+                                                          B._pd(eta), B._pd(xu), B._pd(yu)))
+        else:
+            z = f64(q["elevation"].centroid_values)
+            B._check(lib.swk_call_manning_friction_flat(dev, float(ref.g), float(ref.minimum_allowed_height), N,
+                                                        B._pd(w), B._pd(z), B._pd(uh), B._pd(vh), B._pd(eta),
+                                                        B._pd(xu), B._pd(yu)))
+
+    def compute_forcing_terms_manning_friction_flat(self):
+        self._friction(False)
+
+    def compute_forcing_terms_manning_friction_sloped(self):
+        self._friction(True)
+
     # -- resident time loop behind the reference's evolve wrapper --------------------------------
     def evolve_base(self, yieldstep=None, finaltime=None, duration=None, skip_initial_step=False):
         ref, d = self.ref, self.dev_domain

@@ -84,3 +84,28 @@ def test_adapter_time_loop_matches_golden(name):
     assert rel_err(stage_alias, g["final_stage"]) <= 1e-9          # the alias saw the result
     assert rel_err(ref_like.quantities["xmomentum"].centroid_values, g["final_xmom"]) <= 1e-9
     assert ref_like.timestep == g["dts"][-1]
+
+
+@pytest.mark.gpu
+def test_adapter_friction_methods_of_mode_4():
+    """gpu_interface.compute_forcing_terms_manning_friction_flat / _sloped (friction.py:133-147)"""
+    d = cases.dam_break_de1(ab)
+    q = d.quantities
+    q["xmomentum"].set_values(lambda x, y: 0.3 + 0.01 * x, location="centroids")
+    q["ymomentum"].set_values(lambda x, y: -0.2 + 0.02 * y, location="centroids")
+    iface = ab.B200_interface(d)
+    q["xmomentum"].semi_implicit_update[:] = 0.0
+    q["ymomentum"].semi_implicit_update[:] = 0.0
+    iface.compute_forcing_terms_manning_friction_flat()
+    w, z = q["stage"].centroid_values, q["elevation"].centroid_values
+    uh, vh, eta = q["xmomentum"].centroid_values, q["ymomentum"].centroid_values, q["friction"].centroid_values
+    h = w - z
+    S = -d.g * eta ** 2 * np.sqrt(uh ** 2 + vh ** 2) / h ** (7.0 / 3.0)
+    assert np.all(h > d.minimum_allowed_height)
+    assert rel_err(q["xmomentum"].semi_implicit_update, S * uh) <= 1e-14
+    assert rel_err(q["ymomentum"].semi_implicit_update, S * vh) <= 1e-14
+    flat = q["xmomentum"].semi_implicit_update.copy()
+    q["xmomentum"].semi_implicit_update[:] = 0.0
+    q["ymomentum"].semi_implicit_update[:] = 0.0
+    iface.compute_forcing_terms_manning_friction_sloped()
+    assert np.all(np.abs(q["xmomentum"].semi_implicit_update) >= np.abs(flat) * (1 - 1e-14))   # x sqrt(1 + |grad z|^2)
