@@ -8,7 +8,7 @@ from .boundaries import (Flather_external_stage_zero_velocity_boundary, Reflecti
                          Transmissive_momentum_set_stage_boundary,
                          Transmissive_stage_zero_momentum_boundary, Time_stage_zero_momentum_boundary)
 from .operators import (Rate_operator, Set_quantity, Set_stage, Set_quantity_operator,
-                        Set_stage_operator)
+                        Set_stage_operator, Set_elevation, Set_elevation_operator)
 from .structures import (Region, Inlet, Inlet_operator, Inlet_enquiry, Structure_operator,
                          Boyd_box_operator, Boyd_pipe_operator)
 from .domain import Domain, rectangular_cross_domain, MODE_B200

@@ -121,6 +121,7 @@ SYMBOLS = {
     "swk_set_rate": (C.c_int, [_H, C.c_int, _D, _D]),
     "swk_gather_centroids": (C.c_int, [_H, _PI, _I, _PD]),
     "swk_scatter_centroids": (C.c_int, [_H, _PI, _I, _PD]),
+    "swk_scatter_bed": (C.c_int, [_H, _PI, _I, _PD]),
     "swk_add_fractional_step_volume": (C.c_int, [_H, _D]),
     "swk_set_local_ghost_copy": (C.c_int, [_H, _PI, _PI, _I]),
     "swk_set_time": (C.c_int, [_H, _D]),
@@ -353,6 +354,11 @@ class DeviceDomain:
         ids = _i64(ids)
         v = _f64(values).reshape(ids.size, 3)
         _check(self.lib.swk_scatter_centroids(self.h, _pi(ids), ids.size, _pd(v)))
+
+    def scatter_bed(self, ids, values):
+        ids = _i64(ids)
+        v = _f64(values).reshape(ids.size)
+        _check(self.lib.swk_scatter_bed(self.h, _pi(ids), ids.size, _pd(v)))
 
     def add_fractional_step_volume(self, volume):
         _check(self.lib.swk_add_fractional_step_volume(self.h, float(volume)))

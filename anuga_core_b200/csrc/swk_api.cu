@@ -984,6 +984,21 @@ extern "C" int swk_scatter_centroids(swk_domain *d, const int64_t *ids, int64_t 
   return rc;
 }
 
+extern "C" int swk_scatter_bed(swk_domain *d, const int64_t *ids, int64_t n, const double *in)
+{
+  if (!d || !ids || !in || n < 0) return fail(SWK_ERR_ARG, "bad argument");
+  if (n == 0) return SWK_OK;
+  CK(cudaSetDevice(d->device));
+  int *d_ids = nullptr;
+  CKV(cell_ids_to_device(d, ids, n, &d_ids));
+  CKV(ensure_staging(d, (size_t)std::max<int64_t>(4 * n, 3LL * d->N)));
+  cudaError_t e = cudaMemcpyAsync(d->staging, in, n * sizeof(double), cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) LAUNCH(d, k_scatter_bed, nblk(n), BLOCK, d->D, d_ids, (int)n, d->staging);
+  int rc = (e == cudaSuccess) ? sync_check(d) : fail(SWK_ERR_CUDA, cudaGetErrorString(e));
+  cudaFree(d_ids);
+  return rc;
+}
+
 extern "C" int swk_add_fractional_step_volume(swk_domain *d, double volume)
 {
   if (!d) return fail(SWK_ERR_ARG, "handle is NULL");

@@ -1057,5 +1057,12 @@ __global__ void __launch_bounds__(BLOCK) k_scatter_cells(Dev D, const int *ids, 
   c.x = in[3 * j]; c.y = in[3 * j + 1]; c.z = in[3 * j + 2];
   D.cq[ids[j]] = c;
 }
+
+__global__ void __launch_bounds__(BLOCK) k_scatter_bed(Dev D, const int *ids, int n, const double *in)
+{
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= n) return;
+  D.cq[ids[j]].w = in[j];
+}
 }  // namespace swk
 

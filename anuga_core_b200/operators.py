@@ -240,3 +240,57 @@ class Set_stage_operator(Set_quantity_operator):
                                        test_stage=False)
     get_stage = Set_quantity.get_value
     set_stage = Set_quantity.set_value
+
+
+class Set_elevation(Set_quantity):
+    """bed elevation over a region with the water depth kept (set_elevation.py:14-150, the
+    discontinuous-elevation branch: elevation and stage move together at the centroids)"""
+
+    def __init__(self, domain, elevation=None, region=None, indices=None, polygon=None, center=None,
+                 radius=None, line=None, verbose=False):
+        Set_quantity.__init__(self, domain, "elevation", value=elevation, region=region, indices=indices,
+                              polygon=polygon, center=center, radius=radius, line=line, verbose=verbose,
+                              test_elevation=False)
+
+    def __call__(self):
+        if self.value is None or (self.indices is not None and len(self.indices) == 0):
+            return
+        d = self.domain
+        d.sync_to_host()
+        ids = self._ids()
+        w, z = d.quantities["stage"], d.quantities["elevation"]
+        height = w.centroid_values[ids] - z.centroid_values[ids]
+        z.centroid_values[ids] = self.get_value(x=self.coord_c[ids, 0], y=self.coord_c[ids, 1])
+        w.centroid_values[ids] = z.centroid_values[ids] + height
+        w.host_dirty = z.host_dirty = True
+
+
+class Set_elevation_operator(Set_elevation):
+    """Set_elevation applied every timestep (set_elevation_operator.py): erosion, breaches, slides"""
+    time_dependent = True
+    host_side = True
+
+    def __init__(self, domain, elevation=None, region=None, indices=None, polygon=None, center=None,
+                 radius=None, line=None, description=None, label=None, logging=False, verbose=False):
+        Set_elevation.__init__(self, domain, elevation, region, indices, polygon, center, radius, line, verbose)
+        domain.set_fractional_step_operator(self)
+
+    def __call__(self):
+        if self.value is None or (self.indices is not None and len(self.indices) == 0):
+            return 0.0
+        d = self.domain
+        ids = np.arange(d.number_of_triangles, dtype=np.int64) if self.indices is None \
+            else np.asarray(self.indices, dtype=np.int64)
+        rows = d._dev.gather_centroids(ids)              # stage, xmom, ymom, elevation
+        height = rows[:, 0] - rows[:, 3]
+        bed = np.asarray(self.get_value(x=self.coord_c[ids, 0], y=self.coord_c[ids, 1]), dtype=np.float64) \
+            * np.ones(len(ids))
+        rows[:, 0] = bed + height
+        d._dev.scatter_bed(ids, bed)
+        d._dev.scatter_centroids(ids, rows[:, :3])
+        d.quantities["elevation"].centroid_values[ids] = bed        # host copy of the (otherwise static) bed
+        return 0.0
+
+    def oracle_spec(self):
+        return ("set_elevation", dict(indices=None if self.indices is None else np.asarray(self.indices).copy(),
+                                      value=self.value, value_type=self.value_type))

@@ -219,6 +219,9 @@ int swk_set_rate(swk_domain *d, int op_id, double rate, double factor);
  * handful of cells per step (structures/inlet.py:69-190, inlet_operator.py:78-157).              */
 int swk_gather_centroids(swk_domain *d, const int64_t *ids, int64_t n, double *out);
 int swk_scatter_centroids(swk_domain *d, const int64_t *ids, int64_t n, const double *in);
+/* Bed elevation of `n` triangles (in: (n,)): what Set_elevation writes into elevation.centroid_values
+ * (operators/set_elevation.py:116-150, discontinuous-elevation branch). */
+int swk_scatter_bed(swk_domain *d, const int64_t *ids, int64_t n, const double *in);
 /* fractional_step_volume_integral += volume (host-side operators account their own water) */
 int swk_add_fractional_step_volume(swk_domain *d, double volume);
 

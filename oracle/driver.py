@@ -505,6 +505,16 @@ class OracleDomain:
                 self._inlet_operator(op[1])
             elif op[0] == "boyd_box":
                 self._boyd_box_operator(op[1])
+            elif op[0] == "set_elevation":        # operators/set_elevation.py:116-150 (discontinuous elevation)
+                o = op[1]
+                ids = slice(None) if o["indices"] is None else np.asarray(o["indices"], dtype=np.int64)
+                vt, v = o["value_type"], o["value"]
+                x, y = self.centroid_coordinates[ids, 0], self.centroid_coordinates[ids, 1]
+                value = v(self.get_time()) if vt == "t" else v(x, y) if vt == "x,y" else \
+                    v(x, y, self.get_time()) if vt == "x,y,t" else float(v)
+                height = self.stage_c[ids] - self.bed_c[ids]
+                self.bed_c[ids] = value
+                self.stage_c[ids] = self.bed_c[ids] + height
             elif op[0] == "set_quantity":         # operators/set_quantity.py:76-110
                 o = op[1]
                 ids = slice(None) if o["indices"] is None else np.asarray(o["indices"], dtype=np.int64)

@@ -169,6 +169,13 @@ def rain_xyt_de1(A):
     return d
 
 
+def breach_de1(A):
+    """Set_elevation_operator: an embankment that is lowered over a circle as time goes on"""
+    d = _embankment(A)
+    A.Set_elevation_operator(d, elevation=lambda t: 1.0 - 0.3 * t, center=[8.0, 8.0], radius=1.6)
+    return d
+
+
 def drain_de1(A):
     """negative rate: the clamped branch of Rate_operator (rate_operators.py:213-245)"""
     d = beach_de1(A, n=16)
@@ -301,6 +308,7 @@ CASES = {
     "rain_regions_de1": (rain_regions_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "gate_de1": (gate_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "rain_xyt_de1": (rain_xyt_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "breach_de1": (breach_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "drain_de1": (drain_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "sloped_manning_de1": (sloped_manning_de1, dict(yieldstep=0.5, finaltime=2.0)),
     "low_froude_de1": (low_froude_de1, dict(yieldstep=0.5, finaltime=2.0)),
