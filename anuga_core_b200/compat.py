@@ -104,8 +104,8 @@ def install_as_anuga():
     for sub in ("inlet_operator", "inlet", "inlet_enquiry", "structure_operator", "boyd_box_operator",
                 "boyd_pipe_operator"):
         _alias("anuga.structures." + sub, **sys.modules["anuga.structures"].__dict__)
-    for sub in ("rate_operators", "set_stage", "set_quantity", "set_stage_operator", "set_quantity_operator",
-                "base_operator"):
+    for sub in ("rate_operators", "set_stage", "set_quantity", "set_elevation", "set_stage_operator",
+                "set_quantity_operator", "set_elevation_operator", "base_operator"):
         _alias("anuga.operators." + sub, **sys.modules["anuga.operators"].__dict__)
     _alias("anuga.abstract_2d_finite_volumes.quantity", Quantity=pkg.Quantity)
     _alias("anuga.abstract_2d_finite_volumes.mesh_factory", rectangular=rectangular,
