@@ -33,6 +33,9 @@ namespace swk {
 #ifndef SWK_MINB_FU         // ... for the fused flux + update kernel
 #define SWK_MINB_FU 7
 #endif
+#ifndef SWK_XG_COMPACT      // extrapolation geometry in 2 records (64 B) instead of 3 (96 B), see extrapolate_tri:
+#define SWK_XG_COMPACT 0    // measured 9 % slower (0.805 vs 0.738 ms at 16M triangles) although it moves 13 % fewer bytes
+#endif
 #ifndef SWK_FU_ROLLED       // fused kernel: one edge per trip of a rolled loop (see triangle_flux)
 #define SWK_FU_ROLLED true
 #endif
@@ -117,19 +120,47 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
   const d4 c2 = cq[s.z];
   const d4 g0 = D.xg[k];
   const d4 g1 = D.xg[NP + k];
-  const d4 g2 = D.xg[2 * NP + k];
   XGeom G;
   G.dxv0 = g0.x; G.dxv1 = g0.y; G.dxv2 = g0.z; G.dyv0 = g0.w;
-  G.dyv1 = g1.x; G.dyv2 = g1.y; G.dx1 = g1.z; G.dx2 = g1.w;
+  G.dyv1 = g1.x; G.dyv2 = g1.y;
+#if SWK_XG_COMPACT
+  // two records per triangle: the edge-midpoint offsets and the own centroid.  The auxiliary
+  // triangle of the neighbours' centroids (sw_domain_openmp.c:1477-1484, 1553) or the 1-D gradient
+  // factors of a two-boundary triangle (:1684-1696) are recomputed from the neighbours' centroids
+  // (16-byte gathers next to the centroid-record gathers above) instead of being stored: 32 bytes
+  // less per triangle and pass, one more division.
+  {
+    const double2 p0 = reinterpret_cast<const double2 *>(&D.xg[NP + s.x])[1];
+    const double2 p1 = reinterpret_cast<const double2 *>(&D.xg[NP + s.y])[1];
+    const double2 p2 = reinterpret_cast<const double2 *>(&D.xg[NP + s.z])[1];
+    const int nbq = s.w & 3;
+    if (nbq <= 1) {
+      G.dx1 = p1.x - p0.x; G.dx2 = p2.x - p0.x; G.dy1 = p1.y - p0.y; G.dy2 = p2.y - p0.y;
+      const double area2 = G.dy2 * G.dx1 - G.dy1 * G.dx2;
+      G.inv_area2 = 1.0 / area2;
+    } else {
+      const int wh = (s.w >> 2) & 3;
+      const double2 pn = (wh == 0) ? p0 : ((wh == 1) ? p1 : p2);
+      const double dx1 = pn.x - g1.z, dy1 = pn.y - g1.w;
+      const double dist2 = dx1 * dx1 + dy1 * dy1;
+      double dx2 = 1.0 / dist2;
+      const double dy2 = dx2 * dy1;
+      dx2 *= dx1;
+      G.dx1 = dx1; G.dy1 = dy1; G.dx2 = dx2; G.dy2 = dy2; G.inv_area2 = 0.0;
+    }
+  }
+#else
+  const d4 g2 = D.xg[2 * NP + k];
+  G.dx1 = g1.z; G.dx2 = g1.w;
   G.dy1 = g2.x; G.dy2 = g2.y; G.inv_area2 = g2.z;
-  const double area = g2.w;
+#endif
   connA_flags = s.w;
 
   e = effective(c, K);
   const Eff e0 = effective(c0, K);
   const Eff e1 = effective(c1, K);
   const Eff e2 = effective(c2, K);
-  if (count_mass && e.mass_added != 0.0) atomicAdd(&D.clock->mass_error, e.mass_added * area);
+  if (count_mass && e.mass_added != 0.0) atomicAdd(&D.clock->mass_error, e.mass_added * D.fg[2 * NP + k].w);
 
   const int nb = s.w & 3;
   // loop 2 head (:1486-1495): all neighbours dry (or self) -> no momentum
@@ -229,7 +260,7 @@ __global__ void __launch_bounds__(BLOCK) k_protect_mass(Dev D, Consts K)
   const int k = blockIdx.x * BLOCK + threadIdx.x;
   if (k >= D.N) return;
   const d4 c = D.cq[k];
-  if (c.x < c.w) atomicAdd(&D.clock->mass_error, (c.w - c.x) * D.xg[2 * D.NP + k].w);
+  if (c.x < c.w) atomicAdd(&D.clock->mass_error, (c.w - c.x) * D.fg[2 * D.NP + k].w);
 }
 
 // =============================================================================
@@ -798,7 +829,7 @@ __global__ void __launch_bounds__(BLOCK) k_rate_operator(Dev D, double rate, dou
       c.z = c.z * f;
     }
     D.cq[k] = c;
-    if (D.connB[k].w & 1) contrib = local_rate * D.xg[2 * D.NP + k].w;
+    if (D.connB[k].w & 1) contrib = local_rate * D.fg[2 * D.NP + k].w;
   }
   // deterministic two-stage sum: per-block partials, finished by k_rate_finish
   __shared__ double part[BLOCK];
