@@ -219,3 +219,46 @@ def test_world_size_2_gloo_halo_lists_and_plumbing(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "[rank0-ok]" in res.stdout and "[rank1-ok]" in res.stdout
+
+
+def test_partition_matches_reference_pipeline_on_random_partitions():
+    """live against the reference's distribute_mesh pipeline (when the scratch build exists): irregular
+    element partitions (nearest of P random seeds), several widths - every index array equal"""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("python reference not built (oracle/build_pyref.py)")
+    holder = {}
+    anuga = pyref.import_anuga(epart_fn=lambda nparts, adj: holder["epart"])
+    import anuga.parallel.distribute_mesh as dm
+    import pymetis
+    dm.part_graph = pymetis.part_graph
+    dm.metis_version = "5_part_graph"
+    from anuga.parallel.sequential_distribute import Sequential_distribute
+    rng = np.random.default_rng(11)
+    for (m, n, nparts, width) in [(9, 7, 3, 2), (12, 5, 4, 2), (8, 8, 2, 3), (7, 6, 5, 1)]:
+        ref = anuga.rectangular_cross_domain(m, n, len1=float(m), len2=float(n))
+        ref.set_store(False)
+        c = ref.centroid_coordinates
+        seeds = rng.uniform([0, 0], [m, n], size=(nparts, 2))
+        epart = np.argmin(((c[:, None, :] - seeds[None, :, :]) ** 2).sum(axis=2), axis=1)
+        assert len(np.unique(epart)) == nparts
+        holder["epart"] = epart.tolist()
+        sd = Sequential_distribute(ref, parameters={"ghost_layer_width": width})
+        sd.distribute(nparts)
+        pts, tri, bnd = ab.rectangular_cross(m, n, float(m), float(n))
+        new_tri, new_bnd, tpp, order, _ = P.reorder_by_epart(tri, bnd, epart, nparts)
+        parts = P.partition_mesh(pts, new_tri, new_bnd, tpp, width)
+        for p in range(nparts):
+            (points, vertices, boundary, quantities, ghost_recv, full_send, tri_map, node_map,
+             tri_l2g, node_l2g, glw) = dm.extract_submesh(sd.submesh, sd.triangles_per_proc, sd.p2s_map, p)
+            s = parts[p]
+            assert np.array_equal(s["points"], points) and np.array_equal(s["triangles"], vertices)
+            assert {k: str(v) for k, v in s["boundary"].items()} == {tuple(k): str(v) for k, v in boundary.items()}
+            assert np.array_equal(order[s["tri_l2g"]], np.asarray(tri_l2g))
+            assert np.array_equal(s["node_l2g"], np.asarray(node_l2g))
+            assert s["number_of_full_triangles"] == len(sd.submesh["full_triangles"][p])
+            for mine, theirs in ((s["full_send_dict"], full_send), (s["ghost_recv_dict"], ghost_recv)):
+                assert sorted(mine) == sorted(theirs)
+                for q in mine:
+                    assert np.array_equal(mine[q][0], np.asarray(theirs[q][0]))
+                    assert np.array_equal(mine[q][1], np.asarray(theirs[q][1]))
