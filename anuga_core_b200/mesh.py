@@ -70,6 +70,22 @@ def rectangular_cross(m, n, len1=1.0, len2=1.0, origin=(0.0, 0.0)):
     elements[3::4, 2] = v3
 
     boundary = {}
+
+    def cell(i, j):             # the reference's per-cell order: left, bottom, right, top
+        c = 4 * (i * n + j)
+        if i == 0:
+            boundary[(c + 0, 1)] = "left"
+        if j == 0:
+            boundary[(c + 1, 1)] = "bottom"
+        if i == m - 1:
+            boundary[(c + 2, 1)] = "right"
+        if j == n - 1:
+            boundary[(c + 3, 1)] = "top"
+    # the cells at which the reference's (i, j) scan first meets each tag come first, so that
+    # get_boundary_tags() lists the tags in the reference's order (left, bottom, top, right) ...
+    for i, j in ((0, 0), (0, n - 1), (m - 1, 0)):
+        cell(i, j)
+    # ... then all boundary edges (the enumeration itself is by sorted key, neighbour_mesh.py:441-502)
     for j in range(n):
         boundary[(4 * (0 * n + j) + 0, 1)] = "left"
         boundary[(4 * ((m - 1) * n + j) + 2, 1)] = "right"

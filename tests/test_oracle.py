@@ -139,3 +139,63 @@ def test_riverwall_port_equals_reference_c_code(oracle_libs):
         assert np.array_equal(getattr(res["port"], k), getattr(res["ref"], k)), k
     wet_right = (res["ref"].stage_c - res["ref"].bed_c)[d.centroid_coordinates[:, 0] > 6.5].max()
     assert wet_right > 1e-3          # the wall was overtopped: the weir law was exercised
+
+
+def _random_domain(A, seed):
+    """a small randomly configured scenario, written against the shared API (both packages)"""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(6, 11))
+    L = float(n)
+    d = A.rectangular_cross_domain(n, n, len1=L, len2=L)
+    d.set_flow_algorithm(str(rng.choice(["DE0", "DE1", "DE2", "DE0_7", "DE1_7"])))
+    d.set_store(False)
+    a, b, c0 = rng.uniform(-0.2, 0.2), rng.uniform(-0.1, 0.1), rng.uniform(0.0, 0.4)
+    kx, ky = rng.uniform(0.3, 1.2, size=2)
+    d.set_quantity("elevation", lambda x, y: a * x + b * y + c0 * (x / L) * (1 - y / L) * 4 + 0.05 * (kx * x) * (ky * y) / L)
+    level = float(rng.uniform(-0.3, 0.6))
+    bump = float(rng.uniform(0.1, 0.6))
+    cx, cy = rng.uniform(0.2 * L, 0.8 * L, size=2)
+    d.set_quantity("stage", lambda x, y: level + bump / (1.0 + ((x - cx) ** 2 + (y - cy) ** 2)), location="centroids")
+    d.set_quantity("xmomentum", lambda x, y: 0.05 * (y - cy) / L, location="centroids")
+    d.set_quantity("friction", float(rng.choice([0.0, 0.02, 0.05])))
+    d.set_low_froude(int(rng.integers(0, 3)))
+    if rng.random() < 0.4:
+        d.set_sloped_mannings_function(True)
+    Br = A.Reflective_boundary(d)
+    pool = [Br, A.Dirichlet_boundary([level + 0.1, 0.0, 0.0]), A.Transmissive_boundary(d),
+            A.Transmissive_stage_zero_momentum_boundary(d)]
+    d.set_boundary({t: pool[int(rng.integers(0, len(pool)))] for t in sorted(d.get_boundary_tags())})
+    if rng.random() < 0.5:
+        A.Rate_operator(d, rate=float(rng.uniform(-0.02, 0.03)))
+    return d
+
+
+@pytest.mark.parametrize("seed", list(range(1, 17)))
+def test_oracle_equals_live_python_reference_on_random_scenarios(oracle_libs, seed):
+    """fuzzing the pin: randomly configured scenarios (algorithm, bed, wet/dry level, boundaries, friction
+    form, low-Froude mode, rain or drain) run by the unmodified Python reference in this process and by the
+    oracle - bit for bit"""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("python reference not built (oracle/build_pyref.py)")
+    anuga = pyref.import_anuga()
+    ref = _random_domain(anuga, seed)
+    ref.set_multiprocessor_mode(2)
+    ev = dict(yieldstep=0.4, finaltime=1.2)
+    dts = []
+    orig = ref.apply_fractional_steps
+
+    def hook():
+        orig()
+        dts.append(ref.timestep)
+    ref.apply_fractional_steps = hook
+    for _ in ref.evolve(**ev):
+        pass
+    o = OracleDomain(domain_to_scenario(_random_domain(ab, seed)), backend="port")
+    for _ in o.evolve(**ev):
+        pass
+    assert len(dts) >= 3 and np.array_equal(np.array(o.timestep_history), np.array(dts))
+    q = ref.quantities
+    assert np.array_equal(o.stage_c, q["stage"].centroid_values)
+    assert np.array_equal(o.xmom_c, q["xmomentum"].centroid_values)
+    assert np.array_equal(o.ymom_c, q["ymomentum"].centroid_values)
