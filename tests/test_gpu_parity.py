@@ -110,6 +110,30 @@ def test_known_answers_embedded_in_the_reference_tests(key):
         assert np.allclose(d.recorded_max_timestep, k[key + "_recorded_max_timestep"][0])
 
 
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_cuda_equals_reference_c_code_on_random_scenarios(seed):
+    """fuzzing: randomly configured scenarios (algorithm incl. DE0_7 / DE1_7 / DE2, bed, wet/dry level,
+    boundary mix, friction form, low-Froude mode, rain or drain; tests/test_oracle.py::_random_domain, which
+    the CPU suite runs against the live Python reference) - device time loop vs the reference's C code"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "toracle", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_oracle.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    ev = dict(yieldstep=0.4, finaltime=1.2)
+    d = m._random_domain(ab, seed)
+    o = OracleDomain(domain_to_scenario(m._random_domain(ab, seed)), backend=REF)
+    d.record_timestep_history = True
+    for _ in d.evolve(**ev):
+        pass
+    for _ in o.evolve(**ev):
+        pass
+    assert d.total_steps == len(o.timestep_history) and d.timestep == o.timestep
+    w, uh, vh = conserved(d)
+    e = max(rel_err(w, o.stage_c), rel_err(uh, o.xmom_c), rel_err(vh, o.ymom_c))
+    assert e <= TOL_FINAL, e
+
+
 @pytest.mark.parametrize("name", ["dam_break_de1", "beach_de1", "rain_de1", "inlet_de1", "culvert_de1",
                                   "tsunami_set_stage"])
 def test_volume_balance(name):
