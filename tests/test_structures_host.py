@@ -1,0 +1,114 @@
+"""CPU: the host-side hydraulics of anuga_core_b200/structures.py against the reference's own functions and
+operator objects, live, on random inputs (skipped when the scratch build of the reference is absent; the
+golden evolve cases cover the same code through the oracle and on the GPU)."""
+import numpy as np
+import pytest
+
+import anuga_core_b200 as ab
+from anuga_core_b200 import structures as S
+from oracle import pyref
+
+pytestmark = pytest.mark.skipif(not pyref.available(), reason="python reference not built (oracle/build_pyref.py)")
+
+
+def test_rating_functions_equal_reference_on_random_inputs():
+    anuga = pyref.import_anuga()
+    from anuga.structures.boyd_box_operator import boyd_box_function, total_energy, smooth_discharge
+    from anuga.structures.boyd_pipe_operator import boyd_pipe_function
+    rng = np.random.default_rng(5)
+    cases_seen = set()
+    for _ in range(3000):
+        width, depth = rng.uniform(0.3, 4.0), rng.uniform(0.2, 3.0)
+        blockage = float(rng.choice([0.0, rng.uniform(0, 0.9), rng.uniform(0.9, 1.0), 1.0]))
+        barrels = float(rng.integers(1, 4))
+        length = rng.uniform(1.0, 40.0)
+        drive = rng.uniform(0.011, 4.0)
+        delta = drive * rng.uniform(0.0, 1.5)
+        tail = rng.uniform(0.0, 4.0)
+        loss, manning = rng.uniform(0.0, 3.0), rng.uniform(0.01, 0.05)
+        a = S.boyd_box_function(width, depth, blockage, barrels, width, length, drive, delta, tail, loss, manning)
+        b = boyd_box_function(width, depth, blockage, barrels, width, length, drive, delta, tail, loss, manning)
+        assert tuple(a[:4]) == tuple(b[:4]), (a, b)
+        cases_seen.add(b[4])
+        a = S.boyd_pipe_function(drive, width, blockage, barrels, length, drive, delta, tail, loss, manning)
+        b = boyd_pipe_function(drive, width, blockage, barrels, length, drive, delta, tail, loss, manning)
+        assert tuple(a[:4]) == tuple(b[:4]), (a, b)
+        cases_seen.add(b[4])
+        sm, de, dt, ts = rng.uniform(-1, 1), rng.uniform(-1, 1), float(rng.choice([0.0, rng.uniform(0, 0.2)])), rng.uniform(0, 3)
+        assert S.total_energy(sm, de, dt, ts, True) == total_energy(sm, de, dt, ts, True)
+        assert S.total_energy(sm, de, dt, ts, False) == total_energy(sm, de, dt, ts, False)
+        sq, q, area, tt = rng.uniform(-2, 2), rng.uniform(0, 3), float(rng.choice([0.0, rng.uniform(0.1, 3)])), rng.uniform(0, 1)
+        assert tuple(S.smooth_discharge(sm, sq, q, area, tt, True)) == tuple(smooth_discharge(sm, sq, q, area, tt, True))
+    assert len(cases_seen) >= 8          # weir / orifice / submerged / full / part-full / blocked branches
+
+
+class _HostArrays:
+    """stands in for the device: the gather / scatter entry points on plain arrays"""
+
+    def __init__(self, d):
+        q = d.quantities
+        self.a = [q[k].centroid_values for k in ("stage", "xmomentum", "ymomentum", "elevation")]
+
+    def gather_centroids(self, ids):
+        return np.stack([x[ids] for x in self.a], axis=1)
+
+    def scatter_centroids(self, ids, v):
+        for k in range(3):
+            self.a[k][ids] = v[:, k]
+
+
+def _pair(seed):
+    anuga = pyref.import_anuga()
+    rng = np.random.default_rng(seed)
+    coef = rng.uniform(-1, 1, size=6)
+    level = rng.uniform(0.1, 1.0, size=2)
+
+    def build(A):
+        d = A.rectangular_cross_domain(14, 8, len1=14.0, len2=8.0)
+        d.set_flow_algorithm("DE1")
+        d.set_store(False)
+        d.set_quantity("elevation", lambda x, y: 0.6 / (1.0 + (x - 7.0) ** 2) + 0.02 * coef[0] * y)
+        d.set_quantity("stage", lambda x, y: (x < 7.0) * level[0] + (x >= 7.0) * level[1] + 0.01 * coef[1] * x,
+                       location="centroids")
+        d.set_quantity("xmomentum", lambda x, y: 0.1 * coef[2] + 0.01 * coef[3] * y, location="centroids")
+        d.set_quantity("ymomentum", lambda x, y: 0.1 * coef[4] + 0.01 * coef[5] * x, location="centroids")
+        return d
+    return anuga, build, rng
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_operators_equal_reference_objects_on_random_states(seed):
+    """Inlet_operator, Boyd_box_operator, Boyd_pipe_operator: one application with a random state,
+    parameters and timestep - same arrays and statistics as the reference's objects"""
+    anuga, build, rng = _pair(seed)
+    ref, mine = build(anuga), build(ab)
+    dt = float(rng.uniform(0.01, 0.3))
+    Qin = float(rng.uniform(-3.0, 3.0))
+    kw_box = dict(losses=float(rng.uniform(0, 2)), width=float(rng.uniform(0.8, 2.0)), height=float(rng.uniform(0.3, 1.0)),
+                  barrels=float(rng.integers(1, 3)), blockage=float(rng.choice([0.0, 0.3])),
+                  end_points=[[4.3, 5.3], [9.7, 5.3]], apron=0.55, enquiry_gap=0.4,
+                  smoothing_timescale=float(rng.choice([0.0, 1.0])),
+                  use_momentum_jet=bool(rng.integers(0, 2)), use_velocity_head=bool(rng.integers(0, 2)))
+    kw_pipe = dict(losses=[0.5, 0.7], diameter=float(rng.uniform(0.4, 1.2)), barrels=1.0, blockage=float(rng.choice([0.0, 0.95])),
+                   end_points=[[4.3, 2.3], [9.7, 2.3]], apron=0.55, enquiry_gap=0.45,
+                   use_momentum_jet=bool(rng.integers(0, 2)), use_velocity_head=True)
+    ops = {}
+    for A, d in ((anuga, ref), (ab, mine)):
+        c = d.centroid_coordinates
+        ids = np.flatnonzero((c[:, 0] > 1.1) & (c[:, 0] < 3.2) & (c[:, 1] > 5.8))
+        ops[A] = [A.Inlet_operator(d, A.Region(d, indices=ids), Q=Qin),
+                  A.Boyd_box_operator(d, **kw_box), A.Boyd_pipe_operator(d, **kw_pipe)]
+    mine._dev = _HostArrays(mine)
+    for d in (ref, mine):
+        d.timestep = dt
+        d.yieldstep = 1.0
+    for a, b in zip(ops[anuga], ops[ab]):
+        a()
+        b()
+    for k in ("stage", "xmomentum", "ymomentum"):
+        assert np.array_equal(mine.quantities[k].centroid_values, ref.quantities[k].centroid_values), k
+    for a, b in zip(ops[anuga][1:], ops[ab][1:]):
+        for k in ("discharge", "velocity", "outlet_depth", "accumulated_flow", "delta_total_energy", "driving_energy",
+                  "smooth_Q", "smooth_delta_total_energy", "case"):
+            assert getattr(a, k) == getattr(b, k), k
+    assert ops[anuga][0].applied_Q == ops[ab][0].applied_Q
