@@ -112,3 +112,42 @@ def test_operators_equal_reference_objects_on_random_states(seed):
                   "smooth_Q", "smooth_delta_total_energy", "case"):
             assert getattr(a, k) == getattr(b, k), k
     assert ops[anuga][0].applied_Q == ops[ab][0].applied_Q
+
+
+class _HostArraysWithBed(_HostArrays):
+    def scatter_bed(self, ids, v):
+        self.a[3][ids] = v
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_host_side_operators_equal_reference_objects(seed):
+    """Rate_operator with rate(x, y, t), Set_stage_operator, Set_quantity_operator, Set_elevation_operator and the
+    one-off Set_stage / Set_elevation: one application on a random state == the reference's objects"""
+    anuga, build, rng = _pair(100 + seed)
+    ref, mine = build(anuga), build(ab)
+    dt = float(rng.uniform(0.01, 0.3))
+    k1, k2, k3 = rng.uniform(0.5, 2.0, size=3)
+    poly = [[2.2, 1.3], [9.1, 1.9], [8.4, 6.6], [3.3, 5.2]]
+    ops = {}
+    for A, d in ((anuga, ref), (ab, mine)):
+        A.Set_stage(d, stage=0.55 * k1, center=[10.5, 4.0], radius=1.7)()
+        A.Set_elevation(d, elevation=lambda x, y: 0.1 * k2 + 0.01 * x, polygon=poly)()
+        ops[A] = [A.Rate_operator(d, rate=lambda x, y, t: 0.03 * k1 / (1.0 + (x - 3.0 - t) ** 2)),
+                  A.Rate_operator(d, rate=lambda x, y, t: -0.5 * k2 * (1.0 + 0.1 * y), factor=0.7, polygon=poly),
+                  A.Set_stage_operator(d, stage=lambda t: 0.4 * k3 + t, center=[4.0, 4.0], radius=1.3),
+                  A.Set_quantity_operator(d, "xmomentum", value=lambda x, y: 0.01 * k3 * x, polygon=poly),
+                  A.Set_elevation_operator(d, elevation=lambda x, y, t: 0.05 * k1 * y + t, center=[11.0, 2.0], radius=1.5)]
+    for k in ("stage", "elevation"):      # the one-off setters already agree
+        assert np.array_equal(mine.quantities[k].centroid_values, ref.quantities[k].centroid_values), k
+    mine._dev = _HostArraysWithBed(mine)
+    for d in (ref, mine):
+        d.timestep = dt
+        d.yieldstep = 1.0
+        d.set_time(0.37) if hasattr(d, "set_time") else setattr(d, "relative_time", 0.37)
+    added = 0.0
+    for a, b in zip(ops[anuga], ops[ab]):
+        a()
+        added += b() or 0.0
+    for k in ("stage", "xmomentum", "ymomentum", "elevation"):
+        assert np.array_equal(mine.quantities[k].centroid_values, ref.quantities[k].centroid_values), k
+    assert abs(added - ref.fractional_step_volume_integral) <= 1e-12 * max(1.0, abs(added))
