@@ -450,6 +450,17 @@ class Domain:
     def get_time(self):
         return self.starttime + self.relative_time
 
+    def set_time(self, time=0.0):
+        """generic_domain.py:600-607: model time in absolute terms"""
+        self.relative_time = float(time) - self.starttime
+        if self._dev is not None:
+            self._dev.set_time(self.relative_time)
+
+    def set_relative_time(self, time=0.0):
+        self.relative_time = float(time)
+        if self._dev is not None:
+            self._dev.set_time(self.relative_time)
+
     def get_relative_time(self):
         return self.relative_time
 
