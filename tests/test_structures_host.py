@@ -139,11 +139,11 @@ def test_host_side_operators_equal_reference_objects(seed):
                   A.Set_elevation_operator(d, elevation=lambda x, y, t: 0.05 * k1 * y + t, center=[11.0, 2.0], radius=1.5)]
     for k in ("stage", "elevation"):      # the one-off setters already agree
         assert np.array_equal(mine.quantities[k].centroid_values, ref.quantities[k].centroid_values), k
-    mine._dev = _HostArraysWithBed(mine)
     for d in (ref, mine):
         d.timestep = dt
         d.yieldstep = 1.0
-        d.set_time(0.37) if hasattr(d, "set_time") else setattr(d, "relative_time", 0.37)
+        d.set_time(0.37)
+    mine._dev = _HostArraysWithBed(mine)
     added = 0.0
     for a, b in zip(ops[anuga], ops[ab]):
         a()
