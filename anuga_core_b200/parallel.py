@@ -278,12 +278,37 @@ def finalize():
         c.dist.destroy_process_group()
 
 
+def rcb_partition(centroid_coordinates, nparts):
+    """Element partition by recursive coordinate bisection of the centroids: at every level the longer
+    side of the bounding box is cut so that the two halves get triangle counts proportional to the
+    number of parts they will hold.  A geometric stand-in for the metis partition the reference asks
+    pymetis for (distribute_mesh.py:152-278; pymetis is not in this image): compact parts, balanced to
+    one triangle, deterministic."""
+    c = np.asarray(centroid_coordinates, dtype=np.float64)
+    epart = np.zeros(len(c), dtype=np.int64)
+
+    def split(ids, first, count):
+        if count == 1:
+            epart[ids] = first
+            return
+        left = count // 2
+        span = c[ids].max(axis=0) - c[ids].min(axis=0)
+        axis = 0 if span[0] >= span[1] else 1
+        order = ids[np.argsort(c[ids, axis], kind="stable")]
+        cut = (len(ids) * left) // count
+        split(order[:cut], first, left)
+        split(order[cut:], first + left, count - left)
+    split(np.arange(len(c)), 0, int(nparts))
+    return epart
+
+
 def distribute_collective(domain=None, verbose=False, debug=False, parameters=None, device=None):
     """anuga.distribute(domain, verbose, debug, parameters) as the reference's parallel scripts call
     it: `domain` is the sequential domain on rank 0 (None elsewhere); every rank gets its sub-domain
     with the communicator attached.  The element partition is equal contiguous blocks of the
-    sequential numbering (pymetis is not used).  Boundaries and operators are set on the returned
-    domain, as those scripts do."""
+    sequential numbering, or - parameters={'partition': 'rcb'} - a recursive coordinate bisection of
+    the centroids for meshes whose numbering has no locality (pymetis is not used).  Boundaries and
+    operators are set on the returned domain, as those scripts do."""
     comm = communicator()
     if comm.size == 1:
         return domain
@@ -293,7 +318,10 @@ def distribute_collective(domain=None, verbose=False, debug=False, parameters=No
         if domain.fractional_step_operators:
             raise NotImplementedError("create operators on the distributed domain (after distribute)")
         N = domain.number_of_triangles
-        epart = (np.arange(N) * comm.size) // N
+        if (parameters or {}).get("partition", "blocks") == "rcb":
+            epart = rcb_partition(domain.centroid_coordinates, comm.size)
+        else:
+            epart = (np.arange(N) * comm.size) // N
         new_tri, new_bnd, tpp, order, _ = reorder_by_epart(domain.triangles, domain.mesh.boundary, epart, comm.size)
         parts = partition_mesh(domain.nodes, new_tri, new_bnd, tpp, width)
         for p, sub in parts.items():

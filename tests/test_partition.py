@@ -262,3 +262,26 @@ def test_partition_matches_reference_pipeline_on_random_partitions():
                 for q in mine:
                     assert np.array_equal(mine[q][0], np.asarray(theirs[q][0]))
                     assert np.array_equal(mine[q][1], np.asarray(theirs[q][1]))
+
+
+def test_rcb_partition_is_balanced_and_compact():
+    """the geometric partitioner for meshes without locality in their numbering: parts balanced to one
+    triangle, and far fewer halo triangles than contiguous blocks of a shuffled numbering"""
+    pts, tri, bnd = ab.rectangular_cross(24, 16, 24.0, 16.0)
+    rng = np.random.default_rng(2)
+    perm = rng.permutation(len(tri))                      # destroy the numbering's locality
+    tri = tri[perm]
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    bnd = {(int(inv[k]), e): t for (k, e), t in bnd.items()}
+    c = ab.Mesh(pts, tri, bnd).centroid_coordinates
+    for nparts in (2, 3, 5, 8):
+        epart = P.rcb_partition(c, nparts)
+        counts = np.bincount(epart, minlength=nparts)
+        assert counts.max() - counts.min() <= 1 and counts.sum() == len(tri)
+        halo = {}
+        for name, ep in (("rcb", epart), ("blocks", (np.arange(len(tri)) * nparts) // len(tri))):
+            new_tri, new_bnd, tpp, order, _ = P.reorder_by_epart(tri, bnd, ep, nparts)
+            parts = P.partition_mesh(pts, new_tri, new_bnd, tpp, 2)
+            halo[name] = sum(len(s["tri_l2g"]) - s["number_of_full_triangles"] for s in parts.values())
+        assert halo["rcb"] < 0.35 * halo["blocks"], halo
