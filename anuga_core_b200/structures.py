@@ -514,8 +514,7 @@ class Structure_operator:
         self.enquiry_points = as_array(enquiry_points)
         self.invert_elevations = as_array(invert_elevations)
         assert self.end_points is None or self.exchange_lines is None
-        if force_constant_inlet_elevations:
-            raise NotImplementedError("force_constant_inlet_elevations edits the bed: outside the hot path")
+        self.force_constant_inlet_elevations = force_constant_inlet_elevations
         if height is None:
             height = width
         if width is None:
@@ -564,6 +563,14 @@ class Structure_operator:
             invert = None if self.invert_elevations is None else self.invert_elevations[k]
             self.inlets.append(Inlet_enquiry(domain, poly, self.enquiry_points[k], invert_elevation=invert,
                                              outward_culvert_vector=outward, verbose=verbose))
+            if force_constant_inlet_elevations:
+                # one bed level over the exchange region: its area-weighted mean (structure_operator.py:170-173,
+                # inlet.py:83-86, 176-178); done on the host arrays, before the state is uploaded
+                inlet = self.inlets[-1]
+                z = domain.quantities["elevation"]
+                ids = inlet.triangle_indices
+                z.centroid_values[ids] = np.sum(z.centroid_values[ids] * inlet.areas) / inlet.area
+                z.host_dirty = True
         self.inflow, self.outflow = self.inlets
         domain.set_fractional_step_operator(self)
 

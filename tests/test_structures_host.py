@@ -151,3 +151,14 @@ def test_host_side_operators_equal_reference_objects(seed):
     for k in ("stage", "xmomentum", "ymomentum", "elevation"):
         assert np.array_equal(mine.quantities[k].centroid_values, ref.quantities[k].centroid_values), k
     assert abs(added - ref.fractional_step_volume_integral) <= 1e-12 * max(1.0, abs(added))
+
+
+def test_force_constant_inlet_elevations_matches_reference():
+    anuga, build, rng = _pair(42)
+    ref, mine = build(anuga), build(ab)
+    for A, d in ((anuga, ref), (ab, mine)):
+        A.Structure_operator(d, end_points=[[4.3, 5.3], [9.7, 5.3]], width=1.4, height=0.8, apron=0.7,
+                             enquiry_gap=0.3, force_constant_inlet_elevations=True)
+    a, b = mine.quantities["elevation"].centroid_values, ref.quantities["elevation"].centroid_values
+    assert np.array_equal(a, b)
+    assert len(np.unique(a)) < len(np.unique(build(ab).quantities["elevation"].centroid_values))
