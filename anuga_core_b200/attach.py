@@ -115,7 +115,7 @@ class B200_interface:
                                          default=getattr(op, "default", 0.0))
                 new._mirror = op
                 continue
-            if name in ("Boyd_box_operator", "Boyd_pipe_operator"):
+            if name in ("Boyd_box_operator", "Boyd_pipe_operator", "Weir_orifice_trapezoid_operator"):
                 getattr(_st, name).adopt(d, op)
                 continue
             if name != "Rate_operator":

@@ -102,7 +102,7 @@ def install_as_anuga():
     _alias("anuga.structures", **{k: getattr(structures, k) for k in dir(structures) if not k.startswith("_")})
     _alias("anuga.operators", **{k: getattr(operators, k) for k in dir(operators) if not k.startswith("_")})
     for sub in ("inlet_operator", "inlet", "inlet_enquiry", "structure_operator", "boyd_box_operator",
-                "boyd_pipe_operator"):
+                "boyd_pipe_operator", "weir_orifice_trapezoid_operator"):
         _alias("anuga.structures." + sub, **sys.modules["anuga.structures"].__dict__)
     for sub in ("rate_operators", "set_stage", "set_quantity", "set_elevation", "set_stage_operator",
                 "set_quantity_operator", "set_elevation_operator", "base_operator"):

@@ -42,6 +42,29 @@ def test_rating_functions_equal_reference_on_random_inputs():
     assert len(cases_seen) >= 8          # weir / orifice / submerged / full / part-full / blocked branches
 
 
+def test_weir_orifice_trapezoid_function_equals_reference_on_random_inputs():
+    anuga = pyref.import_anuga()
+    from anuga.structures.weir_orifice_trapezoid_operator import weir_orifice_trapezoid_function
+    rng = np.random.default_rng(9)
+    cases_seen = set()
+    for _ in range(2000):
+        width, depth = rng.uniform(0.3, 4.0), rng.uniform(0.2, 3.0)
+        blockage = float(rng.choice([0.0, rng.uniform(0, 0.9), 1.0]))
+        barrels = float(rng.integers(1, 4))
+        z1, z2 = float(rng.choice([0.0, rng.uniform(0, 2)])), float(rng.uniform(0, 2))
+        length = rng.uniform(1.0, 40.0)
+        drive = rng.uniform(0.011, 4.0)
+        delta = drive * rng.uniform(0.01, 1.5)
+        tail = rng.uniform(0.0, 4.0)
+        loss, manning = rng.uniform(0.0, 3.0), rng.uniform(0.01, 0.05)
+        args = (width, depth, blockage, barrels, z1, z2, width, length, drive, delta, tail, loss, manning)
+        a = S.weir_orifice_trapezoid_function(*args)
+        b = weir_orifice_trapezoid_function(*args)
+        assert tuple(a[:4]) == tuple(b[:4]), (args, a, b)
+        cases_seen.add(b[4])
+    assert len(cases_seen) >= 5
+
+
 class _HostArrays:
     """stands in for the device: the gather / scatter entry points on plain arrays"""
 
@@ -92,12 +115,18 @@ def test_operators_equal_reference_objects_on_random_states(seed):
     kw_pipe = dict(losses=[0.5, 0.7], diameter=float(rng.uniform(0.4, 1.2)), barrels=1.0, blockage=float(rng.choice([0.0, 0.95])),
                    end_points=[[4.3, 2.3], [9.7, 2.3]], apron=0.55, enquiry_gap=0.45,
                    use_momentum_jet=bool(rng.integers(0, 2)), use_velocity_head=True)
+    kw_weir = dict(losses={"in": 0.5, "out": 1.0}, width=float(rng.uniform(0.8, 2.0)), height=float(rng.uniform(0.3, 1.0)),
+                   z1=float(rng.uniform(0, 1.5)), z2=float(rng.uniform(0, 1.5)), barrels=1.0,
+                   end_points=[[4.3, 6.9], [9.7, 6.9]], apron=0.45, enquiry_gap=0.35,
+                   smoothing_timescale=float(rng.choice([0.0, 0.5])), use_momentum_jet=bool(rng.integers(0, 2)),
+                   use_velocity_head=bool(rng.integers(0, 2)))
     ops = {}
     for A, d in ((anuga, ref), (ab, mine)):
         c = d.centroid_coordinates
         ids = np.flatnonzero((c[:, 0] > 1.1) & (c[:, 0] < 3.2) & (c[:, 1] > 5.8))
         ops[A] = [A.Inlet_operator(d, A.Region(d, indices=ids), Q=Qin),
-                  A.Boyd_box_operator(d, **kw_box), A.Boyd_pipe_operator(d, **kw_pipe)]
+                  A.Boyd_box_operator(d, **kw_box), A.Boyd_pipe_operator(d, **kw_pipe),
+                  A.Weir_orifice_trapezoid_operator(d, **kw_weir)]
     mine._dev = _HostArrays(mine)
     for d in (ref, mine):
         d.timestep = dt
