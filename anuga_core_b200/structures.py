@@ -1160,5 +1160,6 @@ class Weir_orifice_trapezoid_operator(_Boyd_operator):
             sum_loss=self.sum_loss, manning=self.manning)
 
     def oracle_spec(self):
-        raise NotImplementedError("no CPU oracle restatement of the weir/orifice rating (checked live against the "
-                                  "reference in tests/test_structures_host.py)")
+        kind, spec = _Boyd_operator.oracle_spec(self)
+        spec.update(z1=self.culvert_z1, z2=self.culvert_z2)
+        return kind, spec

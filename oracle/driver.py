@@ -525,6 +525,8 @@ class OracleDomain:
                 {"stage": self.stage_c, "xmomentum": self.xmom_c, "ymomentum": self.ymom_c}[o["quantity"]][ids] = value
             elif op[0] == "boyd_pipe":
                 self._boyd_box_operator(op[1], pipe=True)
+            elif op[0] == "weir_orifice_trapezoid":
+                self._boyd_box_operator(op[1], weir=True)
             else:
                 raise ValueError("unknown operator %r" % (op[0],))
 
@@ -610,7 +612,7 @@ class OracleDomain:
             self.stage_c[idx] = elev + 0.0
             self.fractional_step_volume_integral -= current_volume
 
-    def _boyd_box_operator(self, o, pipe=False):
+    def _boyd_box_operator(self, o, pipe=False, weir=False):
         """structures/structure_operator.py:215-372 (the transfer) around
         structures/boyd_box_operator.py:150-441 (the rating) with the enquiry formulas of
         structures/inlet_enquiry.py:86-158.  `o` carries the resolved geometry (inlet triangle
@@ -657,7 +659,7 @@ class OracleDomain:
             if E[i_in]["depth"] > 0.01:
                 assert E[i_in]["specific"] >= 0.0
                 drive = E[i_in]["specific"] if o["use_velocity_head"] else E[i_in]["depth"]
-                rating = self._boyd_pipe_rating if pipe else self._boyd_box_rating
+                rating = self._boyd_pipe_rating if pipe else (self._weir_rating if weir else self._boyd_box_rating)
                 Q, speed, outlet_depth, flow_area = rating(o, drive, delta, E[i_out]["depth"])
                 sign = np.sign(sm)
                 o["smooth_Q"] = o["smooth_Q"] + ts * (Q * sign - o["smooth_Q"])
@@ -742,6 +744,53 @@ class OracleDomain:
         if delta < drive:
             if tail_depth > depth:
                 out_d, area, perim = depth, clear * depth, 2.0 * (clear + depth)
+            rh = area / perim
+            vel = math.sqrt(delta / ((o["sum_loss"] / 2 / G) + (o["manning"] ** 2 * o["length"]) / rh ** 1.33333))
+            Q = min(Q, area * vel)
+        return Q, Q / (area + VP / area), out_d, area
+
+    @staticmethod
+    def _weir_rating(o, drive, delta, tail_depth):
+        """weir_orifice_trapezoid_function (weir_orifice_trapezoid_operator.py:279-485): trapezoidal opening
+        with side slopes z1, z2; critical depth by the reference's Newton iteration"""
+        G, VP = 9.8, 1.0e-6
+        width, depth, barrels, z1, z2 = o["width"], o["height"], o["barrels"], o["z1"], o["z2"]
+        bf = 1 - o["blockage"]
+        if o["blockage"] >= 1.0:
+            return 0.0, 0.0, 0.0, 0.00001
+        Qu = 1.7 * bf * barrels * ((2 * width + depth * (z1 + z2)) / 2) * drive ** 1.50
+        Qs = 0.8 * bf * barrels * G ** 0.5 * (0.5 * depth * (2 * width + depth * (z1 + z2))) * drive ** 0.5
+        Q = Qu if Qu < Qs else Qs
+
+        def newton(Q):
+            dcrit, dyc = 0.00001, 0.001
+            while abs(dyc) > 0.00001:
+                Tc = bf * barrels * width + (z1 + z2) * dcrit
+                Ac = 0.5 * dcrit * (bf * barrels * width + Tc)
+                fc = Ac ** 1.5 * Tc ** -0.5 - Q / (9.81 ** 0.5)
+                ffc = Ac ** 1.5 * -0.5 * Tc ** -1.5 * (z1 + z2) + Tc ** -0.5 * 1.5 * Ac ** 0.5 * Tc
+                dyc = -fc / ffc
+                dcrit = dcrit + dyc
+            return dcrit
+        out_d = newton(Q)
+        if out_d > depth:
+            out_d = depth
+        area = bf * barrels * width * out_d + 0.5 * (z1 + z2) * out_d ** 2
+        perim = 2.0 * bf * barrels * width + (z1 + z2) * out_d + (out_d ** 2 + (z1 * out_d) ** 2) ** 0.5 \
+            + (out_d ** 2 + (z2 * out_d) ** 2) ** 0.5
+        rh = area / perim
+        vel = math.sqrt(delta / ((o["sum_loss"] / 2 / G) + (o["manning"] ** 2 * o["length"]) / rh ** 1.33333))
+        Qtail = area * vel
+        if delta < drive:
+            if tail_depth > depth:
+                out_d = depth
+            else:
+                Q = min(Q, Qtail)
+                out_d = newton(Q)
+                if out_d > depth:
+                    out_d = depth
+            area = bf * barrels * width * out_d + 0.5 * (z1 + z2) * out_d ** 2
+            perim = bf * barrels * width + (out_d ** 2 + (z1 * out_d) ** 2) ** 0.5 + (out_d ** 2 + (z2 * out_d) ** 2) ** 0.5
             rh = area / perim
             vel = math.sqrt(delta / ((o["sum_loss"] / 2 / G) + (o["manning"] ** 2 * o["length"]) / rh ** 1.33333))
             Q = min(Q, area * vel)

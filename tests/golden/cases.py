@@ -293,6 +293,16 @@ def culvert_pipe_de1(A):
     return d
 
 
+def culvert_weir_de1(A):
+    """Weir_orifice_trapezoid_operator: trapezoidal opening with side slopes, no jet, smoothed"""
+    d = _embankment(A)
+    A.Weir_orifice_trapezoid_operator(d, losses=1.2, width=1.1, height=0.55, z1=0.6, z2=1.1, barrels=1.0,
+                                      end_points=[[6.1, 5.3], [9.9, 5.3]], apron=0.55, enquiry_gap=0.4,
+                                      manning=0.015, smoothing_timescale=0.3, use_momentum_jet=False,
+                                      use_velocity_head=True, verbose=False)
+    return d
+
+
 CASES = {
     "kat_bedslope_more_steps": (kat_bedslope_more_steps, dict(yieldstep=0.05, finaltime=0.5)),
     "dam_break_de0": (dam_break_de0, dict(yieldstep=1.0, finaltime=6.0)),
@@ -318,6 +328,7 @@ CASES = {
     "flather_de1": (flather_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "culvert_de1": (culvert_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_pipe_de1": (culvert_pipe_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "culvert_weir_de1": (culvert_weir_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_skew_de1": (culvert_skew_de1, dict(yieldstep=1.0, finaltime=4.0)),
 }
 
