@@ -114,3 +114,37 @@ def test_evolve_with_store_writes_the_reference_sww(tmp_path):
     assert np.array_equal(np.array(times), g["var_time"])
     worst = compare(read_sww(os.path.join(str(tmp_path), "mine_evolve.sww")), g, 2.0e-7)
     print("\n[sww] worst scaled difference %.2e (float32 payload)" % worst)
+
+
+@pytest.mark.parametrize("variant", ["unique_vertices", "no_centroids", "dynamic_elevation", "vertex_averaging"])
+def test_static_frames_equal_live_reference_writer_variants(variant, tmp_path):
+    """storage options against the reference's writer run live (when the scratch build exists): vertices
+    stored uniquely (3 values per triangle), no centroid variables, elevation as a dynamic quantity,
+    vertex instead of centroid averaging"""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("python reference not built (oracle/build_pyref.py)")
+    anuga = pyref.import_anuga()
+    files = {}
+    for A, name in ((anuga, "ref_" + variant), (ab, "mine_" + variant)):
+        d = sww_cases.static_domain(A, str(tmp_path), name)
+        if variant == "unique_vertices":
+            d.set_store_vertices_uniquely(True)
+        elif variant == "no_centroids":
+            d.set_store_centroids(False)
+        elif variant == "dynamic_elevation":
+            d.set_quantities_to_be_stored({"elevation": 2, "stage": 2, "xmomentum": 2, "ymomentum": 2, "friction": 1})
+        elif variant == "vertex_averaging":
+            d.set_using_centroid_averaging(False)
+        sww_cases.store_two_frames(d)
+        files[A] = read_sww(os.path.join(str(tmp_path), name + ".sww"))
+    mine, ref = files[ab], files[anuga]
+    assert sorted(mine["vars"]) == sorted(ref["vars"])
+    assert mine["dims"] == ref["dims"]
+    for name in sorted(ref["vars"]):
+        a, da = mine["vars"][name]
+        b, db = ref["vars"][name]
+        assert da == db and a.dtype == b.dtype and np.array_equal(a, b), name
+    for k in ("smoothing", "vertices_are_stored_uniquely", "order"):
+        a, b = mine["atts"][k], ref["atts"][k]
+        assert (a.decode() if isinstance(a, bytes) else a) == (b.decode() if isinstance(b, bytes) else b), k
