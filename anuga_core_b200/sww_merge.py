@@ -89,7 +89,10 @@ def _merge(files, output, smooth):
         fid.close()
 
     fido = _sww._open(output, "w")
-    _sww.write_header(fido, starttime, NT, NN, smooth, 1, s_q, d_q, s_c, d_c, description=description)
+    # the reference writes both kinds of merged file with the default header (smoothing 'Yes') and, for
+    # uniquely stored vertices, 3*NT as the point count (sww_merge.py:464-470, 714-718)
+    _sww.write_header(fido, starttime, NT, NN if smooth else 3 * NT, True, 1, s_q, d_q, s_c, d_c,
+                      description=description)
     _sww.write_georeference(fido, None)
     for k, v in atts.items():
         setattr(fido, k, v)

@@ -148,3 +148,38 @@ def test_static_frames_equal_live_reference_writer_variants(variant, tmp_path):
     for k in ("smoothing", "vertices_are_stored_uniquely", "order"):
         a, b = mine["atts"][k], ref["atts"][k]
         assert (a.decode() if isinstance(a, bytes) else a) == (b.decode() if isinstance(b, bytes) else b), k
+
+
+def test_merge_of_unique_vertex_files_equals_live_reference_merge(tmp_path):
+    """the non-smooth branch of sww_merge (three values per triangle) against the reference's
+    _sww_merge_parallel_non_smooth run live on the same per-rank files"""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("python reference not built (oracle/build_pyref.py)")
+    import shutil
+    from anuga_core_b200 import parallel as P
+    from anuga_core_b200.sww_merge import sww_merge_parallel
+    anuga = pyref.import_anuga()
+    from anuga.utilities.sww_merge import sww_merge_parallel as ref_merge
+    g = sww_cases.static_domain(ab, str(tmp_path), "uniq")
+    g.set_store_vertices_uniquely(True)
+    c = g.centroid_coordinates
+    epart = ((np.floor(c[:, 0]) + 2 * np.floor(c[:, 1])) % 3).astype(int)
+    subs = P.distribute(g, 3, epart=epart)
+    for p in sorted(subs):
+        assert subs[p].smooth is False
+        sww_cases.store_two_frames(subs[p])
+    refdir = tmp_path / "ref"
+    refdir.mkdir()
+    for p in range(3):
+        shutil.copy(os.path.join(str(tmp_path), "uniq_P3_%d.sww" % p), str(refdir))
+    mine = read_sww(sww_merge_parallel(os.path.join(str(tmp_path), "uniq"), 3))
+    ref_merge(os.path.join(str(refdir), "uniq"), 3, verbose=False, delete_old=False)
+    ref = read_sww(os.path.join(str(refdir), "uniq.sww"))
+    assert sorted(mine["vars"]) == sorted(ref["vars"]) and mine["dims"] == ref["dims"]
+    for name in sorted(ref["vars"]):
+        a, b = mine["vars"][name][0], ref["vars"][name][0]
+        assert a.dtype == b.dtype and np.array_equal(a, b), name
+    for k in ("smoothing", "vertices_are_stored_uniquely", "order", "description"):
+        a, b = mine["atts"][k], ref["atts"][k]
+        assert (a.decode() if isinstance(a, bytes) else a) == (b.decode() if isinstance(b, bytes) else b), k
