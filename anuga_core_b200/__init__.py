@@ -11,7 +11,7 @@ from .operators import (Rate_operator, Set_quantity, Set_stage, Set_quantity_ope
                         Set_stage_operator, Set_elevation, Set_elevation_operator)
 from .structures import (Region, Inlet, Inlet_operator, Inlet_enquiry, Structure_operator,
                          Boyd_box_operator, Boyd_pipe_operator, Weir_orifice_trapezoid_operator)
-from .domain import Domain, rectangular_cross_domain, MODE_B200
+from .domain import Domain, rectangular_cross_domain, load_checkpoint_file, MODE_B200
 from .backend import SwkError, device_count
 from .attach import set_multiprocessor_mode_b200, B200_interface
 # the reference's script-level parallel API (anuga.distribute, myid, numprocs, barrier, finalize)

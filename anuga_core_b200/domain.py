@@ -135,6 +135,7 @@ class Domain:
         self.yieldstep_counter = 0
         self.output_frequency = 1
         self.writer = None
+        self.checkpoint = False
         self._dev = None
         self.pin_host_arrays = True
         self._stale = set()
@@ -344,6 +345,56 @@ class Domain:
 
     def set_minimum_storable_height(self, h):
         self.minimum_storable_height = h
+
+    def set_checkpointing(self, checkpoint=True, checkpoint_dir="CHECKPOINTS", checkpoint_step=10,
+                          checkpoint_time=None):
+        """pickle the domain every `checkpoint_step` yields, or every `checkpoint_time` seconds of wall time
+        (shallow_water_domain.py:1123-1157); load_checkpoint_file() picks the run up again"""
+        if not checkpoint:
+            self.checkpoint = False
+            return
+        import os
+        import time
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        self.checkpoint_dir = checkpoint_dir
+        if checkpoint_time is not None:
+            self.walltime_prev = time.time()
+            self.checkpoint_time = checkpoint_time
+            self.checkpoint_step = 0
+        else:
+            self.checkpoint_step = checkpoint_step
+        self.checkpoint = True
+
+    def _checkpoint_if_due(self):
+        """the checkpoint block of Domain.evolve (shallow_water_domain.py:2376-2397)"""
+        import os
+        import time
+        save = False
+        if self.checkpoint_step == 0:
+            save = time.time() - self.walltime_prev > self.checkpoint_time
+            comm = getattr(self, "_comm", None)
+            if comm is not None and comm.size > 1:      # rank 0 decides for everybody
+                flag = comm.allreduce_max(float(save) if comm.rank == 0 else 0.0)
+                save = flag > 0.0
+        elif self.yieldstep_counter % self.checkpoint_step == 0:
+            save = True
+        if save:
+            self.save_checkpoint()
+            self.walltime_prev = time.time()
+
+    def save_checkpoint(self):
+        import os
+        try:
+            import dill as pickle
+        except ImportError:
+            import pickle
+        name = os.path.join(self.checkpoint_dir, self.get_name()) + "_" + str(self.get_time()) + ".pickle"
+        with open(name, "wb") as f:
+            pickle.dump(self, f)
+        comm = getattr(self, "_comm", None)
+        if comm is not None:
+            comm.barrier()
+        return name
 
     def initialise_storage(self):
         """shallow_water_domain.py:2410-2423"""
@@ -933,6 +984,8 @@ class Domain:
                     new_file = False
                 if self.yieldstep_counter % self.output_frequency == 0:
                     self.store_timestep()
+            if self.checkpoint:
+                self._checkpoint_if_due()
             yield t
             self.yieldstep_counter += 1
 
@@ -1137,6 +1190,45 @@ class Domain:
         self.boundary_flux_integral = r.boundary_flux_integral
         self.fractional_step_volume_integral = r.fractional_step_volume_integral
         self.mass_error = r.mass_error
+
+
+def load_checkpoint_file(domain_name="domain", checkpoint_dir=".", time=None):
+    """the most recent (or the given) checkpoint of a run; with several ranks every rank loads its own file
+    and all fall back to an earlier time together if one of them cannot (shallow_water/checkpoint.py:24-76)"""
+    import glob
+    import os
+    from . import parallel
+    try:
+        import dill as pickle
+    except ImportError:
+        import pickle
+    if parallel.numprocs > 1:
+        domain_name = domain_name + "_P{}_{}".format(parallel.numprocs, parallel.myid)
+    if time is None:
+        times = set()
+        for path in glob.glob(os.path.join(checkpoint_dir, domain_name) + "_*.pickle"):
+            try:
+                times.add(float(os.path.basename(path)[len(domain_name) + 1:-len(".pickle")]))
+            except ValueError:
+                pass
+        times = sorted(times)
+    else:
+        times = [float(time)]
+    if len(times) == 0:
+        raise Exception("Unable to open checkpoint file")
+    for t in reversed(times):
+        name = os.path.join(checkpoint_dir, domain_name) + "_" + str(t) + ".pickle"
+        try:
+            with open(name, "rb") as f:
+                domain = pickle.load(f)
+            ok = True
+        except Exception:
+            domain, ok = None, False
+        if parallel.numprocs > 1:
+            ok = parallel.communicator().allreduce_max(0.0 if ok else 1.0) == 0.0
+        if ok:
+            return domain
+    raise Exception("Unable to open checkpoint file")
 
 
 def rectangular_cross_domain(m, n, len1=1.0, len2=1.0, origin=(0.0, 0.0), **kwargs):
