@@ -183,3 +183,27 @@ def test_merge_of_unique_vertex_files_equals_live_reference_merge(tmp_path):
     for k in ("smoothing", "vertices_are_stored_uniquely", "order", "description"):
         a, b = mine["atts"][k], ref["atts"][k]
         assert (a.decode() if isinstance(a, bytes) else a) == (b.decode() if isinstance(b, bytes) else b), k
+
+
+def test_evolve_wrapper_stores_and_checkpoints_in_step(tmp_path):
+    """Domain.evolve's bookkeeping around the time loop (file creation at the first yield, one frame every
+    `outputstep`, checkpoints every `checkpoint_step` yields) with the device loop replaced by a stub"""
+    d = sww_cases.static_domain(ab, str(tmp_path), "wrapper")
+    d.set_checkpointing(checkpoint_dir=str(tmp_path / "CK"), checkpoint_step=2)
+
+    def fake_base(yieldstep=None, finaltime=None, duration=None, skip_initial_step=False):
+        d.evolved_called = True
+        t = 0.0
+        while t <= finaltime + 1e-12:
+            d.relative_time = t
+            yield t
+            t += yieldstep
+    d._evolve_base = fake_base
+    times = [t for t in d.evolve(yieldstep=0.25, outputstep=0.5, finaltime=1.0)]
+    assert times == [0.0, 0.25, 0.5, 0.75, 1.0] and d.yieldstep_counter == 5
+    f = read_sww(os.path.join(str(tmp_path), "wrapper.sww"))
+    assert np.array_equal(f["vars"]["time"][0], np.array([0.0, 0.5, 1.0]))
+    assert f["vars"]["stage"][0].shape == (3, d.number_of_nodes)
+    assert sorted(os.listdir(str(tmp_path / "CK"))) == ["wrapper_0.0.pickle", "wrapper_0.5.pickle", "wrapper_1.0.pickle"]
+    with pytest.raises(AssertionError):
+        list(d.evolve(yieldstep=0.25, outputstep=0.6, finaltime=2.0))
