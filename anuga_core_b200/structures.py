@@ -161,7 +161,14 @@ class Inlet:
 
     def __init__(self, domain, region, verbose=False):
         self.domain = domain
-        self.region = region if isinstance(region, Region) else Region(domain, indices=region)
+        if isinstance(region, Region):
+            self.region = region
+        else:
+            arr = np.asarray(region)
+            if arr.ndim == 2 and arr.shape[1] == 2:      # a line or polygon, as the reference takes it (inlet.py:26-29)
+                self.region = Region(domain, poly=arr.astype(np.float64), expand_polygon=True)
+            else:
+                self.region = Region(domain, indices=arr)
         self.triangle_indices = np.asarray(self.region.indices, dtype=np.int64)
         if len(self.triangle_indices) == 0:
             raise Exception("No triangles have been identified in region ")

@@ -191,3 +191,12 @@ def test_force_constant_inlet_elevations_matches_reference():
     a, b = mine.quantities["elevation"].centroid_values, ref.quantities["elevation"].centroid_values
     assert np.array_equal(a, b)
     assert len(np.unique(a)) < len(np.unique(build(ab).quantities["elevation"].centroid_values))
+
+
+def test_inlet_from_line_or_polygon_matches_reference():
+    anuga, build, rng = _pair(77)
+    ref, mine = build(anuga), build(ab)
+    for shape in ([[2.3, 1.2], [2.9, 6.6]], [[9.1, 1.1], [12.2, 1.4], [11.8, 3.9], [9.4, 3.2]]):
+        a = ab.Inlet_operator(mine, shape, Q=1.0).inlet.triangle_indices
+        b = anuga.Inlet_operator(ref, shape, Q=1.0).inlet.triangle_indices
+        assert np.array_equal(a, np.asarray(b, dtype=np.int64)) and len(a) > 3
