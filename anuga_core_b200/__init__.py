@@ -17,6 +17,7 @@ from .attach import set_multiprocessor_mode_b200, B200_interface
 # the reference's script-level parallel API (anuga.distribute, myid, numprocs, barrier, finalize)
 from .parallel import distribute_collective as distribute, myid, numprocs, barrier, finalize
 
+from .mesh_io import create_domain_from_file, read_tsh
 from .compat import install_as_anuga, Polygon_function, read_polygon, inside_polygon, g, indent
 
 __version__ = "0.1.0"

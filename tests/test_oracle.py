@@ -199,3 +199,50 @@ def test_oracle_equals_live_python_reference_on_random_scenarios(oracle_libs, se
     assert np.array_equal(o.stage_c, q["stage"].centroid_values)
     assert np.array_equal(o.xmom_c, q["xmomentum"].centroid_values)
     assert np.array_equal(o.ymom_c, q["ymomentum"].centroid_values)
+
+
+MERIMBULA = "/root/reference/examples/parallel/data/merimbula_10785_1.tsh"
+
+
+def _merimbula(A):
+    """the Merimbula lake model of the reference's examples/parallel/run_parallel_merimbula.py: a real
+    unstructured mesh (node valences 1..9), a raised patch of water, tidal set-stage boundary on 'open'"""
+    d = A.create_domain_from_file(MERIMBULA)
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    x0, x1 = 756000.0, 756500.0
+    d.set_quantity("stage", lambda x, y: 1.0 * ((x > x0) & (x < x1)), location="centroids")
+    d.set_quantity("friction", 0.02)
+    Br = A.Reflective_boundary(d)
+    Bts = A.Transmissive_n_momentum_zero_t_momentum_set_stage_boundary(d, lambda t: 10 * np.sin(t / 60))
+    d.set_boundary({"exterior": Br, "open": Bts})
+    return d
+
+
+def test_merimbula_lake_oracle_equals_live_python_reference(oracle_libs):
+    """an irregular real-world mesh through mesh.py, the neighbour builder and the oracle's time loop against the
+    unmodified Python reference (live): timestep sequence and state bit for bit"""
+    from oracle import pyref
+    if not pyref.available() or not os.path.exists(MERIMBULA):
+        pytest.skip("needs the reference tree and its scratch build")
+    anuga = pyref.import_anuga()
+    ref = _merimbula(anuga)
+    ref.set_multiprocessor_mode(2)
+    ev = dict(yieldstep=5.0, finaltime=15.0)
+    dts = []
+    orig = ref.apply_fractional_steps
+
+    def hook():
+        orig()
+        dts.append(ref.timestep)
+    ref.apply_fractional_steps = hook
+    for _ in ref.evolve(**ev):
+        pass
+    o = OracleDomain(domain_to_scenario(_merimbula(ab)), backend="port")
+    for _ in o.evolve(**ev):
+        pass
+    assert len(dts) > 10 and np.array_equal(np.array(o.timestep_history), np.array(dts))
+    q = ref.quantities
+    assert np.array_equal(o.stage_c, q["stage"].centroid_values)
+    assert np.array_equal(o.xmom_c, q["xmomentum"].centroid_values)
+    assert np.array_equal(o.ymom_c, q["ymomentum"].centroid_values)

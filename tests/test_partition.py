@@ -285,3 +285,44 @@ def test_rcb_partition_is_balanced_and_compact():
             parts = P.partition_mesh(pts, new_tri, new_bnd, tpp, 2)
             halo[name] = sum(len(s["tri_l2g"]) - s["number_of_full_triangles"] for s in parts.values())
         assert halo["rcb"] < 0.35 * halo["blocks"], halo
+
+
+def test_partition_of_a_real_unstructured_mesh_matches_reference_pipeline():
+    """the Merimbula lake mesh (10 785 triangles) cut in 4 by recursive coordinate bisection: local meshes,
+    ghost layers, send / receive lists == the reference's distribute_mesh pipeline for the same epart"""
+    from oracle import pyref
+    path = "/root/reference/examples/parallel/data/merimbula_10785_1.tsh"
+    if not pyref.available() or not os.path.exists(path):
+        pytest.skip("needs the reference tree and its scratch build")
+    holder = {}
+    anuga = pyref.import_anuga(epart_fn=lambda nparts, adj: holder["epart"])
+    import anuga.parallel.distribute_mesh as dm
+    import pymetis
+    dm.part_graph = pymetis.part_graph
+    dm.metis_version = "5_part_graph"
+    from anuga.parallel.sequential_distribute import Sequential_distribute
+    ref = anuga.create_domain_from_file(path)
+    ref.set_store(False)
+    mine = ab.create_domain_from_file(path)
+    nparts = 4
+    epart = P.rcb_partition(mine.centroid_coordinates, nparts)
+    holder["epart"] = epart.tolist()
+    sd = Sequential_distribute(ref, parameters={"ghost_layer_width": 2})
+    sd.distribute(nparts)
+    new_tri, new_bnd, tpp, order, _ = P.reorder_by_epart(mine.triangles, mine.mesh.boundary, epart, nparts)
+    parts = P.partition_mesh(mine.nodes, new_tri, new_bnd, tpp, 2)
+    halo = 0
+    for p in range(nparts):
+        (points, vertices, boundary, quantities, ghost_recv, full_send, tri_map, node_map,
+         tri_l2g, node_l2g, glw) = dm.extract_submesh(sd.submesh, sd.triangles_per_proc, sd.p2s_map, p)
+        s = parts[p]
+        assert np.array_equal(s["points"], points) and np.array_equal(s["triangles"], vertices)
+        assert {k: str(v) for k, v in s["boundary"].items()} == {tuple(k): str(v) for k, v in boundary.items()}
+        assert np.array_equal(order[s["tri_l2g"]], np.asarray(tri_l2g))
+        assert np.array_equal(s["node_l2g"], np.asarray(node_l2g))
+        for a, b in ((s["full_send_dict"], full_send), (s["ghost_recv_dict"], ghost_recv)):
+            assert sorted(a) == sorted(b)
+            for q in a:
+                assert np.array_equal(a[q][0], np.asarray(b[q][0])) and np.array_equal(a[q][1], np.asarray(b[q][1]))
+        halo += len(s["tri_l2g"]) - s["number_of_full_triangles"]
+    assert halo < 0.12 * mine.number_of_triangles          # compact parts: a thin ghost layer
