@@ -201,48 +201,40 @@ def test_oracle_equals_live_python_reference_on_random_scenarios(oracle_libs, se
     assert np.array_equal(o.ymom_c, q["ymomentum"].centroid_values)
 
 
-MERIMBULA = "/root/reference/examples/parallel/data/merimbula_10785_1.tsh"
+import merimbula_case  # noqa: E402
 
 
-def _merimbula(A):
-    """the Merimbula lake model of the reference's examples/parallel/run_parallel_merimbula.py: a real
-    unstructured mesh (node valences 1..9), a raised patch of water, tidal set-stage boundary on 'open'"""
-    d = A.create_domain_from_file(MERIMBULA)
-    d.set_flow_algorithm("DE1")
-    d.set_store(False)
-    x0, x1 = 756000.0, 756500.0
-    d.set_quantity("stage", lambda x, y: 1.0 * ((x > x0) & (x < x1)), location="centroids")
-    d.set_quantity("friction", 0.02)
-    Br = A.Reflective_boundary(d)
-    Bts = A.Transmissive_n_momentum_zero_t_momentum_set_stage_boundary(d, lambda t: 10 * np.sin(t / 60))
-    d.set_boundary({"exterior": Br, "open": Bts})
-    return d
-
-
-def test_merimbula_lake_oracle_equals_live_python_reference(oracle_libs):
-    """an irregular real-world mesh through mesh.py, the neighbour builder and the oracle's time loop against the
-    unmodified Python reference (live): timestep sequence and state bit for bit"""
-    from oracle import pyref
-    if not pyref.available() or not os.path.exists(MERIMBULA):
-        pytest.skip("needs the reference tree and its scratch build")
-    anuga = pyref.import_anuga()
-    ref = _merimbula(anuga)
-    ref.set_multiprocessor_mode(2)
-    ev = dict(yieldstep=5.0, finaltime=15.0)
-    dts = []
-    orig = ref.apply_fractional_steps
+def test_merimbula_lake_oracle_reproduces_golden_fixture(oracle_libs):
+    """a real unstructured mesh (the reference's Merimbula lake example, 10 785 triangles, node valences 1-9),
+    rebuilt from the arrays in the fixture: mesh.py, the neighbour builder and the oracle's time loop give the
+    Python reference's timestep sequence and state bit for bit"""
+    g = load("merimbula_de1")
+    d = merimbula_case.from_fixture(ab, g)
+    o = OracleDomain(domain_to_scenario(d), backend="port")
+    first = {}
+    orig = o.apply_fractional_steps
 
     def hook():
         orig()
-        dts.append(ref.timestep)
-    ref.apply_fractional_steps = hook
-    for _ in ref.evolve(**ev):
-        pass
-    o = OracleDomain(domain_to_scenario(_merimbula(ab)), backend="port")
-    for _ in o.evolve(**ev):
-        pass
-    assert len(dts) > 10 and np.array_equal(np.array(o.timestep_history), np.array(dts))
-    q = ref.quantities
-    assert np.array_equal(o.stage_c, q["stage"].centroid_values)
-    assert np.array_equal(o.xmom_c, q["xmomentum"].centroid_values)
-    assert np.array_equal(o.ymom_c, q["ymomentum"].centroid_values)
+        if not first:
+            first.update(stage=o.stage_c.copy(), xmom=o.xmom_c.copy(), ymom=o.ymom_c.copy())
+    o.apply_fractional_steps = hook
+    yields = [t for t in o.evolve(**merimbula_case.EVOLVE)]
+    assert np.array_equal(np.array(yields), g["yields"])
+    assert np.array_equal(np.array(o.timestep_history), g["dts"])
+    for k in ("stage", "xmom", "ymom"):
+        assert np.array_equal(first[k], g["step1_" + k]), k
+    assert np.array_equal(o.stage_c, g["final_stage"])
+    assert np.array_equal(o.xmom_c, g["final_xmom"]) and np.array_equal(o.ymom_c, g["final_ymom"])
+
+
+def test_merimbula_fixture_mesh_equals_the_tsh_file():
+    """the mesh stored in the fixture is what create_domain_from_file reads (when the reference tree is here)"""
+    if not os.path.exists(merimbula_case.TSH):
+        pytest.skip("needs the reference tree")
+    g = load("merimbula_de1")
+    a = merimbula_case.from_fixture(ab, g)
+    b = ab.create_domain_from_file(merimbula_case.TSH)
+    assert np.array_equal(a.nodes, b.nodes) and np.array_equal(a.triangles, b.triangles)
+    assert a.mesh.boundary == b.mesh.boundary
+    assert np.array_equal(a.quantities["elevation"].centroid_values, b.quantities["elevation"].centroid_values)
