@@ -52,8 +52,8 @@ static inline double u2d_host(unsigned long long u) { double x; memcpy(&x, &u, 8
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8 };
-enum { ncclSumOp = 0, ncclMinOp = 3 };
+enum { ncclInt64 = 4, ncclUint64 = 5, ncclFloat64 = 8 };
+enum { ncclSumOp = 0, ncclMaxOp = 2, ncclMinOp = 3 };
 struct NcclApi {
   void *lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -124,6 +124,16 @@ struct Peer {
   double *d_send_buf = nullptr, *d_recv_buf = nullptr;
 };
 
+// a process-level NCCL communicator (one per GPU process): shared by the device time loop of
+// every domain attached to it and by the host-level collectives of the Python layer
+struct swk_comm {
+  ncclComm_t nc = nullptr;
+  int rank = 0, nranks = 1, device = 0;
+  cudaStream_t stream = nullptr;      // host-level collectives (swk_comm_allreduce)
+  void *d_buf = nullptr;
+  size_t cap = 0;
+};
+
 struct swk_domain {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -170,6 +180,9 @@ struct swk_domain {
 
   // multi-GPU
   ncclComm_t comm = nullptr;
+  swk_comm *comm_obj = nullptr;
+  bool comm_owned = false;
+  bool nccl_warm = false;      // connections to the halo peers are set up (outside any graph capture)
   int rank = 0, nranks = 1;
   std::vector<Peer> peers;
   int n_full = 0;              // full triangles occupy device ids [0, n_full) (0: not a prefix)
@@ -177,7 +190,6 @@ struct swk_domain {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_update = nullptr, ev_halo = nullptr;
   bool overlap = true;         // SWK_NO_OVERLAP=1: halo exchange in-stream
-  double *d_dt_scratch = nullptr;
 
   int64_t launches = 0;
 
@@ -435,7 +447,7 @@ extern "C" int swk_destroy(swk_domain *d)
   void *ptrs[] = {d->cq, d->eq, d->xg, d->fg, d->bq, d->connA, d->connB, d->eu, d->bk, d->eta, d->max_speed,
                   d->vcoord, d->zflag, d->rw_counter, d->rw_rowIndex, d->rw_elevation, d->rw_hydraulic,
                   d->d_clock, d->staging, d->acct_val, d->pos_b, d->acct_keys, d->acct_keys_pos, d->b_cell, d->b_edge, d->b_seg, d->d_seg_kind,
-                  d->d_seg_val, d->d_new2old, d->d_ghost_full, d->d_ghost_ghost, d->d_dt_scratch, d->d_ident_b};
+                  d->d_seg_val, d->d_new2old, d->d_ghost_full, d->d_ghost_ghost, d->d_ident_b};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &op : d->rate_ops) {
@@ -449,7 +461,7 @@ extern "C" int swk_destroy(swk_domain *d)
     if (pe.d_send_buf) cudaFree(pe.d_send_buf);
     if (pe.d_recv_buf) cudaFree(pe.d_recv_buf);
   }
-  if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+  if (d->comm_obj && d->comm_owned) swk_comm_destroy(d->comm_obj);
   if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
   if (d->graph) cudaGraphDestroy(d->graph);
   if (d->h_clock) cudaFreeHost(d->h_clock);
@@ -567,9 +579,15 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
 
     const double *nr = m->normals + 6 * o;
     const double *el = m->edgelengths + 3 * o;
+#if SWK_FG_EDGE
+    fg[k] = {nr[0], nr[1], el[0], 1.0 / m->areas[o]};                        // inv_area: :714
+    fg[NP + k] = {nr[2], nr[3], el[1], m->radii[o]};
+    fg[2 * NP + k] = {nr[4], nr[5], el[2], m->areas[o]};
+#else
     fg[k] = {nr[0], nr[1], nr[2], nr[3]};
     fg[NP + k] = {nr[4], nr[5], el[0], el[1]};
     fg[2 * NP + k] = {el[2], 1.0 / m->areas[o], m->radii[o], m->areas[o]};   // inv_area: :714
+#endif
 
     int pk[3];
     int flags = (m->tri_full_flag[o] == 1) ? 1 : 0;
@@ -1211,16 +1229,14 @@ static int update_with_exchange(swk_domain *d, bool exchange_after, F f)
   return SWK_OK;
 }
 
-// global dt: min over ranks of the flux kernel's local min (parallel_generic_communications.py:67)
-__global__ void k_bits_to_double(Clock *c, double *out) { *out = u2d(c->dt_min_bits); }
-__global__ void k_double_to_bits(Clock *c, const double *in) { c->dt_min_bits = d2u(*in); }
-
+// global dt: min over ranks of the flux kernel's local min (parallel_generic_communications.py:67).
+// The running minimum lives in the clock as the uint64 image of a positive double, which is
+// monotone, so one in-place unsigned min-allreduce of that word is the exact double minimum.
 static int launch_dt_allreduce(swk_domain *d)
 {
   if (!d->comm || d->nranks == 1) return SWK_OK;
-  LAUNCH(d, k_bits_to_double, 1, 1, d->d_clock, d->d_dt_scratch);
-  NK(g_nccl.AllReduce(d->d_dt_scratch, d->d_dt_scratch, 1, ncclFloat64, ncclMinOp, d->comm, d->stream));
-  LAUNCH(d, k_double_to_bits, 1, 1, d->d_clock, d->d_dt_scratch);
+  void *word = (char *)d->d_clock + offsetof(Clock, dt_min_bits);
+  NK(g_nccl.AllReduce(word, word, 1, ncclUint64, ncclMinOp, d->comm, d->stream));
   return SWK_OK;
 }
 
@@ -1316,13 +1332,19 @@ static int ensure_graph(swk_domain *d)
   return SWK_OK;
 }
 
+// With a communicator the NCCL calls (dt min-allreduce on the main stream, halo send/recv on the
+// communication stream, forked and joined by events) are captured into the step's graph as well,
+// so that a multi-GPU step is one cudaGraphLaunch per rank: no host work between the 2-3 points
+// per step at which the ranks wait for each other.
+static int warm_nccl(swk_domain *d);
 static bool graph_ok(const swk_domain *d)
 {
-  return d->use_graph && !d->comm && !d->timing;
+  return d->use_graph && !d->timing;
 }
 
 static int run_one_step(swk_domain *d)
 {
+  if (d->comm && !d->nccl_warm) CKV(warm_nccl(d));
   if (graph_ok(d)) {
     CKV(ensure_graph(d));
     CKV(push_segments(d));                     // time-independent kinds only; cheap when clean
@@ -1669,23 +1691,121 @@ extern "C" int swk_nccl_unique_id(void *id128)
   return SWK_OK;
 }
 
-extern "C" int swk_comm_init(swk_domain *d, const void *id128, int rank, int nranks)
+extern "C" int swk_comm_create(const void *id128, int rank, int nranks, int device, swk_comm **out)
 {
-  if (!d || !id128) return fail(SWK_ERR_ARG, "NULL argument");
-  CK(cudaSetDevice(d->device));
+  if (!id128 || !out) return fail(SWK_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  CKV(select_device(device));
   CKV(load_nccl());
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
-  NK(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
-  d->rank = rank;
-  d->nranks = nranks;
-  CKV(dalloc(&d->d_dt_scratch, 1));
+  swk_comm *c = new swk_comm();
+  c->rank = rank; c->nranks = nranks; c->device = device;
+  ncclResult_t r = g_nccl.CommInitRank(&c->nc, nranks, id, rank);
+  if (r != 0) {
+    delete c;
+    return fail(SWK_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+  }
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return SWK_OK;
+}
+
+extern "C" int swk_comm_destroy(swk_comm *c)
+{
+  if (!c) return SWK_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->d_buf) cudaFree(c->d_buf);
+  if (c->nc && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nc);
+  delete c;
+  return SWK_OK;
+}
+
+// Host-level collective on a small host buffer (barriers, timing maxima, the bit-exact merges of
+// the structure operators): staged through a device scratch, synchronous.  The caller must not
+// have a device time loop of an attached domain in flight (swk_evolve / swk_run_steps return
+// synchronised, so this holds whenever the host has control).
+extern "C" int swk_comm_allreduce(swk_comm *c, void *host_buf, int64_t n, int dtype, int op)
+{
+  if (!c || (!host_buf && n > 0) || n < 0) return fail(SWK_ERR_ARG, "bad argument");
+  if (dtype != SWK_F64 && dtype != SWK_I64) return fail(SWK_ERR_ARG, "dtype must be SWK_F64 or SWK_I64");
+  if (op < SWK_SUM || op > SWK_MAX) return fail(SWK_ERR_ARG, "op must be SWK_SUM, SWK_MIN or SWK_MAX");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)std::max<int64_t>(n, 1) * 8;
+  if (bytes > c->cap) {
+    if (c->d_buf) cudaFree(c->d_buf);
+    c->d_buf = nullptr;
+    c->cap = 0;
+    CK(cudaMalloc(&c->d_buf, bytes));
+    c->cap = bytes;
+  }
+  if (n == 0) return SWK_OK;
+  CK(cudaMemcpyAsync(c->d_buf, host_buf, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  const int nccl_op = (op == SWK_SUM) ? ncclSumOp : ((op == SWK_MIN) ? ncclMinOp : ncclMaxOp);
+  NK(g_nccl.AllReduce(c->d_buf, c->d_buf, (size_t)n, dtype == SWK_F64 ? ncclFloat64 : ncclInt64, nccl_op, c->nc,
+                      c->stream));
+  CK(cudaMemcpyAsync(host_buf, c->d_buf, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return SWK_OK;
+}
+
+extern "C" int swk_comm_attach(swk_domain *d, swk_comm *c)
+{
+  if (!d || !c) return fail(SWK_ERR_ARG, "NULL argument");
+  if (d->comm) return fail(SWK_ERR_ARG, "the domain already has a communicator");
+  if (c->device != d->device) return fail(SWK_ERR_ARG, "communicator and domain live on different devices");
+  CK(cudaSetDevice(d->device));
+  d->comm = c->nc;
+  d->comm_obj = c;
+  d->rank = c->rank;
+  d->nranks = c->nranks;
+  d->graph_valid = false;
+  d->nccl_warm = false;
   CK(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&d->ev_update, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
   {
     const char *env = getenv("SWK_NO_OVERLAP");
     d->overlap = !(env && env[0] == '1');
+  }
+  return SWK_OK;
+}
+
+extern "C" int swk_comm_init(swk_domain *d, const void *id128, int rank, int nranks)
+{
+  if (!d || !id128) return fail(SWK_ERR_ARG, "NULL argument");
+  swk_comm *c = nullptr;
+  CKV(swk_comm_create(id128, rank, nranks, d->device, &c));
+  int r = swk_comm_attach(d, c);
+  if (r != SWK_OK) { swk_comm_destroy(c); return r; }
+  d->comm_owned = true;
+  return SWK_OK;
+}
+
+// First use of a peer connection makes NCCL set the transport up (host work, allocations): do it
+// once outside any stream capture - one empty-handed round of the step's collectives (the halo
+// buffers travel without pack / unpack, so no state is touched).
+static int warm_nccl(swk_domain *d)
+{
+  d->nccl_warm = true;
+  if (!d->comm) return SWK_OK;
+  if (!d->peers.empty()) {
+    NK(g_nccl.GroupStart());
+    for (auto &pe : d->peers) {
+      if (pe.n_recv > 0) NK(g_nccl.Recv(pe.d_recv_buf, 3 * (size_t)pe.n_recv, ncclFloat64, pe.rank, d->comm, d->comm_stream));
+      if (pe.n_send > 0) NK(g_nccl.Send(pe.d_send_buf, 3 * (size_t)pe.n_send, ncclFloat64, pe.rank, d->comm, d->comm_stream));
+    }
+    NK(g_nccl.GroupEnd());
+    CK(cudaStreamSynchronize(d->comm_stream));
+  }
+  if (d->nranks > 1) {
+    unsigned long long *w = nullptr;
+    CK(cudaMalloc((void **)&w, 8));
+    CK(cudaMemsetAsync(w, 0, 8, d->stream));
+    NK(g_nccl.AllReduce(w, w, 1, ncclUint64, ncclMinOp, d->comm, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    cudaFree(w);
   }
   return SWK_OK;
 }
@@ -1704,6 +1824,8 @@ extern "C" int swk_set_halo(swk_domain *d, int n_peers, const int *peer_ranks, c
   }
   d->peers.clear();
   d->halo_front = 0;
+  d->graph_valid = false;
+  d->nccl_warm = false;
   for (int q = 0; q < n_peers; q++) {
     Peer pe;
     pe.rank = peer_ranks[q];

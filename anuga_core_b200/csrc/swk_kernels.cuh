@@ -39,6 +39,12 @@ namespace swk {
 #ifndef SWK_FU_ROLLED       // fused kernel: one edge per trip of a rolled loop (see triangle_flux)
 #define SWK_FU_ROLLED true
 #endif
+#ifndef SWK_F_ROLLED        // the same for the flux kernel of substep 0
+#define SWK_F_ROLLED false
+#endif
+#ifndef SWK_FG_EDGE         // flux geometry as one record per EDGE {nx, ny, length, aux}: a trip of the rolled loop
+#define SWK_FG_EDGE 1       // loads exactly the three records of its edge (own, neighbour's, geometry)
+#endif
 constexpr int BLOCK = SWK_BLOCK;
 
 // ---- device-side clock: the scalars of Generic_Domain's time loop -------------
@@ -113,13 +119,13 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
                                                 Eff &e, bool &zero_mom, int &connA_flags)
 {
   const int NP = D.NP;
-  const i4 s = D.connA[k];
+  const i4 s = lds(&D.connA[k]);
   const d4 c = cq[k];
   const d4 c0 = cq[s.x];
   const d4 c1 = cq[s.y];
   const d4 c2 = cq[s.z];
-  const d4 g0 = D.xg[k];
-  const d4 g1 = D.xg[NP + k];
+  const d4 g0 = lds(&D.xg[k]);
+  const d4 g1 = lds(&D.xg[NP + k]);
   XGeom G;
   G.dxv0 = g0.x; G.dxv1 = g0.y; G.dxv2 = g0.z; G.dyv0 = g0.w;
   G.dyv1 = g1.x; G.dyv2 = g1.y;
@@ -150,7 +156,7 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
     }
   }
 #else
-  const d4 g2 = D.xg[2 * NP + k];
+  const d4 g2 = lds(&D.xg[2 * NP + k]);
   G.dx1 = g1.z; G.dx2 = g1.w;
   G.dy1 = g2.x; G.dy2 = g2.y; G.inv_area2 = g2.z;
 #endif
@@ -219,6 +225,17 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts
 {
   if (D.clock->stop) return;
   const int k = blockIdx.x * BLOCK + threadIdx.x;
+#if SWK_PF_AHEAD > 0
+  if (threadIdx.x < 5) {      // slabs of the block SWK_PF_AHEAD further on: cq, xg x3, connA
+    const long long t0 = (long long)(blockIdx.x + SWK_PF_AHEAD) * BLOCK;
+    if (t0 + BLOCK <= D.NP) {
+      const int j = threadIdx.x;
+      if (j == 0) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
+      else if (j < 4) prefetch_l2_bulk(D.xg + (long long)(j - 1) * D.NP + t0, BLOCK * 32);
+      else prefetch_l2_bulk(D.connA + t0, BLOCK * 16);
+    }
+  }
+#endif
   if (k >= D.N) return;
   d4 r0, r1, r2;
   Eff e;
@@ -268,6 +285,22 @@ __global__ void __launch_bounds__(BLOCK) k_protect_mass(Dev D, Consts K)
 // with the evaluate_segment arithmetic of each boundary class.  One thread per
 // boundary edge m.
 // =============================================================================
+// Flux geometry of triangle k.  SWK_FG_EDGE: fg[i][k] = {nx_i, ny_i, length_i, aux_i} with
+// aux = {1/area, radius, area}; otherwise fg[0] = {n0x,n0y,n1x,n1y}, fg[1] = {n2x,n2y,l0,l1},
+// fg[2] = {l2, 1/area, radius, area}.
+__device__ __forceinline__ void edge_normal(const Dev &D, int k, int i, double &n1, double &n2)
+{
+#if SWK_FG_EDGE
+  const d4 f = D.fg[i * D.NP + k];
+  n1 = f.x; n2 = f.y;
+#else
+  const d4 f0 = D.fg[k];
+  const d4 f1 = D.fg[D.NP + k];
+  n1 = (i == 0) ? f0.x : ((i == 1) ? f0.z : f1.x);
+  n2 = (i == 0) ? f0.y : ((i == 1) ? f0.w : f1.y);
+#endif
+}
+
 struct Segments {
   const int *b_cell;       // [M] triangle (device numbering)
   const int *b_edge;       // [M]
@@ -352,12 +385,7 @@ __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, 
   const int i = S.b_edge[m];
   const d4 e = D.eq[i * D.NP + k];           // {stage, height, xmom, ymom}
   double n1, n2;
-  {
-    const d4 f0 = D.fg[k];
-    const d4 f1 = D.fg[D.NP + k];
-    n1 = (i == 0) ? f0.x : ((i == 1) ? f0.z : f1.x);
-    n2 = (i == 0) ? f0.y : ((i == 1) ? f0.w : f1.y);
-  }
+  edge_normal(D, k, i, n1, n2);
   double cw = 0.0, cuh = 0.0, cvh = 0.0;
   if (centroid_transmissive && kind == 3) {   // centroid arrays as the reference sees them
     const Eff ef = effective(D.cq[k], K);
@@ -502,9 +530,48 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
   T.su = 0.0; T.xu = 0.0; T.yu = 0.0;
   T.dtmin = 1.0e+100;
   T.speed = 0.0;
-  const d4 f0 = D.fg[k];
-  const d4 f1 = D.fg[NP + k];
-  const d4 f2 = D.fg[2 * NP + k];
+#if SWK_FG_EDGE
+  double inv_area = 0.0, radius = 0.0;
+  if (ROLLED) {
+  // one edge per trip of a rolled loop: the trip loads the three records of its edge (own edge
+  // values, the neighbour's, the edge geometry), so only one edge's operands are live at a time
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) {
+    const int q = (i == 0) ? p.x : ((i == 1) ? p.y : p.z);
+    const d4 el = D.eq[i * NP + k];
+    const d4 ge = lds(&D.fg[i * NP + k]);
+    d4 er;
+    if (q >= 0) er = D.eq[(q & 3) * NP + (q >> 2)];
+    else er = D.bq[-q - 1];
+    if (i == 0) inv_area = ge.w;
+    if (i == 1) radius = ge.w;
+    edge_contribution<RW>(D, K, k, i, q, p.w, el, er, ge.x, ge.y, ge.z, own, first, T);
+  }
+  } else {
+  d4 el[3], ge[3], er[3];
+  const int pn[3] = {p.x, p.y, p.z};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    el[i] = D.eq[i * NP + k];
+    ge[i] = lds(&D.fg[i * NP + k]);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int q = pn[i];
+    if (q >= 0) er[i] = D.eq[(q & 3) * NP + (q >> 2)];
+    else er[i] = D.bq[-q - 1];
+  }
+  inv_area = ge[0].w;
+  radius = ge[1].w;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    edge_contribution<RW>(D, K, k, i, pn[i], p.w, el[i], er[i], ge[i].x, ge[i].y, ge[i].z, own, first, T);
+  }
+  finish_flux(T, radius, inv_area, first);
+#else
+  const d4 f0 = lds(&D.fg[k]);
+  const d4 f1 = lds(&D.fg[NP + k]);
+  const d4 f2 = lds(&D.fg[2 * NP + k]);
   if (ROLLED) {
   // one edge per trip of a rolled loop: operands are loaded inside the trip, so only one edge's
   // records are live at a time (fewer registers, smaller code) at the price of three load phases
@@ -541,7 +608,30 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
     edge_contribution<RW>(D, K, k, i, pn[i], p.w, el[i], er[i], nx[i], ny[i], len[i], own, first, T);
   }
   finish_flux(T, f2.z, f2.y, first);
+#endif
   return T;
+}
+
+// L2 prefetch-ahead for the flux kernels: slabs of the block SWK_PF_AHEAD further on
+__device__ __forceinline__ void prefetch_flux_slabs(const Dev &D, int k0, bool with_update)
+{
+#if SWK_PF_AHEAD > 0
+  const int j = threadIdx.x;
+  if (j < 12) {
+    const long long t0 = (long long)k0 + (long long)(blockIdx.x + SWK_PF_AHEAD) * BLOCK;
+    if (t0 + BLOCK <= D.NP) {
+      const long long NP = D.NP;
+      if (j < 3) prefetch_l2_bulk(D.eq + j * NP + t0, BLOCK * 32);
+      else if (j < 6) prefetch_l2_bulk(D.fg + (j - 3) * NP + t0, BLOCK * 32);
+      else if (j == 6) prefetch_l2_bulk(D.connB + t0, BLOCK * 16);
+      else if (j == 7) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
+      else if (with_update) {
+        if (j == 8) prefetch_l2_bulk(D.eta + t0, BLOCK * 8);
+        else prefetch_l2_bulk(D.bk + (j - 9) * NP + t0, BLOCK * 8);
+      }
+    }
+  }
+#endif
 }
 
 // block-wide min of positive doubles -> one atomicMin per block
@@ -583,9 +673,9 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
   const int NP = D.NP;
   const bool full = (zf & 2) != 0;
   if (U.do_backup) {                                   // backup holds the RAW start-of-step values
-    D.bk[k] = raw.x;
-    D.bk[NP + k] = raw.y;
-    D.bk[2 * NP + k] = raw.z;
+    sts(&D.bk[k], raw.x);
+    sts(&D.bk[NP + k], raw.y);
+    sts(&D.bk[2 * NP + k], raw.z);
   }
   if (zf & 1) { e.uh = 0.0; e.vh = 0.0; }
   double zs = 1.0;
@@ -606,7 +696,7 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
     zs = sqrt(1.0 + zx * zx + zy * zy);
     h = e.w - (z0 + z1 + z2) * (1.0 / 3.0);
   }
-  const double S = manning_S(U.g, K.mah, D.eta[k], h, e.uh, e.vh, zs, U.sloped);
+  const double S = manning_S(U.g, K.mah, lds(&D.eta[k]), h, e.uh, e.vh, zs, U.sloped);
   double w = e.w, uh = e.uh, vh = e.vh;
   w += dt * su;                                        // stage has no semi-implicit term: /1.0 is exact
   bool ok = true;
@@ -618,9 +708,9 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
     atomicAdd((unsigned long long *)&D.clock->negative_cells, 1ULL);
   }
   if (U.do_saxpy) {
-    w = U.a * w + U.b * D.bk[k];
-    uh = U.a * uh + U.b * D.bk[NP + k];
-    vh = U.a * vh + U.b * D.bk[2 * NP + k];
+    w = U.a * w + U.b * lds(&D.bk[k]);
+    uh = U.a * uh + U.b * lds(&D.bk[NP + k]);
+    vh = U.a * vh + U.b * lds(&D.bk[2 * NP + k]);
     if (U.divide_by != 1.0) {
       w = w / U.divide_by;
       uh = uh / U.divide_by;
@@ -640,14 +730,15 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int
 {
   if (D.clock->stop) return;
   const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
+  prefetch_flux_slabs(D, k0, false);
   double dtmin = 1.0e+100;
   if (k < k1) {
-    const i4 p = D.connB[k];
+    const i4 p = lds(&D.connB[k]);
     const Eff own = effective(D.cq[k], K);
-    const TriFlux T = triangle_flux<RW>(D, K, k, p, own, first != 0);
-    D.eu[k] = T.su;
-    D.eu[D.NP + k] = T.xu;
-    D.eu[2 * D.NP + k] = T.yu;
+    const TriFlux T = triangle_flux<RW, SWK_F_ROLLED>(D, K, k, p, own, first != 0);
+    sts(&D.eu[k], T.su);
+    sts(&D.eu[D.NP + k], T.xu);
+    sts(&D.eu[2 * D.NP + k], T.yu);
     if (first && write_speed) D.max_speed[k] = T.speed;
     dtmin = T.dtmin;
   }
@@ -664,7 +755,8 @@ __global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U,
   const double dt = (dt_override >= 0.0) ? dt_override : D.clock->dt;
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
-  triangle_update(D, K, U, k, raw, e, D.zflag[k], D.eu[k], D.eu[D.NP + k], D.eu[2 * D.NP + k], dt, D.cq, nullptr);
+  triangle_update(D, K, U, k, raw, e, D.zflag[k], lds(&D.eu[k]), lds(&D.eu[D.NP + k]), lds(&D.eu[2 * D.NP + k]), dt,
+                  D.cq, nullptr);
 }
 
 // Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
@@ -674,9 +766,10 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Const
 {
   if (D.clock->stop) return;
   const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
+  prefetch_flux_slabs(D, k0, true);
   if (k >= k1) return;
   const double dt = D.clock->dt;
-  const i4 p = D.connB[k];
+  const i4 p = lds(&D.connB[k]);
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
   const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, e, false);

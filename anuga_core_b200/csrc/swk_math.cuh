@@ -25,6 +25,68 @@ struct __align__(16) i4 {
 __device__ __forceinline__ d4 ldg4(const d4 *p) { return *p; }
 
 // ---------------------------------------------------------------------------
+// Streamed operands (static geometry, connectivity, explicit updates, backups): each byte is used
+// once per pass, so they bypass L1 allocation and are marked evict-first in L2, which leaves the
+// caches to the records that neighbours gather (cq in pass A, eq in pass B).
+// ---------------------------------------------------------------------------
+#ifndef SWK_HINTS
+#define SWK_HINTS 1
+#endif
+__device__ __forceinline__ d4 lds(const d4 *p)
+{
+#if SWK_HINTS
+  d4 r;
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ i4 lds(const i4 *p)
+{
+#if SWK_HINTS
+  i4 r;
+  asm volatile("ld.global.cs.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ double lds(const double *p)
+{
+#if SWK_HINTS
+  double r;
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ void sts(double *p, double v)
+{
+#if SWK_HINTS
+  asm volatile("st.global.cs.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+#else
+  *p = v;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// L2 prefetch-ahead of the streamed slabs: one thread per array and block asks the L2 for the
+// slab that the block SWK_PF_AHEAD positions further on will read (UBLKPF.L2, no registers, no
+// smem), so the DRAM stream runs ahead of the resident warps instead of being paced by them.
+// ---------------------------------------------------------------------------
+#ifndef SWK_PF_AHEAD
+#define SWK_PF_AHEAD 0
+#endif
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes));
+}
+
+// ---------------------------------------------------------------------------
 // h^(7/3) with the exponent the reference really uses: the double nearest to
 // 7/3 (sw_domain_openmp.c:1962, 1974 `pow(h, seven_thirds)`).
 // glibc's pow is accurate to ~0.52 ulp; CUDA's pow only to 2 ulp, which is the
@@ -34,6 +96,26 @@ __device__ __forceinline__ d4 ldg4(const d4 *p) { return *p; }
 // correctly rounded value; it agrees with glibc on 99.92 % of arguments and is
 // 1 ulp away on the rest (measured on 2e7 random h in [1e-6, 1e3]).
 // ---------------------------------------------------------------------------
+#ifndef SWK_POW_FAST
+#define SWK_POW_FAST 1
+#endif
+// ln(h) to ~1e-6 absolute: exponent + MUFU.LG2 of the mantissa (it only scales the 2^-53-sized delta term)
+__device__ __forceinline__ double ln_rough(double h)
+{
+  const int hi = __double2hiint(h);
+  const int ex = ((hi >> 20) & 0x7ff) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(h));
+  const float lg = __log2f((float)m) + (float)ex;
+  return (double)lg * 0.6931471805599453;
+}
+// 1/x to ~2^-20 (MUFU.RCP64H): enough for a correction term that is itself 2^-52 relative
+__device__ __forceinline__ double rcp_rough(double x)
+{
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
 __device__ __forceinline__ double pow_7_3(double h)
 {
   const double y = 7.0 / 3.0;
@@ -46,7 +128,11 @@ __device__ __forceinline__ double pow_7_3(double h)
   double qe = __fma_rn(p, c, -q);
   qe = __fma_rn(pe, c, qe);
   const double r = (h - q) - qe;
+#if SWK_POW_FAST
+  const double corr = r * rcp_rough(3.0 * p);             // |corr| <= ~2^-52 c: 20 good bits suffice
+#else
   const double corr = r / (3.0 * p);
+#endif
   const double chi = c + corr;
   const double clo = corr - (chi - c);
   // h^2 exactly
@@ -57,7 +143,11 @@ __device__ __forceinline__ double pow_7_3(double h)
   double Pe = __fma_rn(s, chi, -P);
   Pe = __fma_rn(s, clo, Pe);
   Pe = __fma_rn(se, chi, Pe);
+#if SWK_POW_FAST
+  Pe = __fma_rn(P, delta * ln_rough(h), Pe);
+#else
   Pe = __fma_rn(P, delta * log(h), Pe);
+#endif
   return P + Pe;
 }
 

@@ -292,6 +292,22 @@ int swk_bytes_per_triangle_step(swk_domain *d, double *algorithmic, double *layo
  * full_send_dict[p][0] / ghost_recv_dict[p][0] (distribute_mesh.py:1128-1170).    */
 int swk_nccl_unique_id(void *id128);
 int swk_comm_init(swk_domain *d, const void *id128, int rank, int nranks);
+/* Process-level communicator (one per GPU process), independent of any domain: the device time
+ * loop of every domain attached to it (swk_comm_attach) and the small host-level collectives of
+ * the host layer (swk_comm_allreduce: barriers, maxima of timings, the bit-exact integer merges
+ * of the structure operators) share one ncclComm_t, so multi-GPU runs need nothing but NCCL.
+ * Replaces the pypar/mpi4py calls of parallel/parallel_api.py and
+ * parallel_generic_communications.py:35-67.                                              */
+typedef struct swk_comm swk_comm;
+#define SWK_F64 0
+#define SWK_I64 1
+#define SWK_SUM 0
+#define SWK_MIN 1
+#define SWK_MAX 2
+int swk_comm_create(const void *id128, int rank, int nranks, int device, swk_comm **out);
+int swk_comm_destroy(swk_comm *comm);
+int swk_comm_allreduce(swk_comm *comm, void *host_buf, int64_t n, int dtype, int op);
+int swk_comm_attach(swk_domain *d, swk_comm *comm);
 int swk_set_halo(swk_domain *d, int n_peers, const int *peer_ranks,
                  const int64_t *send_counts, const int64_t *const *send_ids,
                  const int64_t *recv_counts, const int64_t *const *recv_ids);
