@@ -149,6 +149,10 @@ SYMBOLS = {
     "swk_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "swk_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
     "swk_set_halo": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int), _PI, C.POINTER(_PI), _PI, C.POINTER(_PI)]),
+    "swk_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "swk_comm_destroy": (C.c_int, [C.c_void_p]),
+    "swk_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int]),
+    "swk_comm_attach": (C.c_int, [_H, C.c_void_p]),
     "swk_call_open": (C.c_int, [C.POINTER(SwkHostView), C.c_int, C.POINTER(_H)]),
     "swk_call_close": (C.c_int, [_H]),
     "swk_call_compute_fluxes_ext_central": (C.c_int, [_H, C.POINTER(SwkHostView), _D, C.c_int, _PD]),
@@ -477,6 +481,10 @@ class DeviceDomain:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _check(self.lib.swk_comm_init(self.h, buf, int(rank), int(nranks)))
 
+    def comm_attach(self, nccl_comm):
+        """Join the process-level communicator (NcclComm below)."""
+        _check(self.lib.swk_comm_attach(self.h, nccl_comm.h))
+
     def set_halo(self, send, recv):
         """send / recv: {peer_rank: ids (caller numbering)}; both sides list ids sorted by
         global id so that no ids travel (distribute_mesh.py:1128-1170)."""
@@ -490,6 +498,39 @@ class DeviceDomain:
         sp = (_PI * max(n, 1))(*[_pi(a) for a in s_arr])
         rp = (_PI * max(n, 1))(*[_pi(a) for a in r_arr])
         _check(self.lib.swk_set_halo(self.h, n, ranks, _pi(sc), sp, _pi(rc), rp))
+
+
+class NcclComm:
+    """Process-level NCCL communicator of libswk (include/swk.h: swk_comm_*): the device time loops of
+    the attached domains and the small host-level collectives share it; nothing but NCCL is needed."""
+    SUM, MIN, MAX = 0, 1, 2
+
+    def __init__(self, unique_id, rank, nranks, device):
+        self.lib = load_library()
+        self.rank, self.nranks, self.device = int(rank), int(nranks), int(device)
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        h = C.c_void_p()
+        _check(self.lib.swk_comm_create(buf, self.rank, self.nranks, self.device, C.byref(h)))
+        self.h = h
+
+    def allreduce(self, array, op):
+        """In-place all-reduce of a contiguous float64 or int64 numpy array."""
+        a = array
+        if a.dtype == np.float64:
+            dt = 0
+        elif a.dtype == np.int64:
+            dt = 1
+        else:
+            raise TypeError("allreduce: float64 or int64 arrays only")
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("allreduce: array must be C-contiguous")
+        _check(self.lib.swk_comm_allreduce(self.h, a.ctypes.data_as(C.c_void_p), a.size, dt, int(op)))
+        return a
+
+    def close(self):
+        if self.h:
+            self.lib.swk_comm_destroy(self.h)
+            self.h = None
 
 
 def build_neighbour_structure_native(triangles, number_of_nodes):

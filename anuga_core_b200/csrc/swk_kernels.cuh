@@ -535,6 +535,19 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
   if (ROLLED) {
   // one edge per trip of a rolled loop: the trip loads the three records of its edge (own edge
   // values, the neighbour's, the edge geometry), so only one edge's operands are live at a time
+#if SWK_FU_L1PF
+  // the trips' gathers would otherwise pay one L2 round trip each, one after the other: ask for
+  // all of them now (no registers), the trips then hit L1
+  {
+    const int pq[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const int q = pq[i];
+      if (q >= 0) prefetch_l1(&D.eq[(q & 3) * NP + (q >> 2)]);
+      if (i > 0) prefetch_l1(&D.eq[i * NP + k]);
+    }
+  }
+#endif
 #pragma unroll 1
   for (int i = 0; i < 3; i++) {
     const int q = (i == 0) ? p.x : ((i == 1) ? p.y : p.z);
@@ -751,6 +764,17 @@ __global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U,
 {
   if (D.clock->stop) return;
   const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
+#if SWK_PF_AHEAD > 0
+  if (threadIdx.x < 5) {
+    const long long t0 = (long long)k0 + (long long)(blockIdx.x + SWK_PF_AHEAD) * BLOCK;
+    if (t0 + BLOCK <= D.NP) {
+      const int j = threadIdx.x;
+      if (j < 3) prefetch_l2_bulk(D.eu + (long long)j * D.NP + t0, BLOCK * 8);
+      else if (j == 3) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
+      else prefetch_l2_bulk(D.eta + t0, BLOCK * 8);
+    }
+  }
+#endif
   if (k >= k1) return;
   const double dt = (dt_override >= 0.0) ? dt_override : D.clock->dt;
   const d4 raw = D.cq[k];

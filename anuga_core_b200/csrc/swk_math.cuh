@@ -81,6 +81,10 @@ __device__ __forceinline__ void sts(double *p, double v)
 #ifndef SWK_PF_AHEAD
 #define SWK_PF_AHEAD 0
 #endif
+#ifndef SWK_FU_L1PF
+#define SWK_FU_L1PF 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes));

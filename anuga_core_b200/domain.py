@@ -702,9 +702,12 @@ class Domain:
         lib = nccl_library_path()
         if lib and "SWK_NCCL_LIB" not in os.environ:
             os.environ["SWK_NCCL_LIB"] = lib
-        uid = _b.DeviceDomain.nccl_unique_id() if comm.rank == 0 else b""
-        uid = comm.broadcast_bytes(uid, 128)
-        self._dev.comm_init(uid, comm.rank, comm.size)
+        if getattr(comm, "nccl", None) is not None:      # the process-level NCCL communicator
+            self._dev.comm_attach(comm.nccl)
+        else:                                            # a foreign process group ships the id
+            uid = _b.DeviceDomain.nccl_unique_id() if comm.rank == 0 else b""
+            uid = comm.broadcast_bytes(uid, 128)
+            self._dev.comm_init(uid, comm.rank, comm.size)
         send = {int(q): v[0] for q, v in self.full_send_dict.items() if q != self.processor}
         recv = {int(q): v[0] for q, v in self.ghost_recv_dict.items() if q != self.processor}
         self._dev.set_halo(send, recv)

@@ -272,10 +272,11 @@ def barrier():
 
 
 def finalize():
+    global _COMM
     c = _COMM
-    if c is not None and c.dist is not None and c.dist.is_initialized():
-        c.dist.barrier()
-        c.dist.destroy_process_group()
+    if c is not None:
+        c.finalize()
+    _COMM = None
 
 
 def rcb_partition(centroid_coordinates, nparts):
@@ -328,9 +329,7 @@ def distribute_collective(domain=None, verbose=False, debug=False, parameters=No
             l2s = order[sub["tri_l2g"]]
             payload[p] = dict(sub=sub, l2s=l2s, settings=_settings_of(domain), names=_names_of(domain),
                               cv={n: domain.quantities[n].centroid_values[l2s] for n in _QUANTITY_NAMES})
-    mine = [None]
-    comm.dist.scatter_object_list(mine, payload if comm.rank == 0 else None, src=0)
-    m = mine[0]
+    m = comm.scatter_objects(payload)
     order = np.zeros(int(m["sub"]["tri_l2g"].max()) + 1, dtype=np.int64)
     order[m["sub"]["tri_l2g"]] = m["l2s"]
     if device is None:
@@ -454,19 +453,166 @@ def strip_partitioned_sweep_domain(m, n, rank, nranks, device=0, alg="DE1", rain
 
 
 # ----------------------------------------------------------------------------------------
-# process group plumbing (torch.distributed carries the NCCL id and python scalars)
+# process group plumbing.  On GPUs nothing but NCCL is used (no PyTorch, no MPI): the 128-byte NCCL id
+# travels through a rendezvous directory (one node: the launcher's ranks share /tmp), and every
+# host-level collective (barrier, scalar reductions, the bit-exact merges of the structure operators)
+# is a small ncclAllReduce on the process-level communicator of libswk.  The torch.distributed (gloo)
+# variant exists for the CPU tests of the host logic only.
+# Stands in for anuga/parallel/parallel_api.py + the pypar / mpi4py layer underneath it.
 # ----------------------------------------------------------------------------------------
 class Communicator:
-    def __init__(self, rank, size, dist=None):
-        self.rank, self.size, self.dist = rank, size, dist
+    """Single-process communicator (also the base class)."""
+
+    def __init__(self, rank=0, size=1):
+        self.rank, self.size = rank, size
+        self.dist = None
+        self.nccl = None
 
     def barrier(self):
-        if self.dist is not None:
-            self.dist.barrier()
+        pass
+
+    def allreduce_max(self, x):
+        return x
+
+    def allreduce_sum(self, x):
+        return x
+
+    def allreduce_min(self, x):
+        return x
+
+    def merge_disjoint(self, a):
+        """Every element of the float64 array `a` is owned (filled) by exactly one rank and is +0.0
+        elsewhere: returns the array with all owners' values, bit for bit (an integer sum of the
+        bit patterns, so no rounding and no -0.0 -> +0.0)."""
+        return a
+
+    def broadcast_bytes(self, payload, n):
+        return payload
+
+    def scatter_objects(self, objects):
+        """rank 0's list of `size` picklable objects, one to each rank"""
+        return objects[0]
+
+    def finalize(self):
+        pass
+
+
+class NcclCommunicator(Communicator):
+    """One process per GPU over NCCL; bootstrap through a rendezvous directory."""
+
+    def __init__(self, rank, size, device, rdzv_dir=None, timeout=600.0):
+        from . import backend as _b
+        Communicator.__init__(self, rank, size)
+        lib = nccl_library_path()
+        if lib and "SWK_NCCL_LIB" not in os.environ:
+            os.environ["SWK_NCCL_LIB"] = lib
+        self.device = device
+        self.timeout = timeout
+        self.dir = rdzv_dir or default_rendezvous_dir()
+        self._seq = 0
+        if rank == 0:
+            os.makedirs(self.dir, exist_ok=True)
+            uid = _b.DeviceDomain.nccl_unique_id()
+            self._publish("nccl_id", uid)
+        else:
+            uid = self._fetch("nccl_id")
+        self.nccl = _b.NcclComm(uid, rank, size, device)
+        self.barrier()
+        if rank == 0:
+            self._remove("nccl_id")
+
+    # -- rendezvous files (written atomically: temp name + rename) -------------------------
+    def _publish(self, name, payload):
+        tmp = os.path.join(self.dir, ".%s.tmp.%d" % (name, os.getpid()))
+        with open(tmp, "wb") as fh:
+            fh.write(payload)
+        os.replace(tmp, os.path.join(self.dir, name))
+
+    def _fetch(self, name):
+        import time
+        path = os.path.join(self.dir, name)
+        t0 = time.time()
+        while not os.path.exists(path):
+            if time.time() - t0 > self.timeout:
+                raise RuntimeError("rendezvous: %s did not appear within %.0f s" % (path, self.timeout))
+            time.sleep(0.01)
+        with open(path, "rb") as fh:
+            return fh.read()
+
+    def _remove(self, name):
+        try:
+            os.remove(os.path.join(self.dir, name))
+        except OSError:
+            pass
+
+    # -- collectives ------------------------------------------------------------------------
+    def barrier(self):
+        self.nccl.allreduce(np.zeros(1, dtype=np.int64), self.nccl.SUM)
+
+    def _scalar(self, x, op):
+        a = np.array([float(x)], dtype=np.float64)
+        self.nccl.allreduce(a, op)
+        return float(a[0])
+
+    def allreduce_max(self, x):
+        return self._scalar(x, self.nccl.MAX)
+
+    def allreduce_min(self, x):
+        return self._scalar(x, self.nccl.MIN)
+
+    def allreduce_sum(self, x):
+        return self._scalar(x, self.nccl.SUM)
+
+    def merge_disjoint(self, a):
+        t = np.ascontiguousarray(a, dtype=np.float64).view(np.int64).copy()
+        self.nccl.allreduce(t.reshape(-1), self.nccl.SUM)
+        return t.view(np.float64).reshape(np.shape(a))
+
+    def broadcast_bytes(self, payload, n):
+        buf = np.zeros((n + 7) // 8, dtype=np.int64)
+        if self.rank == 0:
+            raw = bytes(payload) + b"\0" * (buf.size * 8 - len(payload))
+            buf[:] = np.frombuffer(raw, dtype=np.int64)
+        self.nccl.allreduce(buf, self.nccl.SUM)
+        return buf.tobytes()[:n]
+
+    def scatter_objects(self, objects):
+        import pickle
+        self._seq += 1
+        if self.rank == 0:
+            for r in range(1, self.size):
+                self._publish("obj_%d_to_%d" % (self._seq, r), pickle.dumps(objects[r], protocol=4))
+            mine = objects[0]
+        else:
+            name = "obj_%d_to_%d" % (self._seq, self.rank)
+            mine = pickle.loads(self._fetch(name))
+            self._remove(name)
+        self.barrier()
+        return mine
+
+    def finalize(self):
+        if self.nccl is not None:
+            self.barrier()
+            self.nccl.close()
+            self.nccl = None
+            if self.rank == 0:
+                try:
+                    os.rmdir(self.dir)
+                except OSError:
+                    pass
+
+
+class TorchCommunicator(Communicator):
+    """torch.distributed process group (gloo on CPU): host-logic tests without GPUs."""
+
+    def __init__(self, rank, size, dist):
+        Communicator.__init__(self, rank, size)
+        self.dist = dist
+
+    def barrier(self):
+        self.dist.barrier()
 
     def _all(self, x, op):
-        if self.dist is None:
-            return x
         import torch
         t = torch.tensor([float(x)], dtype=torch.float64)
         if self.dist.get_backend() == "nccl":
@@ -476,18 +622,17 @@ class Communicator:
 
     def allreduce_max(self, x):
         import torch.distributed as td
-        return self._all(x, td.ReduceOp.MAX) if self.dist is not None else x
+        return self._all(x, td.ReduceOp.MAX)
+
+    def allreduce_min(self, x):
+        import torch.distributed as td
+        return self._all(x, td.ReduceOp.MIN)
 
     def allreduce_sum(self, x):
         import torch.distributed as td
-        return self._all(x, td.ReduceOp.SUM) if self.dist is not None else x
+        return self._all(x, td.ReduceOp.SUM)
 
     def merge_disjoint(self, a):
-        """Every element of the float64 array `a` is owned (filled) by exactly one rank and is +0.0
-        elsewhere: returns the array with all owners' values, bit for bit (an integer sum of the
-        bit patterns, so no rounding and no -0.0 -> +0.0)."""
-        if self.dist is None:
-            return a
         import torch
         import torch.distributed as td
         t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).view(np.int64).copy())
@@ -497,9 +642,6 @@ class Communicator:
         return t.cpu().numpy().view(np.float64).reshape(a.shape)
 
     def broadcast_bytes(self, payload, n):
-        """rank 0's `payload` (n bytes) to everyone"""
-        if self.dist is None:
-            return payload
         import torch
         buf = torch.zeros(n, dtype=torch.uint8)
         if self.rank == 0:
@@ -509,22 +651,52 @@ class Communicator:
         self.dist.broadcast(buf, src=0)
         return bytes(buf.cpu().tolist())
 
+    def scatter_objects(self, objects):
+        mine = [None]
+        self.dist.scatter_object_list(mine, objects if self.rank == 0 else None, src=0)
+        return mine[0]
 
-def init_process_group(backend=None):
-    """RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT from the environment (torchrun)."""
+    def finalize(self):
+        if self.dist.is_initialized():
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def default_rendezvous_dir():
+    """One directory per job on the node: keyed by the launcher's MASTER_PORT and the launcher's pid
+    (all ranks of a torchrun / mpirun job share the parent process), so that neither a concurrent
+    nor a previous job's files can be picked up.  SWK_RDZV_DIR overrides."""
+    env = os.environ.get("SWK_RDZV_DIR")
+    if env:
+        return env
+    import tempfile
+    key = "%s_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "none"),
+                        os.getppid())
+    return os.path.join(tempfile.gettempdir(), "swk_rdzv_" + key)
+
+
+def init_process_group(backend=None, device=None):
+    """RANK / WORLD_SIZE / LOCAL_RANK from the environment (torchrun, mpirun + env, ...).
+    backend 'nccl' (default whenever this process sees an sm_100 device): NCCL only, no PyTorch;
+    backend 'gloo': torch.distributed on CPU, for tests of the host logic."""
     rank = int(os.environ.get("RANK", "0"))
     size = int(os.environ.get("WORLD_SIZE", "1"))
     if size == 1:
-        return Communicator(0, 1, None)
-    import torch
-    import torch.distributed as dist
+        return Communicator(0, 1)
     if backend is None:
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        from . import backend as _b
+        try:
+            backend = "nccl" if _b.device_count() > 0 else "gloo"
+        except Exception:
+            backend = "gloo"
     if backend == "nccl":
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        return NcclCommunicator(rank, size, device)
+    import torch.distributed as dist
     if not dist.is_initialized():
         dist.init_process_group(backend=backend, rank=rank, world_size=size)
-    return Communicator(rank, size, dist)
+    return TorchCommunicator(rank, size, dist)
 
 
 def nccl_library_path():

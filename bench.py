@@ -1,19 +1,28 @@
 #!/usr/bin/env python
-"""bench.py - triangle-steps/s of the DE1 (FP64) shallow-water timestep on B200.
+"""bench.py - triangle-steps/s of the DE (FP64) shallow-water timestep on B200.
 
   python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
   python bench.py --impl reference --gpus N --steps K ...  (the reference's own C/OpenMP
                                                             code on the host cores)
 
-Workload (BASELINE.json configs[2]): synthetic
-rectangular_cross 2000x2000 = 16,000,000 triangles per GPU, smooth everywhere-wet
-fields, DE1 (rk2), Reflective boundaries, Manning 0.03, scalar rain Rate_operator.
-A "step" is one full DE1 timestep (two flux evaluations).  Weak scaling: every rank owns
-a 16M-triangle strip, so --gpus 8 is the 8000x4000... = 128M-triangle mesh of configs[3].
+Workloads (`--config`, BASELINE.json `configs`):
+  sweep      (default) configs[2]: synthetic rectangular_cross 2000x2000 = 16,000,000 triangles per
+             GPU, smooth everywhere-wet fields, DE1 (rk2), Reflective boundaries, Manning 0.03, scalar
+             rain Rate_operator.  Weak scaling: every rank owns a 16M-triangle strip, so --gpus 8 is the
+             8000x4000 = 128M-triangle mesh of configs[3].
+  tsunami    configs[1]: 1000x1000 cells (4M triangles), sloping beach + island, DE1, Manning 0.025,
+             time-dependent set-stage boundary + Transmissive + Reflective.
+  structures configs[4]: 4000x2000 cells (32M triangles), DE1 with rk3, Inlet_operator + Boyd box culvert.
+A "step" is one full timestep (DE1: two flux evaluations).
 
-One JSON line on stdout (rank 0).  `value` is device-timed (CUDA events on the library's
-stream) with the state resident in HBM; `e2e` goes through Domain.evolve with host numpy
-arrays (upload, K steps, download) and is wall-clock timed.
+One JSON line on stdout (rank 0).  `value` is device-timed (CUDA events on the library's stream) with
+the state resident in HBM; `e2e` is the same metric through the public API - host numpy arrays in,
+`for t in domain.evolve(yieldstep, duration)`, host numpy arrays out - wall-clock timed, with the
+host->device and device->host copies inside the timed region.
+
+The reference arm times the reference's own sw_domain_openmp.c + quantity.c (oracle/_ref, compiled
+from /root/reference where it lies) under the numpy restatement of its Python time loop
+(oracle/driver.py) on ALL host cores, on the same mesh and fields as one GPU's share of the workload.
 """
 import argparse
 import json
@@ -27,14 +36,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# the reference arm / cpu baseline use every host core (read by libgomp at load time)
-os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+IS_REFERENCE_ARM = "reference" in sys.argv[1:] and "--impl" in sys.argv[1:]
+# The CPU legs use every host core.  libgomp reads OMP_NUM_THREADS when it is loaded, and torchrun
+# exports OMP_NUM_THREADS=1 to its workers, so the reference arm overrides it before anything loads.
+if IS_REFERENCE_ARM:
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())
+    os.environ["SWK_NO_NATIVE_SETUP"] = "1"      # mesh set-up in numpy only: the arm never maps libswk.so
+elif int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())
 os.environ.setdefault("OMP_PROC_BIND", "close")
 
 import numpy as np  # noqa: E402
 
 ALG_BYTES = {"extrapolate": 204.0, "flux": 260.0, "update": 92.0, "flux_update": 268.0}
 STEP_BYTES = {"DE0": 556.0, "DE1": 1076.0, "DE2": 1572.0}
+METRIC = "triangle-steps/sec (DE1, FP64)"
+
+
+def log(*a):
+    print("[bench r%s]" % os.environ.get("RANK", "0"), *a, file=sys.stderr, flush=True)
 
 
 def measured_peak():
@@ -49,60 +77,116 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons of one GPU sampled DURING the timed region through NVML inside this
+    process (a few microseconds per query).  No nvidia-smi child: starting one initialises NVML for
+    every GPU of the box, which stalls kernel launches of all ranks for tens of milliseconds."""
 
-    def __init__(self, index=0):
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
+
+    def __init__(self, index=0, period=0.02):
         threading.Thread.__init__(self, daemon=True)
-        self.index = index
-        self.samples = []
-        self.proc = None
-
-    def run(self):
+        self.period = period
+        self.sm, self.reasons, self.power = [], set(), []
+        self._stop_evt = threading.Event()
+        self.h = None
+        self.max_mhz = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.samples.append(line.strip())
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; CUDA_VISIBLE_DEVICES may renumber them
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:      # no NVML: one nvidia-smi query before / after instead
+            self.h = None
+            self.err = repr(e)
+
+    def sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self.REASONS:
+            if r & bit:
+                self.reasons.add(name)
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
         except Exception:
             pass
 
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        self.join(timeout=2.0)
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 7:
-                continue
+    def run(self):
+        if self.h is None:
+            return
+        while not self._stop_evt.is_set():
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                self.sample()
+            except Exception:
+                break
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2.0)
+        if self.h is None or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+                    "note": "NVML unavailable: " + getattr(self, "err", "")}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "sm_mhz_min": float(min(self.sm)),
+                "power_w_max": (max(self.power) if self.power else None),
+                "how": "NVML in-process, every %.0f ms during the timed region" % (self.period * 1e3)}
 
 
-def build_domain(size, rank=0, nranks=1, device=0):
+# ------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------
+def workload_config(a):
+    tri = 4 * a.size * a.size
+    if a.config == "sweep":
+        w = ("rectangular_cross %dx%d per GPU (%d triangles/GPU), DE1 rk2 FP64, Reflective, Manning 0.03, "
+             "rain Rate_operator 1e-4 (BASELINE.json configs[2]; --gpus 8 = configs[3])" % (a.size, a.size, tri))
+    elif a.config == "tsunami":
+        w = ("rectangular_cross %dx%d (%d triangles), sloping beach + island, DE1 rk2 FP64, Manning 0.025, "
+             "left: Transmissive_n_momentum_zero_t_momentum_set_stage(0.5 sin(2 pi t/60)), right: Transmissive, "
+             "top/bottom: Reflective (BASELINE.json configs[1])" % (a.size, a.size, tri))
+    else:
+        tri = 2 * a.size * a.size * 4
+        w = ("rectangular_cross %dx%d (%d triangles), DE1 with rk3 FP64, Inlet_operator Q=100 + Boyd_box_operator "
+             "across an embankment (BASELINE.json configs[4])" % (2 * a.size, a.size, tri))
+    return {"workload": w, "triangles_per_gpu": tri,
+            "l2_policy": "inputs larger than L2 (>= 1.7 GB of state per GPU vs 126 MB L2), no flush"}
+
+
+def build_domain(a, rank=0, nranks=1, device=0):
     from anuga_core_b200 import workloads
+    if a.config == "tsunami":
+        return workloads.tsunami_domain(a.size, a.size, device=device)
+    if a.config == "structures":
+        return workloads.structures_domain(2 * a.size, a.size, rank=rank, nranks=nranks, device=device)
     if nranks == 1:
-        return workloads.roofline_sweep_domain(size, size, alg="DE1", rain=1.0e-4, device=device)
+        return workloads.roofline_sweep_domain(a.size, a.size, alg="DE1", rain=1.0e-4, device=device)
     from anuga_core_b200 import parallel
-    m, n = parallel.weak_scaling_shape(size, nranks)
+    m, n = parallel.weak_scaling_shape(a.size, nranks)
     return parallel.strip_partitioned_sweep_domain(m, n, rank, nranks, device=device)
 
 
-def cpu_reference_run(size, steps, warmup, kind_pref="reference"):
+def alg_of(a):
+    return "DE2" if a.config == "structures" else "DE1"
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's CPU implementation (reference arm and cpu_baseline)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(a, size, steps, warmup):
     """The reference's own C/OpenMP kernels (oracle/_ref, compiled from /root/reference) under the
     numpy restatement of its Python time loop, on the host cores.  Falls back to the C port."""
     from anuga_core_b200 import workloads
@@ -114,80 +198,151 @@ def cpu_reference_run(size, steps, warmup, kind_pref="reference"):
     else:
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
         backend, kind = "port", "port"
-    d = workloads.roofline_sweep_domain(size, size, alg="DE1", rain=1.0e-4)
+    t_setup = time.time()
+    if a.config == "tsunami":
+        d = workloads.tsunami_domain(size, size)
+    elif a.config == "structures":
+        d = workloads.structures_domain(2 * size, size, with_structures=False)
+    else:
+        d = workloads.roofline_sweep_domain(size, size, alg="DE1", rain=1.0e-4)
     o = OracleDomain(workloads.domain_to_scenario(d), backend=backend)
+    N = d.number_of_triangles
+    del d
     o.relative_finaltime = None
     o.relative_yieldtime = 1.0e300
     o.distribute_to_vertices_and_edges()
+    step = {"rk2": o.evolve_one_rk2_step, "rk3": o.evolve_one_rk3_step, "euler": o.evolve_one_euler_step}[
+        o.timestepping_method]
 
     def run(k):
         for _ in range(k):
             t0 = o.relative_time
-            o.evolve_one_rk2_step(None, None)
+            step(None, None)
             o.apply_fractional_steps()
             o.relative_time = t0 + o.timestep
+    log("reference arm: %d triangles, set-up %.1f s, backend %s, %s threads" % (
+        N, time.time() - t_setup, backend, os.environ.get("OMP_NUM_THREADS")))
     run(warmup)
     t0 = time.perf_counter()
     run(steps)
     dt = time.perf_counter() - t0
-    N = d.number_of_triangles
     cores = 1 if backend == "port" else int(os.environ.get("OMP_NUM_THREADS", "1"))
+    what = ("reference sw_domain_openmp.c + quantity.c, -O3 -march=x86-64-v3 -fopenmp (multiprocessor_mode 2)"
+            if kind == "reference" else "serial C port")
     return {"value": N * steps / dt, "unit": "triangle-steps/s", "cores": cores, "kind": kind,
-            "sample": "rectangular_cross %dx%d (%d triangles), DE1, %d steps after %d warm-up, %s"
-                      % (size, size, N, steps, warmup,
-                         "reference sw_domain_openmp.c -O3 -march=x86-64-v3 -fopenmp + quantity.c"
-                         if kind == "reference" else "serial C port"),
-            "ms_per_step": dt / steps * 1e3}
+            "sample": "%s: %d triangles (%s cells per side), %d timed steps after %d warm-up steps, %d OpenMP threads; %s"
+                      % (a.config, N, size, steps, warmup, cores, what),
+            "ms_per_step": dt / steps * 1e3, "triangles": N}
 
 
+def reference_arm(a, config):
+    size = a.cpu_size or a.size
+    N = 4 * size * size * (2 if a.config == "structures" else 1)
+    # bounded: keep the timed region within ~150 s of host time (about 1e7 triangle-steps/s on 16 cores)
+    est_step = N / 8.0e6
+    steps = max(1, min(a.steps, int(150.0 / est_step) or 1))
+    warmup = max(1, min(a.warmup, int(40.0 / est_step) or 1))
+    r = cpu_reference_run(a, size, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "triangle-steps/s",
+            "n_gpus": a.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config,
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "triangle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "one GPU's share of the workload (%d triangles) on the host cores; the CPU rate per triangle "
+                    "does not depend on how many such shares a multi-GPU job holds" % r["triangles"]}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# multi-GPU parity check (runs before the timed region at N > 1)
+# ------------------------------------------------------------------------------------------
+def multi_gpu_parity_check(comm, device):
+    """A small wet/dry dam break (DE1, then DE2) distributed over all ranks must reproduce the
+    single-GPU run of the same domain bit for bit (every full triangle, the time and the timestep)."""
+    from anuga_core_b200 import workloads, parallel
+    out = {"ranks": comm.size, "cases": []}
+    bad_total = 0
+    for alg, m, n in (("DE1", 48, 40), ("DE2", 40, 32)):
+        g = workloads.dam_break_domain(m, n, alg=alg, device=device)
+        N = g.number_of_triangles
+        epart = (np.arange(N) * comm.size) // N
+        d = parallel.distribute(g, comm.size, epart=epart, ranks=[comm.rank], domain_kw=dict(device=device))[comm.rank]
+        d.attach_communicator(comm)
+        for _ in d.evolve(yieldstep=0.5, finaltime=1.0):
+            pass
+        for _ in g.evolve(yieldstep=0.5, finaltime=1.0):
+            pass
+        nf = d.number_of_full_triangles
+        ids = d.tri_l2s[:nf]
+        bad = 0
+        for name in ("stage", "xmomentum", "ymomentum"):
+            bad += int(np.count_nonzero(d.quantities[name].centroid_values[:nf] != g.quantities[name].centroid_values[ids]))
+        bad += int(d.total_steps != g.total_steps) + int(d.timestep != g.timestep) + int(d.get_time() != g.get_time())
+        bad = int(comm.allreduce_sum(float(bad)))
+        bad_total += bad
+        out["cases"].append({"case": "dam_break %dx%d %s" % (m, n, alg), "steps": int(g.total_steps),
+                             "values_differing_from_1gpu": bad})
+        d._release_device()
+        g._release_device()
+    out["bit_identical"] = bad_total == 0
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=2000, help="cells per side per GPU (2000 -> 16M triangles)")
-    ap.add_argument("--cpu-size", type=int, default=500, help="cells per side of the bounded CPU sample")
-    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--config", default="sweep", choices=["sweep", "tsunami", "structures"])
+    ap.add_argument("--size", type=int, default=None, help="cells per side per GPU (sweep: 2000 -> 16M triangles)")
+    ap.add_argument("--cpu-size", type=int, default=None,
+                    help="cells per side of the CPU runs (default: the reference arm uses --size; the cpu_baseline "
+                         "of the GPU arm a bounded 1000-cell sample)")
+    ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=None)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    if a.size is None:
+        a.size = {"sweep": 2000, "tsunami": 1000, "structures": 2000}[a.config]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "rectangular_cross %dx%d per GPU (%d triangles/GPU), DE1 rk2 FP64, Reflective, "
-                          "Manning 0.03, rain Rate_operator 1e-4 (BASELINE.json configs[2]; --gpus 8 = configs[3])"
-                          % (a.size, a.size, 4 * a.size * a.size),
-              "triangles_per_gpu": 4 * a.size * a.size,
-              "l2_policy": "inputs larger than L2 (>= 7 GB of state per GPU vs 126 MB L2), no flush"}
+    config = workload_config(a)
 
     if a.impl == "reference":
-        if rank != 0:
-            return 0
-        steps = max(1, min(a.steps, a.cpu_steps))
-        r = cpu_reference_run(a.cpu_size, steps, max(1, min(a.warmup, 2)))
-        line = {"impl": "reference", "metric": "triangle-steps/sec (DE1, FP64)", "value": r["value"],
-                "unit": "triangle-steps/s", "n_gpus": a.gpus, "steps": steps, "warmup": max(1, min(a.warmup, 2)),
-                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": "triangle-steps/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
+        if rank == 0:
+            reference_arm(a, config)
         return 0
 
     import anuga_core_b200 as ab
     if ab.device_count() < 1:
         raise SystemExit("bench.py: no sm_100 device (there is no CPU fallback)")
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # NVML initialised before anything is timed
     comm = None
+    t_all = time.time()
     if world > 1:
         from anuga_core_b200 import parallel
-        comm = parallel.init_process_group()
+        comm = parallel.init_process_group(backend="nccl", device=local_rank)
+    parity = None
+    if comm is not None and not a.no_parity_check:
+        parity = multi_gpu_parity_check(comm, local_rank)
+        if rank == 0:
+            log("parity check:", parity)
+        if not parity["bit_identical"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "multi-GPU run differs from single-GPU run",
+                                  "parity_check": parity}))
+            return 3
     t_setup = time.time()
-    d = build_domain(a.size, rank, world, device=local_rank)
+    d = build_domain(a, rank, world, device=local_rank)
+    t_built = time.time()
     if comm is not None:
         d.attach_communicator(comm)
     # first yield: upload + distribute; leaves the state resident
@@ -195,93 +350,139 @@ def main():
     next(it)
     dev = d._dev
     N_local = d.number_of_full_triangles
-    setup_s = time.time() - t_setup
+    t_up = time.time()
+    setup = {"parity_check_s": t_setup - t_all, "build_domain_s": t_built - t_setup, "upload_first_yield_s": t_up - t_built}
+    log("set-up", setup)
 
     def barrier():
         dev.synchronize()
         if comm is not None:
             comm.barrier()
 
-    dev.run_steps(a.warmup, per_kernel=False)
+    host_ops = [op for op in d.fractional_step_operators if getattr(op, "host_side", False)]
+
+    def run_steps(k, per_kernel):
+        """k timesteps of the device-resident loop; CUDA-event milliseconds"""
+        if not host_ops:
+            return dev.run_steps(k, per_kernel=per_kernel)
+        return d.run_steps_with_host_operators(k)
+
+    run_steps(a.warmup, False)
     barrier()
-    sampler = ClockSampler(local_rank)
+    per_kernel_in_region = (world == 1) and not host_ops
+    launches0 = dev.kernel_launch_count()
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
-    launches0 = dev.kernel_launch_count()
     barrier()
-    ms = dev.run_steps(a.steps, per_kernel=True)
+    ms = run_steps(a.steps, per_kernel_in_region)
     barrier()
     launches = dev.kernel_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if not per_kernel_in_region and not host_ops:
+        dev.run_steps(min(a.steps, 50), per_kernel=True)         # same steps again, bracketed kernel by kernel
+        barrier()
+    ms_local = ms
     if comm is not None:
         ms = comm.allreduce_max(ms)
         N_total = comm.allreduce_sum(N_local)
+        ms_min = comm.allreduce_min(ms_local)
     else:
-        N_total = N_local
+        N_total, ms_min = N_local, ms
     value = N_total * a.steps / (ms * 1e-3)
     ktime = dev.kernel_timing()
+    log("timed region: %.3f ms/step (min over ranks %.3f)" % (ms / a.steps, ms_min / a.steps))
 
-    # ---- end to end through the public API with host arrays ------------------------------
+    # ---- end to end through the public API: host arrays -> evolve -> host arrays ------------------
+    K2 = a.e2e_steps or max(10, min(a.steps, 100))
     q = d.quantities
-    K2 = max(1, a.e2e_steps)
-    d.sync_to_host()
+    dt_now = dev.get_statistics().timestep
     barrier()
+    steps_before = d.total_steps
     t0 = time.perf_counter()
-    d.sync_from_host(d.conserved_quantities) # H2D of stage, xmomentum, ymomentum from page-locked numpy arrays
-    dev.evolve(1.0e300, None, K2)            # K2 timesteps, clock scalars read back per batch
-    d._mark_device_newer()
-    d.sync_to_host()                         # D2H of the conserved centroid arrays
+    d.sync_from_host(d.conserved_quantities)       # the host numpy arrays are the input: H2D of stage, x/ymomentum
+    for _t in d.evolve(yieldstep=K2 * dt_now, duration=K2 * dt_now):
+        pass                                       # the yield leaves the conserved centroid arrays on the host (D2H)
+    checksum = float(q["stage"].centroid_values[0] + q["xmomentum"].centroid_values[-1])
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_steps = d.total_steps - steps_before
     if comm is not None:
         e2e_s = comm.allreduce_max(e2e_s)
-    h2d = 3 * 8 * d.number_of_triangles / K2
-    d2h = 3 * 8 * d.number_of_triangles / K2
-    e2e = {"value": N_total * K2 / e2e_s, "unit": "triangle-steps/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "steps_per_call": K2,
-           "note": "Domain.sync_from_host + swk_evolve(%d steps, clock scalars read back per batch) + "
-                   "sync_to_host, wall clock; numpy arrays page-locked with cudaHostRegister" % K2}
-
+    h2d = 3 * 8 * d.number_of_triangles / max(e2e_steps, 1)
+    d2h = 3 * 8 * d.number_of_triangles / max(e2e_steps, 1)
+    e2e = {"value": N_total * e2e_steps / e2e_s, "unit": "triangle-steps/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps_per_call": int(e2e_steps), "seconds": e2e_s, "checksum": checksum,
+           "note": "Domain.sync_from_host (page-locked numpy arrays -> HBM) + `for t in domain.evolve(yieldstep=T, "
+                   "duration=T)` (%d timesteps in the device loop, then the yield's download of stage / xmomentum / "
+                   "ymomentum into the numpy arrays), wall clock, max over ranks" % e2e_steps}
+    if comm is not None:
+        comm.barrier()
     if rank != 0:
+        if comm is not None:
+            comm.finalize()
         return 0
+
     peak, peak_src = measured_peak()
-    dom = max(ktime, key=lambda k: ktime[k][0])
+    alg = alg_of(a)
     kernels = {}
+    k_steps = a.steps if per_kernel_in_region else min(a.steps, 50)        # steps the per-kernel events cover
+    nsub = {"DE0": 1, "DE1": 2, "DE2": 3}[alg]
+    passes = {"extrapolate": nsub, "flux": 1, "update": 1, "flux_update": nsub - 1}
     for name, (tot, n) in ktime.items():
-        if n > 0:
-            avg_ms = tot / n
-            kernels[name] = {"avg_ms": avg_ms, "launches": int(n), "share_of_step": tot / ms,
-                             "achieved_gbs": ALG_BYTES[name] * d.number_of_triangles / (avg_ms * 1e-3) / 1e9}
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            with open(tpath) as fh:
-                traffic = json.load(fh).get(dom)
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_triangle": ALG_BYTES[dom],
-                "whole_step": {"algorithmic_bytes_per_triangle_step": STEP_BYTES["DE1"],
-                               "achieved_gbs": value / world * STEP_BYTES["DE1"] / 1e9,
-                               "frac_of_peak": value / world * STEP_BYTES["DE1"] / 1e9 / peak,
-                               "frac_of_8TBs": value / world * STEP_BYTES["DE1"] / 8.0e12},
-                "kernels": kernels}
-    line = {"metric": "triangle-steps/sec (DE1, FP64)", "value": value, "unit": "triangle-steps/s",
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": dict(config, setup_seconds=setup_s,
-                                                 parallelism="1 process/GPU, strip partition, NCCL halo + min-allreduce"
-                                                 if world > 1 else "single GPU"),
+        if n > 0 and passes[name] > 0:
+            # one PASS over the triangles (with the halo overlap a pass is two launches: halo sources, rest)
+            pass_ms = tot / k_steps / passes[name]
+            kernels[name] = {"avg_ms": pass_ms, "launches": int(n), "launches_per_pass": n / (k_steps * passes[name]),
+                             "share_of_step": (tot / k_steps) / (ms / a.steps),
+                             "achieved_gbs": ALG_BYTES[name] * n_active_triangles(d, name) / (pass_ms * 1e-3) / 1e9}
+    roofline = None
+    if kernels:
+        dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and a.config == "sweep" and a.size == 2000:
+            try:
+                with open(tpath) as fh:
+                    traffic = json.load(fh).get(dom)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_triangle": ALG_BYTES[dom],
+                    "measured_in": ("the timed region (CUDA events around every launch)" if per_kernel_in_region else
+                                    "a second pass of the same steps right after the timed region, which replays "
+                                    "CUDA graphs (NCCL calls included) and cannot carry per-kernel events"),
+                    "whole_step": {"algorithmic_bytes_per_triangle_step": STEP_BYTES[alg],
+                                   "achieved_gbs": value / world * STEP_BYTES[alg] / 1e9,
+                                   "frac_of_peak": value / world * STEP_BYTES[alg] / 1e9 / peak,
+                                   "frac_of_8TBs": value / world * STEP_BYTES[alg] / 8.0e12},
+                    "kernels": kernels}
+    line = {"metric": METRIC if alg == "DE1" else "triangle-steps/sec (%s, FP64)" % alg, "value": value,
+            "unit": "triangle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config,
+            "parallelism": ("1 process/GPU, strip partition, NCCL halo send/recv + uint64 min-allreduce captured in "
+                            "the step's CUDA graph" if world > 1 else "single GPU"),
+            "setup_seconds": setup, "ms_per_step_min_over_ranks": ms_min / a.steps,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+    if parity is not None:
+        line["parity_check"] = parity
     if world == 1 and not a.no_cpu_baseline:
-        r = cpu_reference_run(a.cpu_size, a.cpu_steps, 2)
+        cs = a.cpu_size or min(a.size, 1000)
+        r = cpu_reference_run(a, cs, a.cpu_steps, 2)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
+    if comm is not None:
+        comm.finalize()
     return 0
+
+
+def n_active_triangles(d, kernel):
+    """triangles one launch of `kernel` processes: pass A covers ghosts too, the flux / update kernels
+    only the full triangles of a sub-domain"""
+    if kernel == "extrapolate" or d.numproc == 1:
+        return d.number_of_triangles
+    return d.number_of_full_triangles
 
 
 if __name__ == "__main__":
