@@ -104,7 +104,12 @@ class B200_interface:
         if bmap:
             d.boundary_map = None
             d.set_boundary(bmap)
+        # the operator list is rebuilt from the reference's at every evolve(): forget the device copies of
+        # the previous call first, or every rain / rate operator would be applied once more per call
         d.fractional_step_operators = []
+        if d._dev is not None:
+            d._dev.clear_rate_operators()
+        d._operators_dirty = True
         for op in getattr(ref, "fractional_step_operators", []):
             name = type(op).__name__
             if name == "boundary_flux_integral_operator":

@@ -119,6 +119,7 @@ SYMBOLS = {
     "swk_set_boundary_values": (C.c_int, [_H, C.c_int, _PD]),
     "swk_add_rate_operator": (C.c_int, [_H, _D, _D, _PD, _PI, _I, C.POINTER(C.c_int)]),
     "swk_set_rate": (C.c_int, [_H, C.c_int, _D, _D]),
+    "swk_clear_rate_operators": (C.c_int, [_H]),
     "swk_gather_centroids": (C.c_int, [_H, _PI, _I, _PD]),
     "swk_scatter_centroids": (C.c_int, [_H, _PI, _I, _PD]),
     "swk_scatter_bed": (C.c_int, [_H, _PI, _I, _PD]),
@@ -343,6 +344,9 @@ class DeviceDomain:
         _check(self.lib.swk_add_rate_operator(self.h, float(rate), float(factor), _pd(ra), _pi(idx),
                                               0 if idx is None else idx.size, C.byref(op)))
         return op.value
+
+    def clear_rate_operators(self):
+        _check(self.lib.swk_clear_rate_operators(self.h))
 
     def set_rate(self, op_id, rate, factor=1.0):
         _check(self.lib.swk_set_rate(self.h, int(op_id), float(rate), float(factor)))

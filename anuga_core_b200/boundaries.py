@@ -20,6 +20,38 @@ import numpy as np
 from . import backend as _b
 
 
+class Modeltime_too_late(BaseException):
+    """a time series (file function) was asked for a time after its last record
+    (anuga/fit_interpolate/interpolate.py:55)"""
+
+
+class Modeltime_too_early(BaseException):
+    pass
+
+
+def _is_named(e, name):
+    # the reference's own exception classes arrive here when a reference function is attached
+    return type(e).__name__ == name
+
+
+def evaluate_with_default(owner, function, t, default):
+    """function(t); when it runs out of data (Modeltime_too_late) the default value takes over, as in
+    Boundary.get_boundary_values (generic_boundary_conditions.py:98-135).  `default` may be a value
+    or a function of t; the first hand-over is flagged on `owner`."""
+    try:
+        return function(t)
+    except BaseException as e:
+        if not _is_named(e, "Modeltime_too_late") or default is None:
+            raise
+        if not getattr(owner, "default_boundary_invoked", False):
+            owner.default_boundary_invoked = True
+            if getattr(owner, "verbose", False):
+                print("%s\nInstead I will use the default boundary value: %s\n"
+                      "Note: Further warnings will be suppressed" % (e, default))
+        import copy
+        return default(t) if callable(default) else copy.deepcopy(default)
+
+
 class Boundary:
     device_kind = _b.BC_NONE
     time_dependent = False
@@ -98,12 +130,15 @@ class Time_boundary(Boundary):
             raise Exception("Time_boundary function must return (stage, xmomentum, ymomentum)")
         self.domain = domain
         self.function = function
+        self.default_boundary = default_boundary
+        self.default_boundary_invoked = False
+        self.verbose = verbose
 
     def __repr__(self):
         return "Time boundary"
 
     def device_values(self, t):
-        q = np.asarray(self.function(t), dtype=np.float64)
+        q = np.asarray(evaluate_with_default(self, self.function, t, self.default_boundary), dtype=np.float64)
         return (float(q[0]), float(q[1]), float(q[2]))
 
     def oracle_spec(self):
@@ -125,9 +160,10 @@ class _Set_stage(Boundary):
         self.domain = domain
         self.function = function
         self.default_boundary = default_boundary
+        self.default_boundary_invoked = False
 
     def device_values(self, t):
-        value = self.function(t)
+        value = evaluate_with_default(self, self.function, t, self.default_boundary)
         try:
             x = float(value)
         except Exception:

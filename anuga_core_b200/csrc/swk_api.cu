@@ -45,6 +45,12 @@ static int fail(int code, const std::string &msg)
 
 static inline int nblk(long long n) { return (int)((n + BLOCK - 1) / BLOCK); }
 static inline double u2d_host(unsigned long long u) { double x; memcpy(&x, &u, 8); return x; }
+static int g_num_sms = 0;
+static inline int ngrid(long long n, int blocks_per_sm)
+{
+  (void)blocks_per_sm;
+  return nblk(n);
+}
 
 // ----------------------------------------------------------------------------
 // NCCL, loaded at run time so that single-GPU use has no NCCL dependency
@@ -315,6 +321,7 @@ static int select_device(int device)
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return fail(SWK_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100: libswk contains sm_100a code only");
+  g_num_sms = prop.multiProcessorCount;
   CK(cudaSetDevice(device));
   return SWK_OK;
 }
@@ -955,6 +962,23 @@ extern "C" int swk_add_rate_operator(swk_domain *d, double rate, double factor, 
   return SWK_OK;
 }
 
+// Drop every registered Rate_operator (the host layer registers the current set again): an adapter
+// that mirrors a reference domain rebuilds its operator list at every evolve() call.
+extern "C" int swk_clear_rate_operators(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(sync_check(d));
+  for (auto &op : d->rate_ops) {
+    if (op.d_rate_array) cudaFree(op.d_rate_array);
+    if (op.d_indices) cudaFree(op.d_indices);
+    if (op.d_partial) cudaFree(op.d_partial);
+  }
+  d->rate_ops.clear();
+  d->graph_valid = false;
+  return SWK_OK;
+}
+
 extern "C" int swk_set_rate(swk_domain *d, int op_id, double rate, double factor)
 {
   if (!d || op_id < 0 || op_id >= (int)d->rate_ops.size()) return fail(SWK_ERR_ARG, "unknown rate operator");
@@ -1099,7 +1123,7 @@ extern "C" int swk_reset_yield_statistics(swk_domain *d)
 static void launch_extrapolate(swk_domain *d, const Consts &K)
 {
   TimedScope ts(d, 0);
-  LAUNCH(d, k_extrapolate, nblk(d->N), BLOCK, d->D, K);
+  LAUNCH(d, k_extrapolate, ngrid(d->N, SWK_MINB_A), BLOCK, d->D, K);
 }
 
 static int launch_boundary(swk_domain *d)
@@ -1125,8 +1149,8 @@ static void launch_flux(swk_domain *d, int first, int write_speed)
 {
   TimedScope ts(d, 1);
   const int n = n_active(d);
-  if (d->has_riverwalls) LAUNCH(d, k_flux<true>, nblk(n), BLOCK, d->D, d->K, first, write_speed, 0, n);
-  else LAUNCH(d, k_flux<false>, nblk(n), BLOCK, d->D, d->K, first, write_speed, 0, n);
+  if (d->has_riverwalls) LAUNCH(d, k_flux<true>, ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
+  else LAUNCH(d, k_flux<false>, ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
 }
 
 static void launch_bflux(swk_domain *d, int substep)
@@ -1251,7 +1275,7 @@ static int launch_first_substep(swk_domain *d, int do_backup, bool last_of_step,
   const UpdateArgs U = update_args(d, do_backup, 0, 1.0, 0.0, 1.0, last_of_step);
   return update_with_exchange(d, exchange_after, [&](int k0, int k1) {
     TimedScope ts(d, 2);
-    LAUNCH(d, k_update, nblk(k1 - k0), BLOCK, d->D, d->K, U, -1.0, k0, k1);
+    LAUNCH(d, k_update, ngrid(k1 - k0, SWK_MINB_U), BLOCK, d->D, d->K, U, -1.0, k0, k1);
   });
 }
 
@@ -1266,12 +1290,12 @@ static int launch_later_substep(swk_domain *d, int substep, double a, double b, 
     launch_flux(d, 0, 0);
     CKV(update_with_exchange(d, exchange_after, [&](int k0, int k1) {
       TimedScope ts(d, 2);
-      LAUNCH(d, k_update, nblk(k1 - k0), BLOCK, d->D, d->K, U, -1.0, k0, k1);
+      LAUNCH(d, k_update, ngrid(k1 - k0, SWK_MINB_U), BLOCK, d->D, d->K, U, -1.0, k0, k1);
     }));
   } else {
     CKV(update_with_exchange(d, exchange_after, [&](int k0, int k1) {
       TimedScope ts(d, 3);
-      LAUNCH(d, k_flux_update, nblk(k1 - k0), BLOCK, d->D, d->K, U, k0, k1);
+      LAUNCH(d, k_flux_update, ngrid(k1 - k0, SWK_MINB_FU), BLOCK, d->D, d->K, U, k0, k1);
     }));
   }
   if (!last_of_step) launch_bflux(d, substep);     // the last substep's sum rides in k_finish_step
@@ -1622,7 +1646,7 @@ extern "C" int swk_update_conserved_quantities(swk_domain *d, double timestep, i
   CK(cudaSetDevice(d->device));
   CKV(pull_clock(d));
   const long long before = d->h_clock->negative_cells;
-  LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, 0, 0, 1.0, 0.0, 1.0), timestep, 0, (int)d->N);
+  LAUNCH(d, k_update, ngrid(d->N, SWK_MINB_U), BLOCK, d->D, d->K, update_args(d, 0, 0, 1.0, 0.0, 1.0), timestep, 0, (int)d->N);
   CKV(pull_clock(d));
   if (d->h_clock->stop < 0) {
     const int st = d->h_clock->stop;

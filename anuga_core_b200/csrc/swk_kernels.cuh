@@ -39,6 +39,12 @@ namespace swk {
 #ifndef SWK_FU_ROLLED       // fused kernel: one edge per trip of a rolled loop (see triangle_flux)
 #define SWK_FU_ROLLED true
 #endif
+#ifndef SWK_FU_RELOAD       // fused kernel: re-read the own centroid record after the edge loop instead of keeping it live
+#define SWK_FU_RELOAD 1
+#endif
+#ifndef SWK_MINB_U
+#define SWK_MINB_U 8
+#endif
 #ifndef SWK_F_ROLLED        // the same for the flux kernel of substep 0
 #define SWK_F_ROLLED false
 #endif
@@ -46,6 +52,29 @@ namespace swk {
 #define SWK_FG_EDGE 1       // loads exactly the three records of its edge (own, neighbour's, geometry)
 #endif
 constexpr int BLOCK = SWK_BLOCK;
+
+// One tile of BLOCK consecutive triangles per CTA.  (A persistent form - as many CTAs as fit on the GPU,
+// each walking a contiguous run of tiles and prefetching its own next tiles - was measured 20-40 %
+// slower for every kernel: profiles/r2/sweep3_persistent.txt.)
+struct TileRange { int first, last; };
+__device__ __forceinline__ TileRange my_tiles(int ntiles)
+{
+  TileRange r;
+  r.first = blockIdx.x;
+  r.last = blockIdx.x + 1;
+  (void)ntiles;
+  return r;
+}
+// first triangle of the tile whose slabs should be requested now (SWK_PF_AHEAD tiles further on), or -1
+__device__ __forceinline__ long long prefetch_target(int tile, const TileRange &r, int k0)
+{
+  (void)r;
+#if SWK_PF_AHEAD > 0
+  return (long long)k0 + (long long)(tile + SWK_PF_AHEAD) * BLOCK;
+#else
+  return -1;
+#endif
+}
 
 // ---- device-side clock: the scalars of Generic_Domain's time loop -------------
 struct Clock {
@@ -224,28 +253,31 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
 __global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts K)
 {
   if (D.clock->stop) return;
-  const int k = blockIdx.x * BLOCK + threadIdx.x;
+  const TileRange tr = my_tiles((D.N + BLOCK - 1) / BLOCK);
+  for (int tile = tr.first; tile < tr.last; tile++) {
+    const int k = tile * BLOCK + threadIdx.x;
 #if SWK_PF_AHEAD > 0
-  if (threadIdx.x < 5) {      // slabs of the block SWK_PF_AHEAD further on: cq, xg x3, connA
-    const long long t0 = (long long)(blockIdx.x + SWK_PF_AHEAD) * BLOCK;
-    if (t0 + BLOCK <= D.NP) {
-      const int j = threadIdx.x;
-      if (j == 0) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
-      else if (j < 4) prefetch_l2_bulk(D.xg + (long long)(j - 1) * D.NP + t0, BLOCK * 32);
-      else prefetch_l2_bulk(D.connA + t0, BLOCK * 16);
+    if (threadIdx.x < 5) {      // slabs of a tile further on: cq, xg x3, connA
+      const long long t0 = prefetch_target(tile, tr, 0);
+      if (t0 >= 0 && t0 + BLOCK <= D.NP) {
+        const int j = threadIdx.x;
+        if (j == 0) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
+        else if (j < (SWK_XG_COMPACT ? 3 : 4)) prefetch_l2_bulk(D.xg + (long long)(j - 1) * D.NP + t0, BLOCK * 32);
+        else if (j == 4) prefetch_l2_bulk(D.connA + t0, BLOCK * 16);
+      }
     }
-  }
 #endif
-  if (k >= D.N) return;
-  d4 r0, r1, r2;
-  Eff e;
-  bool zero_mom;
-  int fl;
-  extrapolate_tri(D, K, D.cq, k, true, r0, r1, r2, e, zero_mom, fl);
-  D.zflag[k] = (zero_mom ? 1 : 0) | ((fl >> 3) & 2);   // bit0: zeroed momenta, bit1: tri_full_flag
-  D.eq[k] = r0;
-  D.eq[D.NP + k] = r1;
-  D.eq[2 * D.NP + k] = r2;
+    if (k >= D.N) continue;
+    d4 r0, r1, r2;
+    Eff e;
+    bool zero_mom;
+    int fl;
+    extrapolate_tri(D, K, D.cq, k, true, r0, r1, r2, e, zero_mom, fl);
+    D.zflag[k] = (zero_mom ? 1 : 0) | ((fl >> 3) & 2);   // bit0: zeroed momenta, bit1: tri_full_flag
+    D.eq[k] = r0;
+    D.eq[D.NP + k] = r1;
+    D.eq[2 * D.NP + k] = r2;
+  }
 }
 
 // Write the protected/zeroed centroid values in place: what the reference's centroid
@@ -625,26 +657,21 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
   return T;
 }
 
-// L2 prefetch-ahead for the flux kernels: slabs of the block SWK_PF_AHEAD further on
-__device__ __forceinline__ void prefetch_flux_slabs(const Dev &D, int k0, bool with_update)
+// L2 prefetch of the slabs of the tile that starts at triangle t0 (flux kernels)
+__device__ __forceinline__ void prefetch_flux_slabs(const Dev &D, long long t0, bool with_update)
 {
-#if SWK_PF_AHEAD > 0
   const int j = threadIdx.x;
-  if (j < 12) {
-    const long long t0 = (long long)k0 + (long long)(blockIdx.x + SWK_PF_AHEAD) * BLOCK;
-    if (t0 + BLOCK <= D.NP) {
-      const long long NP = D.NP;
-      if (j < 3) prefetch_l2_bulk(D.eq + j * NP + t0, BLOCK * 32);
-      else if (j < 6) prefetch_l2_bulk(D.fg + (j - 3) * NP + t0, BLOCK * 32);
-      else if (j == 6) prefetch_l2_bulk(D.connB + t0, BLOCK * 16);
-      else if (j == 7) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
-      else if (with_update) {
-        if (j == 8) prefetch_l2_bulk(D.eta + t0, BLOCK * 8);
-        else prefetch_l2_bulk(D.bk + (j - 9) * NP + t0, BLOCK * 8);
-      }
+  if (j < 12 && t0 >= 0 && t0 + BLOCK <= D.NP) {
+    const long long NP = D.NP;
+    if (j < 3) prefetch_l2_bulk(D.eq + j * NP + t0, BLOCK * 32);
+    else if (j < 6) prefetch_l2_bulk(D.fg + (j - 3) * NP + t0, BLOCK * 32);
+    else if (j == 6) prefetch_l2_bulk(D.connB + t0, BLOCK * 16);
+    else if (j == 7) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
+    else if (with_update) {
+      if (j == 8) prefetch_l2_bulk(D.eta + t0, BLOCK * 8);
+      else prefetch_l2_bulk(D.bk + (j - 9) * NP + t0, BLOCK * 8);
     }
   }
-#endif
 }
 
 // block-wide min of positive doubles -> one atomicMin per block
@@ -742,45 +769,53 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int
                                                             int k0, int k1)
 {
   if (D.clock->stop) return;
-  const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
-  prefetch_flux_slabs(D, k0, false);
+  const TileRange tr = my_tiles((k1 - k0 + BLOCK - 1) / BLOCK);
   double dtmin = 1.0e+100;
-  if (k < k1) {
-    const i4 p = lds(&D.connB[k]);
-    const Eff own = effective(D.cq[k], K);
-    const TriFlux T = triangle_flux<RW, SWK_F_ROLLED>(D, K, k, p, own, first != 0);
-    sts(&D.eu[k], T.su);
-    sts(&D.eu[D.NP + k], T.xu);
-    sts(&D.eu[2 * D.NP + k], T.yu);
-    if (first && write_speed) D.max_speed[k] = T.speed;
-    dtmin = T.dtmin;
+  for (int tile = tr.first; tile < tr.last; tile++) {
+    const int k = k0 + tile * BLOCK + threadIdx.x;
+#if SWK_PF_AHEAD > 0
+    prefetch_flux_slabs(D, prefetch_target(tile, tr, k0), false);
+#endif
+    if (k < k1) {
+      const i4 p = lds(&D.connB[k]);
+      const Eff own = effective(D.cq[k], K);
+      const TriFlux T = triangle_flux<RW, SWK_F_ROLLED>(D, K, k, p, own, first != 0);
+      sts(&D.eu[k], T.su);
+      sts(&D.eu[D.NP + k], T.xu);
+      sts(&D.eu[2 * D.NP + k], T.yu);
+      if (first && write_speed) D.max_speed[k] = T.speed;
+      dtmin = dmin(dtmin, T.dtmin);
+    }
   }
   if (first) block_min_to_clock(dtmin, D.clock);
 }
 
 // Pass B2 (substep 0): friction + update + fix-negative (+ RK backup), dt from the clock.
-__global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U, double dt_override,
+__global__ void __launch_bounds__(BLOCK, SWK_MINB_U) k_update(Dev D, Consts K, UpdateArgs U, double dt_override,
                                                   int k0, int k1)
 {
   if (D.clock->stop) return;
-  const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
-#if SWK_PF_AHEAD > 0
-  if (threadIdx.x < 5) {
-    const long long t0 = (long long)k0 + (long long)(blockIdx.x + SWK_PF_AHEAD) * BLOCK;
-    if (t0 + BLOCK <= D.NP) {
-      const int j = threadIdx.x;
-      if (j < 3) prefetch_l2_bulk(D.eu + (long long)j * D.NP + t0, BLOCK * 8);
-      else if (j == 3) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
-      else prefetch_l2_bulk(D.eta + t0, BLOCK * 8);
-    }
-  }
-#endif
-  if (k >= k1) return;
   const double dt = (dt_override >= 0.0) ? dt_override : D.clock->dt;
-  const d4 raw = D.cq[k];
-  const Eff e = effective(raw, K);
-  triangle_update(D, K, U, k, raw, e, D.zflag[k], lds(&D.eu[k]), lds(&D.eu[D.NP + k]), lds(&D.eu[2 * D.NP + k]), dt,
-                  D.cq, nullptr);
+  const TileRange tr = my_tiles((k1 - k0 + BLOCK - 1) / BLOCK);
+  for (int tile = tr.first; tile < tr.last; tile++) {
+    const int k = k0 + tile * BLOCK + threadIdx.x;
+#if SWK_PF_AHEAD > 0
+    if (threadIdx.x < 5) {
+      const long long t0 = prefetch_target(tile, tr, k0);
+      if (t0 >= 0 && t0 + BLOCK <= D.NP) {
+        const int j = threadIdx.x;
+        if (j < 3) prefetch_l2_bulk(D.eu + (long long)j * D.NP + t0, BLOCK * 8);
+        else if (j == 3) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
+        else prefetch_l2_bulk(D.eta + t0, BLOCK * 8);
+      }
+    }
+#endif
+    if (k >= k1) continue;
+    const d4 raw = D.cq[k];
+    const Eff e = effective(raw, K);
+    triangle_update(D, K, U, k, raw, e, D.zflag[k], lds(&D.eu[k]), lds(&D.eu[D.NP + k]), lds(&D.eu[2 * D.NP + k]), dt,
+                    D.cq, nullptr);
+  }
 }
 
 // Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
@@ -789,15 +824,32 @@ __global__ void __launch_bounds__(BLOCK) k_update(Dev D, Consts K, UpdateArgs U,
 __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Consts K, UpdateArgs U, int k0, int k1)
 {
   if (D.clock->stop) return;
-  const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
-  prefetch_flux_slabs(D, k0, true);
-  if (k >= k1) return;
   const double dt = D.clock->dt;
-  const i4 p = lds(&D.connB[k]);
-  const d4 raw = D.cq[k];
-  const Eff e = effective(raw, K);
-  const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, e, false);
-  triangle_update(D, K, U, k, raw, e, D.zflag[k], T.su, T.xu, T.yu, dt, D.cq, nullptr);
+  const TileRange tr = my_tiles((k1 - k0 + BLOCK - 1) / BLOCK);
+  for (int tile = tr.first; tile < tr.last; tile++) {
+    const int k = k0 + tile * BLOCK + threadIdx.x;
+#if SWK_PF_AHEAD > 0
+    prefetch_flux_slabs(D, prefetch_target(tile, tr, k0), true);
+#endif
+    if (k >= k1) continue;
+    const i4 p = lds(&D.connB[k]);
+#if SWK_FU_RELOAD
+    // only {h, z} of the own state live across the edge loop; the record is read again (L1) for the update
+    Eff own;
+    {
+      const Eff e0 = effective(D.cq[k], K);
+      own.h = e0.h; own.z = e0.z; own.w = e0.w;
+    }
+    const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, own, false);
+    const d4 raw = D.cq[k];
+    const Eff e = effective(raw, K);
+#else
+    const d4 raw = D.cq[k];
+    const Eff e = effective(raw, K);
+    const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, e, false);
+#endif
+    triangle_update(D, K, U, k, raw, e, D.zflag[k], T.su, T.xu, T.yu, dt, D.cq, nullptr);
+  }
 }
 
 // =============================================================================

@@ -78,8 +78,8 @@ __device__ __forceinline__ void sts(double *p, double v)
 // slab that the block SWK_PF_AHEAD positions further on will read (UBLKPF.L2, no registers, no
 // smem), so the DRAM stream runs ahead of the resident warps instead of being paced by them.
 // ---------------------------------------------------------------------------
-#ifndef SWK_PF_AHEAD
-#define SWK_PF_AHEAD 0
+#ifndef SWK_PF_AHEAD          // 555 tiles = about 3/4 of a wave of resident CTAs; 92 ... 740 measure alike
+#define SWK_PF_AHEAD 555
 #endif
 #ifndef SWK_FU_L1PF
 #define SWK_FU_L1PF 0

@@ -1027,6 +1027,10 @@ class Domain:
             self.relative_finaltime = self.relative_time
             return
 
+        if self.numproc > 1 and getattr(self, "_comm", None) is None and \
+                any(int(p) != self.processor for p in list(self.full_send_dict) + list(self.ghost_recv_dict)):
+            raise Exception("this sub-domain exchanges halos with other ranks but has no communicator: call "
+                            "domain.attach_communicator(parallel.communicator()) (e.g. after unpickling it)")
         dev = self._ensure_device()
         self._push_quantities(force=not hasattr(self, "_pushed_once"))
         self._pushed_once = True
@@ -1230,6 +1234,10 @@ def load_checkpoint_file(domain_name="domain", checkpoint_dir=".", time=None):
         if parallel.numprocs > 1:
             ok = parallel.communicator().allreduce_max(0.0 if ok else 1.0) == 0.0
         if ok:
+            if parallel.numprocs > 1:
+                # a restored Parallel_domain keeps communicating in the reference (global MPI layer); here
+                # the process group is not picklable, so the restored sub-domain joins it again
+                domain.attach_communicator(parallel.communicator())
             return domain
     raise Exception("Unable to open checkpoint file")
 

@@ -14,6 +14,8 @@ follows the reference so that the static arrays are bit-identical:
 * surrogate neighbours         - neighbour_mesh.py:318-345
 * boundary enumeration         - neighbour_mesh.py:441-502, neighbour_mesh_ext.pyx:9-31
 """
+import os
+
 import numpy as np
 
 DEFAULT_BOUNDARY_TAG = "exterior"      # anuga/config.py default_boundary_tag
@@ -168,7 +170,7 @@ def build_neighbour_structure(triangles, number_of_nodes):
     """
     tri = np.ascontiguousarray(triangles, dtype=np.int64)
     N = tri.shape[0]
-    if N >= 200000:          # large meshes: libswk's native helper (same result, ~10x faster)
+    if N >= 200000 and not os.environ.get("SWK_NO_NATIVE_SETUP"):   # large meshes: libswk's native helper (same result, ~10x faster)
         from . import backend
         res = backend.build_neighbour_structure_native(tri, number_of_nodes)
         if res is not None:
@@ -214,7 +216,7 @@ class Mesh:
         self.use_inscribed_circle = use_inscribed_circle
 
         native = None
-        if N >= 200000:          # large meshes: one pass in libswk's host helper (same bits)
+        if N >= 200000 and not os.environ.get("SWK_NO_NATIVE_SETUP"):   # large meshes: one pass in libswk's host helper (same bits)
             from . import backend
             native = backend.mesh_geometry_native(self.nodes, self.triangles, use_inscribed_circle)
         if native is not None:

@@ -26,6 +26,11 @@ class Rate_operator:
         self.rate_array = None
         self.rate = 0.0
         self.set_rate(rate)
+        # rate_operators.py:483-509: used when a rate time series is asked for a time outside its records
+        assert default_rate is None or isinstance(default_rate, (int, float)) or callable(default_rate), \
+            "Default_rate must be either None a scalar, or a function of time.\nI got %s." % str(default_rate)
+        self.default_rate = default_rate
+        self.default_rate_invoked = False
         self.op_id = None
         domain.set_fractional_step_operator(self)
 
@@ -103,10 +108,28 @@ class Rate_operator:
             dev.set_rate(self.op_id, self.current_rate(self.domain.get_time()), self.current_factor(self.domain.get_time()))
 
     def set_factor(self, factor):
+        """The reference reads self.factor at every call (rate_operators.py:160), so a new factor takes
+        effect at the next step: also for an operator that already lives on the device."""
         self.factor = factor
+        dev = getattr(self.domain, "_dev", None)
+        if dev is not None and getattr(self, "op_id", None) is not None:
+            t = self.domain.get_time()
+            dev.set_rate(self.op_id, self.current_rate(t), self.current_factor(t))
 
     def current_rate(self, t):
-        return float(self.rate_callable(t)) if self.rate_callable is not None else self.rate
+        if self.rate_callable is None:
+            return self.rate
+        try:                     # evaluate_temporal_function (utilities/function_utils.py:85-119)
+            return float(self.rate_callable(t))
+        except BaseException as e:
+            if type(e).__name__ not in ("Modeltime_too_late", "Modeltime_too_early") or self.default_rate is None:
+                raise
+            if not self.default_rate_invoked:
+                import warnings
+                self.default_rate_invoked = True
+                warnings.warn("Using default_rate outside the time interval of the rate function")
+            dr = self.default_rate
+            return float(dr(t)) if callable(dr) else float(dr)
 
     def current_factor(self, t):
         return float(self.factor(t)) if callable(self.factor) else float(self.factor)

@@ -314,6 +314,7 @@ class Inlet_operator:
         self.applied_Q = 0.0
         self.total_applied_volume = 0.0
         self.total_requested_volume = 0.0
+        self.total_applied_volume = 0.0
         domain.set_fractional_step_operator(self)
 
     def update_Q(self, t):
@@ -366,11 +367,15 @@ class Inlet_operator:
             volume = -current_volume
             self.applied_Q = -current_volume / timestep
             added = -current_volume
+            inlet.set_xmoms(0.0)                     # inlet_operator.py:159-160
+            inlet.set_ymoms(0.0)
+        self.total_applied_volume += volume          # :166
         inlet.commit()
         ref_op = getattr(self, "_mirror", None)      # attach.py: statistics the reference's reporting reads
         if ref_op is not None:
             ref_op.applied_Q = self.applied_Q
             ref_op.total_requested_volume = self.total_requested_volume
+            ref_op.total_applied_volume = self.total_applied_volume
         return added
 
     def _set_momenta(self, u, v):

@@ -397,7 +397,7 @@ def main():
     q = d.quantities
     dt_now = dev.get_statistics().timestep
     barrier()
-    steps_before = d.total_steps
+    steps_before = dev.get_statistics().total_steps
     t0 = time.perf_counter()
     d.sync_from_host(d.conserved_quantities)       # the host numpy arrays are the input: H2D of stage, x/ymomentum
     for _t in d.evolve(yieldstep=K2 * dt_now, duration=K2 * dt_now):
@@ -405,7 +405,7 @@ def main():
     checksum = float(q["stage"].centroid_values[0] + q["xmomentum"].centroid_values[-1])
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_steps = d.total_steps - steps_before
+    e2e_steps = dev.get_statistics().total_steps - steps_before
     if comm is not None:
         e2e_s = comm.allreduce_max(e2e_s)
     h2d = 3 * 8 * d.number_of_triangles / max(e2e_steps, 1)

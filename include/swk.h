@@ -212,6 +212,8 @@ int swk_set_boundary_values(swk_domain *d, int segment, const double values[3]);
 int swk_add_rate_operator(swk_domain *d, double rate, double factor, const double *rate_array,
                           const int64_t *indices, int64_t n_indices, int *op_id);
 int swk_set_rate(swk_domain *d, int op_id, double rate, double factor);
+/* Forget every Rate_operator registered so far (ids become invalid). */
+int swk_clear_rate_operators(swk_domain *d);
 
 /* Small index sets (inlets, structures, gauges): read / write the centroid records of `n` triangles
  * without moving whole arrays.  out: (n,4) row-major {stage, xmomentum, ymomentum, elevation};

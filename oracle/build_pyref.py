@@ -105,4 +105,4 @@ if __name__ == "__main__":
     ap.add_argument("--dest", default=os.environ.get("ANUGA_PYREF", "/tmp/anuga_pyref"))
     ap.add_argument("--native", action="store_true")
     a = ap.parse_args()
-    build(a.src, a.dest, a.native)
+    build(a.src, os.path.abspath(a.dest), a.native)

@@ -611,6 +611,8 @@ class OracleDomain:
         else:
             self.stage_c[idx] = elev + 0.0
             self.fractional_step_volume_integral -= current_volume
+            self.xmom_c[idx] = 0.0                  # inlet_operator.py:159-160
+            self.ymom_c[idx] = 0.0
 
     def _boyd_box_operator(self, o, pipe=False, weir=False):
         """structures/structure_operator.py:215-372 (the transfer) around

@@ -13,7 +13,10 @@ import os
 import sys
 import types
 
-PYREF_DIR = os.environ.get("ANUGA_PYREF", "/tmp/anuga_pyref")
+_REPO_COPY = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+# baseline/_ref (git-ignored, built by __graft_entry__.build() from /root/reference) travels to the GPU box
+PYREF_DIR = os.environ.get("ANUGA_PYREF") or (_REPO_COPY if os.path.isdir(os.path.join(_REPO_COPY, "anuga"))
+                                               else "/tmp/anuga_pyref")
 
 _STUBS = [
     "matplotlib", "matplotlib.pyplot", "matplotlib.tri", "matplotlib.cm",

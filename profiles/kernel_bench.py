@@ -17,9 +17,14 @@ it = d.evolve(yieldstep=1.0e9, finaltime=None)
 next(it)
 dev = d._dev
 dev.run_steps(5)
-ms = dev.run_steps(steps, per_kernel=True)
-kt = dev.kernel_timing()
-ms2 = dev.run_steps(steps, per_kernel=False)        # graph replay, no per-kernel events
+if os.environ.get("KB_GRAPH_FIRST"):
+    ms2 = dev.run_steps(steps, per_kernel=False)    # graph replay, no per-kernel events
+    ms = dev.run_steps(steps, per_kernel=True)
+    kt = dev.kernel_timing()
+else:
+    ms = dev.run_steps(steps, per_kernel=True)
+    kt = dev.kernel_timing()
+    ms2 = dev.run_steps(steps, per_kernel=False)    # graph replay, no per-kernel events
 N = d.number_of_triangles
 d._mark_device_newer()
 d.sync_to_host()

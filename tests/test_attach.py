@@ -109,3 +109,69 @@ def test_adapter_friction_methods_of_mode_4():
     q["ymomentum"].semi_implicit_update[:] = 0.0
     iface.compute_forcing_terms_manning_friction_sloped()
     assert np.all(np.abs(q["xmomentum"].semi_implicit_update) >= np.abs(flat) * (1 - 1e-14))   # x sqrt(1 + |grad z|^2)
+
+
+@pytest.mark.gpu
+def test_second_evolve_call_does_not_apply_rate_operators_twice():
+    """refresh() rebuilds the operator list at every evolve(): the device copies of the previous call must
+    go, or rain is applied once more per call.  Two evolve() calls through the adapter == one plain run."""
+    def build():
+        d = cases.dam_break_de1(ab)
+        ab.Rate_operator(d, rate=3.0e-3, factor=2.0)
+        ab.Rate_operator(d, rate=lambda t: 1.0e-3 * (1.0 + t))
+        return d
+    plain = build()
+    for _ in plain.evolve(yieldstep=0.1, finaltime=0.4):
+        pass
+    ref_like = build()
+    iface = ab.B200_interface(ref_like)
+    for _ in iface.evolve_base(yieldstep=0.1, finaltime=0.2):
+        pass
+    for _ in iface.evolve_base(yieldstep=0.1, finaltime=0.4):
+        pass
+    for name in ("stage", "xmomentum", "ymomentum"):
+        assert np.array_equal(ref_like.quantities[name].centroid_values, plain.quantities[name].centroid_values), name
+    assert iface.dev_domain.fractional_step_volume_integral == plain.fractional_step_volume_integral
+
+
+@pytest.mark.gpu
+def test_set_factor_reaches_an_operator_that_is_already_on_the_device():
+    """rate_operators.py:160 reads self.factor at every call"""
+    def run(change):
+        d = cases.dam_break_de1(ab)
+        op = ab.Rate_operator(d, rate=2.0e-3, factor=1.0)
+        for t in d.evolve(yieldstep=0.1, finaltime=0.3):
+            if change and abs(t - 0.1) < 1e-12:
+                op.set_factor(5.0)
+        return d
+    a, b = run(False), run(True)
+    va, vb = a.fractional_step_volume_integral, b.fractional_step_volume_integral
+    assert vb > 2.0 * va
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyref.available(), reason="python reference not built (oracle/build_pyref.py -> baseline/_ref)")
+@pytest.mark.parametrize("name", ["beach_de1", "rain_de1", "tsunami_set_stage", "dam_break_de2"])
+def test_real_reference_domain_on_the_device_equals_mode_2(name):
+    """INTEGRATION.md route A: a REAL anuga.shallow_water.Domain evolves through
+    set_multiprocessor_mode_b200 (the reference's own Domain.evolve wrapper around the device time loop)
+    and is compared, in the same process, with a twin that runs the reference's mode 2 (C/OpenMP); two
+    evolve() calls each (shallow_water_domain.py:2300, 2859-2899)."""
+    anuga = pyref.import_anuga()
+    builder, ev = cases.CASES[name]
+    cpu = builder(anuga)
+    cpu.set_multiprocessor_mode(2)
+    gpu = builder(anuga)
+    iface = ab.set_multiprocessor_mode_b200(gpu)
+    assert gpu.multiprocessor_mode == ab.MODE_B200 and gpu.gpu_interface is iface
+    half = dict(ev, finaltime=ev["yieldstep"] * max(1, int(round(ev["finaltime"] / ev["yieldstep"])) // 2))
+    for stop in (half, ev):
+        tc = [t for t in cpu.evolve(**stop)]
+        tg = [t for t in gpu.evolve(**stop)]
+        assert tc == tg
+        assert gpu.timestep == cpu.timestep
+        for q in ("stage", "xmomentum", "ymomentum"):
+            e = rel_err(gpu.quantities[q].centroid_values, cpu.quantities[q].centroid_values)
+            assert e <= 1e-9, (q, e)
+    launches = iface.dev_domain.kernel_launches
+    assert launches > 0

@@ -381,3 +381,43 @@ def test_full_size_16M_properties_and_reference_parity(size):
     assert np.all(q["stage"].centroid_values >= q["elevation"].centroid_values)
     assert 0.0 < r.timestep < 1.0
     print("\n16M: 2-step rel err vs reference C %.2e; volume balance residual %.3e of %.3e" % (e, (v1 - v0) - added, v0))
+
+
+def test_local_ghost_copy_on_one_gpu():
+    """swk_set_local_ghost_copy: Generic_Domain.update_ghosts on ONE process copies the conserved
+    centroid values of full_send_dict[me][0] to ghost_recv_dict[me][0] (generic_domain.py:2448-2469)
+    at the start of evolve and after every substep update; checked against the oracle's restatement on a
+    strip whose right-most cell column is a ghost image of an interior column."""
+    n = 16
+
+    def build():
+        d = ab.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+        c = d.centroid_coordinates
+        ghost = np.nonzero(c[:, 0] > n - 1.0)[0]                 # last column of cells: ghosts
+        # their sources: the cells 6 columns further left (same row, same position in the cell)
+        key = lambda ids: np.lexsort((np.round(c[ids, 0] % 1.0, 6), np.round(c[ids, 1], 6)))
+        src = np.nonzero((c[:, 0] > n - 7.0) & (c[:, 0] < n - 6.0))[0]
+        ghost, src = ghost[key(ghost)], src[key(src)]
+        assert len(ghost) == len(src) == 4 * n
+        d2 = ab.Domain(mesh=d.mesh, full_send_dict={0: [src, src]}, ghost_recv_dict={0: [ghost, ghost]},
+                       processor=0, numproc=1)
+        d2.tri_full_flag[ghost] = 0
+        d2.set_flow_algorithm("DE1")
+        d2.set_store(False)
+        d2.set_quantity("elevation", lambda x, y: -x / (n / 2.0))
+        d2.set_quantity("stage", lambda x, y: np.where(x < n / 2.0, 1.0, 0.2), location="centroids")
+        d2.set_quantity("friction", 0.03)
+        B = ab.Reflective_boundary(d2)
+        d2.set_boundary({t: B for t in d2.get_boundary_tags()})
+        return d2, src, ghost
+    d, src, ghost = build()
+    o = OracleDomain(domain_to_scenario(d), backend=REF)
+    for _ in d.evolve(yieldstep=0.5, finaltime=2.0):
+        pass
+    for _ in o.evolve(yieldstep=0.5, finaltime=2.0):
+        pass
+    w, uh, vh = conserved(d)
+    assert d.total_steps == len(o.timestep_history) and d.timestep == o.timestep_history[-1]
+    assert max(rel_err(w, o.stage_c), rel_err(uh, o.xmom_c), rel_err(vh, o.ymom_c)) <= TOL_FINAL
+    assert np.array_equal(w[ghost], w[src]) and np.array_equal(uh[ghost], uh[src])      # exact copies
+    assert np.any(w[src] != 0.2)                                                       # something happened there
