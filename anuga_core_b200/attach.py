@@ -41,6 +41,8 @@ _BOUNDARY_BY_NAME = {
     "Time_stage_zero_momentum_boundary": lambda B, d: _bnd.Time_stage_zero_momentum_boundary(d, B.f),
     "Flather_external_stage_zero_velocity_boundary":
         lambda B, d: _bnd.Flather_external_stage_zero_velocity_boundary(d, B.function),
+    "Characteristic_stage_boundary":
+        lambda B, d: _bnd.Characteristic_stage_boundary(d, B.function, B.default_stage),
 }
 
 _SCALARS = ("epsilon", "H0", "g", "minimum_allowed_height", "maximum_allowed_speed", "evolve_max_timestep",

@@ -34,6 +34,7 @@ BC_NONE, BC_REFLECTIVE, BC_DIRICHLET, BC_TRANSMISSIVE = 0, 1, 2, 3
 BC_TRANSMISSIVE_N_ZERO_T_SET_STAGE, BC_TRANSMISSIVE_MOMENTUM_SET_STAGE = 4, 5
 BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6
 BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY = 7
+BC_CHARACTERISTIC_STAGE = 8
 
 _I = C.c_int64
 _D = C.c_double
@@ -120,6 +121,13 @@ SYMBOLS = {
     "swk_add_rate_operator": (C.c_int, [_H, _D, _D, _PD, _PI, _I, C.POINTER(C.c_int)]),
     "swk_set_rate": (C.c_int, [_H, C.c_int, _D, _D]),
     "swk_clear_rate_operators": (C.c_int, [_H]),
+    "swk_set_momentum_forcing": (C.c_int, [_H, _PD, _PD, _I]),
+    "swk_set_rate_dynamic": (C.c_int, [_H, C.c_int, C.c_int]),
+    "swk_set_boundary_values_substep": (C.c_int, [_H, C.c_int, C.c_int, _PD]),
+    "swk_step_begin": (C.c_int, [_H, _D, _D]),
+    "swk_step_first": (C.c_int, [_H, C.POINTER(SwkEvolveResult)]),
+    "swk_step_rest": (C.c_int, [_H]),
+    "swk_step_end": (C.c_int, [_H, C.POINTER(SwkEvolveResult)]),
     "swk_gather_centroids": (C.c_int, [_H, _PI, _I, _PD]),
     "swk_scatter_centroids": (C.c_int, [_H, _PI, _I, _PD]),
     "swk_scatter_bed": (C.c_int, [_H, _PI, _I, _PD]),
@@ -345,6 +353,14 @@ class DeviceDomain:
                                               0 if idx is None else idx.size, C.byref(op)))
         return op.value
 
+    def set_momentum_forcing(self, fx, fy):
+        if fx is None:
+            _check(self.lib.swk_set_momentum_forcing(self.h, None, None, 0))
+            return
+        fx = np.ascontiguousarray(fx, dtype=np.float64)
+        fy = np.ascontiguousarray(fy, dtype=np.float64)
+        _check(self.lib.swk_set_momentum_forcing(self.h, _pd(fx), _pd(fy), fx.size))
+
     def clear_rate_operators(self):
         _check(self.lib.swk_clear_rate_operators(self.h))
 
@@ -426,6 +442,31 @@ class DeviceDomain:
         ft = -1.0 if relative_finaltime is None else float(relative_finaltime)
         _check(self.lib.swk_evolve(self.h, float(relative_yieldtime), ft, int(max_steps), C.byref(r)))
         return r
+
+    # -- host-paced time loop (time-dependent boundary values / rates) -------------------------
+    def step_begin(self, relative_yieldtime, relative_finaltime=None):
+        ft = -1.0 if relative_finaltime is None else float(relative_finaltime)
+        _check(self.lib.swk_step_begin(self.h, float(relative_yieldtime), ft))
+
+    def step_first(self):
+        r = SwkEvolveResult()
+        _check(self.lib.swk_step_first(self.h, C.byref(r)))
+        return r
+
+    def step_rest(self):
+        _check(self.lib.swk_step_rest(self.h))
+
+    def step_end(self):
+        r = SwkEvolveResult()
+        _check(self.lib.swk_step_end(self.h, C.byref(r)))
+        return r
+
+    def set_boundary_values_substep(self, segment, substep, values):
+        v = (_D * 3)(*[float(x) for x in values])
+        _check(self.lib.swk_set_boundary_values_substep(self.h, int(segment), int(substep), v))
+
+    def set_rate_dynamic(self, op_id, dynamic=True):
+        _check(self.lib.swk_set_rate_dynamic(self.h, int(op_id), int(bool(dynamic))))
 
     def run_steps(self, n_steps, per_kernel=False):
         """exactly n_steps timesteps, CUDA-event timed on the library stream -> elapsed ms"""

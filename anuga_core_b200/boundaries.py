@@ -11,6 +11,7 @@ k_boundary_values (csrc/swk_kernels.cuh) and follows evaluate_segment of
   Transmissive_stage_zero_momentum_boundary                        :543-551
   Time_stage_zero_momentum_boundary                                :616-635
   Flather_external_stage_zero_velocity_boundary                    :1096-1266
+  Characteristic_stage_boundary                                    :639-843
   Transmissive_boundary    anuga/abstract_2d_finite_volumes/generic_boundary_conditions.py:173-193
   Dirichlet_boundary                                               :221-264
   Time_boundary                                                    :370-411
@@ -197,6 +198,20 @@ class Flather_external_stage_zero_velocity_boundary(_Set_stage):
 
     def __init__(self, domain=None, function=None):
         _Set_stage.__init__(self, domain, function)
+
+
+class Characteristic_stage_boundary(_Set_stage):
+    """stage from a function of time, momentum from the Riemann invariants of a simple incoming wave
+    (boundaries.py:639-843, the vectorised evaluate_segment)"""
+    device_kind = _b.BC_CHARACTERISTIC_STAGE
+    _oracle_kind = "characteristic_stage"
+
+    def __init__(self, domain=None, function=None, default_stage=0.0):
+        _Set_stage.__init__(self, domain, function, default_boundary=None)
+        self.default_stage = default_stage
+
+    def __repr__(self):
+        return "Characteristic_stage_boundary (%s) (%s) " % (self.domain, self.default_stage)
 
 
 class Transmissive_stage_zero_momentum_boundary(Boundary):

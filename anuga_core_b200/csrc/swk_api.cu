@@ -7,6 +7,7 @@
 // No CPU fallback: every entry point needs a CUDA device that can run sm_100a code.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -43,6 +44,9 @@ static int fail(int code, const std::string &msg)
     if (r_ != SWK_OK) return r_;                                                        \
   } while (0)
 
+// value table layout (doubles): boundary values [SEG_MAX][3 substeps][3], then [OP_MAX]{rate, factor}
+constexpr int SEG_MAX = 4097, OP_MAX = 1024;
+constexpr size_t VALS_OPS = (size_t)SEG_MAX * 9, VALS_TOTAL = VALS_OPS + 2 * (size_t)OP_MAX;
 static inline int nblk(long long n) { return (int)((n + BLOCK - 1) / BLOCK); }
 static inline double u2d_host(unsigned long long u) { double x; memcpy(&x, &u, 8); return x; }
 static int g_num_sms = 0;
@@ -115,6 +119,7 @@ static int load_nccl()
 // ----------------------------------------------------------------------------
 struct RateOp {
   double rate, factor;
+  bool dynamic = false;        // rate / factor change every step: read from the device value table, never fused
   double *d_rate_array = nullptr;
   int *d_indices = nullptr;
   int n = 0;
@@ -158,9 +163,11 @@ struct swk_domain {
   // owned device memory
   d4 *cq = nullptr, *eq = nullptr, *xg = nullptr, *fg = nullptr, *bq = nullptr;
   i4 *connA = nullptr, *connB = nullptr;
-  double *eu = nullptr, *bk = nullptr, *eta = nullptr, *max_speed = nullptr, *vcoord = nullptr;
+  double *eu = nullptr, *bk = nullptr, *eta = nullptr, *max_speed = nullptr, *vcoord = nullptr, *wind = nullptr;
   unsigned char *zflag = nullptr;
-  int *rw_counter = nullptr, *rw_rowIndex = nullptr;
+  int *rw_counter = nullptr, *rw_rowIndex = nullptr, *rw_list = nullptr;
+  int n_rw_list = 0;           // triangles with at least one riverwall edge (device ids, ascending)
+  std::vector<int> h_rw_list;
   double *rw_elevation = nullptr, *rw_hydraulic = nullptr;
   Clock *d_clock = nullptr, *h_clock = nullptr;
   double *staging = nullptr;     // 3*N doubles
@@ -174,11 +181,15 @@ struct swk_domain {
   int *b_cell = nullptr, *b_edge = nullptr, *b_seg = nullptr;
   std::vector<int> h_b_seg;
   std::vector<int> seg_kind;
-  std::vector<double> seg_val;
   int *d_seg_kind = nullptr;
-  double *d_seg_val = nullptr;
   int seg_cap = 0;
-  bool seg_dirty = true;
+  bool seg_dirty = true;       // kinds / edge->segment map changed (structure; uploaded with a sync)
+  // value table: boundary values [segment][substep][3], then {rate, factor} of every Rate_operator.
+  // Page-locked host copy + device copy, refreshed by one async copy per step when dirty.
+  double *h_vals = nullptr, *d_vals = nullptr;
+  bool vals_dirty = true;
+  cudaEvent_t ev_vals = nullptr;
+  bool vals_inflight = false;
 
   std::vector<RateOp> rate_ops;
   int *d_ghost_full = nullptr, *d_ghost_ghost = nullptr;
@@ -198,14 +209,16 @@ struct swk_domain {
   bool overlap = true;         // SWK_NO_OVERLAP=1: halo exchange in-stream
 
   int64_t launches = 0;
+  int64_t launches_mark = 0;
 
   // one whole timestep captured as a CUDA graph: small meshes are launch-bound (a 40k-triangle
   // step is ~10 kernels of a few microseconds each)
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
+  cudaGraph_t graph[3] = {nullptr, nullptr, nullptr};          // whole step, first half, second half
+  cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};
   bool graph_valid = false;
   bool use_graph = true;
-  int64_t launches_per_step = 0;
+  bool capturing = false;
+  int64_t launches_per_graph[3] = {0, 0, 0};
 
   // optional per-kernel event timing (bench.py roofline)
   bool timing = false;
@@ -250,6 +263,7 @@ static void make_consts(swk_domain *d)
   K.low_froude = (int)p.low_froude;
   K.protect = 1;
   K.pad = 0;
+  K.sqrt_g = pow(p.g, 0.5);             // Python's gravity**0.5 (boundaries.py:802): the host's pow
   TimeParams &T = d->TP;
   T.CFL = p.CFL;
   T.evolve_max_timestep = p.evolve_max_timestep;
@@ -452,9 +466,9 @@ extern "C" int swk_destroy(swk_domain *d)
   cudaSetDevice(d->device);
   if (d->stream) cudaStreamSynchronize(d->stream);
   void *ptrs[] = {d->cq, d->eq, d->xg, d->fg, d->bq, d->connA, d->connB, d->eu, d->bk, d->eta, d->max_speed,
-                  d->vcoord, d->zflag, d->rw_counter, d->rw_rowIndex, d->rw_elevation, d->rw_hydraulic,
+                  d->vcoord, d->wind, d->zflag, d->rw_counter, d->rw_rowIndex, d->rw_list, d->rw_elevation, d->rw_hydraulic,
                   d->d_clock, d->staging, d->acct_val, d->pos_b, d->acct_keys, d->acct_keys_pos, d->b_cell, d->b_edge, d->b_seg, d->d_seg_kind,
-                  d->d_seg_val, d->d_new2old, d->d_ghost_full, d->d_ghost_ghost, d->d_ident_b};
+                  d->d_vals, d->d_new2old, d->d_ghost_full, d->d_ghost_ghost, d->d_ident_b};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &op : d->rate_ops) {
@@ -469,9 +483,13 @@ extern "C" int swk_destroy(swk_domain *d)
     if (pe.d_recv_buf) cudaFree(pe.d_recv_buf);
   }
   if (d->comm_obj && d->comm_owned) swk_comm_destroy(d->comm_obj);
-  if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
-  if (d->graph) cudaGraphDestroy(d->graph);
+  for (int w = 0; w < 3; w++) {
+    if (d->graph_exec[w]) cudaGraphExecDestroy(d->graph_exec[w]);
+    if (d->graph[w]) cudaGraphDestroy(d->graph[w]);
+  }
   if (d->h_clock) cudaFreeHost(d->h_clock);
+  if (d->h_vals) cudaFreeHost(d->h_vals);
+  if (d->ev_vals) cudaEventDestroy(d->ev_vals);
   if (d->ev_update) cudaEventDestroy(d->ev_update);
   if (d->ev_halo) cudaEventDestroy(d->ev_halo);
   if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
@@ -666,6 +684,12 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
       }
     if (maxc > m->number_of_riverwall_edges) return fail(SWK_ERR_ARG, "edge_river_wall_counter exceeds number_of_riverwall_edges");
     CKV(dalloc(&d->rw_counter, 3 * NP)); CKV(upload(d->rw_counter, rc));
+    std::vector<int> wl;
+    for (int64_t k = 0; k < N; k++)
+      if (rc[k] || rc[NP + k] || rc[2 * NP + k]) wl.push_back((int)k);
+    d->n_rw_list = (int)wl.size();
+    CKV(dalloc(&d->rw_list, wl.size())); CKV(upload(d->rw_list, wl));
+    d->h_rw_list = wl;
     const int64_t nrw = m->number_of_riverwall_edges;
     std::vector<double> re(m->riverwall_elevation, m->riverwall_elevation + nrw);
     std::vector<int> ri(nrw);
@@ -714,13 +738,17 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
   d->h_clock->recorded_max_timestep = p->evolve_min_timestep;
   d->h_clock->dt_min_bits = 0x7FF0000000000000ULL;
   CK(cudaMemcpy(d->d_clock, d->h_clock, sizeof(Clock), cudaMemcpyHostToDevice));
+  CK(cudaHostAlloc((void **)&d->h_vals, VALS_TOTAL * sizeof(double), cudaHostAllocDefault));
+  memset(d->h_vals, 0, VALS_TOTAL * sizeof(double));
+  CKV(dalloc(&d->d_vals, VALS_TOTAL)); CK(cudaMemset(d->d_vals, 0, VALS_TOTAL * sizeof(double)));
+  CK(cudaEventCreateWithFlags(&d->ev_vals, cudaEventDisableTiming));
 
   Dev &D = d->D;
   D.N = (int)N; D.NP = (int)NP; D.M = (int)M;
   D.cq = d->cq; D.eq = d->eq; D.xg = d->xg; D.fg = d->fg;
   D.connA = d->connA; D.connB = d->connB;
   D.eu = d->eu; D.bk = d->bk; D.eta = d->eta; D.zflag = d->zflag; D.max_speed = d->max_speed;
-  D.bq = d->bq; D.vcoord = d->vcoord; D.clock = d->d_clock;
+  D.bq = d->bq; D.vcoord = d->vcoord; D.wind = nullptr; D.clock = d->d_clock;
   D.acct_val = d->acct_val; D.pos_b = d->pos_b; D.acct_keys = d->acct_keys; D.acct_keys_pos = d->acct_keys_pos;
   D.n_acct = d->n_acct; D.n_acct_keys = d->n_acct_keys;
   D.rw_counter = d->rw_counter; D.rw_elevation = d->rw_elevation; D.rw_rowIndex = d->rw_rowIndex;
@@ -872,40 +900,61 @@ extern "C" int swk_get_quantity(swk_domain *d, int q, double *host, int64_t n)
 // ----------------------------------------------------------------------------
 // boundaries, operators, ghosts
 // ----------------------------------------------------------------------------
+// the host is about to change h_vals: a copy of the previous contents that is still queued must go first
+static int vals_writable(swk_domain *d)
+{
+  if (d->vals_inflight) {
+    CK(cudaEventSynchronize(d->ev_vals));
+    d->vals_inflight = false;
+  }
+  return SWK_OK;
+}
+
+static int push_values(swk_domain *d)
+{
+  if (!d->vals_dirty) return SWK_OK;
+  const size_t ns = d->seg_kind.size(), no = d->rate_ops.size();
+  if (ns > 0) CK(cudaMemcpyAsync(d->d_vals, d->h_vals, 9 * ns * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  if (no > 0)
+    CK(cudaMemcpyAsync(d->d_vals + VALS_OPS, d->h_vals + VALS_OPS, 2 * no * sizeof(double), cudaMemcpyHostToDevice,
+                       d->stream));
+  CK(cudaEventRecord(d->ev_vals, d->stream));
+  d->vals_inflight = true;
+  d->vals_dirty = false;
+  return SWK_OK;
+}
+
 static int push_segments(swk_domain *d)
 {
-  if (!d->seg_dirty) return SWK_OK;
-  const int ns = (int)d->seg_kind.size();
-  if (ns > d->seg_cap) {
-    if (d->d_seg_kind) cudaFree(d->d_seg_kind);
-    if (d->d_seg_val) cudaFree(d->d_seg_val);
-    d->seg_cap = std::max(16, 2 * ns);
-    CKV(dalloc(&d->d_seg_kind, d->seg_cap));
-    CKV(dalloc(&d->d_seg_val, 3 * d->seg_cap));
+  if (d->seg_dirty) {
+    const int ns = (int)d->seg_kind.size();
+    if (ns > d->seg_cap) {
+      if (d->d_seg_kind) cudaFree(d->d_seg_kind);
+      d->seg_cap = std::max(16, 2 * ns);
+      CKV(dalloc(&d->d_seg_kind, d->seg_cap));
+    }
+    if (ns > 0)
+      CK(cudaMemcpyAsync(d->d_seg_kind, d->seg_kind.data(), ns * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    if (d->M > 0)
+      CK(cudaMemcpyAsync(d->b_seg, d->h_b_seg.data(), d->M * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    CK(cudaStreamSynchronize(d->stream));   // host vectors may change after return
+    d->seg_dirty = false;
   }
-  if (ns > 0) {
-    CK(cudaMemcpyAsync(d->d_seg_kind, d->seg_kind.data(), ns * sizeof(int), cudaMemcpyHostToDevice, d->stream));
-    CK(cudaMemcpyAsync(d->d_seg_val, d->seg_val.data(), 3 * ns * sizeof(double), cudaMemcpyHostToDevice, d->stream));
-  }
-  if (d->M > 0)
-    CK(cudaMemcpyAsync(d->b_seg, d->h_b_seg.data(), d->M * sizeof(int), cudaMemcpyHostToDevice, d->stream));
-  CK(cudaStreamSynchronize(d->stream));   // host vectors may change after return
-  d->seg_dirty = false;
-  return SWK_OK;
+  return push_values(d);
 }
 
 extern "C" int swk_set_boundary_segment(swk_domain *d, int segment, int kind, const int64_t *ids, int64_t n_ids,
                                         const double values[3])
 {
   if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
-  if (segment < 0 || segment > 4096) return fail(SWK_ERR_ARG, "segment id out of range");
-  if (kind < SWK_BC_NONE || kind > SWK_BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY) return fail(SWK_ERR_ARG, "unknown boundary kind");
-  if ((int)d->seg_kind.size() <= segment) {
-    d->seg_kind.resize(segment + 1, 0);
-    d->seg_val.resize(3 * (segment + 1), 0.0);
-  }
+  if (segment < 0 || segment >= SEG_MAX) return fail(SWK_ERR_ARG, "segment id out of range");
+  if (kind < SWK_BC_NONE || kind > SWK_BC_CHARACTERISTIC_STAGE) return fail(SWK_ERR_ARG, "unknown boundary kind");
+  if ((int)d->seg_kind.size() <= segment) d->seg_kind.resize(segment + 1, 0);
   d->seg_kind[segment] = kind;
-  for (int j = 0; j < 3; j++) d->seg_val[3 * segment + j] = values ? values[j] : 0.0;
+  CKV(vals_writable(d));
+  for (int sub = 0; sub < 3; sub++)
+    for (int j = 0; j < 3; j++) d->h_vals[(3 * segment + sub) * 3 + j] = values ? values[j] : 0.0;
+  d->vals_dirty = true;
   for (int64_t j = 0; j < n_ids; j++) {
     if (ids[j] < 0 || ids[j] >= d->M) return fail(SWK_ERR_ARG, "boundary id out of range");
     d->h_b_seg[ids[j]] = segment;
@@ -919,8 +968,22 @@ extern "C" int swk_set_boundary_values(swk_domain *d, int segment, const double 
 {
   if (!d || !values) return fail(SWK_ERR_ARG, "NULL argument");
   if (segment < 0 || segment >= (int)d->seg_kind.size()) return fail(SWK_ERR_ARG, "unknown segment");
-  for (int j = 0; j < 3; j++) d->seg_val[3 * segment + j] = values[j];
-  d->seg_dirty = true;                 // values live in device tables: the graph stays valid
+  CKV(vals_writable(d));
+  for (int sub = 0; sub < 3; sub++)
+    for (int j = 0; j < 3; j++) d->h_vals[(3 * segment + sub) * 3 + j] = values[j];
+  d->vals_dirty = true;                // values live in device tables: the graph stays valid
+  return SWK_OK;
+}
+
+// values of one RK substep only (0: at the start of the step, 1: second flux evaluation, 2: third)
+extern "C" int swk_set_boundary_values_substep(swk_domain *d, int segment, int substep, const double values[3])
+{
+  if (!d || !values) return fail(SWK_ERR_ARG, "NULL argument");
+  if (segment < 0 || segment >= (int)d->seg_kind.size()) return fail(SWK_ERR_ARG, "unknown segment");
+  if (substep < 0 || substep > 2) return fail(SWK_ERR_ARG, "substep must be 0, 1 or 2");
+  CKV(vals_writable(d));
+  for (int j = 0; j < 3; j++) d->h_vals[(3 * segment + substep) * 3 + j] = values[j];
+  d->vals_dirty = true;
   return SWK_OK;
 }
 
@@ -956,9 +1019,41 @@ extern "C" int swk_add_rate_operator(swk_domain *d, double rate, double factor, 
   }
   op.nblocks = nblk(op.n);
   CKV(dalloc(&op.d_partial, op.nblocks));
+  if ((int)d->rate_ops.size() >= OP_MAX) return fail(SWK_ERR_ARG, "too many rate operators");
+  CKV(vals_writable(d));
+  d->h_vals[VALS_OPS + 2 * d->rate_ops.size()] = rate;
+  d->h_vals[VALS_OPS + 2 * d->rate_ops.size() + 1] = factor;
+  d->vals_dirty = true;
   d->rate_ops.push_back(op);
   d->graph_valid = false;
   if (op_id) *op_id = (int)d->rate_ops.size() - 1;
+  return SWK_OK;
+}
+
+// Explicit momentum forcing that does not depend on the state (Wind_stress, shallow_water/forcing.py:80-215:
+// explicit_update += S*u, S*v per triangle): two (N,) arrays in the caller's triangle order, added to the
+// explicit updates inside the update kernels.  NULL, NULL switches it off.
+extern "C" int swk_set_momentum_forcing(swk_domain *d, const double *xmom_force, const double *ymom_force, int64_t n)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(sync_check(d));
+  const bool was_on = d->D.wind != nullptr;
+  if (!xmom_force || !ymom_force) {
+    d->D.wind = nullptr;
+    if (was_on) d->graph_valid = false;
+    return SWK_OK;
+  }
+  if (n != d->N) return fail(SWK_ERR_ARG, "forcing arrays must have one entry per triangle");
+  if (!d->wind) CKV(dalloc(&d->wind, 2 * d->NP));
+  std::vector<double> w(2 * d->NP, 0.0);
+  for (int64_t k = 0; k < d->N; k++) {
+    w[k] = xmom_force[d->new2old[k]];
+    w[d->NP + k] = ymom_force[d->new2old[k]];
+  }
+  CKV(upload(d->wind, w));
+  d->D.wind = d->wind;
+  if (!was_on) d->graph_valid = false;      // the pointer is a kernel argument
   return SWK_OK;
 }
 
@@ -986,6 +1081,21 @@ extern "C" int swk_set_rate(swk_domain *d, int op_id, double rate, double factor
   op.rate = rate;
   op.factor = factor;
   if (!op.d_rate_array) op.all_nonneg = (rate >= 0.0) ? 1 : 0;
+  CKV(vals_writable(d));
+  d->h_vals[VALS_OPS + 2 * op_id] = rate;
+  d->h_vals[VALS_OPS + 2 * op_id + 1] = factor;
+  d->vals_dirty = true;
+  if (!op.dynamic) d->graph_valid = false;     // a static operator's scalars are baked into the launches
+  return SWK_OK;
+}
+
+// Mark an operator whose rate / factor are functions of time: its scalars are then read from the device
+// value table at every step (refreshed by swk_set_rate), it is applied by its own kernel, and changing
+// them does not invalidate the captured step.
+extern "C" int swk_set_rate_dynamic(swk_domain *d, int op_id, int dynamic)
+{
+  if (!d || op_id < 0 || op_id >= (int)d->rate_ops.size()) return fail(SWK_ERR_ARG, "unknown rate operator");
+  d->rate_ops[op_id].dynamic = dynamic != 0;
   d->graph_valid = false;
   return SWK_OK;
 }
@@ -1126,13 +1236,13 @@ static void launch_extrapolate(swk_domain *d, const Consts &K)
   LAUNCH(d, k_extrapolate, ngrid(d->N, SWK_MINB_A), BLOCK, d->D, K);
 }
 
-static int launch_boundary(swk_domain *d)
+static int launch_boundary(swk_domain *d, int substep = 0)
 {
-  CKV(push_segments(d));
+  if (!d->capturing) CKV(push_segments(d));     // (table copies are not part of a captured step)
   if (d->M == 0) return SWK_OK;
   Segments S;
   S.b_cell = d->b_cell; S.b_edge = d->b_edge; S.b_seg = d->b_seg;
-  S.seg_kind = d->d_seg_kind; S.seg_val = d->d_seg_val;
+  S.seg_kind = d->d_seg_kind; S.seg_val = d->d_vals; S.substep = substep;
   if (d->seg_kind.empty()) return SWK_OK;
   LAUNCH(d, k_boundary_values, nblk(d->M), BLOCK, d->D, S, d->K, (int)d->P.centroid_transmissive_bc);
   return SWK_OK;
@@ -1164,7 +1274,7 @@ static bool rain_is_fusable(const swk_domain *d)
 {
   if (d->rate_ops.size() != 1) return false;
   const RateOp &op = d->rate_ops[0];
-  return !op.d_indices && !op.d_rate_array && op.all_nonneg;
+  return !op.d_indices && !op.d_rate_array && op.all_nonneg && !op.dynamic;
 }
 
 static UpdateArgs update_args(swk_domain *d, int do_backup, int do_saxpy, double a, double b, double divide_by,
@@ -1186,9 +1296,11 @@ static UpdateArgs update_args(swk_domain *d, int do_backup, int do_saxpy, double
 
 static void launch_rate_ops(swk_domain *d)
 {
+  if (!d->capturing) push_values(d);             // dynamic operators read {rate, factor} from the device table
   for (auto &op : d->rate_ops) {
+    const double *rf = op.dynamic ? d->d_vals + VALS_OPS + 2 * (&op - &d->rate_ops[0]) : nullptr;
     LAUNCH(d, k_rate_operator, op.nblocks, BLOCK, d->D, op.rate, op.factor, op.d_rate_array, op.d_indices, op.n,
-           op.all_nonneg, op.d_partial);
+           op.all_nonneg, op.d_partial, rf);
     LAUNCH(d, k_rate_finish, 1, 1024, d->d_clock, op.d_partial, op.nblocks);
   }
 }
@@ -1264,14 +1376,27 @@ static int launch_dt_allreduce(swk_domain *d)
   return SWK_OK;
 }
 
-// one substep-0 sequence: A, boundary, B1 (+ boundary-flux sum, dt), B2 [+ ghost update]
-static int launch_first_substep(swk_domain *d, int do_backup, bool last_of_step, bool exchange_after)
+// ---- one timestep, in two halves ------------------------------------------------------------
+// first half : A, boundary values, B1 (+ boundary-flux sum), global dt, update_timestep
+//              -> the clock holds the timestep
+// second half: B2 [+ ghost update], the later RK substeps (A, boundary, fused B [+ ghost update]),
+//              fractional steps, k_finish_step
+// A resident run launches both back to back (one graph); a run with time-dependent boundary values or
+// rates stops between the halves, once per step, so that the host can evaluate its functions at the
+// substep times t + dt (and t + dt/2), which exist only now (swk_step_first / swk_step_rest).
+static int launch_first_half(swk_domain *d)
 {
   launch_extrapolate(d, d->K);
-  CKV(launch_boundary(d));
+  CKV(launch_boundary(d, 0));
   launch_flux(d, 1, (int)d->P.track_max_speed);
   CKV(launch_dt_allreduce(d));
   LAUNCH(d, k_update_timestep, 1, 1024, d->D, d->TP, 1);
+  return SWK_OK;
+}
+
+// B2 of substep 0 [+ ghost update]
+static int launch_first_update(swk_domain *d, int do_backup, bool last_of_step, bool exchange_after)
+{
   const UpdateArgs U = update_args(d, do_backup, 0, 1.0, 0.0, 1.0, last_of_step);
   return update_with_exchange(d, exchange_after, [&](int k0, int k1) {
     TimedScope ts(d, 2);
@@ -1284,40 +1409,45 @@ static int launch_later_substep(swk_domain *d, int substep, double a, double b, 
                                 bool last_of_step, bool exchange_after)
 {
   launch_extrapolate(d, d->K);
-  CKV(launch_boundary(d));
+  CKV(launch_boundary(d, substep));
   const UpdateArgs U = update_args(d, 0, 1, a, b, divide_by, last_of_step);
   if (d->has_riverwalls) {
-    launch_flux(d, 0, 0);
-    CKV(update_with_exchange(d, exchange_after, [&](int k0, int k1) {
-      TimedScope ts(d, 2);
-      LAUNCH(d, k_update, ngrid(k1 - k0, SWK_MINB_U), BLOCK, d->D, d->K, U, -1.0, k0, k1);
-    }));
+    // fused everywhere except on the wall triangles, which follow in k_update_list; the halo exchange
+    // (if any) starts after both, so a wall triangle that is a halo source travels with its new state
+    const int n = n_active(d);
+    {
+      TimedScope ts(d, 3);
+      LAUNCH(d, k_flux_update<true>, ngrid(n, SWK_MINB_FU), BLOCK, d->D, d->K, U, 0, n);
+    }
+    // (ghost triangles are not evaluated under a communicator: only the wall triangles below n)
+    const int nw = (int)(std::lower_bound(d->h_rw_list.begin(), d->h_rw_list.end(), n) - d->h_rw_list.begin());
+    if (nw > 0) LAUNCH(d, k_update_list, nblk(nw), BLOCK, d->D, d->K, U, d->rw_list, nw);
+    if (exchange_after) CKV(launch_ghosts(d));
   } else {
     CKV(update_with_exchange(d, exchange_after, [&](int k0, int k1) {
       TimedScope ts(d, 3);
-      LAUNCH(d, k_flux_update, ngrid(k1 - k0, SWK_MINB_FU), BLOCK, d->D, d->K, U, k0, k1);
+      LAUNCH(d, k_flux_update<false>, ngrid(k1 - k0, SWK_MINB_FU), BLOCK, d->D, d->K, U, k0, k1);
     }));
   }
   if (!last_of_step) launch_bflux(d, substep);     // the last substep's sum rides in k_finish_step
   return SWK_OK;
 }
 
-// one full timestep = one iteration of _evolve_base's while loop (generic_domain.py:1835-1862)
-static int launch_step(swk_domain *d)
+static int launch_second_half(swk_domain *d)
 {
   // step_start_time / dt_min_bits are (re)set by the previous k_finish_step (or by the host before
-  // the first step of a call), so a step is: [A, bc, B1, dt, B2] [A, bc, B]* finish.
-  // Ghost updates (:1857, 2013-2015, 2096, 2135) ride with the update kernel that precedes them; the
-  // one after the step can do so only when no separate fractional-step kernel still changes the state.
+  // the first step of a call).  Ghost updates (generic_domain.py:1857, 2013-2015, 2096, 2135) ride with
+  // the update kernel that precedes them; the one after the step can do so only when no separate
+  // fractional-step kernel still changes the state.
   const int method = (int)d->P.timestepping_method;
   const bool ops_fused = d->rate_ops.empty() || rain_is_fusable(d);
   if (method == 1) {
-    CKV(launch_first_substep(d, 0, true, ops_fused));
+    CKV(launch_first_update(d, 0, true, ops_fused));
   } else if (method == 2) {
-    CKV(launch_first_substep(d, 1, false, d->P.ghost_layer_width < 4));
+    CKV(launch_first_update(d, 1, false, d->P.ghost_layer_width < 4));
     CKV(launch_later_substep(d, 1, 0.5, 0.5, 1.0, true, ops_fused));
   } else {
-    CKV(launch_first_substep(d, 1, false, true));
+    CKV(launch_first_update(d, 1, false, true));
     CKV(launch_later_substep(d, 1, 0.25, 0.75, 1.0, false, true));
     CKV(launch_later_substep(d, 2, 2.0, 1.0, 3.0, true, ops_fused));
   }
@@ -1335,24 +1465,38 @@ static int launch_step(swk_domain *d)
   return SWK_OK;
 }
 
-// Capture launch_step once; every parameter baked into the kernel nodes (scalars, boundary tables,
-// rain rate, halo lists) invalidates the graph through d->graph_valid = false.
-static int ensure_graph(swk_domain *d)
+// one full timestep = one iteration of _evolve_base's while loop (generic_domain.py:1835-1862)
+static int launch_step(swk_domain *d)
 {
-  if (d->graph_exec && d->graph_valid) return SWK_OK;
-  if (d->graph_exec) { cudaGraphExecDestroy(d->graph_exec); d->graph_exec = nullptr; }
-  if (d->graph) { cudaGraphDestroy(d->graph); d->graph = nullptr; }
+  CKV(launch_first_half(d));
+  return launch_second_half(d);
+}
+
+// Capture a launch sequence once (which: 0 whole step, 1 first half, 2 second half); every parameter
+// baked into the kernel nodes (scalars, boundary kinds, static rain rate, halo lists) invalidates the
+// graphs through d->graph_valid = false.  Boundary VALUES and dynamic rates live in device tables.
+static int ensure_graph(swk_domain *d, int which)
+{
+  if (!d->graph_valid) {
+    for (int w = 0; w < 3; w++) {
+      if (d->graph_exec[w]) { cudaGraphExecDestroy(d->graph_exec[w]); d->graph_exec[w] = nullptr; }
+      if (d->graph[w]) { cudaGraphDestroy(d->graph[w]); d->graph[w] = nullptr; }
+    }
+    d->graph_valid = true;
+  }
+  if (d->graph_exec[which]) return SWK_OK;
   CKV(push_segments(d));                       // host->device table copies must not be captured
   const int64_t l0 = d->launches;
   CK(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
-  int rc = launch_step(d);
-  cudaError_t e = cudaStreamEndCapture(d->stream, &d->graph);
+  d->capturing = true;
+  int rc = (which == 0) ? launch_step(d) : ((which == 1) ? launch_first_half(d) : launch_second_half(d));
+  d->capturing = false;
+  cudaError_t e = cudaStreamEndCapture(d->stream, &d->graph[which]);
   if (rc != SWK_OK) return rc;
   if (e != cudaSuccess) return fail(SWK_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-  d->launches_per_step = d->launches - l0;
+  d->launches_per_graph[which] = d->launches - l0;
   d->launches = l0;
-  CK(cudaGraphInstantiate(&d->graph_exec, d->graph, 0));
-  d->graph_valid = true;
+  CK(cudaGraphInstantiate(&d->graph_exec[which], d->graph[which], 0));
   return SWK_OK;
 }
 
@@ -1366,18 +1510,22 @@ static bool graph_ok(const swk_domain *d)
   return d->use_graph && !d->timing;
 }
 
-static int run_one_step(swk_domain *d)
+// which: 0 whole step, 1 first half, 2 second half
+static int run_part(swk_domain *d, int which)
 {
   if (d->comm && !d->nccl_warm) CKV(warm_nccl(d));
   if (graph_ok(d)) {
-    CKV(ensure_graph(d));
-    CKV(push_segments(d));                     // time-independent kinds only; cheap when clean
-    CK(cudaGraphLaunch(d->graph_exec, d->stream));
-    d->launches += d->launches_per_step;
+    CKV(ensure_graph(d, which));
+    CKV(push_segments(d));                     // value tables (async copy when dirty); cheap when clean
+    CK(cudaGraphLaunch(d->graph_exec[which], d->stream));
+    d->launches += d->launches_per_graph[which];
     return SWK_OK;
   }
-  return launch_step(d);
+  CKV(push_segments(d));
+  return (which == 0) ? launch_step(d) : ((which == 1) ? launch_first_half(d) : launch_second_half(d));
 }
+
+static int run_one_step(swk_domain *d) { return run_part(d, 0); }
 
 static int status_from_stop(int stop)
 {
@@ -1409,6 +1557,8 @@ static void fill_result(swk_domain *d, swk_evolve_result *r, int64_t launches0)
   r->stop_reason = (c->stop == 1) ? 1 : ((c->stop == 2) ? 2 : 0);
   r->kernel_launches = d->launches - launches0;
 }
+
+static int yield_epilogue(swk_domain *d, int reason, swk_evolve_result *result, int64_t launches0);
 
 extern "C" int swk_evolve(swk_domain *d, double relative_yieldtime, double relative_finaltime, int64_t max_steps,
                           swk_evolve_result *result)
@@ -1442,9 +1592,57 @@ extern "C" int swk_evolve(swk_domain *d, double relative_yieldtime, double relat
     if (c->step_budget > 0) batch = std::min<int64_t>(batch, std::max<int64_t>(1, c->step_budget - c->total_steps));
   }
   if (c->stop < 0) return status_from_stop(c->stop);
-  const int reason = c->stop;
+  return yield_epilogue(d, c->stop, result, launches0);
+}
+
+// ---- host-paced run: one host visit per timestep, between its two halves -------------------------
+// For boundary values / rates that are Python functions of time.  Everything stays resident and fused
+// (the halves replay as CUDA graphs); the host learns (t, dt) after the first half - one small D2H read -
+// evaluates its functions at the substep times, writes the value tables (swk_set_boundary_values_substep,
+// swk_set_rate; one small async H2D copy) and releases the second half.  Sequence per evolve segment:
+//   swk_step_begin;  { swk_step_first -> stop? break : set values; swk_step_rest }*;  swk_step_end
+extern "C" int swk_step_begin(swk_domain *d, double relative_yieldtime, double relative_finaltime)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  d->launches_mark = d->launches;
+  CKV(pull_clock(d));
+  Clock *c = d->h_clock;
+  if (c->stop < 0) return status_from_stop(c->stop);
+  c->yieldtime = relative_yieldtime;
+  c->finaltime = relative_finaltime;
+  c->step_budget = 0;
+  c->stop = 0;
+  c->step_start_time = c->time;
+  c->dt_min_bits = 0x54B249AD2594C37DULL;          // bits of 1.0e+100
+  return push_clock(d);
+}
+
+extern "C" int swk_step_first(swk_domain *d, swk_evolve_result *result)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(run_part(d, 1));
+  CKV(pull_clock(d));
+  Clock *c = d->h_clock;
+  if (c->stop < 0) return status_from_stop(c->stop);
+  fill_result(d, result, d->launches_mark);
+  if (result) result->time = (c->stop != 0) ? c->time : c->step_start_time;
+  return SWK_OK;
+}
+
+extern "C" int swk_step_rest(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  return run_part(d, 2);
+}
+
+// the yield: distribute_to_vertices_and_edges + update_boundary (generic_domain.py:1884-1885, 1899-1900)
+static int yield_epilogue(swk_domain *d, int reason, swk_evolve_result *result, int64_t launches0)
+{
+  Clock *c = d->h_clock;
   if (reason == 1 || reason == 2) {
-    // distribute_to_vertices_and_edges + update_boundary before the yield (:1884-1885, 1899-1900)
     c->stop = 0;
     CKV(push_clock(d));
     launch_extrapolate(d, d->K);
@@ -1455,8 +1653,17 @@ extern "C" int swk_evolve(swk_domain *d, double relative_yieldtime, double relat
   c->stop = reason;
   fill_result(d, result, launches0);
   c->stop = 0;
-  CKV(push_clock(d));
-  return SWK_OK;
+  return push_clock(d);
+}
+
+extern "C" int swk_step_end(swk_domain *d, swk_evolve_result *result)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  CKV(pull_clock(d));
+  Clock *c = d->h_clock;
+  if (c->stop < 0) return status_from_stop(c->stop);
+  return yield_epilogue(d, c->stop, result, d->launches_mark);
 }
 
 extern "C" int swk_run_steps(swk_domain *d, int64_t n_steps, int per_kernel, float *elapsed_ms)

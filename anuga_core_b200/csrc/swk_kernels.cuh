@@ -117,6 +117,7 @@ struct Dev {
   double *max_speed;
   d4 *bq;
   const double *vcoord;          // (6*NP) vertex coordinates x0,y0,x1,y1,x2,y2 planes (sloped Manning), may be null
+  const double *wind;            // [2][NP] explicit momentum forcing S*u, S*v (Wind_stress, forcing.py:80-215), may be null
   Clock *clock;
   // boundary-flux accounting (sw_domain_openmp.c:696-701): slot per accounting edge, in (k, i) order
   double *acct_val;              // [n_acct]
@@ -338,7 +339,8 @@ struct Segments {
   const int *b_edge;       // [M]
   const int *b_seg;        // [M] segment id or -1
   const int *seg_kind;     // [nseg]
-  const double *seg_val;   // [nseg][3]
+  const double *seg_val;   // [nseg][3 substeps][3]: values of time-dependent kinds differ per RK substep
+  int substep;
 };
 
 // boundary value of one edge from the triangle's own edge record e = {stage, height, xmom, ymom},
@@ -398,6 +400,29 @@ __device__ __forceinline__ bool boundary_value_core(int kind, double v0, double 
         out.z = qperp * n2 - qpar * n1;
       }
     } break;
+    case 8: {                                  // Characteristic_stage (boundaries.py:760-843, vectorised form)
+      const double sb = e.x, xb = e.z, yb = e.w, eb = e.x - e.y;
+      const double h_inside = dmax0(sb - eb);
+      const double w_outside = 0.0 * sb + v0;
+      const double uh_inside = n1 * xb + n2 * yb;
+      const double vh_inside = n2 * xb - n1 * yb;
+      const double u_inside = (h_inside > 0.0) ? uh_inside / h_inside : 0.0;
+      const double h_outside = dmax0(w_outside - eb);
+      if (h_inside == 0.0 || h_outside == 0.0) {
+        out.x = w_outside; out.y = 0.0; out.z = 0.0;
+      } else {
+        const double sqrt_g = g;                 // the caller passes gravity**0.5 for this kind
+        const double sqrt_h_inside = sqrt(h_inside), sqrt_h_outside = sqrt(h_outside);
+        const double r = 0.5 * (sqrt_h_inside + sqrt_h_outside) + u_inside / 4.0 / sqrt_g;
+        const double h_m = r * r;
+        const double u_m = 0.5 * u_inside + sqrt_g * (sqrt_h_inside - sqrt_h_outside);
+        const double uh_m = h_m * u_m;
+        const double vh_m = (uh_inside > 0.0) ? vh_inside : 0.0;    // outflow keeps its tangential momentum
+        out.x = h_m + eb;
+        out.y = uh_m * n1 + vh_m * n2;
+        out.z = uh_m * n2 - vh_m * n1;
+      }
+    } break;
     default:
       return false;
   }
@@ -425,8 +450,9 @@ __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, 
     if (D.zflag[k] & 1) { cuh = 0.0; cvh = 0.0; }
   }
   const double bed_c = (kind == 7) ? D.cq[k].w : 0.0;
-  touched = boundary_value_core(kind, S.seg_val[3 * seg], S.seg_val[3 * seg + 1], S.seg_val[3 * seg + 2], e,
-                                n1, n2, centroid_transmissive, cw, cuh, cvh, out, bed_c, K.g);
+  const double *sv = S.seg_val + (3 * seg + S.substep) * 3;
+  touched = boundary_value_core(kind, sv[0], sv[1], sv[2], e,
+                                n1, n2, centroid_transmissive, cw, cuh, cvh, out, bed_c, (kind == 8) ? K.sqrt_g : K.g);
 }
 
 __global__ void __launch_bounds__(BLOCK) k_boundary_values(Dev D, Segments S, Consts K, int centroid_transmissive)
@@ -718,6 +744,10 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
     sts(&D.bk[2 * NP + k], raw.z);
   }
   if (zf & 1) { e.uh = 0.0; e.vh = 0.0; }
+  if (D.wind) {                                        // compute_forcing_terms: explicit_update += S*(u, v)
+    xu += lds(&D.wind[k]);
+    yu += lds(&D.wind[NP + k]);
+  }
   double zs = 1.0;
   double h = e.w - e.z;
   if (U.sloped) {                                      // :2003-2023 with the dynamic bed vertex values
@@ -819,8 +849,13 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_U) k_update(Dev D, Consts K, U
 }
 
 // Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
-// dt is already known, so explicit updates never touch HBM.  (Not used with
-// riverwalls: the weir branch reads the neighbour's stage centroid, :635.)
+// dt is already known, so explicit updates never touch HBM.
+// Riverwalls (RW): the weir branch reads the NEIGHBOUR's centroid record (sw_domain_openmp.c:635), which
+// this very kernel overwrites.  Both triangles of a wall edge carry the wall flag, so it is enough that
+// triangles with a wall edge do not update in here: they store their explicit updates like pass B1 and
+// are updated afterwards by k_update_list over the (short) list of wall triangles; every other triangle
+// reads no neighbour centroid and stays fused.
+template <bool RW>
 __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Consts K, UpdateArgs U, int k0, int k1)
 {
   if (D.clock->stop) return;
@@ -833,6 +868,14 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Const
 #endif
     if (k >= k1) continue;
     const i4 p = lds(&D.connB[k]);
+    if (RW && (p.w & 0xE)) {                    // a triangle with a wall edge: flux only
+      const Eff own = effective(D.cq[k], K);
+      const TriFlux T = triangle_flux<true, false>(D, K, k, p, own, false);
+      D.eu[k] = T.su;
+      D.eu[D.NP + k] = T.xu;
+      D.eu[2 * D.NP + k] = T.yu;
+      continue;
+    }
 #if SWK_FU_RELOAD
     // only {h, z} of the own state live across the edge loop; the record is read again (L1) for the update
     Eff own;
@@ -850,6 +893,19 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Const
 #endif
     triangle_update(D, K, U, k, raw, e, D.zflag[k], T.su, T.xu, T.yu, dt, D.cq, nullptr);
   }
+}
+
+// update of the listed triangles from their stored explicit updates (the wall triangles of the fused pass)
+__global__ void __launch_bounds__(BLOCK) k_update_list(Dev D, Consts K, UpdateArgs U, const int *list, int n)
+{
+  if (D.clock->stop) return;
+  const int j = blockIdx.x * BLOCK + threadIdx.x;
+  if (j >= n) return;
+  const int k = list[j];
+  const double dt = D.clock->dt;
+  const d4 raw = D.cq[k];
+  const Eff e = effective(raw, K);
+  triangle_update(D, K, U, k, raw, e, D.zflag[k], D.eu[k], D.eu[D.NP + k], D.eu[2 * D.NP + k], dt, D.cq, nullptr);
 }
 
 // =============================================================================
@@ -974,11 +1030,19 @@ __global__ void __launch_bounds__(1024) k_finish_step(Dev D, TimeParams P, int l
 // all_nonneg mirrors `num.all(rate >= 0.0)` and is decided on the host from the
 // operator's rate (scalar or array); dt comes from the clock.
 // =============================================================================
+// rf != null: {rate, factor} live in a device table (time-dependent operator: the host refreshes the
+// table every step, nothing is baked into the launch) and a scalar rate decides all_nonneg itself.
 __global__ void __launch_bounds__(BLOCK) k_rate_operator(Dev D, double rate, double factor,
                                                          const double *rate_array, const int *indices,
-                                                         int n, int all_nonneg, double *influx_partial)
+                                                         int n, int all_nonneg, double *influx_partial,
+                                                         const double *rf)
 {
   if (D.clock->stop) return;
+  if (rf) {
+    rate = rf[0];
+    factor = rf[1];
+    if (!rate_array) all_nonneg = (rate >= 0.0) ? 1 : 0;
+  }
   const int j = blockIdx.x * BLOCK + threadIdx.x;
   double contrib = 0.0;
   if (j < n) {

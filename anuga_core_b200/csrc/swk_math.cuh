@@ -197,6 +197,7 @@ struct Consts {
   int protect;                          // 1: protect precedes the extrapolation (always, except the
                                         //    per-call extrapolate entry point called on its own)
   int pad;
+  double sqrt_g;                        // gravity**0.5 as the host's libm gives it (Characteristic_stage_boundary)
 };
 
 // ---------------------------------------------------------------------------

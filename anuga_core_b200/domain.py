@@ -106,6 +106,11 @@ class Domain:
         self.multiprocessor_mode = MODE_B200
         self.boundary_map = None
         self.fractional_step_operators = []
+        from .riverwall import RiverWall
+        self.riverwallData = RiverWall(self)                # shallow_water_domain.py:402
+        from .forcing import manning_friction_implicit
+        self.forcing_terms = [manning_friction_implicit]     # shallow_water_domain.py:300
+        self._forcing_on_device = False
         self.starttime = 0.0
         self.relative_time = 0.0
         self.evolve_starttime = 0.0
@@ -804,11 +809,47 @@ class Domain:
             if op.op_id is None:
                 op.op_id = dev.add_rate_operator(op.current_rate(t), op.current_factor(t),
                                                  op.rate_array, op.indices)
+                if op.time_dependent:       # scalars read from the device value table, refreshed every step
+                    dev.set_rate_dynamic(op.op_id, True)
             elif op.time_dependent:
                 dev.set_rate(op.op_id, op.current_rate(t), op.current_factor(t))
         self._operators_dirty = False
 
+    def _device_forcing_terms(self):
+        out = []
+        for f in self.forcing_terms:
+            if hasattr(f, "momentum_forcing"):
+                out.append(f)
+            elif getattr(f, "__name__", "") not in ("manning_friction_implicit", "manning_friction_explicit"):
+                raise NotImplementedError("forcing term %r has no device implementation (SURVEY.md 8(f))" % (f,))
+        return out
+
+    def _push_forcing(self, t, force=False):
+        """compute_forcing_terms (generic_domain.py:2417-2427) for the state-independent terms: their
+        per-triangle momentum forcing is evaluated on the host and handed to the update kernels"""
+        terms = self._device_forcing_terms()
+        if not terms:
+            if self._forcing_on_device:
+                self._dev.set_momentum_forcing(None, None)
+                self._forcing_on_device = False
+            return
+        if self._forcing_on_device and not force and not any(f.time_dependent for f in terms):
+            return
+        fx = np.zeros(self.number_of_triangles)
+        fy = np.zeros(self.number_of_triangles)
+        for f in terms:
+            ax, ay = f.momentum_forcing(self, t)
+            fx += ax
+            fy += ay
+        self._dev.set_momentum_forcing(fx, fy)
+        self._forcing_on_device = True
+
+    def _forcing_depends_on_time(self):
+        return any(f.time_dependent for f in self._device_forcing_terms())
+
     def _needs_host_stepping(self):
+        if self._forcing_depends_on_time():
+            return True
         if self.boundary_map:
             for B in self.boundary_map.values():
                 if B is not None and B.time_dependent:
@@ -917,6 +958,7 @@ class Domain:
             dev.distribute_to_vertices_and_edges()
             self._push_boundaries(self.get_time())
             dev.update_boundary()
+            self._push_forcing(self.get_time())        # compute_forcing_terms at the substep's time
             return dev.compute_fluxes(k)
 
         if method != "euler":
@@ -1037,6 +1079,7 @@ class Domain:
         dev.set_time(self.relative_time)
         self._push_boundaries(self.get_time())
         self._push_operators(self.get_time())
+        self._push_forcing(self.get_time(), force=True)
 
         self.relative_yieldtime = self.relative_time + yieldstep
         self.recorded_min_timestep = self.evolve_max_timestep
@@ -1067,6 +1110,8 @@ class Domain:
             if self._needs_host_stepping():
                 if self._only_host_side_operators_need_the_host():
                     reason = self._evolve_device_steps_host_operators()
+                elif self._only_values_depend_on_time():
+                    reason = self._evolve_split_steps()
                 else:
                     reason = self._evolve_host_stepped()
             else:
@@ -1113,6 +1158,8 @@ class Domain:
     def _only_host_side_operators_need_the_host(self):
         """static boundaries and rates: the step itself can stay in the device time loop and only the
         host-side operators (inlets, culverts) run between steps"""
+        if self._forcing_depends_on_time():
+            return False
         if self.boundary_map:
             for B in self.boundary_map.values():
                 if B is not None and B.time_dependent:
@@ -1120,33 +1167,115 @@ class Domain:
         return all(getattr(op, "host_side", False) or not op.time_dependent
                    for op in self.fractional_step_operators)
 
-    def _evolve_device_steps_host_operators(self):
-        """_evolve_base's loop with one device-resident step (fused kernels, device clock, device-side
-        operators) per iteration, followed by the host-side operators on their gathered cells."""
+    def _only_values_depend_on_time(self):
+        """time-dependent boundary values / rate(t) of device operators, no host-side operator: the fused
+        device step runs in two halves with one host visit per step (_evolve_split_steps)"""
+        return not self._forcing_depends_on_time() and \
+            not any(getattr(op, "host_side", False) for op in self.fractional_step_operators)
+
+    def _evolve_split_steps(self):
+        """_evolve_base's while loop for boundary values / rates that are Python functions of time
+        (boundaries.py:384-517, 553-635; generic_boundary_conditions.py:297-411; rate_operators.py:276-289).
+        The device runs the same fused, graph-replayed step as the resident loop, in two halves
+        (include/swk.h: swk_step_*): after the first half the timestep exists, the host evaluates its
+        functions at the times the reference's substeps see - t + dt (rk2, rk3), t + dt/2 (rk3's third
+        substep), and t + dt for the next step's first substep (generic_domain.py:2011, 2093, 2132) -
+        and the second half is released.  One D2H scalar read and one small H2D copy per step."""
         dev = self._dev
+        method = self.timestepping_method
+        segs = [(seg, B) for (seg, B) in self._segments.values() if B is not None and B.time_dependent]
+        ops = [op for op in self.fractional_step_operators
+               if not getattr(op, "host_side", False) and op.time_dependent]
+        dev.step_begin(self.relative_yieldtime, self.relative_finaltime)
+        steps = 0
+        while True:
+            r = dev.step_first()
+            if r.stop_reason != 0:
+                break
+            t0, dt = r.time, r.timestep
+            steps += 1
+            if self.record_timestep_history:
+                self.timestep_history.append(dt)
+            self.timestep = dt
+            self.relative_time = t0 + dt
+            T1 = self.get_time()
+            if method != "euler":
+                for seg, B in segs:
+                    dev.set_boundary_values_substep(seg, 1, B.device_values(T1))
+            if method == "rk3":
+                self.relative_time = t0 + dt * 0.5
+                T2 = self.get_time()
+                for seg, B in segs:
+                    dev.set_boundary_values_substep(seg, 2, B.device_values(T2))
+            # fractional-step operators see t0 after an euler step and t0 + dt after rk2 / rk3 (see _host_step)
+            self.relative_time = t0 if method == "euler" else t0 + dt
+            Top = self.get_time()
+            for op in ops:
+                dev.set_rate(op.op_id, op.current_rate(Top), op.current_factor(Top))
+            # the next step's first substep (and the yield's update_boundary) see the time after this step
+            self.relative_time = t0 + dt
+            for seg, B in segs:
+                dev.set_boundary_values_substep(seg, 0, B.device_values(T1))
+            dev.step_rest()
+        reason = r.stop_reason
+        if reason == 2:
+            # time snapped to finaltime (generic_domain.py:1870-1888): the yield's boundary update sees it
+            self.relative_time = r.time
+            for seg, B in segs:
+                dev.set_boundary_values(seg, B.device_values(self.get_time()))
+        r = dev.step_end()
+        self._absorb(r)
+        return reason
+
+    def _evolve_device_steps_host_operators(self):
+        """_evolve_base's while loop when only host-side operators (inlets, culverts, rate(x, y, t)) need the
+        host: one device-resident timestep (with its fused device
+        operators) per iteration, followed by the host-side operators on their gathered cells."""
         host_ops = [op for op in self.fractional_step_operators if getattr(op, "host_side", False)]
         while True:
-            t0 = self.relative_time
-            r = dev.evolve(self.relative_yieldtime, self.relative_finaltime, 1)
-            self._absorb(r)
-            if self.record_timestep_history:
-                self.timestep_history.append(self.timestep)
-            # operators see t0 after an euler step and t0 + dt after rk2 / rk3 (see _host_step)
-            self.relative_time = t0 if self.timestepping_method == "euler" else t0 + self.timestep
-            for op in host_ops:
-                added = op()
-                if added != 0.0:
-                    dev.add_fractional_step_volume(added)
-            self.relative_time = r.time
-            dev.update_ghosts()
-            if host_ops:
-                st = dev.get_statistics()
-                self.fractional_step_volume_integral = st.fractional_step_volume_integral
-            if r.stop_reason in (1, 2):
+            reason = self._one_device_step_then_host_operators(host_ops)
+            if reason in (1, 2):
                 # the device extrapolated for the yield before the operators ran: redo it
-                dev.distribute_to_vertices_and_edges()
-                dev.update_boundary()
-                return r.stop_reason
+                self._dev.distribute_to_vertices_and_edges()
+                self._dev.update_boundary()
+                return reason
+
+    def _one_device_step_then_host_operators(self, host_ops):
+        dev = self._dev
+        t0 = self.relative_time
+        r = dev.evolve(self.relative_yieldtime, self.relative_finaltime, 1)
+        self._absorb(r)
+        if self.record_timestep_history:
+            self.timestep_history.append(self.timestep)
+        # operators see t0 after an euler step and t0 + dt after rk2 / rk3 (see _host_step)
+        self.relative_time = t0 if self.timestepping_method == "euler" else t0 + self.timestep
+        for op in host_ops:
+            added = op()
+            if added != 0.0:
+                dev.add_fractional_step_volume(added)
+        self.relative_time = r.time
+        dev.update_ghosts()
+        if host_ops:
+            st = dev.get_statistics()
+            self.fractional_step_volume_integral = st.fractional_step_volume_integral
+        return r.stop_reason
+
+    def run_steps_with_host_operators(self, n_steps):
+        """Exactly n_steps timesteps of the loop above (benchmarks): returns the elapsed milliseconds between
+        two device synchronisations (the host-side hydraulics are part of the step, so wall clock)."""
+        import time as _time
+        host_ops = [op for op in self.fractional_step_operators if getattr(op, "host_side", False)]
+        keep = (self.relative_yieldtime, self.relative_finaltime)
+        self.relative_yieldtime, self.relative_finaltime = 1.0e300, None
+        self._dev.synchronize()
+        t0 = _time.perf_counter()
+        for _ in range(int(n_steps)):
+            self._one_device_step_then_host_operators(host_ops)
+        self._dev.synchronize()
+        ms = (_time.perf_counter() - t0) * 1.0e3
+        self.relative_yieldtime, self.relative_finaltime = keep
+        self._mark_device_newer()
+        return ms
 
     def _evolve_host_stepped(self):
         """_evolve_base's while loop with host-evaluated callbacks (time-dependent

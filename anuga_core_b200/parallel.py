@@ -424,9 +424,9 @@ def weak_scaling_shape(size, nranks):
     return m, n
 
 
-def strip_partitioned_sweep_domain(m, n, rank, nranks, device=0, alg="DE1", rain=1.0e-4):
-    """configs[3]/[4] building block: rank's strip of rectangular_cross(m, n) with the
-    roofline-sweep fields of workloads.roofline_sweep_domain."""
+def strip_partitioned_mesh_domain(m, n, rank, nranks, device=0):
+    """rank's sub-domain (full triangles + two ghost rings, halo lists) of rectangular_cross(m, n) cut in
+    `nranks` strips of cell columns; no fields, boundaries or operators yet."""
     sub = strip_slab(m, n, rank, nranks)
     d = Domain(mesh=Mesh(sub["points"], sub["triangles"], sub["boundary"],
                          neighbour_structure=sub["neighbour_structure"]),
@@ -437,6 +437,13 @@ def strip_partitioned_sweep_domain(m, n, rank, nranks, device=0, alg="DE1", rain
     d.node_l2g = sub["node_l2g"]
     d.number_of_global_triangles = 4 * m * n
     d.number_of_global_nodes = (m + 1) * (n + 1) + m * n
+    return d
+
+
+def strip_partitioned_sweep_domain(m, n, rank, nranks, device=0, alg="DE1", rain=1.0e-4):
+    """configs[3]/[4] building block: rank's strip of rectangular_cross(m, n) with the
+    roofline-sweep fields of workloads.roofline_sweep_domain."""
+    d = strip_partitioned_mesh_domain(m, n, rank, nranks, device=device)
     d.set_flow_algorithm(alg)
     d.set_store(False)
     d.set_quantity("elevation", workloads.sweep_elevation)

@@ -143,7 +143,8 @@ enum {
   SWK_BC_TRANSMISSIVE_N_ZERO_T_SET_STAGE = 4,   /* boundaries.py:477-517 */
   SWK_BC_TRANSMISSIVE_MOMENTUM_SET_STAGE = 5,   /* boundaries.py:344-372 */
   SWK_BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6,  /* boundaries.py:543-551 */
-  SWK_BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY = 7 /* boundaries.py:1096-1266 (evaluate_segment); v0 = external stage */
+  SWK_BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY = 7, /* boundaries.py:1096-1266 (evaluate_segment); v0 = external stage */
+  SWK_BC_CHARACTERISTIC_STAGE = 8                  /* boundaries.py:639-843 (evaluate_segment); v0 = outside stage */
 };
 
 /* ---- evolve result ------------------------------------------------------------ */
@@ -206,12 +207,24 @@ int swk_get_quantity(swk_domain *d, int quantity_id, double *host, int64_t n);
 int swk_set_boundary_segment(swk_domain *d, int segment, int kind, const int64_t *ids,
                              int64_t n_ids, const double values[3]);
 int swk_set_boundary_values(swk_domain *d, int segment, const double values[3]);
+/* The values one RK substep sees (0: start of the step, 1: second flux evaluation, 2: third): the
+ * reference evaluates time-dependent boundaries at the substep's own time (generic_domain.py:2011,
+ * 2093, 2132).  swk_set_boundary_values sets all three.  Values live in a device table; changing them
+ * is one small asynchronous copy and leaves the captured step valid.                              */
+int swk_set_boundary_values_substep(swk_domain *d, int segment, int substep, const double values[3]);
 
 /* Rate_operator (operators/rate_operators.py:24-269): stage += factor*dt*rate on
  * `indices` (NULL = all).  rate_array (N,) optional per-centroid rates (NULL: scalar). */
 int swk_add_rate_operator(swk_domain *d, double rate, double factor, const double *rate_array,
                           const int64_t *indices, int64_t n_indices, int *op_id);
 int swk_set_rate(swk_domain *d, int op_id, double rate, double factor);
+/* State-independent explicit momentum forcing (Wind_stress.__call__ + assign_windfield_values,
+ * shallow_water/forcing.py:170-215): xmom/ymom explicit_update[k] += force[k] at every flux evaluation.
+ * Arrays of n = N doubles in the caller's order; NULL pointers switch the term off.                   */
+int swk_set_momentum_forcing(swk_domain *d, const double *xmom_force, const double *ymom_force, int64_t n);
+/* Mark a Rate_operator whose rate / factor are functions of time (rate_operators.py:276-289): its
+ * scalars are read from a device table that swk_set_rate refreshes, without touching the captured step. */
+int swk_set_rate_dynamic(swk_domain *d, int op_id, int dynamic);
 /* Forget every Rate_operator registered so far (ids become invalid). */
 int swk_clear_rate_operators(swk_domain *d);
 
@@ -264,6 +277,22 @@ int swk_get_statistics(swk_domain *d, swk_evolve_result *result);
  * distribute_to_vertices_and_edges + update_boundary do (generic_domain.py:1884-1902). */
 int swk_evolve(swk_domain *d, double relative_yieldtime, double relative_finaltime,
                int64_t max_steps, swk_evolve_result *result);
+/* Host-paced time loop for boundary values / rates that are host functions of time
+ * (shallow_water/boundaries.py:384-517, 553-635; generic_boundary_conditions.py:297-411): same kernels,
+ * same graphs, but the step is launched in two halves with one host visit in between -
+ *     swk_step_begin(yieldtime, finaltime)
+ *     loop:  swk_step_first(&r)    first half: extrapolate, boundary, flux, global dt, update_timestep;
+ *                                  returns synchronised with r.time = start of the step, r.timestep = dt,
+ *                                  r.stop_reason != 0 when the previous step reached the yield / final time
+ *                                  (then nothing was computed: leave the loop)
+ *            ... host evaluates f(t + dt) [, f(t + dt/2)], f(next step's t) and calls
+ *                swk_set_boundary_values_substep / swk_set_rate ...
+ *            swk_step_rest()       second half: update, later RK substeps, fractional steps, finish (async)
+ *     swk_step_end(&r)             the yield's extrapolation + boundary update, final statistics        */
+int swk_step_begin(swk_domain *d, double relative_yieldtime, double relative_finaltime);
+int swk_step_first(swk_domain *d, swk_evolve_result *result);
+int swk_step_rest(swk_domain *d);
+int swk_step_end(swk_domain *d, swk_evolve_result *result);
 /* reset per-yield statistics (generic_domain.py:1906-1912) */
 int swk_reset_yield_statistics(swk_domain *d);
 

@@ -187,6 +187,7 @@ class OracleDomain:
         self.tag_boundary_cells = {t: np.asarray(v, dtype=np.int64)
                                    for t, v in sc.get("tag_boundary_cells", {}).items()}
         self.operators = list(sc.get("operators", []))
+        self.forcing = list(sc.get("forcing", []))
         # single-process ghost copy (generic_domain.py:2448-2469)
         self.ghost_copy = sc.get("ghost_copy")      # (Idf, Idg) or None
 
@@ -283,6 +284,26 @@ class OracleDomain:
                                              _pd(self.stage_c), _pd(self.bed_c), _pd(self.xmom_c),
                                              _pd(self.ymom_c), _pd(self.friction_c),
                                              _pd(self.xmom_siu), _pd(self.ymom_siu))
+
+        for spec in self.forcing:
+            if spec[0] == "wind":                 # Wind_stress.__call__ + assign_windfield_values (forcing.py:133-215)
+                W = spec[1]
+                t = self.get_time()
+                xc = self.centroid_coordinates
+                N = self.N
+
+                def field(f):
+                    if callable(f):
+                        return np.asarray(f(t, xc[:, 0], xc[:, 1]), dtype=np.float64) * np.ones(N)
+                    return f * np.ones(N, dtype=np.float64)
+                s_vec, phi_vec = field(W.speed), field(W.phi)
+                for k in range(N):
+                    phi = phi_vec[k] * math.pi / 180.0
+                    u = s_vec[k] * math.cos(phi)
+                    v = s_vec[k] * math.sin(phi)
+                    S = W.const * math.sqrt(u ** 2 + v ** 2)
+                    self.xmom_eu[k] += S * u
+                    self.ymom_eu[k] += S * v
 
     def update_conserved_quantities(self):
         dt = self.timestep
@@ -390,6 +411,38 @@ class OracleDomain:
                 self.stage_b[ids] = np.where(dry, q0_dry, q0_wet)
                 self.xmom_b[ids] = np.where(dry, 0.0 * xb, q1_wet)
                 self.ymom_b[ids] = np.where(dry, 0.0 * yb, q2_wet)
+            elif kind == "characteristic_stage":
+                # boundaries.py:760-843 (evaluate_segment), gravity = anuga.config.g
+                value = spec[1](t)
+                try:
+                    w_outside = float(value)
+                except Exception:
+                    w_outside = float(value[0])
+                sb = self.stage_e[vol, edge]
+                xb = self.xmom_e[vol, edge]
+                yb = self.ymom_e[vol, edge]
+                eb = self.bed_e[vol, edge]
+                w_outside = 0.0 * sb + w_outside
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    sqrt_g = 9.8 ** 0.5
+                    h_inside = np.maximum(sb - eb, 0)
+                    uh_inside = n1 * xb + n2 * yb
+                    vh_inside = n2 * xb - n1 * yb
+                    u_inside = np.where(h_inside > 0.0, uh_inside / h_inside, 0.0)
+                    h_outside = np.maximum(w_outside - eb, 0)
+                    sqrt_h_inside = h_inside ** 0.5
+                    sqrt_h_outside = h_outside ** 0.5
+                    h_m = (0.5 * (sqrt_h_inside + sqrt_h_outside) + u_inside / 4.0 / sqrt_g) ** 2
+                    u_m = 0.5 * u_inside + sqrt_g * (sqrt_h_inside - sqrt_h_outside)
+                    uh_m = h_m * u_m
+                    vh_m = np.where(uh_inside > 0.0, vh_inside, 0.0)
+                    w_m = h_m + eb
+                    dry_test = np.logical_or(h_inside == 0.0, h_outside == 0.0)
+                    q1 = uh_m * n1 + vh_m * n2
+                    q2 = uh_m * n2 - vh_m * n1
+                self.stage_b[ids] = np.where(dry_test, w_outside, w_m)
+                self.xmom_b[ids] = np.where(dry_test, 0.0, q1)
+                self.ymom_b[ids] = np.where(dry_test, 0.0, q2)
             elif kind == "time_stage_zero_momentum":
                 self.stage_b[ids] = float(spec[1](t))
                 self.xmom_b[ids] = 0.0

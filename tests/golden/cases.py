@@ -303,6 +303,59 @@ def culvert_weir_de1(A):
     return d
 
 
+def characteristic_de1(A, n=16):
+    """Characteristic_stage_boundary: a solitary-wave style stage signal enters from the left over a
+    sloping beach whose upper part is dry (the boundary's dry branch is exercised on the right)"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: -1.0 + 1.4 * x / L + 0.02 * np.sin(y))
+    d.set_quantity("stage", 0.0)
+    d.set_quantity("friction", 0.02)
+    Br = A.Reflective_boundary(d)
+    Bc = A.Characteristic_stage_boundary(d, lambda t: 0.3 / np.cosh(0.8 * (t - 2.5)) ** 2, default_stage=0.0)
+    d.set_boundary({"left": Bc, "right": Bc, "top": Br, "bottom": Br})
+    return d
+
+
+def wind_de1(A, n=14):
+    """Wind_stress forcing term (shallow_water/forcing.py:80): a gust front that moves across a shallow
+    lake, speed a function of (t, x, y), constant direction; plus a steady scalar breeze"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: -0.6 + 0.3 * x / L)
+    d.set_quantity("stage", 0.0)
+    d.set_quantity("friction", 0.02)
+    _reflective_all(A, d)
+
+    def speed(t, x, y):
+        return 30.0 * (x < 2.0 + 4.0 * t) + 0.0 * y
+    d.forcing_terms.append(A.Wind_stress(speed, 20.0))
+    d.forcing_terms.append(A.Wind_stress(s=8.0, phi=250.0))
+    return d
+
+
+def riverwall_de1(A, n=14):
+    """riverwalls from breaklines (structures/riverwall.py:151): a levee along the cell boundaries x = n/2
+    with a crest that dips below the upstream water level in the middle (weir flow over it), and a spur with
+    its own hydraulic parameters; water behind the levee, nearly dry bed in front"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: 0.1 * (x > L / 2) * (x - L / 2) / L)
+    d.set_quantity("stage", lambda x, y: np.where(x < L / 2, 0.9, 0.05), location="centroids")
+    d.set_quantity("friction", 0.03)
+    _reflective_all(A, d)
+    walls = {"levee": [[L / 2, 0.0, 1.1], [L / 2, 0.4 * L, 0.6], [L / 2, 0.6 * L, 0.7], [L / 2, L, 1.2]],
+             "spur": [[L / 2, 0.5 * L, 0.5], [L / 2 + 3.0, 0.5 * L, 0.3]]}
+    d.riverwallData.create_riverwalls(walls, riverwallPar={"spur": {"Qfactor": 0.8, "s1": 0.5}}, verbose=False)
+    return d
+
+
 CASES = {
     "kat_bedslope_more_steps": (kat_bedslope_more_steps, dict(yieldstep=0.05, finaltime=0.5)),
     "dam_break_de0": (dam_break_de0, dict(yieldstep=1.0, finaltime=6.0)),
@@ -326,6 +379,9 @@ CASES = {
     "rain_time_de1": (rain_time_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "expression_de0": (expression_de0, dict(yieldstep=0.5, finaltime=1.5)),
     "flather_de1": (flather_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "characteristic_de1": (characteristic_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "wind_de1": (wind_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "riverwall_de1": (riverwall_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_de1": (culvert_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_pipe_de1": (culvert_pipe_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_weir_de1": (culvert_weir_de1, dict(yieldstep=1.0, finaltime=4.0)),
