@@ -1682,7 +1682,8 @@ extern "C" int swk_run_steps(swk_domain *d, int64_t n_steps, int per_kernel, flo
   CKV(push_clock(d));
   d->timing = false;
   if (per_kernel) {
-    const size_t want = (size_t)std::min<int64_t>(n_steps, 512) * 5 * 2;
+    // up to 3 extrapolations + flux + 2 x (update | fused) launches per substep with the halo overlap
+    const size_t want = (size_t)std::min<int64_t>(n_steps, 512) * 12 * 2;
     while (d->ev_pool.size() < want) {
       cudaEvent_t e;
       CK(cudaEventCreate(&e));

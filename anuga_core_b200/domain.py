@@ -1107,13 +1107,13 @@ class Domain:
                 dev.set_params(self._param_dict())
                 self._params_dirty = False
 
-            if self._needs_host_stepping():
-                if self._only_host_side_operators_need_the_host():
-                    reason = self._evolve_device_steps_host_operators()
-                elif self._only_values_depend_on_time():
-                    reason = self._evolve_split_steps()
-                else:
-                    reason = self._evolve_host_stepped()
+            path = self._evolve_path()
+            if path == 1:
+                reason = self._evolve_device_steps_host_operators()
+            elif path == 2:
+                reason = self._evolve_split_steps()
+            elif path == 3:
+                reason = self._evolve_host_stepped()
             else:
                 r = dev.evolve(self.relative_yieldtime, self.relative_finaltime, 0)
                 self._absorb(r)
@@ -1154,6 +1154,33 @@ class Domain:
         self.mass_error = r.mass_error
         self._negative_device = r.negative_cells
         self.kernel_launches += r.kernel_launches
+
+    def _evolve_path(self):
+        """Which time loop runs this yield segment: 0 device-resident, 1 device steps + host-side operators,
+        2 two-half steps (time-dependent boundary values / rates), 3 host-stepped passes.  Under a
+        communicator the choice is COLLECTIVE: the loops differ in how many steps they launch ahead, so every
+        rank must run the same one even if only some ranks hold the time-dependent boundary or the inlet."""
+        if not self._needs_host_stepping():
+            mine = 0
+        elif self._only_host_side_operators_need_the_host():
+            mine = 1
+        elif self._only_values_depend_on_time():
+            mine = 2
+        else:
+            mine = 3
+        comm = getattr(self, "_comm", None)
+        if comm is None or comm.size <= 1:
+            return mine
+        # flags: bit 0 = somebody needs path 1, bit 1 = path 2, bit 2 = path 3
+        seen = 0
+        for bit, p in enumerate((1, 2, 3)):
+            if comm.allreduce_max(1.0 if mine == p else 0.0) > 0.0:
+                seen |= 1 << bit
+        if seen == 0:
+            return 0
+        if seen in (1, 2):
+            return 1 if seen == 1 else 2
+        return 3
 
     def _only_host_side_operators_need_the_host(self):
         """static boundaries and rates: the step itself can stay in the device time loop and only the

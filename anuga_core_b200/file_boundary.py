@@ -1,0 +1,351 @@
+"""Boundaries driven by a time-space field: File_boundary, Field_boundary, Time_space_boundary.
+
+Reference: anuga/abstract_2d_finite_volumes/generic_boundary_conditions.py:419-700 (Time_space_boundary,
+File_boundary), anuga/shallow_water/boundaries.py:993-1090 (Field_boundary), with the machinery underneath
+them: abstract_2d_finite_volumes/file_function.py:226-494 (time axis, thinning, time limit, start-time
+alignment) and fit_interpolate/interpolate.py:710-1110 (Interpolation_function: spatial interpolation of
+every stored frame to the boundary-edge midpoints once, linear interpolation in time at every call).
+
+B200 design: the frames interpolated to the segment's edge midpoints are uploaded ONCE ([frame][edge][3],
+resident in HBM); at every flux evaluation the host only sends the time slot {ratio, frame index} through
+the boundary value table and the boundary kernel does q = Q0 + ratio*(Q1 - Q0) per edge (kinds
+SWK_BC_TIME_SPACE_TABLE / _MEAN_STAGE), inside the same two-half fused step as every other time-dependent
+boundary.  A Time_space_boundary (a Python function of t, x, y) uses the same kind with one frame per RK
+substep that the host rewrites every step.
+"""
+import numpy as np
+
+from . import backend as _b
+from .boundaries import Boundary, Modeltime_too_early, Modeltime_too_late
+
+NAN = np.inf          # anuga/utilities/numerical_tools.py:15 (the value the reference stores outside the mesh)
+
+
+# ----------------------------------------------------------------------------------------
+# source data
+# ----------------------------------------------------------------------------------------
+def read_sww_series(filename, quantity_names):
+    """x, y, triangles, time, starttime, georeference and the (frames, nodes) arrays of an SWW file"""
+    from scipy.io import netcdf_file
+    fid = netcdf_file(filename, "r", mmap=False)
+    try:
+        out = dict(
+            starttime=float(np.asarray(fid.starttime).reshape(-1)[0]),
+            xllcorner=float(np.asarray(getattr(fid, "xllcorner", 0.0)).reshape(-1)[0]),
+            yllcorner=float(np.asarray(getattr(fid, "yllcorner", 0.0)).reshape(-1)[0]),
+            time=np.array(fid.variables["time"][:], dtype=np.float64),
+            x=np.array(fid.variables["x"][:], dtype=np.float64),
+            y=np.array(fid.variables["y"][:], dtype=np.float64),
+            triangles=np.array(fid.variables["volumes"][:], dtype=np.int64),
+        )
+        for name in quantity_names:
+            if name not in fid.variables:
+                raise Exception("Quantity %s is missing from file %s" % (name, filename))
+            out[name] = np.array(fid.variables[name][:])       # float32 in the file; promoted when used
+    finally:
+        fid.close()
+    return out
+
+
+def barycentric_weights(vertex_coordinates, triangles, points):
+    """For every point the triangle that holds it and its three weights, with the arithmetic of
+    calculate_sigma / new_triangle (anuga/utilities/quad_tree.c:26-94): sigma_i = distance from the opposite
+    edge along that edge's unit normal, over the same for vertex i.  Returns (triangle or -1, (n, 3))."""
+    V = np.asarray(vertex_coordinates, dtype=np.float64)
+    T = np.asarray(triangles, dtype=np.int64)
+    x1, y1 = V[T[:, 0], 0], V[T[:, 0], 1]
+    x2, y2 = V[T[:, 1], 0], V[T[:, 1], 1]
+    x3, y3 = V[T[:, 2], 0], V[T[:, 2], 1]
+
+    def unit_normal(xa, ya, xb, yb, xo, yo):
+        # normal of the edge a->b, flipped so that it points away from ... the way new_triangle flips it
+        ny = xb - xa
+        nx = -(yb - ya)
+        ln = np.sqrt(nx * nx + ny * ny)
+        nx, ny = nx / ln, ny / ln
+        flip = (nx * xo + ny * yo) > 0
+        return np.where(flip, -nx, nx), np.where(flip, -ny, ny)
+    nx3, ny3 = unit_normal(x1, y1, x2, y2, x3 - x2, y3 - y2)
+    nx1, ny1 = unit_normal(x2, y2, x3, y3, x1 - x3, y1 - y3)
+    nx2, ny2 = unit_normal(x3, y3, x1, y1, x2 - x1, y2 - y1)
+    d0 = (x1 - x2) * nx1 + (y1 - y2) * ny1
+    d1 = (x2 - x3) * nx2 + (y2 - y3) * ny2
+    d2 = (x3 - x1) * nx3 + (y3 - y1) * ny3
+    P = np.asarray(points, dtype=np.float64)
+    found = np.full(len(P), -1, dtype=np.int64)
+    sig = np.zeros((len(P), 3))
+    xmin, xmax = np.minimum(np.minimum(x1, x2), x3), np.maximum(np.maximum(x1, x2), x3)
+    ymin, ymax = np.minimum(np.minimum(y1, y2), y3), np.maximum(np.maximum(y1, y2), y3)
+    eps = 1.0e-12
+    for i, (x, y) in enumerate(P):
+        cand = np.flatnonzero((x >= xmin - eps) & (x <= xmax + eps) & (y >= ymin - eps) & (y <= ymax + eps))
+        if len(cand) == 0:
+            continue
+        s0 = ((x - x2[cand]) * nx1[cand] + (y - y2[cand]) * ny1[cand]) / d0[cand]
+        s1 = ((x - x3[cand]) * nx2[cand] + (y - y3[cand]) * ny2[cand]) / d1[cand]
+        s2 = ((x - x1[cand]) * nx3[cand] + (y - y1[cand]) * ny3[cand]) / d2[cand]
+        inside = np.flatnonzero((s0 >= -1.0e-10) & (s1 >= -1.0e-10) & (s2 >= -1.0e-10))
+        if len(inside) == 0:
+            continue
+        # the triangle that holds the point most comfortably (a point on a shared edge gets the same
+        # value from either side up to rounding)
+        j = inside[np.argmax(np.minimum(np.minimum(s0[inside], s1[inside]), s2[inside]))]
+        found[i] = cand[j]
+        sig[i] = (s0[j], s1[j], s2[j])
+    return found, sig
+
+
+class Interpolation_function:
+    """f(t, point_id): frames of nodal values -> values at fixed points, linear in time
+    (fit_interpolate/interpolate.py:710-1110, the spatial-with-interpolation-points use)."""
+
+    def __init__(self, time, quantities, quantity_names, vertex_coordinates, triangles, interpolation_points,
+                 time_thinning=1):
+        time = np.asarray(time, dtype=np.float64)
+        if not np.all(time[1:] - time[:-1] >= 0):
+            raise Exception("Time must be a monotonuosly increasing sequence %s" % time)
+        self.time = np.array(time[::time_thinning])
+        self.quantity_names = list(quantity_names)
+        self.interpolation_points = np.asarray(interpolation_points, dtype=np.float64)
+        self.spatial = True
+        self.index = 0
+        tri, sig = barycentric_weights(vertex_coordinates, triangles, self.interpolation_points)
+        self.indices_outside_mesh = np.flatnonzero(tri < 0)
+        T = np.asarray(triangles, dtype=np.int64)
+        ok = tri >= 0
+        nodes = T[np.where(ok, tri, 0)]                     # (m, 3) node ids
+        # one row of the interpolation matrix per point; the sparse product adds the three terms in the
+        # order of increasing node id (CSR column order)
+        order = np.argsort(nodes, axis=1, kind="stable")
+        nodes_s = np.take_along_axis(nodes, order, axis=1)
+        sig_s = np.take_along_axis(sig, order, axis=1)
+        self.precomputed_values = {}
+        for name in self.quantity_names:
+            Q = np.asarray(quantities[name])
+            if Q.ndim == 2:
+                Q = np.array(Q[::time_thinning, :])
+            frames = Q if Q.ndim == 2 else np.broadcast_to(Q, (len(self.time),) + Q.shape)
+            out = np.zeros((len(self.time), len(self.interpolation_points)))
+            for i in range(len(self.time)):
+                q = np.asarray(frames[i], dtype=np.float64)
+                r = sig_s[:, 0] * q[nodes_s[:, 0]]
+                r = r + sig_s[:, 1] * q[nodes_s[:, 1]]
+                r = r + sig_s[:, 2] * q[nodes_s[:, 2]]
+                out[i] = np.where(ok, r, NAN)
+            self.precomputed_values[name] = out
+
+    def time_slot(self, t):
+        """(index, ratio) of model time t: interpolate.py:1045-1062"""
+        msg = "Model time %.16f is not contained in function domain [%.16f:%.16f].\n" % (t, self.time[0], self.time[-1])
+        if t < self.time[0]:
+            raise Modeltime_too_early(msg)
+        if t > self.time[-1]:
+            raise Modeltime_too_late(msg)
+        while t > self.time[self.index]:
+            self.index += 1
+        while t < self.time[self.index]:
+            self.index -= 1
+        if t == self.time[self.index]:
+            return self.index, 0.0
+        return self.index, (t - self.time[self.index]) / (self.time[self.index + 1] - self.time[self.index])
+
+    def __call__(self, t, point_id=None):
+        if point_id is None:
+            raise Exception("Either point_id or x and y must be specified")
+        index, ratio = self.time_slot(t)
+        q = np.zeros(len(self.quantity_names))
+        for i, name in enumerate(self.quantity_names):
+            Q = self.precomputed_values[name]
+            Q0 = Q[index, point_id]
+            if ratio > 0:
+                Q1 = Q[index + 1, point_id]
+                q[i] = Q0 if (Q0 == NAN and Q1 == NAN) else Q0 + ratio * (Q1 - Q0)
+            else:
+                q[i] = Q0
+        return q
+
+
+def file_function(filename, domain=None, quantities=None, interpolation_points=None, time_thinning=1,
+                  time_limit=None, verbose=False, use_cache=False, boundary_polygon=None):
+    """file_function.py:29-168 + get_netcdf_file_function :226-494 for SWW files: returns the
+    Interpolation_function with attribute starttime; moves domain.starttime forward to the file's if the
+    file starts later."""
+    if not filename.endswith(".sww"):
+        raise NotImplementedError("file_function: only SWW files are supported (got %s)" % filename)
+    if boundary_polygon is not None:
+        raise NotImplementedError("boundary_polygon applies to STS files only")
+    names = list(quantities) if quantities is not None else list(domain.conserved_quantities)
+    src = read_sww_series(filename, names)
+    starttime = src["starttime"]
+    time = src["time"]
+    upper = len(time)
+    assert upper > 0, "Time vector obtained from file %s has length 0" % filename
+    if time_limit is not None:
+        limit = time_limit - starttime
+        for i, t in enumerate(time):
+            if t > limit:
+                upper = i
+                break
+        assert upper > 0, "Time vector is zero. Requested time limit is %f" % limit
+    time = time[:upper]
+    pts = np.array(interpolation_points, dtype=np.float64)
+    pts[:, 0] -= src["xllcorner"]
+    pts[:, 1] -= src["yllcorner"]
+    domain_starttime = None if domain is None else domain.starttime
+    if domain_starttime is not None and domain_starttime > starttime:
+        time = time - domain_starttime + starttime
+    vertex_coordinates = np.stack([src["x"], src["y"]], axis=1)
+    F = Interpolation_function(time, {n: src[n][:upper] for n in names}, names, vertex_coordinates,
+                               src["triangles"], pts, time_thinning=time_thinning)
+    F.starttime = starttime
+    if domain is not None and starttime > domain.starttime:
+        domain.set_starttime(starttime)
+    return F
+
+
+# ----------------------------------------------------------------------------------------
+# boundary objects
+# ----------------------------------------------------------------------------------------
+class _Table_boundary(Boundary):
+    """common part: frames at the midpoints of the segment's boundary edges, resident on the device"""
+    device_kind = _b.BC_TIME_SPACE_TABLE
+    time_dependent = True
+    mean_stage = 0.0
+
+    def boundary_point_ids(self, ids):
+        """rows of the frames for the boundary edges `ids` (boundary indices)"""
+        raise NotImplementedError
+
+    def frames_for(self, ids):
+        """(frames, len(ids), 3) array for the device table"""
+        raise NotImplementedError
+
+
+class File_boundary(_Table_boundary):
+    """generic_boundary_conditions.py:518-700"""
+
+    def __init__(self, filename, domain, time_thinning=1, time_limit=None, boundary_polygon=None,
+                 default_boundary=None, use_cache=False, verbose=False):
+        self.domain = domain
+        self.verbose = verbose
+        # one interpolation point per boundary edge, in the order of the sorted (triangle, edge) keys
+        keys = sorted(domain.boundary.keys())
+        self.boundary_indices = {key: i for i, key in enumerate(keys)}
+        vol = np.array([k[0] for k in keys], dtype=np.int64)
+        edge = np.array([k[1] for k in keys], dtype=np.int64)
+        geo = getattr(domain.mesh, "geo_reference", None)
+        xll = geo.get_xllcorner() if geo is not None else 0.0
+        yll = geo.get_yllcorner() if geo is not None else 0.0
+        self.midpoint_coordinates = domain.edge_midpoint_coordinates[3 * vol + edge] + np.array([xll, yll])
+        self.F = file_function(filename, domain, quantities=domain.conserved_quantities,
+                               interpolation_points=self.midpoint_coordinates, time_thinning=time_thinning,
+                               time_limit=time_limit, verbose=verbose, boundary_polygon=boundary_polygon)
+        assert default_boundary is None or isinstance(default_boundary, Boundary), \
+            "Keyword argument default_boundary must be either None or a boundary object.\n I got %s" % default_boundary
+        self.default_boundary = default_boundary
+        self.default_boundary_invoked = False
+        q = self.F(self.F.time[0], point_id=0)
+        assert len(q) == len(domain.conserved_quantities)
+        self._point_of_boundary_index = None
+
+    def __repr__(self):
+        return "File boundary"
+
+    def _rows(self, ids):
+        d = self.domain
+        return np.array([self.boundary_indices[(int(d.boundary_cells[m]), int(d.boundary_edges[m]))] for m in ids],
+                        dtype=np.int64)
+
+    def frames_for(self, ids):
+        rows = self._rows(ids)
+        names = self.F.quantity_names
+        fr = np.stack([self.F.precomputed_values[n][:, rows] for n in names], axis=2)     # (T, P, 3)
+        if not np.all(np.isfinite(fr)):
+            bad = rows[np.flatnonzero(~np.all(np.isfinite(fr), axis=(0, 2)))[0]]
+            x, y = self.midpoint_coordinates[bad]
+            raise Exception("NAN value found in file_boundary at point id #%d: (%.2f, %.2f).\n"
+                            "The point lies outside the mesh stored in the file." % (bad, x, y))
+        return np.ascontiguousarray(fr)
+
+    def device_values(self, t):
+        """{ratio, frame index, mean stage}: the time slot the boundary kernel interpolates in"""
+        index, ratio = self.F.time_slot(t)
+        return (float(ratio), float(index), float(self.mean_stage))
+
+    def evaluate(self, vol_id=None, edge_id=None):
+        q = self.F(self.domain.get_time(), point_id=self.boundary_indices[(vol_id, edge_id)])
+        q[0] += 0.0 if self.mean_stage == 0.0 else self.mean_stage
+        return q
+
+    def oracle_spec(self):
+        return ("file", self)
+
+
+class Field_boundary(File_boundary):
+    """shallow_water/boundaries.py:993-1090: a File_boundary whose stage is offset by mean_stage"""
+    device_kind = _b.BC_TIME_SPACE_TABLE_MEAN_STAGE
+
+    def __init__(self, filename, domain, mean_stage=0.0, time_thinning=1, time_limit=None, boundary_polygon=None,
+                 default_boundary=None, use_cache=False, verbose=False):
+        File_boundary.__init__(self, filename, domain, time_thinning=time_thinning, time_limit=time_limit,
+                               boundary_polygon=boundary_polygon, default_boundary=default_boundary,
+                               use_cache=use_cache, verbose=verbose)
+        self.file_boundary = self
+        self.mean_stage = mean_stage
+
+    def __repr__(self):
+        return "Field boundary"
+
+    def evaluate(self, vol_id=None, edge_id=None):
+        q = self.F(self.domain.get_time(), point_id=self.boundary_indices[(vol_id, edge_id)])
+        q[0] += self.mean_stage
+        return q
+
+
+class Time_space_boundary(_Table_boundary):
+    """generic_boundary_conditions.py:419-516: values from a Python function of (t, x, y), evaluated at the
+    edge midpoints on the host for every RK substep (three frames on the device, rewritten every step)."""
+
+    def __init__(self, domain=None, function=None, default_boundary=None, verbose=False):
+        if function is None:
+            raise Exception("You must specify a function to Time_space_boundary")
+        try:
+            q = function(0.0, 0.0, 0.0)
+        except Exception as e:
+            raise Exception("Function for time_space_boundary could not be executed:\n%s" % e)
+        q = np.array(q, dtype=np.float64)
+        assert len(q.shape) == 1, "ERROR: Time_space_boundary function must return a 1d list or array "
+        assert len(q) == len(domain.conserved_quantities), \
+            "Return value for function must be a list or an array of length %d" % len(domain.conserved_quantities)
+        self.domain = domain
+        self.function = function
+        self.default_boundary = default_boundary
+        self.default_boundary_invoked = False
+        self.verbose = verbose
+        self._ids = None
+
+    def __repr__(self):
+        return "Time space boundary"
+
+    def evaluate_all(self, ids, t):
+        d = self.domain
+        mid = d.edge_midpoint_coordinates[3 * d.boundary_cells[ids] + d.boundary_edges[ids]]
+        out = np.empty((len(ids), 3))
+        for j, (x, y) in enumerate(mid):
+            out[j] = np.asarray(self.function(t, x, y), dtype=np.float64)[:3]
+        return out
+
+    def frames_for(self, ids):
+        self._ids = np.asarray(ids, dtype=np.int64)
+        f = self.evaluate_all(self._ids, self.domain.get_time())
+        return np.ascontiguousarray(np.stack([f, f, f], axis=0))
+
+    def values_for_substep(self, dev, seg, substep, t):
+        dev.set_boundary_table_frame(seg, substep, self.evaluate_all(self._ids, t))
+        return (0.0, float(substep), 0.0)
+
+    def device_values(self, t):
+        return (0.0, 0.0, 0.0)
+
+    def oracle_spec(self):
+        return ("time_space", self.function)

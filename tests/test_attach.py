@@ -43,7 +43,7 @@ def test_adapter_snapshots_a_real_reference_domain():
 def test_adapter_rejects_what_it_cannot_run():
     anuga = pyref.import_anuga()
     ref = cases.dam_break_de0(anuga, n=4)
-    ref.boundary_map["left"] = type("Characteristic_stage_boundary", (object,), {})()
+    ref.boundary_map["left"] = type("Inflow_boundary", (object,), {})()
     with pytest.raises(NotImplementedError):
         ab.B200_interface(ref)
 

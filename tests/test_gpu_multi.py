@@ -21,7 +21,7 @@ def run_distributed(case, nranks, tmp_path, rule, extra=()):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "multi_gpu_worker.py"), case, str(tmp_path), rule] + list(extra)
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     return [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(nranks)]
 
