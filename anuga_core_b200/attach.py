@@ -23,6 +23,7 @@ What it does:
 import numpy as np
 
 from . import boundaries as _bnd
+from . import file_boundary as _fb
 from . import structures as _st
 from .domain import Domain, MODE_B200
 from .operators import Rate_operator
@@ -41,6 +42,9 @@ _BOUNDARY_BY_NAME = {
     "Time_stage_zero_momentum_boundary": lambda B, d: _bnd.Time_stage_zero_momentum_boundary(d, B.f),
     "Flather_external_stage_zero_velocity_boundary":
         lambda B, d: _bnd.Flather_external_stage_zero_velocity_boundary(d, B.function),
+    "File_boundary": lambda B, d: _fb.File_boundary.adopt(B, d),
+    "Field_boundary": lambda B, d: _fb.Field_boundary.adopt(B, d),
+    "Time_space_boundary": lambda B, d: _fb.Time_space_boundary(d, B.function, B.default_boundary),
     "Characteristic_stage_boundary":
         lambda B, d: _bnd.Characteristic_stage_boundary(d, B.function, B.default_stage),
 }

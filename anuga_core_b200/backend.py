@@ -35,6 +35,7 @@ BC_TRANSMISSIVE_N_ZERO_T_SET_STAGE, BC_TRANSMISSIVE_MOMENTUM_SET_STAGE = 4, 5
 BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6
 BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY = 7
 BC_CHARACTERISTIC_STAGE = 8
+BC_TIME_SPACE_TABLE, BC_TIME_SPACE_TABLE_MEAN_STAGE = 9, 10
 
 _I = C.c_int64
 _D = C.c_double
@@ -124,6 +125,8 @@ SYMBOLS = {
     "swk_set_momentum_forcing": (C.c_int, [_H, _PD, _PD, _I]),
     "swk_set_rate_dynamic": (C.c_int, [_H, C.c_int, C.c_int]),
     "swk_set_boundary_values_substep": (C.c_int, [_H, C.c_int, C.c_int, _PD]),
+    "swk_set_boundary_table": (C.c_int, [_H, C.c_int, _I, _I, _PD]),
+    "swk_set_boundary_table_frame": (C.c_int, [_H, C.c_int, _I, _PD]),
     "swk_step_begin": (C.c_int, [_H, _D, _D]),
     "swk_step_first": (C.c_int, [_H, C.POINTER(SwkEvolveResult)]),
     "swk_step_rest": (C.c_int, [_H]),
@@ -464,6 +467,15 @@ class DeviceDomain:
     def set_boundary_values_substep(self, segment, substep, values):
         v = (_D * 3)(*[float(x) for x in values])
         _check(self.lib.swk_set_boundary_values_substep(self.h, int(segment), int(substep), v))
+
+    def set_boundary_table(self, segment, frames):
+        f = np.ascontiguousarray(frames, dtype=np.float64)
+        assert f.ndim == 3 and f.shape[2] == 3
+        _check(self.lib.swk_set_boundary_table(self.h, int(segment), f.shape[0], f.shape[1], _pd(f)))
+
+    def set_boundary_table_frame(self, segment, frame, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        _check(self.lib.swk_set_boundary_table_frame(self.h, int(segment), int(frame), _pd(v)))
 
     def set_rate_dynamic(self, op_id, dynamic=True):
         _check(self.lib.swk_set_rate_dynamic(self.h, int(op_id), int(bool(dynamic))))

@@ -183,6 +183,12 @@ struct swk_domain {
   std::vector<int> seg_kind;
   int *d_seg_kind = nullptr;
   int seg_cap = 0;
+  // time-space tables of the table kinds: one device buffer per segment
+  std::vector<double *> seg_tab;      // device pointers (null: none)
+  std::vector<int> seg_np, seg_nframes;
+  std::vector<int> h_b_point;         // [M]
+  double **d_seg_tab = nullptr;
+  int *d_seg_np = nullptr, *d_b_point = nullptr;
   bool seg_dirty = true;       // kinds / edge->segment map changed (structure; uploaded with a sync)
   // value table: boundary values [segment][substep][3], then {rate, factor} of every Rate_operator.
   // Page-locked host copy + device copy, refreshed by one async copy per step when dirty.
@@ -476,6 +482,11 @@ extern "C" int swk_destroy(swk_domain *d)
     if (op.d_indices) cudaFree(op.d_indices);
     if (op.d_partial) cudaFree(op.d_partial);
   }
+  for (double *t : d->seg_tab)
+    if (t) cudaFree(t);
+  if (d->d_seg_tab) cudaFree(d->d_seg_tab);
+  if (d->d_seg_np) cudaFree(d->d_seg_np);
+  if (d->d_b_point) cudaFree(d->d_b_point);
   for (auto &pe : d->peers) {
     if (pe.d_send_ids) cudaFree(pe.d_send_ids);
     if (pe.d_recv_ids) cudaFree(pe.d_recv_ids);
@@ -930,13 +941,27 @@ static int push_segments(swk_domain *d)
     const int ns = (int)d->seg_kind.size();
     if (ns > d->seg_cap) {
       if (d->d_seg_kind) cudaFree(d->d_seg_kind);
+      if (d->d_seg_tab) cudaFree(d->d_seg_tab);
+      if (d->d_seg_np) cudaFree(d->d_seg_np);
       d->seg_cap = std::max(16, 2 * ns);
       CKV(dalloc(&d->d_seg_kind, d->seg_cap));
+      CKV(dalloc(&d->d_seg_tab, d->seg_cap));
+      CKV(dalloc(&d->d_seg_np, d->seg_cap));
     }
-    if (ns > 0)
+    d->seg_tab.resize(ns, nullptr);
+    d->seg_np.resize(ns, 0);
+    d->seg_nframes.resize(ns, 0);
+    if (ns > 0) {
       CK(cudaMemcpyAsync(d->d_seg_kind, d->seg_kind.data(), ns * sizeof(int), cudaMemcpyHostToDevice, d->stream));
-    if (d->M > 0)
+      CK(cudaMemcpyAsync(d->d_seg_tab, d->seg_tab.data(), ns * sizeof(double *), cudaMemcpyHostToDevice, d->stream));
+      CK(cudaMemcpyAsync(d->d_seg_np, d->seg_np.data(), ns * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    }
+    if (d->M > 0) {
       CK(cudaMemcpyAsync(d->b_seg, d->h_b_seg.data(), d->M * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+      if (!d->d_b_point) CKV(dalloc(&d->d_b_point, d->M));
+      d->h_b_point.resize(d->M, 0);
+      CK(cudaMemcpyAsync(d->d_b_point, d->h_b_point.data(), d->M * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    }
     CK(cudaStreamSynchronize(d->stream));   // host vectors may change after return
     d->seg_dirty = false;
   }
@@ -948,16 +973,18 @@ extern "C" int swk_set_boundary_segment(swk_domain *d, int segment, int kind, co
 {
   if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
   if (segment < 0 || segment >= SEG_MAX) return fail(SWK_ERR_ARG, "segment id out of range");
-  if (kind < SWK_BC_NONE || kind > SWK_BC_CHARACTERISTIC_STAGE) return fail(SWK_ERR_ARG, "unknown boundary kind");
+  if (kind < SWK_BC_NONE || kind > SWK_BC_TIME_SPACE_TABLE_MEAN_STAGE) return fail(SWK_ERR_ARG, "unknown boundary kind");
   if ((int)d->seg_kind.size() <= segment) d->seg_kind.resize(segment + 1, 0);
   d->seg_kind[segment] = kind;
   CKV(vals_writable(d));
   for (int sub = 0; sub < 3; sub++)
     for (int j = 0; j < 3; j++) d->h_vals[(3 * segment + sub) * 3 + j] = values ? values[j] : 0.0;
   d->vals_dirty = true;
+  d->h_b_point.resize(d->M, 0);
   for (int64_t j = 0; j < n_ids; j++) {
     if (ids[j] < 0 || ids[j] >= d->M) return fail(SWK_ERR_ARG, "boundary id out of range");
     d->h_b_seg[ids[j]] = segment;
+    d->h_b_point[ids[j]] = (int)j;          // position in the segment: row of its time-space table
   }
   d->seg_dirty = true;
   d->graph_valid = false;
@@ -972,6 +999,48 @@ extern "C" int swk_set_boundary_values(swk_domain *d, int segment, const double 
   for (int sub = 0; sub < 3; sub++)
     for (int j = 0; j < 3; j++) d->h_vals[(3 * segment + sub) * 3 + j] = values[j];
   d->vals_dirty = true;                // values live in device tables: the graph stays valid
+  return SWK_OK;
+}
+
+// Time-space table of a segment bound to SWK_BC_TIME_SPACE_TABLE[_MEAN_STAGE]: frames[n_frames][n_points][3]
+// (stage, xmomentum, ymomentum), point j belonging to the j-th boundary index given to
+// swk_set_boundary_segment.  Uploaded once and kept resident; the boundary values of the segment are then
+// {ratio, frame index, mean_stage} (swk_set_boundary_values*).
+extern "C" int swk_set_boundary_table(swk_domain *d, int segment, int64_t n_frames, int64_t n_points,
+                                      const double *frames)
+{
+  if (!d || !frames) return fail(SWK_ERR_ARG, "NULL argument");
+  if (segment < 0 || segment >= (int)d->seg_kind.size()) return fail(SWK_ERR_ARG, "unknown segment");
+  if (n_frames < 1 || n_points < 0) return fail(SWK_ERR_ARG, "bad table shape");
+  CK(cudaSetDevice(d->device));
+  CKV(sync_check(d));
+  d->seg_tab.resize(d->seg_kind.size(), nullptr);
+  d->seg_np.resize(d->seg_kind.size(), 0);
+  d->seg_nframes.resize(d->seg_kind.size(), 0);
+  if (d->seg_tab[segment]) { cudaFree(d->seg_tab[segment]); d->seg_tab[segment] = nullptr; }
+  const size_t n = (size_t)n_frames * (size_t)n_points * 3;
+  CKV(dalloc(&d->seg_tab[segment], n));
+  if (n > 0) CK(cudaMemcpy(d->seg_tab[segment], frames, n * sizeof(double), cudaMemcpyHostToDevice));
+  d->seg_np[segment] = (int)n_points;
+  d->seg_nframes[segment] = (int)n_frames;
+  d->seg_dirty = true;
+  d->graph_valid = false;
+  return SWK_OK;
+}
+
+// rewrite one frame of a segment's table (Time_space_boundary: one frame per RK substep, every step)
+extern "C" int swk_set_boundary_table_frame(swk_domain *d, int segment, int64_t frame, const double *values)
+{
+  if (!d || !values) return fail(SWK_ERR_ARG, "NULL argument");
+  if (segment < 0 || segment >= (int)d->seg_tab.size() || !d->seg_tab[segment])
+    return fail(SWK_ERR_ARG, "the segment has no table");
+  if (frame < 0 || frame >= d->seg_nframes[segment]) return fail(SWK_ERR_ARG, "frame out of range");
+  CK(cudaSetDevice(d->device));
+  const size_t n = (size_t)d->seg_np[segment] * 3;
+  // (pageable source: the copy has left the host buffer when the call returns)
+  CK(cudaMemcpyAsync(d->seg_tab[segment] + (size_t)frame * n, values, n * sizeof(double), cudaMemcpyHostToDevice,
+                     d->stream));
+  CK(cudaStreamSynchronize(d->stream));
   return SWK_OK;
 }
 
@@ -1243,6 +1312,7 @@ static int launch_boundary(swk_domain *d, int substep = 0)
   Segments S;
   S.b_cell = d->b_cell; S.b_edge = d->b_edge; S.b_seg = d->b_seg;
   S.seg_kind = d->d_seg_kind; S.seg_val = d->d_vals; S.substep = substep;
+  S.seg_tab = d->d_seg_tab; S.seg_np = d->d_seg_np; S.b_point = d->d_b_point;
   if (d->seg_kind.empty()) return SWK_OK;
   LAUNCH(d, k_boundary_values, nblk(d->M), BLOCK, d->D, S, d->K, (int)d->P.centroid_transmissive_bc);
   return SWK_OK;

@@ -341,6 +341,11 @@ struct Segments {
   const int *seg_kind;     // [nseg]
   const double *seg_val;   // [nseg][3 substeps][3]: values of time-dependent kinds differ per RK substep
   int substep;
+  // time-space tables (File_boundary / Field_boundary / Time_space_boundary): frames[frame][point][3] of
+  // segment s start at seg_tab[s], hold seg_np[s] points per frame; b_point[m] = point of boundary edge m
+  const double *const *seg_tab;
+  const int *seg_np;
+  const int *b_point;
 };
 
 // boundary value of one edge from the triangle's own edge record e = {stage, height, xmom, ymom},
@@ -438,6 +443,27 @@ __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, 
   if (seg < 0) return;
   const int kind = S.seg_kind[seg];
   if (kind == 0) return;
+  const double *sv = S.seg_val + (3 * seg + S.substep) * 3;
+  if (kind >= 9) {
+    // frames resident in HBM, linear in time between frame idx and idx + 1 (Interpolation_function.__call__,
+    // fit_interpolate/interpolate.py:1056-1092): q = Q0 + ratio*(Q1 - Q0); kind 10 adds mean_stage to the stage
+    const double ratio = sv[0];
+    const int idx = (int)sv[1];
+    const int np_ = S.seg_np[seg];
+    const double *q0 = S.seg_tab[seg] + ((long long)idx * np_ + S.b_point[m]) * 3;
+    double v[3] = {q0[0], q0[1], q0[2]};
+    if (ratio > 0.0) {
+      const double *q1 = q0 + (long long)np_ * 3;
+#pragma unroll
+      for (int j = 0; j < 3; j++) v[j] = q0[j] + ratio * (q1[j] - q0[j]);
+    }
+    out.x = (kind == 10) ? v[0] + sv[2] : v[0];
+    out.y = v[1];
+    out.z = v[2];
+    out.w = 0.0;
+    touched = true;
+    return;
+  }
   const int k = S.b_cell[m];
   const int i = S.b_edge[m];
   const d4 e = D.eq[i * D.NP + k];           // {stage, height, xmom, ymom}
@@ -450,7 +476,6 @@ __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, 
     if (D.zflag[k] & 1) { cuh = 0.0; cvh = 0.0; }
   }
   const double bed_c = (kind == 7) ? D.cq[k].w : 0.0;
-  const double *sv = S.seg_val + (3 * seg + S.substep) * 3;
   touched = boundary_value_core(kind, sv[0], sv[1], sv[2], e,
                                 n1, n2, centroid_transmissive, cw, cuh, cvh, out, bed_c, (kind == 8) ? K.sqrt_g : K.g);
 }

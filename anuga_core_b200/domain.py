@@ -792,14 +792,38 @@ class Domain:
                 B = self.boundary_map[tag]
                 ids = self.tag_boundary_cells[tag]
                 kind = _b.BC_NONE if B is None else B.device_kind
-                vals = (0.0, 0.0, 0.0) if B is None else B.device_values(t)
-                dev.set_boundary_segment(seg, kind, ids, vals)
+                if hasattr(B, "frames_for"):          # time-space table kinds: frames resident on the device
+                    dev.set_boundary_segment(seg, kind, ids, (0.0, 0.0, 0.0))
+                    dev.set_boundary_table(seg, B.frames_for(ids))
+                    dev.set_boundary_values(seg, self._segment_values(seg, tag, B, 0, t))
+                else:
+                    vals = (0.0, 0.0, 0.0) if B is None else B.device_values(t)
+                    dev.set_boundary_segment(seg, kind, ids, vals)
                 self._segments[tag] = (seg, B)
             self._boundary_dirty = False
         else:
-            for tag, (seg, B) in self._segments.items():
+            for tag, (seg, B) in list(self._segments.items()):
                 if B is not None and B.time_dependent:
-                    dev.set_boundary_values(seg, B.device_values(t))
+                    dev.set_boundary_values(seg, self._segment_values(seg, tag, B, 0, t))
+
+    def _segment_values(self, seg, tag, B, substep, t):
+        """value-table entries of a time-dependent boundary at time t; when its data has run out
+        (Modeltime_too_late) and it carries a default_boundary OBJECT, that boundary takes the segment over
+        (generic_boundary_conditions.py:486-516, 655-684)"""
+        try:
+            return B.values_for_substep(self._dev, seg, substep, t)
+        except BaseException as e:
+            default = getattr(B, "default_boundary", None)
+            if type(e).__name__ != "Modeltime_too_late" or not hasattr(default, "device_kind"):
+                raise
+            if getattr(B, "verbose", False) and not getattr(B, "default_boundary_invoked", False):
+                print("%s\nInstead I will use the default boundary: %s\nNote: Further warnings will be supressed"
+                      % (e, default))
+            B.default_boundary_invoked = True
+            self._dev.set_boundary_segment(seg, default.device_kind, self.tag_boundary_cells[tag],
+                                           default.device_values(t))
+            self._segments[tag] = (seg, default)
+            return default.device_values(t)
 
     def _push_operators(self, t):
         dev = self._dev
@@ -1210,7 +1234,13 @@ class Domain:
         and the second half is released.  One D2H scalar read and one small H2D copy per step."""
         dev = self._dev
         method = self.timestepping_method
-        segs = [(seg, B) for (seg, B) in self._segments.values() if B is not None and B.time_dependent]
+        segs = [(seg, tag) for tag, (seg, B) in self._segments.items() if B is not None and B.time_dependent]
+
+        def values(seg, tag, substep, t):
+            B = self._segments[tag][1]
+            if not B.time_dependent:        # a default boundary took over
+                return B.device_values(t)
+            return self._segment_values(seg, tag, B, substep, t)
         ops = [op for op in self.fractional_step_operators
                if not getattr(op, "host_side", False) and op.time_dependent]
         dev.step_begin(self.relative_yieldtime, self.relative_finaltime)
@@ -1227,13 +1257,13 @@ class Domain:
             self.relative_time = t0 + dt
             T1 = self.get_time()
             if method != "euler":
-                for seg, B in segs:
-                    dev.set_boundary_values_substep(seg, 1, B.device_values(T1))
+                for seg, tag in segs:
+                    dev.set_boundary_values_substep(seg, 1, values(seg, tag, 1, T1))
             if method == "rk3":
                 self.relative_time = t0 + dt * 0.5
                 T2 = self.get_time()
-                for seg, B in segs:
-                    dev.set_boundary_values_substep(seg, 2, B.device_values(T2))
+                for seg, tag in segs:
+                    dev.set_boundary_values_substep(seg, 2, values(seg, tag, 2, T2))
             # fractional-step operators see t0 after an euler step and t0 + dt after rk2 / rk3 (see _host_step)
             self.relative_time = t0 if method == "euler" else t0 + dt
             Top = self.get_time()
@@ -1241,15 +1271,15 @@ class Domain:
                 dev.set_rate(op.op_id, op.current_rate(Top), op.current_factor(Top))
             # the next step's first substep (and the yield's update_boundary) see the time after this step
             self.relative_time = t0 + dt
-            for seg, B in segs:
-                dev.set_boundary_values_substep(seg, 0, B.device_values(T1))
+            for seg, tag in segs:
+                dev.set_boundary_values_substep(seg, 0, values(seg, tag, 0, T1))
             dev.step_rest()
         reason = r.stop_reason
         if reason == 2:
             # time snapped to finaltime (generic_domain.py:1870-1888): the yield's boundary update sees it
             self.relative_time = r.time
-            for seg, B in segs:
-                dev.set_boundary_values(seg, B.device_values(self.get_time()))
+            for seg, tag in segs:
+                dev.set_boundary_values(seg, values(seg, tag, 0, self.get_time()))
         r = dev.step_end()
         self._absorb(r)
         return reason

@@ -114,11 +114,9 @@ class Interpolation_function:
         T = np.asarray(triangles, dtype=np.int64)
         ok = tri >= 0
         nodes = T[np.where(ok, tri, 0)]                     # (m, 3) node ids
-        # one row of the interpolation matrix per point; the sparse product adds the three terms in the
-        # order of increasing node id (CSR column order)
-        order = np.argsort(nodes, axis=1, kind="stable")
-        nodes_s = np.take_along_axis(nodes, order, axis=1)
-        sig_s = np.take_along_axis(sig, order, axis=1)
+        # one row of the interpolation matrix per point; the reference's dictionary-of-keys product adds the
+        # three terms in the triangle's vertex order, starting from zero (anuga/utilities/sparse.py:125-131)
+        nodes_s, sig_s = nodes, sig
         self.precomputed_values = {}
         for name in self.quantity_names:
             Q = np.asarray(quantities[name])
@@ -128,31 +126,16 @@ class Interpolation_function:
             out = np.zeros((len(self.time), len(self.interpolation_points)))
             for i in range(len(self.time)):
                 q = np.asarray(frames[i], dtype=np.float64)
-                r = sig_s[:, 0] * q[nodes_s[:, 0]]
+                r = 0.0 + sig_s[:, 0] * q[nodes_s[:, 0]]
                 r = r + sig_s[:, 1] * q[nodes_s[:, 1]]
                 r = r + sig_s[:, 2] * q[nodes_s[:, 2]]
                 out[i] = np.where(ok, r, NAN)
             self.precomputed_values[name] = out
 
-    def time_slot(self, t):
-        """(index, ratio) of model time t: interpolate.py:1045-1062"""
-        msg = "Model time %.16f is not contained in function domain [%.16f:%.16f].\n" % (t, self.time[0], self.time[-1])
-        if t < self.time[0]:
-            raise Modeltime_too_early(msg)
-        if t > self.time[-1]:
-            raise Modeltime_too_late(msg)
-        while t > self.time[self.index]:
-            self.index += 1
-        while t < self.time[self.index]:
-            self.index -= 1
-        if t == self.time[self.index]:
-            return self.index, 0.0
-        return self.index, (t - self.time[self.index]) / (self.time[self.index + 1] - self.time[self.index])
-
     def __call__(self, t, point_id=None):
         if point_id is None:
             raise Exception("Either point_id or x and y must be specified")
-        index, ratio = self.time_slot(t)
+        index, ratio = time_slot(self, t)
         q = np.zeros(len(self.quantity_names))
         for i, name in enumerate(self.quantity_names):
             Q = self.precomputed_values[name]
@@ -163,6 +146,23 @@ class Interpolation_function:
             else:
                 q[i] = Q0
         return q
+
+
+def time_slot(F, t):
+    """(frame index, ratio) of model time t in the time axis of an interpolation function - this module's or
+    the reference's own (an attached reference File_boundary): interpolate.py:1045-1062"""
+    msg = "Model time %.16f is not contained in function domain [%.16f:%.16f].\n" % (t, F.time[0], F.time[-1])
+    if t < F.time[0]:
+        raise Modeltime_too_early(msg)
+    if t > F.time[-1]:
+        raise Modeltime_too_late(msg)
+    while t > F.time[F.index]:
+        F.index += 1
+    while t < F.time[F.index]:
+        F.index -= 1
+    if t == F.time[F.index]:
+        return F.index, 0.0
+    return F.index, (t - F.time[F.index]) / (F.time[F.index + 1] - F.time[F.index])
 
 
 def file_function(filename, domain=None, quantities=None, interpolation_points=None, time_thinning=1,
@@ -269,8 +269,27 @@ class File_boundary(_Table_boundary):
 
     def device_values(self, t):
         """{ratio, frame index, mean stage}: the time slot the boundary kernel interpolates in"""
-        index, ratio = self.F.time_slot(t)
+        index, ratio = time_slot(self.F, t)
         return (float(ratio), float(index), float(self.mean_stage))
+
+    @classmethod
+    def adopt(cls, ref_boundary, domain):
+        """take over a reference File_boundary / Field_boundary object (attach.py): its interpolation
+        function with the frames it precomputed, its point numbering, its mean stage"""
+        fb = getattr(ref_boundary, "file_boundary", ref_boundary)
+        self = cls.__new__(cls)
+        self.domain = domain
+        self.verbose = getattr(fb, "verbose", False)
+        self.boundary_indices = dict(fb.boundary_indices)
+        self.midpoint_coordinates = np.asarray(fb.midpoint_coordinates)
+        self.F = fb.F
+        default = getattr(fb, "default_boundary", None)
+        self.default_boundary = None if default is None else default
+        self.default_boundary_invoked = False
+        self.mean_stage = getattr(ref_boundary, "mean_stage", 0.0)
+        if cls is Field_boundary:
+            self.file_boundary = self
+        return self
 
     def evaluate(self, vol_id=None, edge_id=None):
         q = self.F(self.domain.get_time(), point_id=self.boundary_indices[(vol_id, edge_id)])

@@ -144,7 +144,12 @@ enum {
   SWK_BC_TRANSMISSIVE_MOMENTUM_SET_STAGE = 5,   /* boundaries.py:344-372 */
   SWK_BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6,  /* boundaries.py:543-551 */
   SWK_BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY = 7, /* boundaries.py:1096-1266 (evaluate_segment); v0 = external stage */
-  SWK_BC_CHARACTERISTIC_STAGE = 8                  /* boundaries.py:639-843 (evaluate_segment); v0 = outside stage */
+  SWK_BC_CHARACTERISTIC_STAGE = 8,                 /* boundaries.py:639-843 (evaluate_segment); v0 = outside stage */
+  /* File_boundary / Time_space_boundary (generic_boundary_conditions.py:419-700) and Field_boundary
+   * (boundaries.py:993-1090): values interpolated in time between two frames of a device-resident table
+   * (swk_set_boundary_table); v0 = ratio, v1 = frame index, v2 = mean_stage (added to the stage by kind 10) */
+  SWK_BC_TIME_SPACE_TABLE = 9,
+  SWK_BC_TIME_SPACE_TABLE_MEAN_STAGE = 10
 };
 
 /* ---- evolve result ------------------------------------------------------------ */
@@ -207,6 +212,12 @@ int swk_get_quantity(swk_domain *d, int quantity_id, double *host, int64_t n);
 int swk_set_boundary_segment(swk_domain *d, int segment, int kind, const int64_t *ids,
                              int64_t n_ids, const double values[3]);
 int swk_set_boundary_values(swk_domain *d, int segment, const double values[3]);
+/* Time-space table of a segment of kind SWK_BC_TIME_SPACE_TABLE[_MEAN_STAGE]: frames[n_frames][n_points][3],
+ * point j = the j-th boundary index passed to swk_set_boundary_segment; resident in HBM.  The time
+ * interpolation q = Q0 + ratio*(Q1 - Q0) (fit_interpolate/interpolate.py:1056-1092) runs in the boundary
+ * kernel.  swk_set_boundary_table_frame rewrites one frame in place.                              */
+int swk_set_boundary_table(swk_domain *d, int segment, int64_t n_frames, int64_t n_points, const double *frames);
+int swk_set_boundary_table_frame(swk_domain *d, int segment, int64_t frame, const double *values);
 /* The values one RK substep sees (0: start of the step, 1: second flux evaluation, 2: third): the
  * reference evaluates time-dependent boundaries at the substep's own time (generic_domain.py:2011,
  * 2093, 2132).  swk_set_boundary_values sets all three.  Values live in a device table; changing them

@@ -411,6 +411,21 @@ class OracleDomain:
                 self.stage_b[ids] = np.where(dry, q0_dry, q0_wet)
                 self.xmom_b[ids] = np.where(dry, 0.0 * xb, q1_wet)
                 self.ymom_b[ids] = np.where(dry, 0.0 * yb, q2_wet)
+            elif kind == "file":
+                # File_boundary.evaluate / Field_boundary.evaluate per edge (generic_boundary_conditions.py:636-700,
+                # boundaries.py:1072-1086): the interpolation function at the edge's point, stage + mean_stage
+                B = spec[1]
+                for m, v, e in zip(ids, vol, edge):
+                    q = B.F(t, point_id=B.boundary_indices[(int(v), int(e))])
+                    self.stage_b[m] = q[0] + B.mean_stage if B.device_kind == 10 else q[0]
+                    self.xmom_b[m] = q[1]
+                    self.ymom_b[m] = q[2]
+            elif kind == "time_space":
+                # Time_space_boundary.evaluate (generic_boundary_conditions.py:480-484) at the edge midpoints
+                for m, v, e in zip(ids, vol, edge):
+                    x, y = self.edge_coordinates[3 * v + e]
+                    q = spec[1](t, x, y)
+                    self.stage_b[m], self.xmom_b[m], self.ymom_b[m] = q[0], q[1], q[2]
             elif kind == "characteristic_stage":
                 # boundaries.py:760-843 (evaluate_segment), gravity = anuga.config.g
                 value = spec[1](t)

@@ -356,6 +356,26 @@ def riverwall_de1(A, n=14):
     return d
 
 
+def file_boundary_de1(A, n=8):
+    """a small basin nested inside the field stored in file_boundary_source.sww (written by the reference,
+    make_file_boundary_source.py): left File_boundary, right Field_boundary with a raised mean stage, top a
+    Time_space_boundary function of (t, x, y), bottom Reflective"""
+    import os
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "file_boundary_source.sww")
+    d = A.rectangular_cross_domain(n, n, len1=7.0, len2=6.0, origin=(3.3, 4.7))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    d.set_quantity("elevation", lambda x, y: -1.0 + 0.02 * x)
+    d.set_quantity("stage", 0.0)
+    d.set_quantity("friction", 0.01)
+    Br = A.Reflective_boundary(d)
+    Bf = A.File_boundary(src, d)
+    Bm = A.Field_boundary(src, d, mean_stage=0.02)
+    Bt = A.Time_space_boundary(d, function=lambda t, x, y: [0.01 * t + 0.001 * (x - 3.0), 0.0, 0.002 * y])
+    d.set_boundary({"left": Bf, "right": Bm, "top": Bt, "bottom": Br})
+    return d
+
+
 CASES = {
     "kat_bedslope_more_steps": (kat_bedslope_more_steps, dict(yieldstep=0.05, finaltime=0.5)),
     "dam_break_de0": (dam_break_de0, dict(yieldstep=1.0, finaltime=6.0)),
@@ -382,6 +402,7 @@ CASES = {
     "characteristic_de1": (characteristic_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "wind_de1": (wind_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "riverwall_de1": (riverwall_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "file_boundary_de1": (file_boundary_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_de1": (culvert_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_pipe_de1": (culvert_pipe_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_weir_de1": (culvert_weir_de1, dict(yieldstep=1.0, finaltime=4.0)),
