@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Const
     const i4 p = lds(&D.connB[k]);
     if (RW && (p.w & 0xE)) {                    // a triangle with a wall edge: flux only
       const Eff own = effective(D.cq[k], K);
-      const TriFlux T = triangle_flux<true, false>(D, K, k, p, own, false);
+      const TriFlux T = triangle_flux<true, SWK_FU_ROLLED>(D, K, k, p, own, false);
       D.eu[k] = T.su;
       D.eu[D.NP + k] = T.xu;
       D.eu[2 * D.NP + k] = T.yu;

@@ -314,6 +314,26 @@ def distribute_collective(domain=None, verbose=False, debug=False, parameters=No
     if comm.size == 1:
         return domain
     width = int((parameters or {}).get("ghost_layer_width", 2))
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    # Replicated build: when EVERY rank holds the sequential domain (each built or loaded it itself), every
+    # rank cuts out its own sub-domain - no serial pass over all parts on rank 0, nothing shipped.  This
+    # is the scalable route for large general meshes with a metis-style partition vector
+    # (parameters={'epart': vector}); the reference's rank-0 pipeline (distribute_mesh.py:152-278 +
+    # send_submesh) is kept below for scripts that build the domain on rank 0 only.
+    everybody = comm.allreduce_min(1.0 if domain is not None else 0.0) > 0.0
+    if everybody:
+        N = domain.number_of_triangles
+        epart = (parameters or {}).get("epart")
+        if epart is None:
+            if (parameters or {}).get("partition", "blocks") == "rcb":
+                epart = rcb_partition(domain.centroid_coordinates, comm.size)
+            else:
+                epart = (np.arange(N) * comm.size) // N
+        d = distribute(domain, comm.size, epart=np.asarray(epart, dtype=np.int64), ghost_layer_width=width,
+                       ranks=[comm.rank], domain_kw=dict(device=device))[comm.rank]
+        d.attach_communicator(comm)
+        return d
     payload = [None] * comm.size
     if comm.rank == 0:
         if domain.fractional_step_operators:
@@ -332,8 +352,6 @@ def distribute_collective(domain=None, verbose=False, debug=False, parameters=No
     m = comm.scatter_objects(payload)
     order = np.zeros(int(m["sub"]["tri_l2g"].max()) + 1, dtype=np.int64)
     order[m["sub"]["tri_l2g"]] = m["l2s"]
-    if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0"))
     d = _subdomain(m["sub"], order, comm.size, comm.rank, width, m["settings"], m["cv"], {}, m["names"],
                    dict(device=device))
     d.attach_communicator(comm)
@@ -598,10 +616,12 @@ class NcclCommunicator(Communicator):
         return mine
 
     def finalize(self):
+        """Last collective of the job: a barrier.  The NCCL communicator itself is left to the end of the
+        process (ncclCommDestroy is a collective that must not race with domains that still hold captured
+        NCCL work; measured: it can block for minutes at 8 ranks), like the reference leaves MPI_Finalize to
+        the interpreter's exit."""
         if self.nccl is not None:
             self.barrier()
-            self.nccl.close()
-            self.nccl = None
             if self.rank == 0:
                 try:
                     os.rmdir(self.dir)

@@ -418,9 +418,7 @@ def main():
     if comm is not None:
         comm.barrier()
     if rank != 0:
-        if comm is not None:
-            comm.finalize()
-        return 0
+        return finish(comm)
 
     peak, peak_src = measured_peak()
     alg = alg_of(a)
@@ -472,9 +470,17 @@ def main():
         r = cpu_reference_run(a, cs, a.cpu_steps, 2)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
+    return finish(comm)
+
+
+def finish(comm):
+    """End of a GPU-arm process: last barrier, flush, and leave without running destructors (device handles
+    and the NCCL communicator go with the process; tearing them down rank by rank can block on the others)."""
     if comm is not None:
         comm.finalize()
-    return 0
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def n_active_triangles(d, kernel):
