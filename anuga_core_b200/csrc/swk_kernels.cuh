@@ -219,9 +219,27 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
     const double hc = e.h;
     const double hmin = dmin(dmin(e0.h, dmin(e1.h, e2.h)), hc);
     const double hmax = dmax(dmax(e0.h, dmax(e1.h, e2.h)), hc);
-    double hfactor = dmax0(dmin(c_tmp * dmax0(hmin) / dmax(hc, 1.0e-06) + d_tmp,
-                                dmin(c_tmp * dmax0(hc) / dmax(hmax, 1.0e-06) + d_tmp, 1.0)));
+    double hfactor;
+#if SWK_LIMITER_FAST
+    // Well inside the wet region all three quotients below are >= 1 and hfactor is exactly 1.0; that is
+    // decided without dividing (margin 1e-12 over the roundings: x/y + d >= 1 whenever x >= y*(1 - d)*(1 + 1e-12))
+    // and taken only when every active lane of the warp agrees.  Otherwise the reference's expression runs.
+    const double n1_ = c_tmp * dmax0(hmin), y1_ = dmax(hc, 1.0e-06);
+    const double n2_ = c_tmp * dmax0(hc), y2_ = dmax(hmax, 1.0e-06);
+    const double n3_ = 1.2 * dmax0(hmin - K.mah), y3_ = dmax0(hmin) + 1. * K.mah;
+    const double lift = (1.0 - d_tmp) * (1.0 + 1.0e-12);
+    const bool all_one = (n1_ >= y1_ * lift) & (n2_ >= y2_ * lift) & (n3_ >= y3_ * (1.0 + 1.0e-12));
+    if (__all_sync(__activemask(), all_one)) {
+      hfactor = 1.0;
+    } else {
+      hfactor = dmax0(dmin(n1_ / y1_ + d_tmp, dmin(n2_ / y2_ + d_tmp, 1.0)));
+      hfactor = dmin(n3_ / y3_, hfactor);
+    }
+#else
+    hfactor = dmax0(dmin(c_tmp * dmax0(hmin) / dmax(hc, 1.0e-06) + d_tmp,
+                         dmin(c_tmp * dmax0(hc) / dmax(hmax, 1.0e-06) + d_tmp, 1.0)));
     hfactor = dmin(1.2 * dmax0(hmin - K.mah) / (dmax0(hmin) + 1. * K.mah), hfactor);
+#endif
     double beta = K.beta_w_dry + (K.beta_w - K.beta_w_dry) * hfactor;
     edge_values_3(beta, e.w, e0.w, e1.w, e2.w, G, w0, w1, w2);
     edge_values_3(beta, e.h, e0.h, e1.h, e2.h, G, h0, h1, h2);

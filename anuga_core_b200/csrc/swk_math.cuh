@@ -246,6 +246,9 @@ __device__ __forceinline__ Eff effective(const d4 c, const Consts &K)
 //     min_i fl(qmax/dq_i) = fl(qmax / max_i dq_i),   min_i fl(qmin/dq_i) = fl(qmin / min_i dq_i):
 // two branch-free divisions per quantity instead of the reference's three (the sign of dq differs from
 // thread to thread, so a branching form would execute every division in almost every warp anyway).
+#ifndef SWK_LIMITER_FAST
+#define SWK_LIMITER_FAST 1
+#endif
 __device__ __forceinline__ void limit_gradient(double &d0, double &d1, double &d2,
                                                double qmin, double qmax, double beta)
 {
@@ -253,6 +256,20 @@ __device__ __forceinline__ void limit_gradient(double &d0, double &d1, double &d
   const double dhi = dmax(d0, dmax(d1, d2));
   const double dlo = dmin(d0, dmin(d1, d2));
   const bool pos = dhi > TINY, neg = dlo < -TINY;
+#if SWK_LIMITER_FAST
+  // Where the field is smooth nothing is limited: phi = min(r*beta, 1) is exactly 1 and d*1 = d.  That can
+  // be decided without the two divisions: fl(fl(q/d)*beta) >= 1 whenever q*beta >= d*(1 + 1e-12) (the margin
+  // swamps the three roundings involved), the inactive sides give r = 1000, and an invalid edge 0 caps r at
+  // 1.  Taken only when every active lane of the warp agrees, so the branch costs no divergence; in all other
+  // cases the full computation below runs and gives, by construction, the same bits.
+  {
+    const double m = 1.0 + 1.0e-12;
+    const bool valid0f = (d0 < -TINY) | (d0 > TINY);
+    const bool fast = (beta >= 0.001) & (valid0f | (beta >= 1.0)) &
+                      (!pos | (qmax * beta >= dhi * m)) & (!neg | (qmin * beta <= dlo * m));
+    if (__all_sync(__activemask(), fast)) return;
+  }
+#endif
   const double rp = (pos ? qmax : 1000.0) / (pos ? dhi : 1.0);
   const double rn = (neg ? qmin : 1000.0) / (neg ? dlo : 1.0);
   double r = dmin(dmin(rp, rn), 1000.0);

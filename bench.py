@@ -44,7 +44,7 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-IS_REFERENCE_ARM = "reference" in sys.argv[1:] and "--impl" in sys.argv[1:]
+IS_REFERENCE_ARM = ("reference" in sys.argv[1:] and "--impl" in sys.argv[1:]) or "--impl=reference" in sys.argv[1:]
 # The CPU legs use every host core.  libgomp reads OMP_NUM_THREADS when it is loaded, and torchrun
 # exports OMP_NUM_THREADS=1 to its workers, so the reference arm overrides it before anything loads.
 if IS_REFERENCE_ARM:
@@ -171,7 +171,15 @@ def build_domain(a, rank=0, nranks=1, device=0):
     if a.config == "tsunami":
         return workloads.tsunami_domain(a.size, a.size, device=device)
     if a.config == "structures":
-        return workloads.structures_domain(2 * a.size, a.size, rank=rank, nranks=nranks, device=device)
+        if nranks == 1:
+            return workloads.structures_domain(2 * a.size, a.size, device=device)
+        # the structures are created on the sequential domain and localised by distribute(): every rank
+        # builds the sequential domain and cuts out its own part (replicated build)
+        from anuga_core_b200 import parallel
+        g = workloads.structures_domain(2 * a.size, a.size)
+        N = g.number_of_triangles
+        return parallel.distribute(g, nranks, epart=(np.arange(N) * nranks) // N, ranks=[rank],
+                                   domain_kw=dict(device=device))[rank]
     if nranks == 1:
         return workloads.roofline_sweep_domain(a.size, a.size, alg="DE1", rain=1.0e-4, device=device)
     from anuga_core_b200 import parallel
@@ -378,7 +386,7 @@ def main():
     barrier()
     launches = dev.kernel_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    if not per_kernel_in_region and not host_ops:
+    if not per_kernel_in_region:
         dev.run_steps(min(a.steps, 50), per_kernel=True)         # same steps again, bracketed kernel by kernel
         barrier()
     ms_local = ms
@@ -448,8 +456,9 @@ def main():
                     "unit": "GB/s", "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_triangle": ALG_BYTES[dom],
                     "measured_in": ("the timed region (CUDA events around every launch)" if per_kernel_in_region else
-                                    "a second pass of the same steps right after the timed region, which replays "
-                                    "CUDA graphs (NCCL calls included) and cannot carry per-kernel events"),
+                                    "a second pass of the same steps right after the timed region (the timed region "
+                                    "replays CUDA graphs - NCCL calls included - or runs host-side operators between "
+                                    "steps and cannot carry per-kernel events)"),
                     "whole_step": {"algorithmic_bytes_per_triangle_step": STEP_BYTES[alg],
                                    "achieved_gbs": value / world * STEP_BYTES[alg] / 1e9,
                                    "frac_of_peak": value / world * STEP_BYTES[alg] / 1e9 / peak,
@@ -457,7 +466,8 @@ def main():
                     "kernels": kernels}
     line = {"metric": METRIC if alg == "DE1" else "triangle-steps/sec (%s, FP64)" % alg, "value": value,
             "unit": "triangle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak" if a.config == "sweep" else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config,
             "parallelism": ("1 process/GPU, strip partition, NCCL halo send/recv + uint64 min-allreduce captured in "
                             "the step's CUDA graph" if world > 1 else "single GPU"),

@@ -421,3 +421,34 @@ def test_local_ghost_copy_on_one_gpu():
     assert max(rel_err(w, o.stage_c), rel_err(uh, o.xmom_c), rel_err(vh, o.ymom_c)) <= TOL_FINAL
     assert np.array_equal(w[ghost], w[src]) and np.array_equal(uh[ghost], uh[src])      # exact copies
     assert np.any(w[src] != 0.2)                                                       # something happened there
+
+
+def test_file_boundary_hands_over_to_its_default_boundary_when_the_file_runs_out():
+    """generic_boundary_conditions.py:655-684: model time beyond the file's last frame (here cut by time_limit)
+    -> Modeltime_too_late -> the default_boundary object takes the segment over; without one the error surfaces"""
+    import os
+    src = os.path.join(os.path.dirname(os.path.abspath(cases.__file__)), "file_boundary_source.sww")
+
+    def build(default):
+        d = ab.rectangular_cross_domain(8, 8, len1=7.0, len2=6.0, origin=(3.3, 4.7))
+        d.set_flow_algorithm("DE1")
+        d.set_store(False)
+        d.set_quantity("elevation", lambda x, y: -1.0 + 0.02 * x)
+        d.set_quantity("stage", 0.0)
+        Br = ab.Reflective_boundary(d)
+        Bf = ab.File_boundary(src, d, time_limit=1.0, default_boundary=default)
+        d.set_boundary({"left": Bf, "right": Br, "top": Br, "bottom": Br})
+        return d, Bf
+    d, Bf = build(ab.Dirichlet_boundary([0.05, 0.0, 0.0]))
+    assert len(Bf.F.time) == 3                       # frames at 0, 0.5, 1.0
+    for _ in d.evolve(yieldstep=0.5, finaltime=2.0):
+        pass
+    assert Bf.default_boundary_invoked
+    left = d.tag_boundary_cells["left"]
+    assert np.all(d._dev.get_quantity("STAGE_B")[left] == 0.05)
+    assert np.all(d._dev.get_quantity("XMOM_B")[left] == 0.0)
+    d2, _ = build(None)
+    with pytest.raises(BaseException) as e:
+        for _ in d2.evolve(yieldstep=0.5, finaltime=2.0):
+            pass
+    assert type(e.value).__name__ == "Modeltime_too_late"
