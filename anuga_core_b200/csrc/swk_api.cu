@@ -164,6 +164,7 @@ struct swk_domain {
   d4 *cq = nullptr, *eq = nullptr, *xg = nullptr, *fg = nullptr, *bq = nullptr;
   i4 *connA = nullptr, *connB = nullptr;
   double *eu = nullptr, *bk = nullptr, *eta = nullptr, *max_speed = nullptr, *vcoord = nullptr, *wind = nullptr;
+  double *xbed = nullptr;      // per-call layer: [3][NP] edge beds + [NP] centroid heights as the caller gave them
   unsigned char *zflag = nullptr;
   int *rw_counter = nullptr, *rw_rowIndex = nullptr, *rw_list = nullptr;
   int n_rw_list = 0;           // triangles with at least one riverwall edge (device ids, ascending)
@@ -472,7 +473,7 @@ extern "C" int swk_destroy(swk_domain *d)
   cudaSetDevice(d->device);
   if (d->stream) cudaStreamSynchronize(d->stream);
   void *ptrs[] = {d->cq, d->eq, d->xg, d->fg, d->bq, d->connA, d->connB, d->eu, d->bk, d->eta, d->max_speed,
-                  d->vcoord, d->wind, d->zflag, d->rw_counter, d->rw_rowIndex, d->rw_list, d->rw_elevation, d->rw_hydraulic,
+                  d->vcoord, d->wind, d->xbed, d->zflag, d->rw_counter, d->rw_rowIndex, d->rw_list, d->rw_elevation, d->rw_hydraulic,
                   d->d_clock, d->staging, d->acct_val, d->pos_b, d->acct_keys, d->acct_keys_pos, d->b_cell, d->b_edge, d->b_seg, d->d_seg_kind,
                   d->d_vals, d->d_new2old, d->d_ghost_full, d->d_ghost_ghost, d->d_ident_b};
   for (void *p : ptrs)
@@ -760,6 +761,7 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
   D.connA = d->connA; D.connB = d->connB;
   D.eu = d->eu; D.bk = d->bk; D.eta = d->eta; D.zflag = d->zflag; D.max_speed = d->max_speed;
   D.bq = d->bq; D.vcoord = d->vcoord; D.wind = nullptr; D.clock = d->d_clock;
+  D.bed_e_x = nullptr; D.hc_x = nullptr;
   D.acct_val = d->acct_val; D.pos_b = d->pos_b; D.acct_keys = d->acct_keys; D.acct_keys_pos = d->acct_keys_pos;
   D.n_acct = d->n_acct; D.n_acct_keys = d->n_acct_keys;
   D.rw_counter = d->rw_counter; D.rw_elevation = d->rw_elevation; D.rw_rowIndex = d->rw_rowIndex;
@@ -1329,6 +1331,11 @@ static void launch_flux(swk_domain *d, int first, int write_speed)
 {
   TimedScope ts(d, 1);
   const int n = n_active(d);
+  if (d->D.bed_e_x) {        // per-call layer with edge beds / centroid heights given explicitly
+    if (d->has_riverwalls) LAUNCH(d, (k_flux<true, true>), ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
+    else LAUNCH(d, (k_flux<false, true>), ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
+    return;
+  }
   if (d->has_riverwalls) LAUNCH(d, k_flux<true>, ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
   else LAUNCH(d, k_flux<false>, ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
 }
@@ -2188,13 +2195,29 @@ extern "C" int swk_call_compute_fluxes_ext_central(swk_domain *d, const swk_host
   const int64_t N = d->N, M = d->M;
   // The device edge record carries (stage, height, xmom, ymom); bed_edge = stage_edge - height_edge and
   // height_centroid = max(stage - bed, 0) are what extrapolate always leaves behind
-  // (sw_domain_openmp.c:1376-1378, 1863-1865).  Refuse inconsistent input instead of silently differing.
-  for (int64_t j = 0; j < 3 * N; j++)
-    if (v->bed_edge_values[j] != v->stage_edge_values[j] - v->height_edge_values[j])
-      return fail(SWK_ERR_UNSUPPORTED, "bed_edge_values != stage_edge_values - height_edge_values: call extrapolate first");
-  for (int64_t k = 0; k < N; k++)
-    if (v->height_centroid_values[k] != fmax(v->stage_centroid_values[k] - v->bed_centroid_values[k], 0.0))
-      return fail(SWK_ERR_UNSUPPORTED, "height_centroid_values != max(stage - bed, 0): call extrapolate first");
+  // (sw_domain_openmp.c:1376-1378, 1863-1865) and what the kernels recompute.  The reference's entry point
+  // takes ANY arrays: when the caller's do not satisfy those identities, they are uploaded as they are and
+  // the flux kernel variant that reads them is launched.
+  bool consistent = true;
+  for (int64_t j = 0; j < 3 * N && consistent; j++)
+    if (v->bed_edge_values[j] != v->stage_edge_values[j] - v->height_edge_values[j]) consistent = false;
+  for (int64_t k = 0; k < N && consistent; k++)
+    if (v->height_centroid_values[k] != fmax(v->stage_centroid_values[k] - v->bed_centroid_values[k], 0.0)) consistent = false;
+  d->D.bed_e_x = nullptr;
+  d->D.hc_x = nullptr;
+  if (!consistent) {
+    const int64_t NP = d->NP;
+    if (!d->xbed) CKV(dalloc(&d->xbed, 4 * NP));
+    std::vector<double> x(4 * NP, 0.0);
+    for (int64_t k = 0; k < N; k++) {
+      const int64_t o = d->new2old[k];
+      for (int i = 0; i < 3; i++) x[i * NP + k] = v->bed_edge_values[3 * o + i];
+      x[3 * NP + k] = v->height_centroid_values[o];
+    }
+    CKV(upload(d->xbed, x));
+    d->D.bed_e_x = d->xbed;
+    d->D.hc_x = d->xbed + 3 * NP;
+  }
   CKV(swk_set_quantity(d, SWK_Q_STAGE_C, v->stage_centroid_values, N));
   CKV(swk_set_quantity(d, SWK_Q_ELEVATION_C, v->bed_centroid_values, N));
   CKV(swk_set_quantity(d, SWK_Q_STAGE_E, v->stage_edge_values, 3 * N));

@@ -117,6 +117,10 @@ struct Dev {
   double *max_speed;
   d4 *bq;
   const double *vcoord;          // (6*NP) vertex coordinates x0,y0,x1,y1,x2,y2 planes (sloped Manning), may be null
+  // per-call layer only: edge beds / centroid heights taken from the caller's arrays instead of being
+  // recomputed as stage_e - height_e and max(stage_c - bed_c, 0) (any consistent or inconsistent input)
+  const double *bed_e_x;         // [3][NP] or null
+  const double *hc_x;            // [NP] or null
   const double *wind;            // [2][NP] explicit momentum forcing S*u, S*v (Wind_stress, forcing.py:80-215), may be null
   Clock *clock;
   // boundary-flux accounting (sw_domain_openmp.c:696-701): slot per accounting edge, in (k, i) order
@@ -535,16 +539,16 @@ __device__ __noinline__ int acct_slot_lookup(const int *keys, const int *keys_po
 // (pn[i] < 0) the boundary value {stage, xmom, ymom, -}.
 // contribution of edge i of triangle k: el = own edge record, er = the neighbour's record of the shared
 // edge or, for a boundary edge (q < 0), the boundary value {stage, xmom, ymom, -}
-template <bool RW>
+template <bool RW, bool XB = false>
 __device__ __forceinline__ void edge_contribution(const Dev &D, const Consts &K, int k, int i, int q, int flags,
                                                   const d4 el, const d4 er, double nx, double ny, double length,
                                                   const Eff &own, bool first, TriFlux &T)
 {
   const int NP = D.NP;
   const bool full = flags & 1;
-  const double hc = own.h, zc = own.z;
+  const double hc = XB ? D.hc_x[k] : own.h, zc = own.z;
   const double wl = el.x, hle = el.y, uhl = el.z, vhl = el.w;
-  const double zl = wl - hle;                         // bed_edge = stage_edge - height_edge (:1863)
+  const double zl = XB ? D.bed_e_x[i * NP + k] : wl - hle;   // bed_edge = stage_edge - height_edge (:1863)
   double wr, uhr, vhr, zr, hre;
   if (q < 0) {                                        // :551-561
     wr = er.x; uhr = er.y; vhr = er.z;
@@ -552,7 +556,7 @@ __device__ __forceinline__ void edge_contribution(const Dev &D, const Consts &K,
     hre = dmax0(wr - zr);
   } else {                                            // :562-576
     wr = er.x; hre = er.y; uhr = er.z; vhr = er.w;
-    zr = wr - hre;
+    zr = XB ? D.bed_e_x[(q & 3) * NP + (q >> 2)] : wr - hre;
   }
   double z_half = dmax(zl, zr);
   bool rw_edge = false;
@@ -622,7 +626,7 @@ __device__ __forceinline__ void finish_flux(TriFlux &T, double radius, double in
   T.yu *= inv_area;
 }
 
-template <bool RW, bool ROLLED = false>
+template <bool RW, bool ROLLED = false, bool XB = false>
 __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, int k, const i4 p,
                                                  const Eff &own, bool first)
 {
@@ -659,7 +663,7 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
     else er = D.bq[-q - 1];
     if (i == 0) inv_area = ge.w;
     if (i == 1) radius = ge.w;
-    edge_contribution<RW>(D, K, k, i, q, p.w, el, er, ge.x, ge.y, ge.z, own, first, T);
+    edge_contribution<RW, XB>(D, K, k, i, q, p.w, el, er, ge.x, ge.y, ge.z, own, first, T);
   }
   } else {
   d4 el[3], ge[3], er[3];
@@ -679,7 +683,7 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
   radius = ge[1].w;
 #pragma unroll
   for (int i = 0; i < 3; i++)
-    edge_contribution<RW>(D, K, k, i, pn[i], p.w, el[i], er[i], ge[i].x, ge[i].y, ge[i].z, own, first, T);
+    edge_contribution<RW, XB>(D, K, k, i, pn[i], p.w, el[i], er[i], ge[i].x, ge[i].y, ge[i].z, own, first, T);
   }
   finish_flux(T, radius, inv_area, first);
 #else
@@ -837,7 +841,7 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
 }
 
 // Pass B1 (substep 0): flux + dt partials.  writes eu, max_speed, dt_min_bits.
-template <bool RW>
+template <bool RW, bool XB = false>
 __global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int first, int write_speed,
                                                             int k0, int k1)
 {
@@ -852,7 +856,7 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int
     if (k < k1) {
       const i4 p = lds(&D.connB[k]);
       const Eff own = effective(D.cq[k], K);
-      const TriFlux T = triangle_flux<RW, SWK_F_ROLLED>(D, K, k, p, own, first != 0);
+      const TriFlux T = triangle_flux<RW, SWK_F_ROLLED, XB>(D, K, k, p, own, first != 0);
       sts(&D.eu[k], T.su);
       sts(&D.eu[D.NP + k], T.xu);
       sts(&D.eu[2 * D.NP + k], T.yu);

@@ -168,23 +168,24 @@ def workload_config(a):
 
 def build_domain(a, rank=0, nranks=1, device=0):
     from anuga_core_b200 import workloads
-    if a.config == "tsunami":
-        return workloads.tsunami_domain(a.size, a.size, device=device)
-    if a.config == "structures":
+    if a.config == "sweep":
         if nranks == 1:
-            return workloads.structures_domain(2 * a.size, a.size, device=device)
-        # the structures are created on the sequential domain and localised by distribute(): every rank
-        # builds the sequential domain and cuts out its own part (replicated build)
+            return workloads.roofline_sweep_domain(a.size, a.size, alg="DE1", rain=1.0e-4, device=device)
         from anuga_core_b200 import parallel
-        g = workloads.structures_domain(2 * a.size, a.size)
-        N = g.number_of_triangles
-        return parallel.distribute(g, nranks, epart=(np.arange(N) * nranks) // N, ranks=[rank],
-                                   domain_kw=dict(device=device))[rank]
+        m, n = parallel.weak_scaling_shape(a.size, nranks)
+        return parallel.strip_partitioned_sweep_domain(m, n, rank, nranks, device=device)
+    make = (lambda **kw: workloads.tsunami_domain(a.size, a.size, **kw)) if a.config == "tsunami" else \
+           (lambda **kw: workloads.structures_domain(2 * a.size, a.size, **kw))
     if nranks == 1:
-        return workloads.roofline_sweep_domain(a.size, a.size, alg="DE1", rain=1.0e-4, device=device)
+        return make(device=device)
+    # fixed total size shared out over the ranks (strong scaling).  Boundaries and structures are created on the
+    # sequential domain and localised by distribute(): every rank builds the sequential domain and cuts out
+    # its own part (replicated build, no rank-0 pass over all parts)
     from anuga_core_b200 import parallel
-    m, n = parallel.weak_scaling_shape(a.size, nranks)
-    return parallel.strip_partitioned_sweep_domain(m, n, rank, nranks, device=device)
+    g = make()
+    N = g.number_of_triangles
+    return parallel.distribute(g, nranks, epart=(np.arange(N) * nranks) // N, ranks=[rank],
+                               domain_kw=dict(device=device))[rank]
 
 
 def alg_of(a):

@@ -94,17 +94,28 @@ def test_per_call_sequence_matches_reference_functions():
         lib.swk_call_close(h)
 
 
-def test_per_call_flux_refuses_inconsistent_edge_arrays():
+def test_per_call_flux_takes_any_edge_arrays_like_the_reference_entry_point():
+    """compute_fluxes_ext_central (sw_domain_openmp_ext.pyx:371) accepts whatever the arrays hold: edge beds
+    that are not stage_e - height_e and centroid heights that are not max(stage - bed, 0) are used as given"""
     lib = B.load_library()
-    d, ref, mine = twin(n=6)
-    mine.distribute_to_vertices_and_edges()
-    mine.bed_e[0, 0] += 1.0
+    d, ref, mine = twin(n=8)
+    for o in (ref, mine):
+        o.distribute_to_vertices_and_edges()
+        o.update_boundary()
+        o.bed_e[::3, 0] += 0.05               # user-modified edge beds
+        o.bed_e[1::4, 2] -= 0.02
+        o.height_c[::5] *= 1.1                # ... and centroid heights
     v, keep = host_view(mine, d)
     h = B._H()
     B._check(lib.swk_call_open(C.byref(v), 0, C.byref(h)))
     try:
         ft = C.c_double()
-        assert lib.swk_call_compute_fluxes_ext_central(h, C.byref(v), 1000.0, 0, C.byref(ft)) == -6
+        B._check(lib.swk_call_compute_fluxes_ext_central(h, C.byref(v), 1000.0, 0, C.byref(ft)))
+        ref.compute_fluxes(0)
+        assert ft.value == ref.flux_timestep
+        for name in ("stage_eu", "xmom_eu", "ymom_eu", "max_speed"):
+            assert rel_err(getattr(mine, name), getattr(ref, name)) <= 1e-12, name
+        assert np.any(ref.xmom_eu != 0.0)
     finally:
         lib.swk_call_close(h)
 

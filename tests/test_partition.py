@@ -205,6 +205,33 @@ for q in mine.full_send_dict:
     assert np.array_equal(mine.full_send_dict[q][0], ref.full_send_dict[q][0])
 mine.set_boundary({t: ab.Reflective_boundary(mine) for t in ("left", "right", "top", "bottom") if t in mine.get_boundary_tags()})
 assert mine.boundary_map.get("ghost", 0) is None
+# replicated build: the sequential domain on every rank, every rank cuts out its own part (no shipping)
+mine2 = ab.distribute(plain(), parameters=dict(ghost_layer_width=2))
+assert np.array_equal(mine2.triangles, ref.triangles) and np.array_equal(mine2.tri_l2g, ref.tri_l2g)
+for k in ("stage", "elevation"):
+    assert np.array_equal(mine2.quantities[k].centroid_values, ref.quantities[k].centroid_values), k
+# the time loop is chosen collectively: only rank 0 holds the time-dependent boundary ('left'), yet both ranks
+# must run the two-half loop (a rank in the resident loop would launch steps ahead of the other)
+bm = {t: ab.Reflective_boundary(mine) for t in mine.get_boundary_tags()}
+if "left" in bm:
+    bm["left"] = ab.Time_boundary(mine, lambda t: [0.1 * t, 0.0, 0.0])
+assert ("left" in bm) == (rank == 0)
+bm["ghost"] = None
+mine.set_boundary(bm)
+assert mine._needs_host_stepping() == (rank == 0)
+assert mine._evolve_path() == 2
+# ... and a host-side operator on one rank plus a time-dependent boundary on the other -> host-stepped passes
+class HostOp:
+    host_side, time_dependent = True, True        # as Inlet_operator / Structure_operator declare themselves
+if rank == 1:
+    mine.fractional_step_operators.append(HostOp())
+assert mine._evolve_path() == 3
+mine.fractional_step_operators[:] = []
+mine.set_boundary({t: (None if t == "ghost" else ab.Reflective_boundary(mine)) for t in mine.get_boundary_tags()})
+assert mine._evolve_path() == 0
+assert comm.allreduce_min(float(rank)) == 0.0
+got = comm.scatter_objects([{"for": r, "data": np.arange(3) + r} for r in range(size)] if rank == 0 else None)
+assert got["for"] == rank and np.array_equal(got["data"], np.arange(3) + rank)
 comm.barrier()
 sys.stdout.write("[rank" + str(rank) + "-ok]"); sys.stdout.flush()
 '''
