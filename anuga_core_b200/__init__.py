@@ -3,7 +3,7 @@ shallow-water timestep (DE0/DE1/DE2): hand-written sm_100a CUDA behind the
 reference's shallow_water.Domain API.  See DESIGN.md and INTEGRATION.md."""
 from .mesh import Mesh, rectangular_cross, rectangular, morton_order
 from .quantity import Quantity
-from .boundaries import (Characteristic_stage_boundary, Flather_external_stage_zero_velocity_boundary, Reflective_boundary, Dirichlet_boundary, Transmissive_boundary, Time_boundary,
+from .boundaries import (Characteristic_stage_boundary, Dirichlet_discharge_boundary, Flather_external_stage_zero_velocity_boundary, Reflective_boundary, Dirichlet_boundary, Transmissive_boundary, Time_boundary,
                          Transmissive_n_momentum_zero_t_momentum_set_stage_boundary,
                          Transmissive_momentum_set_stage_boundary,
                          Transmissive_stage_zero_momentum_boundary, Time_stage_zero_momentum_boundary)
@@ -11,7 +11,7 @@ from .operators import (Rate_operator, Set_quantity, Set_stage, Set_quantity_ope
                         Set_stage_operator, Set_elevation, Set_elevation_operator)
 from .structures import (Region, Inlet, Inlet_operator, Inlet_enquiry, Structure_operator,
                          Boyd_box_operator, Boyd_pipe_operator, Weir_orifice_trapezoid_operator)
-from .forcing import Wind_stress
+from .forcing import Wind_stress, General_forcing, Rainfall, Inflow
 from .file_boundary import File_boundary, Field_boundary, Time_space_boundary, file_function
 from .domain import Domain, rectangular_cross_domain, load_checkpoint_file, MODE_B200
 from .backend import SwkError, device_count

@@ -45,6 +45,7 @@ _BOUNDARY_BY_NAME = {
     "File_boundary": lambda B, d: _fb.File_boundary.adopt(B, d),
     "Field_boundary": lambda B, d: _fb.Field_boundary.adopt(B, d),
     "Time_space_boundary": lambda B, d: _fb.Time_space_boundary(d, B.function, B.default_boundary),
+    "Dirichlet_discharge_boundary": lambda B, d: _bnd.Dirichlet_discharge_boundary(d, B.stage0, B.wh0),
     "Characteristic_stage_boundary":
         lambda B, d: _bnd.Characteristic_stage_boundary(d, B.function, B.default_stage),
 }

@@ -36,6 +36,7 @@ BC_TRANSMISSIVE_STAGE_ZERO_MOMENTUM = 6
 BC_FLATHER_EXTERNAL_STAGE_ZERO_VELOCITY = 7
 BC_CHARACTERISTIC_STAGE = 8
 BC_TIME_SPACE_TABLE, BC_TIME_SPACE_TABLE_MEAN_STAGE = 9, 10
+BC_DIRICHLET_DISCHARGE = 11
 
 _I = C.c_int64
 _D = C.c_double
@@ -122,7 +123,7 @@ SYMBOLS = {
     "swk_add_rate_operator": (C.c_int, [_H, _D, _D, _PD, _PI, _I, C.POINTER(C.c_int)]),
     "swk_set_rate": (C.c_int, [_H, C.c_int, _D, _D]),
     "swk_clear_rate_operators": (C.c_int, [_H]),
-    "swk_set_momentum_forcing": (C.c_int, [_H, _PD, _PD, _I]),
+    "swk_set_explicit_forcing": (C.c_int, [_H, _PD, _PD, _PD, _I]),
     "swk_set_rate_dynamic": (C.c_int, [_H, C.c_int, C.c_int]),
     "swk_set_boundary_values_substep": (C.c_int, [_H, C.c_int, C.c_int, _PD]),
     "swk_set_boundary_table": (C.c_int, [_H, C.c_int, _I, _I, _PD]),
@@ -356,13 +357,13 @@ class DeviceDomain:
                                               0 if idx is None else idx.size, C.byref(op)))
         return op.value
 
-    def set_momentum_forcing(self, fx, fy):
-        if fx is None:
-            _check(self.lib.swk_set_momentum_forcing(self.h, None, None, 0))
+    def set_explicit_forcing(self, fs, fx, fy):
+        """per-triangle additions to the explicit updates of stage, xmomentum, ymomentum (None: switch off)"""
+        if fs is None and fx is None and fy is None:
+            _check(self.lib.swk_set_explicit_forcing(self.h, None, None, None, 0))
             return
-        fx = np.ascontiguousarray(fx, dtype=np.float64)
-        fy = np.ascontiguousarray(fy, dtype=np.float64)
-        _check(self.lib.swk_set_momentum_forcing(self.h, _pd(fx), _pd(fy), fx.size))
+        arrs = [np.ascontiguousarray(a if a is not None else np.zeros(self.N), dtype=np.float64) for a in (fs, fx, fy)]
+        _check(self.lib.swk_set_explicit_forcing(self.h, _pd(arrs[0]), _pd(arrs[1]), _pd(arrs[2]), arrs[0].size))
 
     def clear_rate_operators(self):
         _check(self.lib.swk_clear_rate_operators(self.h))

@@ -12,6 +12,7 @@ k_boundary_values (csrc/swk_kernels.cuh) and follows evaluate_segment of
   Time_stage_zero_momentum_boundary                                :616-635
   Flather_external_stage_zero_velocity_boundary                    :1096-1266
   Characteristic_stage_boundary                                    :639-843
+  Dirichlet_discharge_boundary                                     :845-890
   Transmissive_boundary    anuga/abstract_2d_finite_volumes/generic_boundary_conditions.py:173-193
   Dirichlet_boundary                                               :221-264
   Time_boundary                                                    :370-411
@@ -217,6 +218,29 @@ class Characteristic_stage_boundary(_Set_stage):
 
     def __repr__(self):
         return "Characteristic_stage_boundary (%s) (%s) " % (self.domain, self.default_stage)
+
+
+class Dirichlet_discharge_boundary(Boundary):
+    """sets the stage (stage0) and the momentum wh0 along the inward normal (boundaries.py:845-890)"""
+    device_kind = _b.BC_DIRICHLET_DISCHARGE
+
+    def __init__(self, domain=None, stage0=None, wh0=None):
+        if domain is None:
+            raise Exception("Domain must be specified for this type of boundary")
+        if stage0 is None:
+            raise Exception("Stage must be specified for this type of boundary")
+        self.domain = domain
+        self.stage0 = stage0
+        self.wh0 = 0.0 if wh0 is None else wh0
+
+    def __repr__(self):
+        return "Dirichlet_Discharge_boundary(%s)" % self.domain
+
+    def device_values(self, t):
+        return (float(self.stage0), float(self.wh0), 0.0)
+
+    def oracle_spec(self):
+        return ("dirichlet_discharge", float(self.stage0), float(self.wh0))
 
 
 class Transmissive_stage_zero_momentum_boundary(Boundary):

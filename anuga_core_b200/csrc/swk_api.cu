@@ -975,7 +975,7 @@ extern "C" int swk_set_boundary_segment(swk_domain *d, int segment, int kind, co
 {
   if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
   if (segment < 0 || segment >= SEG_MAX) return fail(SWK_ERR_ARG, "segment id out of range");
-  if (kind < SWK_BC_NONE || kind > SWK_BC_TIME_SPACE_TABLE_MEAN_STAGE) return fail(SWK_ERR_ARG, "unknown boundary kind");
+  if (kind < SWK_BC_NONE || kind > SWK_BC_DIRICHLET_DISCHARGE) return fail(SWK_ERR_ARG, "unknown boundary kind");
   if ((int)d->seg_kind.size() <= segment) d->seg_kind.resize(segment + 1, 0);
   d->seg_kind[segment] = kind;
   CKV(vals_writable(d));
@@ -1101,26 +1101,30 @@ extern "C" int swk_add_rate_operator(swk_domain *d, double rate, double factor, 
   return SWK_OK;
 }
 
-// Explicit momentum forcing that does not depend on the state (Wind_stress, shallow_water/forcing.py:80-215:
-// explicit_update += S*u, S*v per triangle): two (N,) arrays in the caller's triangle order, added to the
-// explicit updates inside the update kernels.  NULL, NULL switches it off.
-extern "C" int swk_set_momentum_forcing(swk_domain *d, const double *xmom_force, const double *ymom_force, int64_t n)
+// Explicit forcing that does not depend on the state (shallow_water/forcing.py: Wind_stress :80-215 adds S*u, S*v
+// to the momentum updates; General_forcing / Rainfall / Inflow :215-640 add a rate to the stage update over a
+// region): three (N,) arrays in the caller's triangle order (stage may be NULL = zero), added to the explicit
+// updates inside the update kernels.  All NULL switches it off.
+extern "C" int swk_set_explicit_forcing(swk_domain *d, const double *stage_force, const double *xmom_force,
+                                        const double *ymom_force, int64_t n)
 {
   if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
   CK(cudaSetDevice(d->device));
   CKV(sync_check(d));
   const bool was_on = d->D.wind != nullptr;
-  if (!xmom_force || !ymom_force) {
+  if (!stage_force && !xmom_force && !ymom_force) {
     d->D.wind = nullptr;
     if (was_on) d->graph_valid = false;
     return SWK_OK;
   }
   if (n != d->N) return fail(SWK_ERR_ARG, "forcing arrays must have one entry per triangle");
-  if (!d->wind) CKV(dalloc(&d->wind, 2 * d->NP));
-  std::vector<double> w(2 * d->NP, 0.0);
+  if (!d->wind) CKV(dalloc(&d->wind, 3 * d->NP));
+  std::vector<double> w(3 * d->NP, 0.0);
   for (int64_t k = 0; k < d->N; k++) {
-    w[k] = xmom_force[d->new2old[k]];
-    w[d->NP + k] = ymom_force[d->new2old[k]];
+    const int64_t o = d->new2old[k];
+    if (stage_force) w[k] = stage_force[o];
+    if (xmom_force) w[d->NP + k] = xmom_force[o];
+    if (ymom_force) w[2 * d->NP + k] = ymom_force[o];
   }
   CKV(upload(d->wind, w));
   d->D.wind = d->wind;

@@ -121,7 +121,8 @@ struct Dev {
   // recomputed as stage_e - height_e and max(stage_c - bed_c, 0) (any consistent or inconsistent input)
   const double *bed_e_x;         // [3][NP] or null
   const double *hc_x;            // [NP] or null
-  const double *wind;            // [2][NP] explicit momentum forcing S*u, S*v (Wind_stress, forcing.py:80-215), may be null
+  const double *wind;            // [3][NP] state-independent explicit forcing of stage, xmom, ymom (Wind_stress,
+                                 // General_forcing / Rainfall / Inflow: forcing.py:80-640), may be null
   Clock *clock;
   // boundary-flux accounting (sw_domain_openmp.c:696-701): slot per accounting edge, in (k, i) order
   double *acct_val;              // [n_acct]
@@ -450,6 +451,11 @@ __device__ __forceinline__ bool boundary_value_core(int kind, double v0, double 
         out.z = uh_m * n2 - vh_m * n1;
       }
     } break;
+    case 11:                                   // Dirichlet_discharge (boundaries.py:845-890): stage0, wh0 inwards
+      out.x = v0;
+      out.y = -v1 * n1;
+      out.z = -v1 * n2;
+      break;
     default:
       return false;
   }
@@ -791,9 +797,10 @@ __device__ __forceinline__ void triangle_update(const Dev &D, const Consts &K, c
     sts(&D.bk[2 * NP + k], raw.z);
   }
   if (zf & 1) { e.uh = 0.0; e.vh = 0.0; }
-  if (D.wind) {                                        // compute_forcing_terms: explicit_update += S*(u, v)
-    xu += lds(&D.wind[k]);
-    yu += lds(&D.wind[NP + k]);
+  if (D.wind) {                                        // compute_forcing_terms: explicit_update += forcing
+    su += lds(&D.wind[k]);
+    xu += lds(&D.wind[NP + k]);
+    yu += lds(&D.wind[2 * NP + k]);
   }
   double zs = 1.0;
   double h = e.w - e.z;

@@ -842,7 +842,7 @@ class Domain:
     def _device_forcing_terms(self):
         out = []
         for f in self.forcing_terms:
-            if hasattr(f, "momentum_forcing"):
+            if hasattr(f, "explicit_forcing"):
                 out.append(f)
             elif getattr(f, "__name__", "") not in ("manning_friction_implicit", "manning_friction_explicit"):
                 raise NotImplementedError("forcing term %r has no device implementation (SURVEY.md 8(f))" % (f,))
@@ -854,18 +854,16 @@ class Domain:
         terms = self._device_forcing_terms()
         if not terms:
             if self._forcing_on_device:
-                self._dev.set_momentum_forcing(None, None)
+                self._dev.set_explicit_forcing(None, None, None)
                 self._forcing_on_device = False
             return
         if self._forcing_on_device and not force and not any(f.time_dependent for f in terms):
             return
-        fx = np.zeros(self.number_of_triangles)
-        fy = np.zeros(self.number_of_triangles)
+        # the terms add to the explicit updates one after the other, in list order (generic_domain.py:2426)
+        F = {name: np.zeros(self.number_of_triangles) for name in self.conserved_quantities}
         for f in terms:
-            ax, ay = f.momentum_forcing(self, t)
-            fx += ax
-            fy += ay
-        self._dev.set_momentum_forcing(fx, fy)
+            f.explicit_forcing(self, t, F)
+        self._dev.set_explicit_forcing(F["stage"], F["xmomentum"], F["ymomentum"])
         self._forcing_on_device = True
 
     def _forcing_depends_on_time(self):

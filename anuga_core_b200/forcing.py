@@ -86,6 +86,12 @@ class Wind_stress:
             return np.array([f(t, i) for i in range(N)], dtype=np.float64)
         return f * np.ones(N, dtype=np.float64)
 
+    def explicit_forcing(self, domain, t, F):
+        """add this term to the explicit-update additions F = {quantity: (N,) array}"""
+        fx, fy = self.momentum_forcing(domain, t)
+        F["xmomentum"] += fx
+        F["ymomentum"] += fy
+
     def momentum_forcing(self, domain, t):
         """(S*u, S*v) per triangle with the arithmetic of assign_windfield_values (forcing.py:189-215):
         Python's math functions on every distinct (s, phi) pair."""
@@ -114,3 +120,146 @@ class Wind_stress:
 
     def oracle_spec(self):
         return ("wind", self)
+
+
+class General_forcing:
+    """General explicit forcing term: a rate [quantity/s] added to the explicit update of one conserved
+    quantity over a circle, a polygon or the whole domain (forcing.py:215-495).  rate: a number or a function
+    of time; default_rate takes over when the rate function runs out of data (Modeltime_too_late)."""
+
+    def __init__(self, domain, quantity_name, rate=0.0, center=None, radius=None, polygon=None,
+                 default_rate=None, verbose=False):
+        if center is None:
+            assert radius is None, "I got radius but no center."
+        if radius is None:
+            assert center is None, "I got center but no radius."
+        if quantity_name not in domain.conserved_quantities:
+            raise Exception("%s is not a conserved quantity" % quantity_name)
+        self.domain = domain
+        self.quantity_name = quantity_name
+        self.rate = rate
+        self.center = None if center is None else np.asarray(center, dtype=np.float64)
+        self.radius = radius
+        self.polygon = polygon
+        self.verbose = verbose
+        self.value = 0.0
+        points = domain.get_centroid_coordinates(absolute=True)
+        self.exchange_indices = None
+        if self.center is not None and self.radius is not None:
+            assert len(self.center) == 2
+            assert polygon is None, "Polygon cannot be specified when center and radius are"
+            c = self.center
+            inside = ((points[:, 0] - c[0]) ** 2 + (points[:, 1] - c[1]) ** 2) < self.radius ** 2
+            self.exchange_indices = np.flatnonzero(inside)
+        if self.polygon is not None:
+            from .structures import Region
+            self.exchange_indices = np.asarray(Region(domain, polygon=self.polygon).indices, dtype=np.int64)
+        if self.exchange_indices is None:
+            self.exchange_area = None          # (polygon_area of the mesh boundary in the reference; only Inflow divides by it)
+        else:
+            if len(self.exchange_indices) == 0:
+                raise Exception("No triangles have been identified in specified region: center=%s, radius=%s"
+                                % (self.center, self.radius))
+            area = 0.0
+            for i in self.exchange_indices:        # the reference's running sum, in index order (:373-375)
+                area += domain.areas[i]
+            self.exchange_area = area
+            assert self.exchange_area > 0.0
+        assert default_rate is None or isinstance(default_rate, (int, float)) or callable(default_rate), \
+            "Keyword argument default_rate must be either None or a function of time.\nI got %s." % str(default_rate)
+        if default_rate is not None and not callable(default_rate):
+            tmp = default_rate
+            default_rate = lambda t: tmp
+        self.default_rate = default_rate
+        self.default_rate_invoked = False
+
+    @property
+    def time_dependent(self):
+        return callable(self.rate)
+
+    def update_rate(self, t):
+        return self.rate(t) if callable(self.rate) else self.rate
+
+    def current_rate(self, t):
+        try:
+            rate = self.update_rate(t)
+        except BaseException as e:
+            if type(e).__name__ != "Modeltime_too_late":
+                raise
+            if self.default_rate is None:
+                raise type(e)("%s: ANUGA is trying to run longer than specified data.\nYou can specify keyword "
+                              "argument default_rate in the forcing function to tell it what to do in the absence "
+                              "of time data." % str(e))
+            rate = self.default_rate(t)
+            if not self.default_rate_invoked:
+                import warnings
+                warnings.warn("%s\nInstead I will use the default rate: %s\nNote: Further warnings will be supressed"
+                              % (str(e), str(self.default_rate)))
+                self.default_rate_invoked = True
+        if rate is None:
+            raise Exception("Attribute rate must be specified in General_forcing or its descendants before "
+                            "attempting to call it")
+        return rate
+
+    def explicit_forcing(self, domain, t, F):
+        rate = self.current_rate(t)
+        if self.exchange_indices is None:
+            F[self.quantity_name][:] += rate
+        else:
+            F[self.quantity_name][self.exchange_indices] += rate
+
+    def __call__(self, domain):
+        """host form (the reference's call): add to the explicit update of the host array"""
+        upd = domain.quantities[self.quantity_name].explicit_update
+        rate = self.current_rate(domain.get_time())
+        if self.exchange_indices is None:
+            upd[:] += rate
+        else:
+            upd[self.exchange_indices] += rate
+
+    def get_quantity_values(self, quantity_name=None):
+        q = self.domain.quantities[quantity_name or self.quantity_name]
+        v = q.centroid_values
+        return v.copy() if self.exchange_indices is None else v[self.exchange_indices]
+
+    def parallel_safe(self):
+        return True
+
+    def oracle_spec(self):
+        return ("general_forcing", self)
+
+
+class Rainfall(General_forcing):
+    """rain [mm/s] over a region or the whole domain, added to the stage update (forcing.py:497-575)"""
+
+    def __init__(self, domain, rate=0.0, center=None, radius=None, polygon=None, default_rate=None, verbose=False):
+        if callable(rate):
+            rain = lambda t: rate(t) / 1000.0
+        else:
+            rain = rate / 1000.0
+        if default_rate is not None:
+            if callable(default_rate):
+                default_rain = lambda t: default_rate(t) / 1000.0
+            else:
+                default_rain = default_rate / 1000.0
+        else:
+            default_rain = None
+        General_forcing.__init__(self, domain, "stage", rate=rain, center=center, radius=radius, polygon=polygon,
+                                 default_rate=default_rain, verbose=verbose)
+
+
+class Inflow(General_forcing):
+    """flow [m^3/s] into (or out of) a region: divided by the region's area and added to the stage update
+    (forcing.py:578-640)"""
+
+    def __init__(self, domain, rate=0.0, center=None, radius=None, polygon=None, default_rate=None, verbose=False):
+        General_forcing.__init__(self, domain, "stage", rate=rate, center=center, radius=radius, polygon=polygon,
+                                 default_rate=default_rate, verbose=verbose)
+        if self.exchange_area is None:
+            raise NotImplementedError("Inflow over the whole domain (the reference divides by the area of the "
+                                      "mesh boundary polygon): give center/radius or a polygon")
+
+    def update_rate(self, t):
+        if callable(self.rate):
+            return self.rate(t) / self.exchange_area
+        return self.rate / self.exchange_area

@@ -149,7 +149,8 @@ enum {
    * (boundaries.py:993-1090): values interpolated in time between two frames of a device-resident table
    * (swk_set_boundary_table); v0 = ratio, v1 = frame index, v2 = mean_stage (added to the stage by kind 10) */
   SWK_BC_TIME_SPACE_TABLE = 9,
-  SWK_BC_TIME_SPACE_TABLE_MEAN_STAGE = 10
+  SWK_BC_TIME_SPACE_TABLE_MEAN_STAGE = 10,
+  SWK_BC_DIRICHLET_DISCHARGE = 11                  /* boundaries.py:845-890; v0 = stage0, v1 = wh0 (momentum along the inward normal) */
 };
 
 /* ---- evolve result ------------------------------------------------------------ */
@@ -229,10 +230,12 @@ int swk_set_boundary_values_substep(swk_domain *d, int segment, int substep, con
 int swk_add_rate_operator(swk_domain *d, double rate, double factor, const double *rate_array,
                           const int64_t *indices, int64_t n_indices, int *op_id);
 int swk_set_rate(swk_domain *d, int op_id, double rate, double factor);
-/* State-independent explicit momentum forcing (Wind_stress.__call__ + assign_windfield_values,
- * shallow_water/forcing.py:170-215): xmom/ymom explicit_update[k] += force[k] at every flux evaluation.
- * Arrays of n = N doubles in the caller's order; NULL pointers switch the term off.                   */
-int swk_set_momentum_forcing(swk_domain *d, const double *xmom_force, const double *ymom_force, int64_t n);
+/* State-independent explicit forcing: Wind_stress.__call__ + assign_windfield_values (shallow_water/forcing.py:
+ * 133-215, momentum) and General_forcing.__call__ with its descendants Rainfall and Inflow (:400-640, stage over a
+ * region): explicit_update[k] += force[k] at every flux evaluation.  Arrays of n = N doubles in the caller's order;
+ * a NULL array is zero, all NULL switches the term off.                                                  */
+int swk_set_explicit_forcing(swk_domain *d, const double *stage_force, const double *xmom_force,
+                             const double *ymom_force, int64_t n);
 /* Mark a Rate_operator whose rate / factor are functions of time (rate_operators.py:276-289): its
  * scalars are read from a device table that swk_set_rate refreshes, without touching the captured step. */
 int swk_set_rate_dynamic(swk_domain *d, int op_id, int dynamic);

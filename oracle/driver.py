@@ -286,6 +286,15 @@ class OracleDomain:
                                              _pd(self.xmom_siu), _pd(self.ymom_siu))
 
         for spec in self.forcing:
+            if spec[0] == "general_forcing":      # General_forcing.__call__ (forcing.py:400-452): update[k] += rate
+                G = spec[1]
+                rate = G.current_rate(self.get_time())
+                upd = {"stage": self.stage_eu, "xmomentum": self.xmom_eu, "ymomentum": self.ymom_eu}[G.quantity_name]
+                if G.exchange_indices is None:
+                    upd[:] += rate
+                else:
+                    for k in G.exchange_indices:
+                        upd[k] += rate
             if spec[0] == "wind":                 # Wind_stress.__call__ + assign_windfield_values (forcing.py:133-215)
                 W = spec[1]
                 t = self.get_time()
@@ -426,6 +435,10 @@ class OracleDomain:
                     x, y = self.edge_coordinates[3 * v + e]
                     q = spec[1](t, x, y)
                     self.stage_b[m], self.xmom_b[m], self.ymom_b[m] = q[0], q[1], q[2]
+            elif kind == "dirichlet_discharge":      # boundaries.py:881-885 (evaluate, edge by edge)
+                self.stage_b[ids] = spec[1]
+                self.xmom_b[ids] = -spec[2] * n1
+                self.ymom_b[ids] = -spec[2] * n2
             elif kind == "characteristic_stage":
                 # boundaries.py:760-843 (evaluate_segment), gravity = anuga.config.g
                 value = spec[1](t)

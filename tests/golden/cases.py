@@ -376,6 +376,40 @@ def file_boundary_de1(A, n=8):
     return d
 
 
+def forcing_de1(A, n=14):
+    """the older forcing-term API (shallow_water/forcing.py): Rainfall as a function of time over a polygon and
+    as a constant over the whole domain, Inflow through a circle, all added to the stage update"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: 0.3 * x / L + 0.05 * np.cos(y))
+    d.set_quantity("stage", lambda x, y: np.maximum(0.3 * x / L + 0.05 * np.cos(y), 0.12), location="centroids")
+    d.set_quantity("friction", 0.03)
+    _reflective_all(A, d)
+    d.forcing_terms.append(A.Rainfall(d, rate=lambda t: 40.0 + 10.0 * t,
+                                      polygon=[[2.1, 2.2], [9.3, 2.4], [8.7, 9.1], [2.9, 8.3]]))
+    d.forcing_terms.append(A.Rainfall(d, rate=3.0))
+    d.forcing_terms.append(A.Inflow(d, rate=0.9, center=(10.2, 4.1), radius=1.7))
+    return d
+
+
+def discharge_de1(A, n=14):
+    """Dirichlet_discharge_boundary: a fixed stage and a discharge per unit width entering through the left
+    boundary of a gently sloping channel, leaving through a Dirichlet stage on the right"""
+    d = A.rectangular_cross_domain(n, n, len1=float(n), len2=float(n))
+    d.set_flow_algorithm("DE1")
+    d.set_store(False)
+    L = float(n)
+    d.set_quantity("elevation", lambda x, y: -0.2 * x / L)
+    d.set_quantity("stage", 0.3)
+    d.set_quantity("friction", 0.03)
+    Br = A.Reflective_boundary(d)
+    d.set_boundary({"left": A.Dirichlet_discharge_boundary(d, 0.45, 0.35), "right": A.Dirichlet_boundary([0.1, 0.0, 0.0]),
+                    "top": Br, "bottom": Br})
+    return d
+
+
 CASES = {
     "kat_bedslope_more_steps": (kat_bedslope_more_steps, dict(yieldstep=0.05, finaltime=0.5)),
     "dam_break_de0": (dam_break_de0, dict(yieldstep=1.0, finaltime=6.0)),
@@ -402,6 +436,8 @@ CASES = {
     "characteristic_de1": (characteristic_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "wind_de1": (wind_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "riverwall_de1": (riverwall_de1, dict(yieldstep=1.0, finaltime=4.0)),
+    "forcing_de1": (forcing_de1, dict(yieldstep=1.0, finaltime=3.0)),
+    "discharge_de1": (discharge_de1, dict(yieldstep=1.0, finaltime=3.0)),
     "file_boundary_de1": (file_boundary_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_de1": (culvert_de1, dict(yieldstep=1.0, finaltime=4.0)),
     "culvert_pipe_de1": (culvert_pipe_de1, dict(yieldstep=1.0, finaltime=4.0)),
