@@ -405,7 +405,11 @@ def discharge_de1(A, n=14):
     d.set_quantity("stage", 0.3)
     d.set_quantity("friction", 0.03)
     Br = A.Reflective_boundary(d)
-    d.set_boundary({"left": A.Dirichlet_discharge_boundary(d, 0.45, 0.35), "right": A.Dirichlet_boundary([0.1, 0.0, 0.0]),
+    # (the reference exports this class from anuga.shallow_water.boundaries only)
+    DDB = getattr(A, "Dirichlet_discharge_boundary", None)
+    if DDB is None:
+        from anuga.shallow_water.boundaries import Dirichlet_discharge_boundary as DDB
+    d.set_boundary({"left": DDB(d, 0.45, 0.35), "right": A.Dirichlet_boundary([0.1, 0.0, 0.0]),
                     "top": Br, "bottom": Br})
     return d
 
