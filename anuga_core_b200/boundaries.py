@@ -61,9 +61,10 @@ class Boundary:
     def device_values(self, t):
         return (0.0, 0.0, 0.0)
 
-    def values_for_substep(self, dev, seg, substep, t):
-        """the segment's three value-table entries for RK substep `substep` at time t (boundaries that keep
-        per-substep data on the device, e.g. Time_space_boundary, refresh it here)"""
+    def values_for_substep(self, dev, seg, substep, t, ids=None):
+        """the segment's three value-table entries for RK substep `substep` at time t; `ids` are the boundary
+        indices of the segment (boundaries that keep per-substep data on the device, e.g. Time_space_boundary,
+        refresh it here)"""
         return self.device_values(t)
 
     def oracle_spec(self):

@@ -811,7 +811,7 @@ class Domain:
         (Modeltime_too_late) and it carries a default_boundary OBJECT, that boundary takes the segment over
         (generic_boundary_conditions.py:486-516, 655-684)"""
         try:
-            return B.values_for_substep(self._dev, seg, substep, t)
+            return B.values_for_substep(self._dev, seg, substep, t, self.tag_boundary_cells[tag])
         except BaseException as e:
             default = getattr(B, "default_boundary", None)
             if type(e).__name__ != "Modeltime_too_late" or not hasattr(default, "device_kind"):

@@ -341,7 +341,6 @@ class Time_space_boundary(_Table_boundary):
         self.default_boundary = default_boundary
         self.default_boundary_invoked = False
         self.verbose = verbose
-        self._ids = None
 
     def __repr__(self):
         return "Time space boundary"
@@ -355,12 +354,12 @@ class Time_space_boundary(_Table_boundary):
         return out
 
     def frames_for(self, ids):
-        self._ids = np.asarray(ids, dtype=np.int64)
-        f = self.evaluate_all(self._ids, self.domain.get_time())
+        f = self.evaluate_all(np.asarray(ids, dtype=np.int64), self.domain.get_time())
         return np.ascontiguousarray(np.stack([f, f, f], axis=0))
 
-    def values_for_substep(self, dev, seg, substep, t):
-        dev.set_boundary_table_frame(seg, substep, self.evaluate_all(self._ids, t))
+    def values_for_substep(self, dev, seg, substep, t, ids=None):
+        # (one object may be bound to several tags: the segment's own edges come with the call)
+        dev.set_boundary_table_frame(seg, substep, self.evaluate_all(np.asarray(ids, dtype=np.int64), t))
         return (0.0, float(substep), 0.0)
 
     def device_values(self, t):

@@ -5,7 +5,7 @@
 list holds descriptors: Manning friction is built into the update kernels (the placeholder below keeps
 the list's shape: the reference's list starts with ``manning_friction_implicit``), and a ``Wind_stress``
 is evaluated on the host into two per-triangle arrays that the update kernels add to the explicit
-momentum updates (swk_set_momentum_forcing).
+updates (swk_set_explicit_forcing); General_forcing, Rainfall and Inflow add their rate to the stage update the same way.
 """
 import math
 

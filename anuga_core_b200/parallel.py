@@ -238,6 +238,12 @@ def distribute(domain, nparts, epart=None, ghost_layer_width=2, ranks=None, doma
                        domain_kw)
         if domain.boundary_map is not None:
             bmap = dict(domain.boundary_map)
+            for t, B in bmap.items():
+                if hasattr(B, "frames_for"):
+                    # their interpolation points are the boundary-edge midpoints of the domain they were made
+                    # for: like the reference's parallel scripts, build them on the sub-domain after distribute
+                    raise NotImplementedError("%r on tag %r: create File / Field / Time_space boundaries on the "
+                                              "distributed domain, after distribute()" % (B, t))
             bmap["ghost"] = None                    # parallel_api.py:129
             d.set_boundary({t: bmap[t] for t in d.get_boundary_tags()})
         for op in domain.fractional_step_operators:
@@ -337,7 +343,9 @@ def distribute_collective(domain=None, verbose=False, debug=False, parameters=No
     payload = [None] * comm.size
     if comm.rank == 0:
         if domain.fractional_step_operators:
-            raise NotImplementedError("create operators on the distributed domain (after distribute)")
+            raise NotImplementedError("the rank-0 pipeline ships no operators: create them on the distributed "
+                                      "domain, after distribute(), as the reference's parallel scripts do "
+                                      "(inlets and culverts resolve their geometry across ranks)")
         N = domain.number_of_triangles
         if (parameters or {}).get("partition", "blocks") == "rcb":
             epart = rcb_partition(domain.centroid_coordinates, comm.size)
@@ -452,6 +460,7 @@ def strip_partitioned_mesh_domain(m, n, rank, nranks, device=0):
                ghost_recv_dict=sub["ghost_recv_dict"], processor=rank, numproc=nranks,
                number_of_full_triangles=sub["number_of_full_triangles"], ghost_layer_width=2, device=device)
     d.tri_l2g = sub["tri_l2g"]
+    d.tri_l2s = sub["tri_l2g"]            # the strips keep the sequential numbering
     d.node_l2g = sub["node_l2g"]
     d.number_of_global_triangles = 4 * m * n
     d.number_of_global_nodes = (m + 1) * (n + 1) + m * n

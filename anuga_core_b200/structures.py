@@ -29,6 +29,9 @@ class Region:
     def __init__(self, domain, indices=None, polygon=None, center=None, radius=None, line=None, poly=None,
                  expand_polygon=False, verbose=False):
         self.domain = domain
+        # how the region was specified: a distributed domain re-evaluates it on the gathered patch
+        self.spec = dict(indices=indices, polygon=polygon, center=center, radius=radius, line=line, poly=poly,
+                         expand_polygon=expand_polygon)
         c = domain.centroid_coordinates
         if poly is not None:                      # region.py:118-131: 2 points = line, more = polygon
             assert indices is None and polygon is None and line is None and center is None
@@ -140,6 +143,98 @@ def triangle_containing_point(domain, point):
     if len(ids) == 0:
         raise Exception("Point %s not found within a triangle" % str(point))
     return int(ids[0])
+
+
+# ----------------------------------------------------------------------------------------
+# structures created directly on a distributed domain (the reference's parallel scripts create them after
+# distribute(): parallel/parallel_operator_factory.py, parallel_inlet.py, parallel_structure_operator.py)
+# ----------------------------------------------------------------------------------------
+def is_distributed(domain):
+    return getattr(domain, "numproc", 1) > 1 and getattr(domain, "_comm", None) is not None \
+        and getattr(domain, "tri_l2s", None) is not None and not isinstance(domain, PatchDomain)
+
+
+class _PatchQuantity:
+    def __init__(self, values):
+        self.centroid_values = values
+        self.host_dirty = False
+
+
+class PatchDomain:
+    """The triangles of a distributed domain that lie near a structure, gathered on EVERY rank in the order
+    of their ids in the undistributed numbering.  It stands in for the sequential domain while an inlet or a
+    culvert resolves its geometry (regions, enquiry triangles, areas, the initial state that primes the
+    smoothing memory), so that every rank ends up with the same object the sequential constructor would have
+    made; `seq_ids` then takes patch indices back to undistributed ids."""
+
+    conserved_quantities = ["stage", "xmomentum", "ymomentum"]
+
+    def __getattr__(self, name):
+        # scalars of the model (timestep, g, yieldstep, ...) are the distributed domain's
+        if name.startswith("__") or "_sub" not in self.__dict__:
+            raise AttributeError(name)
+        return getattr(self.__dict__["_sub"], name)
+
+    def __init__(self, sub, lo, hi):
+        self._sub = sub
+        comm = sub._comm
+        nf = sub.number_of_full_triangles
+        # reach of the exact predicates' candidate filter (_near): the longest edge of the WHOLE mesh
+        self.pad = comm.allreduce_max(float(np.max(sub.edgelengths)))
+        lo = np.asarray(lo, dtype=np.float64) - 2.0 * self.pad
+        hi = np.asarray(hi, dtype=np.float64) + 2.0 * self.pad
+        c = sub.centroid_coordinates[:nf]
+        mine = np.flatnonzero((c[:, 0] >= lo[0]) & (c[:, 0] <= hi[0]) & (c[:, 1] >= lo[1]) & (c[:, 1] <= hi[1]))
+        q = sub.quantities
+        rows = np.concatenate([
+            np.asarray(sub.tri_l2s[mine], dtype=np.int64).view(np.float64)[:, None],   # ids travel as bit patterns
+            np.asarray(sub.vertex_coordinates, dtype=np.float64).reshape(-1, 6)[mine],
+            c[mine], sub.areas[mine][:, None], sub.edgelengths[mine],
+            np.stack([q[n].centroid_values[mine] for n in ("stage", "xmomentum", "ymomentum", "elevation")], axis=1),
+        ], axis=1)
+        counts = np.zeros(comm.size)
+        counts[comm.rank] = len(mine)
+        counts = comm.merge_disjoint(counts).astype(np.int64)
+        start = int(np.sum(counts[:comm.rank]))
+        allrows = np.zeros((int(np.sum(counts)), rows.shape[1]))
+        allrows[start:start + len(mine)] = rows
+        allrows = comm.merge_disjoint(allrows)                 # bit-exact: every row has one owner
+        ids = np.ascontiguousarray(allrows[:, 0]).view(np.int64)
+        order = np.argsort(ids, kind="stable")
+        allrows = allrows[order]
+        self.seq_ids = ids[order]
+        P = len(self.seq_ids)
+        self.number_of_triangles = P
+        self.vertex_coordinates = np.ascontiguousarray(allrows[:, 1:7]).reshape(3 * P, 2)
+        self.centroid_coordinates = np.ascontiguousarray(allrows[:, 7:9])
+        self.areas = np.ascontiguousarray(allrows[:, 9])
+        self.edgelengths = np.ascontiguousarray(allrows[:, 10:13])
+        if P:
+            self.edgelengths[0, 0] = max(self.edgelengths[0, 0], self.pad)     # _near reads the maximum
+        self.tri_full_flag = np.ones(P, dtype=np.int64)
+        self.quantities = {n: _PatchQuantity(np.ascontiguousarray(allrows[:, 13 + j]))
+                           for j, n in enumerate(("stage", "xmomentum", "ymomentum", "elevation"))}
+        self.operators = []
+
+    def set_fractional_step_operator(self, op):
+        self.operators.append(op)
+
+    def get_centroid_coordinates(self, absolute=False):
+        return self.centroid_coordinates
+
+
+def _bbox(*point_sets):
+    pts = np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 2) for p in point_sets if p is not None])
+    return pts.min(axis=0), pts.max(axis=0)
+
+
+def _relabel_inlet(inlet, patch):
+    inlet.triangle_indices = patch.seq_ids[inlet.triangle_indices]
+    inlet.region = None
+    if hasattr(inlet, "enquiry_index"):
+        inlet.enquiry_index = int(patch.seq_ids[inlet.enquiry_index])
+        inlet._extra_ids = np.array([inlet.enquiry_index], dtype=np.int64)
+    return inlet
 
 
 def _owned(sub, global_ids):
@@ -303,8 +398,25 @@ class Inlet_operator:
 
     def __init__(self, domain, region, Q=0.0, velocity=None, zero_velocity=False, default=0.0,
                  description=None, label=None, logging=False, verbose=False):
-        self.domain = domain
-        self.inlet = Inlet(domain, region, verbose=verbose)
+        if is_distributed(domain):
+            # resolve the region on the gathered patch (identical on every rank), then keep the owned rows
+            sub = domain
+            spec = region.spec if isinstance(region, Region) else dict(poly=np.asarray(region, dtype=np.float64),
+                                                                      expand_polygon=True)
+            if spec.get("indices") is not None:
+                raise NotImplementedError("a Region given by local indices cannot be resolved across ranks: "
+                                          "give a line, polygon or circle")
+            geom = [spec.get(k) for k in ("polygon", "line", "poly")]
+            if spec.get("center") is not None:
+                ctr, r = np.asarray(spec["center"], dtype=np.float64), float(spec["radius"])
+                geom.append(np.array([ctr - r, ctr + r]))
+            patch = PatchDomain(sub, *_bbox(*geom))
+            inlet = _relabel_inlet(Inlet(patch, Region(patch, **spec), verbose=verbose), patch)
+            self.domain = sub
+            self.inlet = inlet.localise(sub)
+        else:
+            self.domain = domain
+            self.inlet = Inlet(domain, region, verbose=verbose)
         self.Q = Q
         if velocity is not None:
             assert len(velocity) == 2
@@ -519,6 +631,17 @@ class Structure_operator:
                  use_momentum_jet=False, zero_outflow_momentum=True, use_old_momentum_method=True,
                  always_use_Q_wetdry_adjustment=True, force_constant_inlet_elevations=False,
                  description=None, label=None, structure_type=None, logging=None, verbose=None):
+        sub = None
+        if is_distributed(domain):
+            # build on the gathered patch around the culvert (identical on every rank), localise below
+            if force_constant_inlet_elevations:
+                raise NotImplementedError("force_constant_inlet_elevations on a distributed domain: set it before "
+                                          "distribute()")
+            sub = domain
+            reach = 2.0 * sum(abs(float(v)) for v in (width, height, diameter, apron, enquiry_gap) if v is not None)
+            lo, hi = _bbox(end_points, exchange_lines, enquiry_points)
+            domain = PatchDomain(sub, lo - reach, hi + reach)
+        self._sub = sub
         self.domain = domain
         as_array = lambda a: None if a is None else np.array(a, dtype=np.float64)
         self.end_points = as_array(end_points)
@@ -584,7 +707,23 @@ class Structure_operator:
                 z.centroid_values[ids] = np.sum(z.centroid_values[ids] * inlet.areas) / inlet.area
                 z.host_dirty = True
         self.inflow, self.outflow = self.inlets
-        domain.set_fractional_step_operator(self)
+        if sub is None:
+            domain.set_fractional_step_operator(self)
+        # (a distributed structure registers itself in _localise_from_patch, once its subclass has primed its
+        # smoothing memory on the patch's copy of the initial state)
+
+    def _localise_from_patch(self):
+        """second half of the distributed construction: patch indices -> undistributed ids, keep the owned rows"""
+        sub, patch = self._sub, self.domain
+        if sub is None:
+            return
+        for inlet in self.inlets:
+            _relabel_inlet(inlet, patch)
+        self.domain = sub
+        self.inlets = [i.localise(sub) for i in self.inlets]
+        self.inflow, self.outflow = self.inlets
+        self._sub = None
+        sub.set_fractional_step_operator(self)
 
     # -- geometry (structure_operator.py:396-480) -----------------------------------------
     def _straight_geometry(self):
@@ -836,6 +975,7 @@ class _Boyd_operator(Structure_operator):
         self.smooth_delta_total_energy = 1.0 * self.delta_total_energy
         self.smooth_Q = Qvd[0]
         self.smoothing_timescale = smoothing_timescale
+        self._localise_from_patch()          # distributed construction: now take the owned rows
 
     def _fetch_initial(self):
         """the constructor runs before the device handle exists: read the host arrays"""

@@ -166,7 +166,7 @@ def workload_config(a):
             "l2_policy": "inputs larger than L2 (>= 1.7 GB of state per GPU vs 126 MB L2), no flush"}
 
 
-def build_domain(a, rank=0, nranks=1, device=0):
+def build_domain(a, rank=0, nranks=1, device=0, comm=None):
     from anuga_core_b200 import workloads
     if a.config == "sweep":
         if nranks == 1:
@@ -174,15 +174,16 @@ def build_domain(a, rank=0, nranks=1, device=0):
         from anuga_core_b200 import parallel
         m, n = parallel.weak_scaling_shape(a.size, nranks)
         return parallel.strip_partitioned_sweep_domain(m, n, rank, nranks, device=device)
-    make = (lambda **kw: workloads.tsunami_domain(a.size, a.size, **kw)) if a.config == "tsunami" else \
-           (lambda **kw: workloads.structures_domain(2 * a.size, a.size, **kw))
+    if a.config == "structures":
+        # fixed total size shared out over the ranks (strong scaling): the rank's strip of the mesh, the
+        # structures created on the distributed domain with their global geometry (as the reference's parallel
+        # scripts do after distribute)
+        return workloads.structures_domain(2 * a.size, a.size, rank=rank, nranks=nranks, comm=comm, device=device)
     if nranks == 1:
-        return make(device=device)
-    # fixed total size shared out over the ranks (strong scaling).  Boundaries and structures are created on the
-    # sequential domain and localised by distribute(): every rank builds the sequential domain and cuts out
-    # its own part (replicated build, no rank-0 pass over all parts)
+        return workloads.tsunami_domain(a.size, a.size, device=device)
+    # tsunami at N > 1: every rank builds the sequential domain and cuts out its own part (replicated build)
     from anuga_core_b200 import parallel
-    g = make()
+    g = workloads.tsunami_domain(a.size, a.size)
     N = g.number_of_triangles
     return parallel.distribute(g, nranks, epart=(np.arange(N) * nranks) // N, ranks=[rank],
                                domain_kw=dict(device=device))[rank]
@@ -350,7 +351,7 @@ def main():
                                   "parity_check": parity}))
             return 3
     t_setup = time.time()
-    d = build_domain(a, rank, world, device=local_rank)
+    d = build_domain(a, rank, world, device=local_rank, comm=comm)
     t_built = time.time()
     if comm is not None:
         d.attach_communicator(comm)

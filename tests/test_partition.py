@@ -183,6 +183,48 @@ for k in ("stage", "xmomentum", "ymomentum"):
     changed += int(np.sum(ref.quantities[k].centroid_values[ids] != g.quantities[k].centroid_values[ids]))
 assert comm.allreduce_sum(changed) > 20
 
+# structures created directly on the distributed domain (what the reference's parallel scripts do after
+# distribute) == the same structures created on the sequential domain and localised
+def build2(with_ops):
+    d = ab.rectangular_cross_domain(12, 6, len1=12.0, len2=6.0)
+    d.set_flow_algorithm("DE1")
+    d.set_quantity("elevation", lambda x, y: 0.8 * np.exp(-((x - 6.0) / 0.8) ** 2))
+    d.set_quantity("stage", lambda x, y: np.where(x < 6.0, 0.9, 0.3) + 0.01 * y, location="centroids")
+    d.set_quantity("xmomentum", lambda x, y: 0.05 * np.sin(x + y), location="centroids")
+    if with_ops:
+        add_ops(d)
+    return d
+
+def add_ops(d):
+    ab.Inlet_operator(d, ab.Region(d, polygon=[[5.1, -0.1], [6.9, -0.1], [6.9, 2.0], [5.1, 2.0]]), Q=lambda t: 3.0 + t)
+    ab.Inlet_operator(d, [[2.2, 1.1], [2.2, 4.9]], Q=0.7)                    # a line, as the reference takes it
+    ab.Boyd_box_operator(d, losses=1.5, width=1.3, height=0.5, end_points=[[4.3, 3.3], [7.7, 3.3]],
+                         apron=0.55, enquiry_gap=0.4)
+    ab.Boyd_pipe_operator(d, losses=1.2, diameter=0.6, exchange_lines=[[[4.6, 4.4], [4.6, 5.3]], [[7.4, 4.6], [7.4, 5.4]]],
+                          enquiry_points=[[3.9, 4.9], [8.1, 5.0]], smoothing_timescale=2.0)
+
+subA = P.distribute(build2(True), size, ranks=[rank])[rank]          # sequential construction, localised
+subA.attach_communicator(comm)
+subB = P.distribute(build2(False), size, ranks=[rank])[rank]         # ... vs construction on the sub-domain
+subB.attach_communicator(comm)
+add_ops(subB)
+assert len(subA.fractional_step_operators) == len(subB.fractional_step_operators) == 4
+for a, b in zip(subA.fractional_step_operators, subB.fractional_step_operators):
+    assert type(a) is type(b)
+    for ia, ib in zip(getattr(a, "inlets", None) or [a.inlet], getattr(b, "inlets", None) or [b.inlet]):
+        assert np.array_equal(ia.triangle_indices, ib.triangle_indices) and np.array_equal(ia.local_rows, ib.local_rows)
+        assert np.array_equal(ia.areas, ib.areas) and ia.area == ib.area
+        assert np.array_equal(ia._extra_ids, ib._extra_ids) and np.array_equal(ia._extra_rows, ib._extra_rows)
+    if hasattr(a, "smooth_Q"):
+        assert a.smooth_Q == b.smooth_Q and a.smooth_delta_total_energy == b.smooth_delta_total_energy
+        assert a.culvert_length == b.culvert_length
+for s_ in (subA, subB):
+    s_._dev = HostArrays(s_); s_.timestep = 0.05; s_.yieldstep = 1.0
+    for op in s_.fractional_step_operators:
+        op()
+for k in ("stage", "xmomentum", "ymomentum"):
+    assert np.array_equal(subA.quantities[k].centroid_values, subB.quantities[k].centroid_values), k
+
 # anuga.distribute as the reference's parallel scripts use it: rank 0 holds the sequential domain
 def plain():
     d = ab.rectangular_cross_domain(10, 6, len1=10.0, len2=6.0)
