@@ -472,7 +472,7 @@ __device__ __forceinline__ void boundary_value(const Dev &D, const Segments &S, 
   const int kind = S.seg_kind[seg];
   if (kind == 0) return;
   const double *sv = S.seg_val + (3 * seg + S.substep) * 3;
-  if (kind >= 9) {
+  if (kind == 9 || kind == 10) {
     // frames resident in HBM, linear in time between frame idx and idx + 1 (Interpolation_function.__call__,
     // fit_interpolate/interpolate.py:1056-1092): q = Q0 + ratio*(Q1 - Q0); kind 10 adds mean_stage to the stage
     const double ratio = sv[0];

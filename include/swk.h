@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SWK_ABI_VERSION 1
+#define SWK_ABI_VERSION 2   /* 2: value tables per substep, swk_step_*, swk_comm_*, table boundaries, explicit forcing */
 
 /* ---- status codes ------------------------------------------------------- */
 #define SWK_OK                 0
