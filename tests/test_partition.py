@@ -272,6 +272,27 @@ mine.fractional_step_operators[:] = []
 mine.set_boundary({t: (None if t == "ghost" else ab.Reflective_boundary(mine)) for t in mine.get_boundary_tags()})
 assert mine._evolve_path() == 0
 assert comm.allreduce_min(float(rank)) == 0.0
+# a sub-domain restored from its checkpoint joins the process group again (the pickle cannot carry it);
+# without a communicator a sub-domain that has halo peers refuses to evolve instead of running uncoupled
+import tempfile
+ckdir = os.path.join(tempfile.gettempdir(), "swk_ck_test_%%s" %% os.environ.get("MASTER_PORT", "0"))
+mine.set_checkpointing(checkpoint_dir=ckdir, checkpoint_step=1)
+mine.save_checkpoint()
+back = ab.load_checkpoint_file(domain_name="collective", checkpoint_dir=ckdir)
+assert back._comm is not None and back._comm.size == size and back.numproc == size
+assert np.array_equal(back.quantities["stage"].centroid_values, mine.quantities["stage"].centroid_values)
+import pickle
+lone = pickle.loads(pickle.dumps(mine))
+assert lone._comm is None
+try:
+    next(lone.evolve(yieldstep=1.0, finaltime=1.0))
+    raise SystemExit("an uncoupled sub-domain must not evolve")
+except Exception as e:
+    assert "no communicator" in str(e), e
+comm.barrier()
+if rank == 0:
+    import shutil
+    shutil.rmtree(ckdir, ignore_errors=True)
 got = comm.scatter_objects([{"for": r, "data": np.arange(3) + r} for r in range(size)] if rank == 0 else None)
 assert got["for"] == rank and np.array_equal(got["data"], np.arange(3) + rank)
 comm.barrier()
