@@ -49,12 +49,6 @@ constexpr int SEG_MAX = 4097, OP_MAX = 1024;
 constexpr size_t VALS_OPS = (size_t)SEG_MAX * 9, VALS_TOTAL = VALS_OPS + 2 * (size_t)OP_MAX;
 static inline int nblk(long long n) { return (int)((n + BLOCK - 1) / BLOCK); }
 static inline double u2d_host(unsigned long long u) { double x; memcpy(&x, &u, 8); return x; }
-static int g_num_sms = 0;
-static inline int ngrid(long long n, int blocks_per_sm)
-{
-  (void)blocks_per_sm;
-  return nblk(n);
-}
 
 // ----------------------------------------------------------------------------
 // NCCL, loaded at run time so that single-GPU use has no NCCL dependency
@@ -342,7 +336,6 @@ static int select_device(int device)
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return fail(SWK_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100: libswk contains sm_100a code only");
-  g_num_sms = prop.multiProcessorCount;
   CK(cudaSetDevice(device));
   return SWK_OK;
 }
@@ -1308,7 +1301,7 @@ extern "C" int swk_reset_yield_statistics(swk_domain *d)
 static void launch_extrapolate(swk_domain *d, const Consts &K)
 {
   TimedScope ts(d, 0);
-  LAUNCH(d, k_extrapolate, ngrid(d->N, SWK_MINB_A), BLOCK, d->D, K);
+  LAUNCH(d, k_extrapolate, nblk(d->N), BLOCK, d->D, K);
 }
 
 static int launch_boundary(swk_domain *d, int substep = 0)
@@ -1336,12 +1329,12 @@ static void launch_flux(swk_domain *d, int first, int write_speed)
   TimedScope ts(d, 1);
   const int n = n_active(d);
   if (d->D.bed_e_x) {        // per-call layer with edge beds / centroid heights given explicitly
-    if (d->has_riverwalls) LAUNCH(d, (k_flux<true, true>), ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
-    else LAUNCH(d, (k_flux<false, true>), ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
+    if (d->has_riverwalls) LAUNCH(d, (k_flux<true, true>), nblk(n), BLOCK, d->D, d->K, first, write_speed, 0, n);
+    else LAUNCH(d, (k_flux<false, true>), nblk(n), BLOCK, d->D, d->K, first, write_speed, 0, n);
     return;
   }
-  if (d->has_riverwalls) LAUNCH(d, k_flux<true>, ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
-  else LAUNCH(d, k_flux<false>, ngrid(n, SWK_MINB_F), BLOCK, d->D, d->K, first, write_speed, 0, n);
+  if (d->has_riverwalls) LAUNCH(d, k_flux<true>, nblk(n), BLOCK, d->D, d->K, first, write_speed, 0, n);
+  else LAUNCH(d, k_flux<false>, nblk(n), BLOCK, d->D, d->K, first, write_speed, 0, n);
 }
 
 static void launch_bflux(swk_domain *d, int substep)
@@ -1481,7 +1474,7 @@ static int launch_first_update(swk_domain *d, int do_backup, bool last_of_step, 
   const UpdateArgs U = update_args(d, do_backup, 0, 1.0, 0.0, 1.0, last_of_step);
   return update_with_exchange(d, exchange_after, [&](int k0, int k1) {
     TimedScope ts(d, 2);
-    LAUNCH(d, k_update, ngrid(k1 - k0, SWK_MINB_U), BLOCK, d->D, d->K, U, -1.0, k0, k1);
+    LAUNCH(d, k_update, nblk(k1 - k0), BLOCK, d->D, d->K, U, -1.0, k0, k1);
   });
 }
 
@@ -1498,7 +1491,7 @@ static int launch_later_substep(swk_domain *d, int substep, double a, double b, 
     const int n = n_active(d);
     {
       TimedScope ts(d, 3);
-      LAUNCH(d, k_flux_update<true>, ngrid(n, SWK_MINB_FU), BLOCK, d->D, d->K, U, 0, n);
+      LAUNCH(d, k_flux_update<true>, nblk(n), BLOCK, d->D, d->K, U, 0, n);
     }
     // (ghost triangles are not evaluated under a communicator: only the wall triangles below n)
     const int nw = (int)(std::lower_bound(d->h_rw_list.begin(), d->h_rw_list.end(), n) - d->h_rw_list.begin());
@@ -1507,7 +1500,7 @@ static int launch_later_substep(swk_domain *d, int substep, double a, double b, 
   } else {
     CKV(update_with_exchange(d, exchange_after, [&](int k0, int k1) {
       TimedScope ts(d, 3);
-      LAUNCH(d, k_flux_update<false>, ngrid(k1 - k0, SWK_MINB_FU), BLOCK, d->D, d->K, U, k0, k1);
+      LAUNCH(d, k_flux_update<false>, nblk(k1 - k0), BLOCK, d->D, d->K, U, k0, k1);
     }));
   }
   if (!last_of_step) launch_bflux(d, substep);     // the last substep's sum rides in k_finish_step
@@ -1935,7 +1928,7 @@ extern "C" int swk_update_conserved_quantities(swk_domain *d, double timestep, i
   CK(cudaSetDevice(d->device));
   CKV(pull_clock(d));
   const long long before = d->h_clock->negative_cells;
-  LAUNCH(d, k_update, ngrid(d->N, SWK_MINB_U), BLOCK, d->D, d->K, update_args(d, 0, 0, 1.0, 0.0, 1.0), timestep, 0, (int)d->N);
+  LAUNCH(d, k_update, nblk(d->N), BLOCK, d->D, d->K, update_args(d, 0, 0, 1.0, 0.0, 1.0), timestep, 0, (int)d->N);
   CKV(pull_clock(d));
   if (d->h_clock->stop < 0) {
     const int st = d->h_clock->stop;

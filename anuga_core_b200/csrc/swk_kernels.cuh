@@ -56,22 +56,13 @@ constexpr int BLOCK = SWK_BLOCK;
 // One tile of BLOCK consecutive triangles per CTA.  (A persistent form - as many CTAs as fit on the GPU,
 // each walking a contiguous run of tiles and prefetching its own next tiles - was measured 20-40 %
 // slower for every kernel: profiles/r2/sweep3_persistent.txt.)
-struct TileRange { int first, last; };
-__device__ __forceinline__ TileRange my_tiles(int ntiles)
+// First triangle of the tile whose slabs a CTA asks the L2 for (SWK_PF_AHEAD tiles further on), or -1.
+__device__ __forceinline__ long long prefetch_target(int k0)
 {
-  TileRange r;
-  r.first = blockIdx.x;
-  r.last = blockIdx.x + 1;
-  (void)ntiles;
-  return r;
-}
-// first triangle of the tile whose slabs should be requested now (SWK_PF_AHEAD tiles further on), or -1
-__device__ __forceinline__ long long prefetch_target(int tile, const TileRange &r, int k0)
-{
-  (void)r;
 #if SWK_PF_AHEAD > 0
-  return (long long)k0 + (long long)(tile + SWK_PF_AHEAD) * BLOCK;
+  return (long long)k0 + (long long)(blockIdx.x + SWK_PF_AHEAD) * BLOCK;
 #else
+  (void)k0;
   return -1;
 #endif
 }
@@ -277,31 +268,28 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
 __global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts K)
 {
   if (D.clock->stop) return;
-  const TileRange tr = my_tiles((D.N + BLOCK - 1) / BLOCK);
-  for (int tile = tr.first; tile < tr.last; tile++) {
-    const int k = tile * BLOCK + threadIdx.x;
+  const int k = blockIdx.x * BLOCK + threadIdx.x;
 #if SWK_PF_AHEAD > 0
-    if (threadIdx.x < 5) {      // slabs of a tile further on: cq, xg x3, connA
-      const long long t0 = prefetch_target(tile, tr, 0);
-      if (t0 >= 0 && t0 + BLOCK <= D.NP) {
-        const int j = threadIdx.x;
-        if (j == 0) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
-        else if (j < (SWK_XG_COMPACT ? 3 : 4)) prefetch_l2_bulk(D.xg + (long long)(j - 1) * D.NP + t0, BLOCK * 32);
-        else if (j == 4) prefetch_l2_bulk(D.connA + t0, BLOCK * 16);
-      }
+  if (threadIdx.x < 5) {      // slabs of a tile further on: cq, xg x3, connA
+    const long long t0 = prefetch_target(0);
+    if (t0 + BLOCK <= D.NP) {
+      const int j = threadIdx.x;
+      if (j == 0) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
+      else if (j < (SWK_XG_COMPACT ? 3 : 4)) prefetch_l2_bulk(D.xg + (long long)(j - 1) * D.NP + t0, BLOCK * 32);
+      else if (j == 4) prefetch_l2_bulk(D.connA + t0, BLOCK * 16);
     }
-#endif
-    if (k >= D.N) continue;
-    d4 r0, r1, r2;
-    Eff e;
-    bool zero_mom;
-    int fl;
-    extrapolate_tri(D, K, D.cq, k, true, r0, r1, r2, e, zero_mom, fl);
-    D.zflag[k] = (zero_mom ? 1 : 0) | ((fl >> 3) & 2);   // bit0: zeroed momenta, bit1: tri_full_flag
-    D.eq[k] = r0;
-    D.eq[D.NP + k] = r1;
-    D.eq[2 * D.NP + k] = r2;
   }
+#endif
+  if (k >= D.N) return;
+  d4 r0, r1, r2;
+  Eff e;
+  bool zero_mom;
+  int fl;
+  extrapolate_tri(D, K, D.cq, k, true, r0, r1, r2, e, zero_mom, fl);
+  D.zflag[k] = (zero_mom ? 1 : 0) | ((fl >> 3) & 2);   // bit0: zeroed momenta, bit1: tri_full_flag
+  D.eq[k] = r0;
+  D.eq[D.NP + k] = r1;
+  D.eq[2 * D.NP + k] = r2;
 }
 
 // Write the protected/zeroed centroid values in place: what the reference's centroid
@@ -853,23 +841,20 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_F) k_flux(Dev D, Consts K, int
                                                             int k0, int k1)
 {
   if (D.clock->stop) return;
-  const TileRange tr = my_tiles((k1 - k0 + BLOCK - 1) / BLOCK);
-  double dtmin = 1.0e+100;
-  for (int tile = tr.first; tile < tr.last; tile++) {
-    const int k = k0 + tile * BLOCK + threadIdx.x;
+  const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
 #if SWK_PF_AHEAD > 0
-    prefetch_flux_slabs(D, prefetch_target(tile, tr, k0), false);
+  prefetch_flux_slabs(D, prefetch_target(k0), false);
 #endif
-    if (k < k1) {
-      const i4 p = lds(&D.connB[k]);
-      const Eff own = effective(D.cq[k], K);
-      const TriFlux T = triangle_flux<RW, SWK_F_ROLLED, XB>(D, K, k, p, own, first != 0);
-      sts(&D.eu[k], T.su);
-      sts(&D.eu[D.NP + k], T.xu);
-      sts(&D.eu[2 * D.NP + k], T.yu);
-      if (first && write_speed) D.max_speed[k] = T.speed;
-      dtmin = dmin(dtmin, T.dtmin);
-    }
+  double dtmin = 1.0e+100;
+  if (k < k1) {
+    const i4 p = lds(&D.connB[k]);
+    const Eff own = effective(D.cq[k], K);
+    const TriFlux T = triangle_flux<RW, SWK_F_ROLLED, XB>(D, K, k, p, own, first != 0);
+    sts(&D.eu[k], T.su);
+    sts(&D.eu[D.NP + k], T.xu);
+    sts(&D.eu[2 * D.NP + k], T.yu);
+    if (first && write_speed) D.max_speed[k] = T.speed;
+    dtmin = T.dtmin;
   }
   if (first) block_min_to_clock(dtmin, D.clock);
 }
@@ -880,26 +865,23 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_U) k_update(Dev D, Consts K, U
 {
   if (D.clock->stop) return;
   const double dt = (dt_override >= 0.0) ? dt_override : D.clock->dt;
-  const TileRange tr = my_tiles((k1 - k0 + BLOCK - 1) / BLOCK);
-  for (int tile = tr.first; tile < tr.last; tile++) {
-    const int k = k0 + tile * BLOCK + threadIdx.x;
+  const int k = k0 + blockIdx.x * BLOCK + threadIdx.x;
 #if SWK_PF_AHEAD > 0
-    if (threadIdx.x < 5) {
-      const long long t0 = prefetch_target(tile, tr, k0);
-      if (t0 >= 0 && t0 + BLOCK <= D.NP) {
-        const int j = threadIdx.x;
-        if (j < 3) prefetch_l2_bulk(D.eu + (long long)j * D.NP + t0, BLOCK * 8);
-        else if (j == 3) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
-        else prefetch_l2_bulk(D.eta + t0, BLOCK * 8);
-      }
+  if (threadIdx.x < 5) {
+    const long long t0 = prefetch_target(k0);
+    if (t0 + BLOCK <= D.NP) {
+      const int j = threadIdx.x;
+      if (j < 3) prefetch_l2_bulk(D.eu + (long long)j * D.NP + t0, BLOCK * 8);
+      else if (j == 3) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
+      else prefetch_l2_bulk(D.eta + t0, BLOCK * 8);
     }
-#endif
-    if (k >= k1) continue;
-    const d4 raw = D.cq[k];
-    const Eff e = effective(raw, K);
-    triangle_update(D, K, U, k, raw, e, D.zflag[k], lds(&D.eu[k]), lds(&D.eu[D.NP + k]), lds(&D.eu[2 * D.NP + k]), dt,
-                    D.cq, nullptr);
   }
+#endif
+  if (k >= k1) return;
+  const d4 raw = D.cq[k];
+  const Eff e = effective(raw, K);
+  triangle_update(D, K, U, k, raw, e, D.zflag[k], lds(&D.eu[k]), lds(&D.eu[D.NP + k]), lds(&D.eu[2 * D.NP + k]), dt,
+                  D.cq, nullptr);
 }
 
 // Fused pass B (substeps >= 1): flux + friction + update + fix-negative + RK combine.
@@ -914,38 +896,39 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Const
 {
   if (D.clock->stop) return;
   const double dt = D.clock->dt;
-  const TileRange tr = my_tiles((k1 - k0 + BLOCK - 1) / BLOCK);
-  for (int tile = tr.first; tile < tr.last; tile++) {
-    const int k = k0 + tile * BLOCK + threadIdx.x;
+  // (written as a loop over the CTA's single tile: with this shape ptxas keeps the edge loop at 32 bytes of
+  // spills instead of 52 / 88, see profiles/r2/ptxas_table.txt)
+  for (unsigned tile = blockIdx.x; tile < blockIdx.x + 1; tile++) {
+  const int k = k0 + tile * BLOCK + threadIdx.x;
 #if SWK_PF_AHEAD > 0
-    prefetch_flux_slabs(D, prefetch_target(tile, tr, k0), true);
+  prefetch_flux_slabs(D, prefetch_target(k0), true);
 #endif
-    if (k >= k1) continue;
-    const i4 p = lds(&D.connB[k]);
-    if (RW && (p.w & 0xE)) {                    // a triangle with a wall edge: flux only
-      const Eff own = effective(D.cq[k], K);
-      const TriFlux T = triangle_flux<true, SWK_FU_ROLLED>(D, K, k, p, own, false);
-      D.eu[k] = T.su;
-      D.eu[D.NP + k] = T.xu;
-      D.eu[2 * D.NP + k] = T.yu;
-      continue;
-    }
+  if (k >= k1) continue;
+  const i4 p = lds(&D.connB[k]);
+  if (RW && (p.w & 0xE)) {                      // a triangle with a wall edge: flux only
+    const Eff own = effective(D.cq[k], K);
+    const TriFlux T = triangle_flux<true, SWK_FU_ROLLED>(D, K, k, p, own, false);
+    D.eu[k] = T.su;
+    D.eu[D.NP + k] = T.xu;
+    D.eu[2 * D.NP + k] = T.yu;
+    continue;
+  }
 #if SWK_FU_RELOAD
-    // only {h, z} of the own state live across the edge loop; the record is read again (L1) for the update
-    Eff own;
-    {
-      const Eff e0 = effective(D.cq[k], K);
-      own.h = e0.h; own.z = e0.z; own.w = e0.w;
-    }
-    const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, own, false);
-    const d4 raw = D.cq[k];
-    const Eff e = effective(raw, K);
+  // only {h, z} of the own state live across the edge loop; the record is read again (L1) for the update
+  Eff own;
+  {
+    const Eff e0 = effective(D.cq[k], K);
+    own.h = e0.h; own.z = e0.z; own.w = e0.w;
+  }
+  const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, own, false);
+  const d4 raw = D.cq[k];
+  const Eff e = effective(raw, K);
 #else
-    const d4 raw = D.cq[k];
-    const Eff e = effective(raw, K);
-    const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, e, false);
+  const d4 raw = D.cq[k];
+  const Eff e = effective(raw, K);
+  const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, e, false);
 #endif
-    triangle_update(D, K, U, k, raw, e, D.zflag[k], T.su, T.xu, T.yu, dt, D.cq, nullptr);
+  triangle_update(D, K, U, k, raw, e, D.zflag[k], T.su, T.xu, T.yu, dt, D.cq, nullptr);
   }
 }
 
