@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound(lib):
         assert hasattr(lib, n), "libswk.so does not export %s" % n
         assert n in backend.SYMBOLS, "backend.py does not bind %s" % n
     assert sorted(backend.SYMBOLS) == names
-    assert lib.swk_abi_version() == 1
+    assert lib.swk_abi_version() == 2
 
 
 def test_library_contains_sm100a_code_only():
