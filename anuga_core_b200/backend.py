@@ -123,6 +123,10 @@ SYMBOLS = {
     "swk_add_rate_operator": (C.c_int, [_H, _D, _D, _PD, _PI, _I, C.POINTER(C.c_int)]),
     "swk_set_rate": (C.c_int, [_H, C.c_int, _D, _D]),
     "swk_clear_rate_operators": (C.c_int, [_H]),
+    "swk_register_cells": (C.c_int, [_H, _PI, _I, C.POINTER(C.c_int)]),
+    "swk_gather_set": (C.c_int, [_H, C.c_int, _PD]),
+    "swk_scatter_set": (C.c_int, [_H, C.c_int, _PD]),
+    "swk_update_ghosts_async": (C.c_int, [_H]),
     "swk_set_explicit_forcing": (C.c_int, [_H, _PD, _PD, _PD, _I]),
     "swk_set_rate_dynamic": (C.c_int, [_H, C.c_int, C.c_int]),
     "swk_set_boundary_values_substep": (C.c_int, [_H, C.c_int, C.c_int, _PD]),
@@ -371,17 +375,42 @@ class DeviceDomain:
     def set_rate(self, op_id, rate, factor=1.0):
         _check(self.lib.swk_set_rate(self.h, int(op_id), float(rate), float(factor)))
 
+    _SET_LIMIT = 1 << 16      # id lists up to this length are registered once and reused (inlets, enquiry cells)
+
+    def _use_set(self, ids):
+        # (a caller that moves a different id list every time would only pile up registrations)
+        cache = self.__dict__.get("_cell_sets", {})
+        return 0 < ids.size <= self._SET_LIMIT and (len(cache) < 256 or ids.tobytes() in cache)
+
+    def _cell_set(self, ids):
+        """id of the registered cell set for this id list (include/swk.h: swk_register_cells)"""
+        cache = self.__dict__.setdefault("_cell_sets", {})
+        key = ids.tobytes()
+        sid = cache.get(key)
+        if sid is None:
+            c = C.c_int(-1)
+            _check(self.lib.swk_register_cells(self.h, _pi(ids), ids.size, C.byref(c)))
+            sid = cache[key] = c.value
+        return sid
+
     def gather_centroids(self, ids):
         """(n,4) {stage, xmomentum, ymomentum, elevation} of the listed triangles"""
         ids = _i64(ids)
         out = np.empty((ids.size, 4), dtype=np.float64)
-        _check(self.lib.swk_gather_centroids(self.h, _pi(ids), ids.size, _pd(out)))
+        if self._use_set(ids):
+            _check(self.lib.swk_gather_set(self.h, self._cell_set(ids), _pd(out)))
+        else:
+            _check(self.lib.swk_gather_centroids(self.h, _pi(ids), ids.size, _pd(out)))
         return out
 
     def scatter_centroids(self, ids, values):
+        """new {stage, xmomentum, ymomentum} of the listed triangles; queued in stream order"""
         ids = _i64(ids)
         v = _f64(values).reshape(ids.size, 3)
-        _check(self.lib.swk_scatter_centroids(self.h, _pi(ids), ids.size, _pd(v)))
+        if self._use_set(ids):
+            _check(self.lib.swk_scatter_set(self.h, self._cell_set(ids), _pd(v)))
+        else:
+            _check(self.lib.swk_scatter_centroids(self.h, _pi(ids), ids.size, _pd(v)))
 
     def scatter_bed(self, ids, values):
         ids = _i64(ids)
@@ -431,6 +460,9 @@ class DeviceDomain:
 
     def update_ghosts(self):
         _check(self.lib.swk_update_ghosts(self.h))
+
+    def update_ghosts_async(self):
+        _check(self.lib.swk_update_ghosts_async(self.h))
 
     def apply_fractional_steps(self, timestep):
         _check(self.lib.swk_apply_fractional_steps(self.h, float(timestep)))

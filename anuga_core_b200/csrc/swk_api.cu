@@ -122,6 +122,17 @@ struct RateOp {
   int nblocks = 0;
 };
 
+// A registered set of triangles that the host layer gathers / scatters every step (the rows of an inlet):
+// device ids and a page-locked staging buffer live with the handle, so a transfer is one kernel + one copy.
+struct CellSet {
+  int n = 0;
+  int *d_ids = nullptr;
+  double *d_buf = nullptr;       // 4*n doubles
+  double *h_buf = nullptr;       // page-locked, 4*n doubles
+  cudaEvent_t ev = nullptr;      // last H2D copy out of h_buf
+  bool inflight = false;
+};
+
 struct Peer {
   int rank;
   int n_send = 0, n_recv = 0;
@@ -193,6 +204,7 @@ struct swk_domain {
   bool vals_inflight = false;
 
   std::vector<RateOp> rate_ops;
+  std::vector<CellSet> cell_sets;
   int *d_ghost_full = nullptr, *d_ghost_ghost = nullptr;
   int n_ghost_copy = 0;
 
@@ -478,6 +490,12 @@ extern "C" int swk_destroy(swk_domain *d)
   }
   for (double *t : d->seg_tab)
     if (t) cudaFree(t);
+  for (auto &cs : d->cell_sets) {
+    if (cs.d_ids) cudaFree(cs.d_ids);
+    if (cs.d_buf) cudaFree(cs.d_buf);
+    if (cs.h_buf) cudaFreeHost(cs.h_buf);
+    if (cs.ev) cudaEventDestroy(cs.ev);
+  }
   if (d->d_seg_tab) cudaFree(d->d_seg_tab);
   if (d->d_seg_np) cudaFree(d->d_seg_np);
   if (d->d_b_point) cudaFree(d->d_b_point);
@@ -1224,14 +1242,75 @@ extern "C" int swk_scatter_bed(swk_domain *d, const int64_t *ids, int64_t n, con
   return rc;
 }
 
+__global__ void k_add_volume(Clock *c, double v) { c->fractional_step_volume_integral += v; }
+
 extern "C" int swk_add_fractional_step_volume(swk_domain *d, double volume)
 {
   if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
   CK(cudaSetDevice(d->device));
-  CKV(pull_clock(d));
-  d->h_clock->fractional_step_volume_integral += volume;
-  return push_clock(d);
+  LAUNCH(d, k_add_volume, 1, 1, d->d_clock, volume);       // in stream order, no host round trip
+  return SWK_OK;
 }
+
+// ---- registered cell sets: what Inlet.fetch / Inlet.commit move every step (structures/inlet.py:135-330) ----
+extern "C" int swk_register_cells(swk_domain *d, const int64_t *ids, int64_t n, int *set_id)
+{
+  if (!d || (!ids && n > 0) || n < 0 || !set_id) return fail(SWK_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(d->device));
+  CellSet cs;
+  cs.n = (int)n;
+  if (n > 0) {
+    CKV(cell_ids_to_device(d, ids, n, &cs.d_ids));
+    CKV(dalloc(&cs.d_buf, 4 * (size_t)n));
+    CK(cudaHostAlloc((void **)&cs.h_buf, 4 * (size_t)n * sizeof(double), cudaHostAllocDefault));
+  }
+  CK(cudaEventCreateWithFlags(&cs.ev, cudaEventDisableTiming));
+  d->cell_sets.push_back(cs);
+  *set_id = (int)d->cell_sets.size() - 1;
+  return SWK_OK;
+}
+
+static int cell_set_writable(CellSet &cs)
+{
+  if (cs.inflight) {
+    CK(cudaEventSynchronize(cs.ev));
+    cs.inflight = false;
+  }
+  return SWK_OK;
+}
+
+// out: (n, 4) stage, xmomentum, ymomentum, elevation of the set's triangles, in the order they were registered
+extern "C" int swk_gather_set(swk_domain *d, int set_id, double *out)
+{
+  if (!d || set_id < 0 || set_id >= (int)d->cell_sets.size() || !out) return fail(SWK_ERR_ARG, "bad argument");
+  CellSet &cs = d->cell_sets[set_id];
+  if (cs.n == 0) return SWK_OK;
+  CK(cudaSetDevice(d->device));
+  CKV(cell_set_writable(cs));
+  LAUNCH(d, k_gather_cells, nblk(cs.n), BLOCK, d->D, cs.d_ids, cs.n, cs.d_buf);
+  CK(cudaMemcpyAsync(cs.h_buf, cs.d_buf, 4 * (size_t)cs.n * sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  CKV(sync_check(d));
+  memcpy(out, cs.h_buf, 4 * (size_t)cs.n * sizeof(double));
+  return SWK_OK;
+}
+
+// in: (n, 3) new stage, xmomentum, ymomentum; queued in stream order, returns without waiting
+extern "C" int swk_scatter_set(swk_domain *d, int set_id, const double *in)
+{
+  if (!d || set_id < 0 || set_id >= (int)d->cell_sets.size() || !in) return fail(SWK_ERR_ARG, "bad argument");
+  CellSet &cs = d->cell_sets[set_id];
+  if (cs.n == 0) return SWK_OK;
+  CK(cudaSetDevice(d->device));
+  CKV(cell_set_writable(cs));
+  memcpy(cs.h_buf, in, 3 * (size_t)cs.n * sizeof(double));
+  CK(cudaMemcpyAsync(cs.d_buf, cs.h_buf, 3 * (size_t)cs.n * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+  CK(cudaEventRecord(cs.ev, d->stream));
+  cs.inflight = true;
+  LAUNCH(d, k_scatter_cells, nblk(cs.n), BLOCK, d->D, cs.d_ids, cs.n, cs.d_buf);
+  return SWK_OK;
+}
+
+
 
 extern "C" int swk_set_local_ghost_copy(swk_domain *d, const int64_t *full_ids, const int64_t *ghost_ids, int64_t n)
 {
@@ -1982,6 +2061,15 @@ extern "C" int swk_update_ghosts(swk_domain *d)
   CK(cudaSetDevice(d->device));
   CKV(launch_ghosts(d));
   return sync_check(d);
+}
+
+// update_ghosts queued in stream order (the next synchronising call covers it)
+extern "C" int swk_update_ghosts_async(swk_domain *d)
+{
+  if (!d) return fail(SWK_ERR_ARG, "handle is NULL");
+  CK(cudaSetDevice(d->device));
+  if (d->comm && !d->nccl_warm) CKV(warm_nccl(d));
+  return launch_ghosts(d);
 }
 
 // ----------------------------------------------------------------------------

@@ -1284,51 +1284,53 @@ class Domain:
 
     def _evolve_device_steps_host_operators(self):
         """_evolve_base's while loop when only host-side operators (inlets, culverts, rate(x, y, t)) need the
-        host: one device-resident timestep (with its fused device
-        operators) per iteration, followed by the host-side operators on their gathered cells."""
-        host_ops = [op for op in self.fractional_step_operators if getattr(op, "host_side", False)]
-        while True:
-            reason = self._one_device_step_then_host_operators(host_ops)
-            if reason in (1, 2):
-                # the device extrapolated for the yield before the operators ran: redo it
-                self._dev.distribute_to_vertices_and_edges()
-                self._dev.update_boundary()
-                return reason
-
-    def _one_device_step_then_host_operators(self, host_ops):
+        host: per timestep one fused device step - launched in its two halves, the host learning (t, dt) in
+        between with the step's only synchronisation - followed by the host-side operators on their registered
+        cell sets (one small gather, the scalar hydraulics, a queued scatter) and the ghost update."""
         dev = self._dev
-        t0 = self.relative_time
-        r = dev.evolve(self.relative_yieldtime, self.relative_finaltime, 1)
+        host_ops = [op for op in self.fractional_step_operators if getattr(op, "host_side", False)]
+        dev.step_begin(self.relative_yieldtime, self.relative_finaltime)
+        while True:
+            r = dev.step_first()
+            if r.stop_reason != 0:
+                break
+            dev.step_rest()
+            self._host_operators_after_step(host_ops, r.time, r.timestep)
+        reason = r.stop_reason
+        r = dev.step_end()          # the yield's extrapolation sees the state the operators left
         self._absorb(r)
+        return reason
+
+    def _host_operators_after_step(self, host_ops, t0, dt):
+        dev = self._dev
+        self.timestep = dt
         if self.record_timestep_history:
-            self.timestep_history.append(self.timestep)
+            self.timestep_history.append(dt)
         # operators see t0 after an euler step and t0 + dt after rk2 / rk3 (see _host_step)
-        self.relative_time = t0 if self.timestepping_method == "euler" else t0 + self.timestep
+        self.relative_time = t0 if self.timestepping_method == "euler" else t0 + dt
         for op in host_ops:
             added = op()
             if added != 0.0:
                 dev.add_fractional_step_volume(added)
-        self.relative_time = r.time
-        dev.update_ghosts()
-        if host_ops:
-            st = dev.get_statistics()
-            self.fractional_step_volume_integral = st.fractional_step_volume_integral
-        return r.stop_reason
+        self.relative_time = t0 + dt
+        dev.update_ghosts_async()
 
     def run_steps_with_host_operators(self, n_steps):
         """Exactly n_steps timesteps of the loop above (benchmarks): returns the elapsed milliseconds between
         two device synchronisations (the host-side hydraulics are part of the step, so wall clock)."""
         import time as _time
+        dev = self._dev
         host_ops = [op for op in self.fractional_step_operators if getattr(op, "host_side", False)]
-        keep = (self.relative_yieldtime, self.relative_finaltime)
-        self.relative_yieldtime, self.relative_finaltime = 1.0e300, None
-        self._dev.synchronize()
+        dev.synchronize()
         t0 = _time.perf_counter()
+        dev.step_begin(1.0e300, None)
         for _ in range(int(n_steps)):
-            self._one_device_step_then_host_operators(host_ops)
-        self._dev.synchronize()
+            r = dev.step_first()
+            dev.step_rest()
+            self._host_operators_after_step(host_ops, r.time, r.timestep)
+        dev.synchronize()
         ms = (_time.perf_counter() - t0) * 1.0e3
-        self.relative_yieldtime, self.relative_finaltime = keep
+        self._absorb(dev.step_end())
         self._mark_device_newer()
         return ms
 

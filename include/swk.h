@@ -253,6 +253,14 @@ int swk_scatter_centroids(swk_domain *d, const int64_t *ids, int64_t n, const do
 int swk_scatter_bed(swk_domain *d, const int64_t *ids, int64_t n, const double *in);
 /* fractional_step_volume_integral += volume (host-side operators account their own water) */
 int swk_add_fractional_step_volume(swk_domain *d, double volume);
+/* Registered cell sets: the triangles an inlet reads and writes at every timestep (structures/inlet.py:135-330).
+ * Device ids and a page-locked staging buffer are kept with the handle, so that Inlet.fetch is one small kernel +
+ * one copy and Inlet.commit is queued without a host round trip.  Rows keep the order of `ids`.            */
+int swk_register_cells(swk_domain *d, const int64_t *ids, int64_t n, int *set_id);
+int swk_gather_set(swk_domain *d, int set_id, double *out);        /* (n,4) stage, xmom, ymom, elevation */
+int swk_scatter_set(swk_domain *d, int set_id, const double *in);  /* (n,3) stage, xmom, ymom; asynchronous */
+/* update_ghosts queued in stream order, without waiting for it */
+int swk_update_ghosts_async(swk_domain *d);
 
 /* Single-process ghost copy (Generic_Domain.update_ghosts :2448-2469):
  * centroid values of full_ids are copied onto ghost_ids after each update.       */
