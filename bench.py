@@ -86,6 +86,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index=0, period=0.02):
         threading.Thread.__init__(self, daemon=True)
+        self.index = index
         self.period = period
         self.sm, self.reasons, self.power = [], set(), []
         self._stop_evt = threading.Event()
@@ -138,8 +139,23 @@ class ClockSampler(threading.Thread):
         if self.is_alive():
             self.join(timeout=2.0)
         if self.h is None or not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
-                    "note": "NVML unavailable: " + getattr(self, "err", "")}
+            # no NVML binding: one nvidia-smi query right AFTER the timed region (never next to it, see above)
+            out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+                   "note": "NVML unavailable (%s): nvidia-smi queried once right after the timed region"
+                           % getattr(self, "err", "no samples")}
+            try:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                line = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                       "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                      timeout=20).stdout.strip().splitlines()[0]
+                f = [x.strip() for x in line.split(",")]
+                out.update(sm_mhz=float(f[0]), sm_max_mhz=float(f[1]), samples=1,
+                           reasons=[n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                       "sw_power_cap"), f[2:6]) if v.lower().startswith("active")])
+            except Exception:
+                pass
+            return out
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.sm), "sm_mhz_min": float(min(self.sm)),
                 "power_w_max": (max(self.power) if self.power else None),
