@@ -237,6 +237,28 @@ def _relabel_inlet(inlet, patch):
     return inlet
 
 
+def fetch_inlets(inlets):
+    """Load the rows of several inlets that are read at the same point of the time loop (the two ends of a
+    culvert): every rank gathers the rows it owns and ONE exact merge makes all of them visible everywhere."""
+    parts = [i._gather_local() for i in inlets]
+    if all(rows is None for rows, _ in parts):
+        for inlet, (_, got) in zip(inlets, parts):
+            inlet._take(got)
+        return
+    sizes = [i._n_rows() + i._n_extra for i in inlets]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    allgot = np.zeros((int(offs[-1]), 4), dtype=np.float64)
+    for (rows, got), o in zip(parts, offs[:-1]):
+        if len(rows):
+            allgot[o + rows] = got
+    comm = getattr(inlets[0].domain, "_comm", None)
+    if comm is None:
+        raise RuntimeError("a distributed inlet needs domain.attach_communicator(comm) before evolve")
+    allgot = comm.merge_disjoint(allgot)
+    for inlet, o, n in zip(inlets, offs[:-1], sizes):
+        inlet._take(allgot[o:o + n].copy())
+
+
 def _owned(sub, global_ids):
     """rows of `global_ids` (ids in the undistributed numbering) that are FULL triangles of
     sub-domain `sub`, and their local ids"""
@@ -294,19 +316,16 @@ class Inlet:
 
     # -- device exchange ---------------------------------------------------------------
     def fetch(self):
+        fetch_inlets([self])
+
+    def _gather_local(self):
+        """(rows of this rank in the inlet's full layout, their values) - or (None, all rows) undistributed"""
         dev = self.domain._dev
         ids = np.concatenate([self.triangle_indices, self._extra_ids]).astype(np.int64)
         if self.local_rows is None:
-            got = dev.gather_centroids(ids)
-        else:
-            got = np.zeros((self._n_rows() + self._n_extra, 4), dtype=np.float64)
-            if len(ids):
-                got[np.concatenate([self.local_rows, self._extra_rows])] = dev.gather_centroids(ids)
-            comm = getattr(self.domain, "_comm", None)
-            if comm is None:
-                raise RuntimeError("a distributed inlet needs domain.attach_communicator(comm) before evolve")
-            got = comm.merge_disjoint(got)
-        self._take(got)
+            return None, dev.gather_centroids(ids)
+        rows = np.concatenate([self.local_rows, self._extra_rows]).astype(np.int64)
+        return rows, (dev.gather_centroids(ids) if len(ids) else np.zeros((0, 4)))
 
     def _take(self, got):
         self.values = got
@@ -784,8 +803,7 @@ class Structure_operator:
         raise NotImplementedError
 
     def _fetch(self):
-        for inlet in self.inlets:
-            inlet.fetch()
+        fetch_inlets(self.inlets)          # both ends in one gather + one cross-rank merge
 
     def localise(self, sub):
         """this structure on sub-domain `sub` of a distributed run (parallel_structure_operator.py
