@@ -537,6 +537,59 @@ class Domain:
 
     get_water_volume = compute_total_volume
 
+    # -- yield-time diagnostics on the host arrays (valid at yields; shallow_water_domain.py:1563-1625, 2611-2716)
+    def get_wet_elements(self, indices=None, minimum_height=None):
+        """indices (relative to `indices` if given) of the elements with depth > minimum_height (centroids)"""
+        if minimum_height is None:
+            minimum_height = _CONFIG["minimum_allowed_height"]
+        self._pull_centroids()
+        elevation = self.quantities["elevation"].get_values(location="centroids", indices=indices)
+        stage = self.quantities["stage"].get_values(location="centroids", indices=indices)
+        depth = stage - elevation
+        return np.compress(depth > minimum_height, np.arange(len(depth)))
+
+    def get_maximum_inundation_elevation(self, indices=None, minimum_height=None):
+        """highest bed elevation among the wet elements"""
+        wet = self.get_wet_elements(indices, minimum_height)
+        return self.quantities["elevation"].get_maximum_value(indices=wet)
+
+    def get_maximum_inundation_location(self, indices=None):
+        wet = self.get_wet_elements(indices)
+        return self.quantities["elevation"].get_maximum_location(indices=wet)
+
+    def compute_boundary_flows(self):
+        """approximate flows across the boundary from the edge momenta (not the fluxes of evolve; see
+        get_boundary_flux_integral for the exact figure): {tag: flow}, total inflow, total outflow"""
+        uh = self.quantities["xmomentum"].get_values(location="edges")
+        vh = self.quantities["ymomentum"].get_values(location="edges")
+        flows, inflow, outflow = {}, 0.0, 0.0
+        for (vol_id, edge_id), tag in self.boundary.items():
+            momentum = [uh[vol_id, edge_id], vh[vol_id, edge_id]]
+            normal = self.normals[vol_id, 2 * edge_id:2 * edge_id + 2]
+            edge_flow = -(np.dot(momentum, normal) * self.edgelengths[vol_id, edge_id])
+            if edge_flow > 0:
+                inflow += edge_flow
+            else:
+                outflow += edge_flow
+            flows[tag] = flows.get(tag, 0.0) + edge_flow
+        return flows, inflow, outflow
+
+    def volumetric_balance_statistics(self):
+        flows, inflow, outflow = self.compute_boundary_flows()
+        message = "---------------------------\nVolumetric balance report:\nNote: Boundary fluxes are not exact\n"
+        message += "See get_boundary_flux_integral for exact computation\n--------------------------\n"
+        message += "Total boundary inflow [m^3/s]: %.2f\n" % inflow
+        message += "Total boundary outflow [m^3/s]: %.2f\n" % outflow
+        message += "Net boundary flow by tags [m^3/s]\n"
+        for tag in flows:
+            message += "    %s [m^3/s]: %.2f\n" % (tag, flows[tag])
+        message += "Total net boundary flow [m^3/s]: %.2f\n" % (inflow + outflow)
+        message += "Total volume in domain [m^3]: %.2f\n" % self.compute_total_volume()
+        return message
+
+    def print_volumetric_balance_statistics(self):
+        print(self.volumetric_balance_statistics())
+
     def report_water_volume_statistics(self, verbose=True, returnStats=False):
         """volume, boundary-flux integral, fractional-step volume integral and their balance
         (shallow_water_domain.py:2749-2781)"""

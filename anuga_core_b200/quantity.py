@@ -297,6 +297,37 @@ class Quantity:
             return points[:, 0].astype(precision), points[:, 1].astype(precision), A, V
         return A, V
 
+    # -- extrema on centroids (quantity.py:1796-1930): ties go to the first cell ----------------------------
+    def get_extremum_index(self, mode=None, indices=None):
+        V = self.get_values(location="centroids", indices=indices)
+        if mode is None or mode == "max":
+            i = np.argmax(V)
+        elif mode == "min":
+            i = np.argmin(V)
+        else:
+            raise ValueError("Bad mode value, got: %s" % str(mode))
+        return i if indices is None else indices[i]
+
+    def get_maximum_index(self, indices=None):
+        return self.get_extremum_index(mode="max", indices=indices)
+
+    def get_maximum_value(self, indices=None):
+        return self.get_values(location="centroids")[self.get_maximum_index(indices)]
+
+    def get_maximum_location(self, indices=None):
+        x, y = self.domain.get_centroid_coordinates()[self.get_maximum_index(indices)]
+        return x, y
+
+    def get_minimum_index(self, indices=None):
+        return self.get_extremum_index(mode="min", indices=indices)
+
+    def get_minimum_value(self, indices=None):
+        return self.get_values(location="centroids")[self.get_minimum_index(indices)]
+
+    def get_minimum_location(self, indices=None):
+        x, y = self.domain.get_centroid_coordinates()[self.get_minimum_index(indices)]
+        return x, y
+
     def get_integral(self, full_only=True):
         areas = self.domain.areas
         if full_only:
