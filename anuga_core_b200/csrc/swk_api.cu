@@ -574,7 +574,7 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
 
   // ---- static records, built in device order with the reference's arithmetic ----
   std::vector<i4> connA(NP), connB(NP);
-  std::vector<d4> xg((SWK_XG_COMPACT ? 2 : 3) * NP), fg(3 * NP);
+  std::vector<d4> xg(3 * NP), fg(3 * NP);
   const double *cc = m->centroid_coordinates, *ec = m->edge_coordinates;
   for (int64_t k = 0; k < NP; k++) {
     if (k >= N) {   // padding: self-referencing dry cell, never executed (k >= N guards) but keep it sane
@@ -617,25 +617,14 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
     const int fullbit = (m->tri_full_flag[o] == 1) ? 1 : 0;
     connA[k] = {o2n[s0], o2n[s1], o2n[s2], (nb & 3) | (which << 2) | (fullbit << 4)};
     xg[k] = {dxv[0], dxv[1], dxv[2], dyv[0]};
-#if SWK_XG_COMPACT
-    xg[NP + k] = {dyv[1], dyv[2], x, y};            // own centroid: neighbours gather it (extrapolate_tri)
-    (void)dx2; (void)dy2; (void)inv_area2;
-#else
     xg[NP + k] = {dyv[1], dyv[2], dx1, dx2};
     xg[2 * NP + k] = {dy1, dy2, inv_area2, m->areas[o]};
-#endif
 
     const double *nr = m->normals + 6 * o;
     const double *el = m->edgelengths + 3 * o;
-#if SWK_FG_EDGE
     fg[k] = {nr[0], nr[1], el[0], 1.0 / m->areas[o]};                        // inv_area: :714
     fg[NP + k] = {nr[2], nr[3], el[1], m->radii[o]};
     fg[2 * NP + k] = {nr[4], nr[5], el[2], m->areas[o]};
-#else
-    fg[k] = {nr[0], nr[1], nr[2], nr[3]};
-    fg[NP + k] = {nr[4], nr[5], el[0], el[1]};
-    fg[2 * NP + k] = {el[2], 1.0 / m->areas[o], m->radii[o], m->areas[o]};   // inv_area: :714
-#endif
 
     int pk[3];
     int flags = (m->tri_full_flag[o] == 1) ? 1 : 0;
@@ -682,7 +671,7 @@ static int create_impl(const swk_mesh *m, const swk_params *p, int device, swk_d
 
   CKV(dalloc(&d->connA, NP)); CKV(upload(d->connA, connA));
   CKV(dalloc(&d->connB, NP)); CKV(upload(d->connB, connB));
-  CKV(dalloc(&d->xg, (SWK_XG_COMPACT ? 2 : 3) * NP)); CKV(upload(d->xg, xg));
+  CKV(dalloc(&d->xg, 3 * NP)); CKV(upload(d->xg, xg));
   CKV(dalloc(&d->fg, 3 * NP)); CKV(upload(d->fg, fg));
   CKV(dalloc(&d->d_new2old, N)); CKV(upload(d->d_new2old, d->new2old));
   {
@@ -1931,7 +1920,7 @@ extern "C" int swk_bytes_per_triangle_step(swk_domain *d, double *algorithmic, d
   // DE0 556 B, DE1 1076 B, DE2 1572 B per triangle-step
   const double alg[4] = {0, 556.0, 1076.0, 1572.0};
   // this library's records: pass A 241, B1 264, B2 121, fused B 297
-  const double A = 32 + 16 + (SWK_XG_COMPACT ? 64 : 96) + 96 + 1, B1 = 96 + 16 + 96 + 32 + 24, B2 = 24 + 32 + 8 + 1 + 32, B = 96 + 16 + 96 + 32 + 8 + 1 + 24 + 32;
+  const double A = 32 + 16 + 96 + 96 + 1, B1 = 96 + 16 + 96 + 32 + 24, B2 = 24 + 32 + 8 + 1 + 32, B = 96 + 16 + 96 + 32 + 8 + 1 + 24 + 32;
   double lay = A + B1 + B2 + (method >= 2 ? 24 : 0);
   for (int s = 1; s < method; s++) lay += A + B;
   if (algorithmic) *algorithmic = alg[method];

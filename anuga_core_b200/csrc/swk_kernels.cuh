@@ -33,23 +33,14 @@ namespace swk {
 #ifndef SWK_MINB_FU         // ... for the fused flux + update kernel
 #define SWK_MINB_FU 7
 #endif
-#ifndef SWK_XG_COMPACT      // extrapolation geometry in 2 records (64 B) instead of 3 (96 B), see extrapolate_tri:
-#define SWK_XG_COMPACT 0    // measured 9 % slower (0.805 vs 0.738 ms at 16M triangles) although it moves 13 % fewer bytes
-#endif
 #ifndef SWK_FU_ROLLED       // fused kernel: one edge per trip of a rolled loop (see triangle_flux)
 #define SWK_FU_ROLLED true
-#endif
-#ifndef SWK_FU_RELOAD       // fused kernel: re-read the own centroid record after the edge loop instead of keeping it live
-#define SWK_FU_RELOAD 1
 #endif
 #ifndef SWK_MINB_U
 #define SWK_MINB_U 8
 #endif
 #ifndef SWK_F_ROLLED        // the same for the flux kernel of substep 0
 #define SWK_F_ROLLED false
-#endif
-#ifndef SWK_FG_EDGE         // flux geometry as one record per EDGE {nx, ny, length, aux}: a trip of the rolled loop
-#define SWK_FG_EDGE 1       // loads exactly the three records of its edge (own, neighbour's, geometry)
 #endif
 constexpr int BLOCK = SWK_BLOCK;
 
@@ -155,37 +146,9 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
   XGeom G;
   G.dxv0 = g0.x; G.dxv1 = g0.y; G.dxv2 = g0.z; G.dyv0 = g0.w;
   G.dyv1 = g1.x; G.dyv2 = g1.y;
-#if SWK_XG_COMPACT
-  // two records per triangle: the edge-midpoint offsets and the own centroid.  The auxiliary
-  // triangle of the neighbours' centroids (sw_domain_openmp.c:1477-1484, 1553) or the 1-D gradient
-  // factors of a two-boundary triangle (:1684-1696) are recomputed from the neighbours' centroids
-  // (16-byte gathers next to the centroid-record gathers above) instead of being stored: 32 bytes
-  // less per triangle and pass, one more division.
-  {
-    const double2 p0 = reinterpret_cast<const double2 *>(&D.xg[NP + s.x])[1];
-    const double2 p1 = reinterpret_cast<const double2 *>(&D.xg[NP + s.y])[1];
-    const double2 p2 = reinterpret_cast<const double2 *>(&D.xg[NP + s.z])[1];
-    const int nbq = s.w & 3;
-    if (nbq <= 1) {
-      G.dx1 = p1.x - p0.x; G.dx2 = p2.x - p0.x; G.dy1 = p1.y - p0.y; G.dy2 = p2.y - p0.y;
-      const double area2 = G.dy2 * G.dx1 - G.dy1 * G.dx2;
-      G.inv_area2 = 1.0 / area2;
-    } else {
-      const int wh = (s.w >> 2) & 3;
-      const double2 pn = (wh == 0) ? p0 : ((wh == 1) ? p1 : p2);
-      const double dx1 = pn.x - g1.z, dy1 = pn.y - g1.w;
-      const double dist2 = dx1 * dx1 + dy1 * dy1;
-      double dx2 = 1.0 / dist2;
-      const double dy2 = dx2 * dy1;
-      dx2 *= dx1;
-      G.dx1 = dx1; G.dy1 = dy1; G.dx2 = dx2; G.dy2 = dy2; G.inv_area2 = 0.0;
-    }
-  }
-#else
   const d4 g2 = lds(&D.xg[2 * NP + k]);
   G.dx1 = g1.z; G.dx2 = g1.w;
   G.dy1 = g2.x; G.dy2 = g2.y; G.inv_area2 = g2.z;
-#endif
   connA_flags = s.w;
 
   e = effective(c, K);
@@ -216,7 +179,6 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
     const double hmin = dmin(dmin(e0.h, dmin(e1.h, e2.h)), hc);
     const double hmax = dmax(dmax(e0.h, dmax(e1.h, e2.h)), hc);
     double hfactor;
-#if SWK_LIMITER_FAST
     // Well inside the wet region all three quotients below are >= 1 and hfactor is exactly 1.0; that is
     // decided without dividing (margin 1e-12 over the roundings: x/y + d >= 1 whenever x >= y*(1 - d)*(1 + 1e-12))
     // and taken only when every active lane of the warp agrees.  Otherwise the reference's expression runs.
@@ -231,11 +193,6 @@ __device__ __forceinline__ void extrapolate_tri(const Dev &D, const Consts &K, c
       hfactor = dmax0(dmin(n1_ / y1_ + d_tmp, dmin(n2_ / y2_ + d_tmp, 1.0)));
       hfactor = dmin(n3_ / y3_, hfactor);
     }
-#else
-    hfactor = dmax0(dmin(c_tmp * dmax0(hmin) / dmax(hc, 1.0e-06) + d_tmp,
-                         dmin(c_tmp * dmax0(hc) / dmax(hmax, 1.0e-06) + d_tmp, 1.0)));
-    hfactor = dmin(1.2 * dmax0(hmin - K.mah) / (dmax0(hmin) + 1. * K.mah), hfactor);
-#endif
     double beta = K.beta_w_dry + (K.beta_w - K.beta_w_dry) * hfactor;
     edge_values_3(beta, e.w, e0.w, e1.w, e2.w, G, w0, w1, w2);
     edge_values_3(beta, e.h, e0.h, e1.h, e2.h, G, h0, h1, h2);
@@ -275,7 +232,7 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_A) k_extrapolate(Dev D, Consts
     if (t0 + BLOCK <= D.NP) {
       const int j = threadIdx.x;
       if (j == 0) prefetch_l2_bulk(D.cq + t0, BLOCK * 32);
-      else if (j < (SWK_XG_COMPACT ? 3 : 4)) prefetch_l2_bulk(D.xg + (long long)(j - 1) * D.NP + t0, BLOCK * 32);
+      else if (j < 4) prefetch_l2_bulk(D.xg + (long long)(j - 1) * D.NP + t0, BLOCK * 32);
       else if (j == 4) prefetch_l2_bulk(D.connA + t0, BLOCK * 16);
     }
   }
@@ -329,20 +286,11 @@ __global__ void __launch_bounds__(BLOCK) k_protect_mass(Dev D, Consts K)
 // with the evaluate_segment arithmetic of each boundary class.  One thread per
 // boundary edge m.
 // =============================================================================
-// Flux geometry of triangle k.  SWK_FG_EDGE: fg[i][k] = {nx_i, ny_i, length_i, aux_i} with
-// aux = {1/area, radius, area}; otherwise fg[0] = {n0x,n0y,n1x,n1y}, fg[1] = {n2x,n2y,l0,l1},
-// fg[2] = {l2, 1/area, radius, area}.
+// Flux geometry of triangle k: fg[i][k] = {nx_i, ny_i, length_i, aux_i}, aux = {1/area, radius, area}.
 __device__ __forceinline__ void edge_normal(const Dev &D, int k, int i, double &n1, double &n2)
 {
-#if SWK_FG_EDGE
   const d4 f = D.fg[i * D.NP + k];
   n1 = f.x; n2 = f.y;
-#else
-  const d4 f0 = D.fg[k];
-  const d4 f1 = D.fg[D.NP + k];
-  n1 = (i == 0) ? f0.x : ((i == 1) ? f0.z : f1.x);
-  n2 = (i == 0) ? f0.y : ((i == 1) ? f0.w : f1.y);
-#endif
 }
 
 struct Segments {
@@ -629,24 +577,10 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
   T.su = 0.0; T.xu = 0.0; T.yu = 0.0;
   T.dtmin = 1.0e+100;
   T.speed = 0.0;
-#if SWK_FG_EDGE
   double inv_area = 0.0, radius = 0.0;
   if (ROLLED) {
   // one edge per trip of a rolled loop: the trip loads the three records of its edge (own edge
   // values, the neighbour's, the edge geometry), so only one edge's operands are live at a time
-#if SWK_FU_L1PF
-  // the trips' gathers would otherwise pay one L2 round trip each, one after the other: ask for
-  // all of them now (no registers), the trips then hit L1
-  {
-    const int pq[3] = {p.x, p.y, p.z};
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      const int q = pq[i];
-      if (q >= 0) prefetch_l1(&D.eq[(q & 3) * NP + (q >> 2)]);
-      if (i > 0) prefetch_l1(&D.eq[i * NP + k]);
-    }
-  }
-#endif
 #pragma unroll 1
   for (int i = 0; i < 3; i++) {
     const int q = (i == 0) ? p.x : ((i == 1) ? p.y : p.z);
@@ -680,47 +614,6 @@ __device__ __forceinline__ TriFlux triangle_flux(const Dev &D, const Consts &K, 
     edge_contribution<RW, XB>(D, K, k, i, pn[i], p.w, el[i], er[i], ge[i].x, ge[i].y, ge[i].z, own, first, T);
   }
   finish_flux(T, radius, inv_area, first);
-#else
-  const d4 f0 = lds(&D.fg[k]);
-  const d4 f1 = lds(&D.fg[NP + k]);
-  const d4 f2 = lds(&D.fg[2 * NP + k]);
-  if (ROLLED) {
-  // one edge per trip of a rolled loop: operands are loaded inside the trip, so only one edge's
-  // records are live at a time (fewer registers, smaller code) at the price of three load phases
-#pragma unroll 1
-  for (int i = 0; i < 3; i++) {
-    const int q = (i == 0) ? p.x : ((i == 1) ? p.y : p.z);
-    const d4 el = D.eq[i * NP + k];
-    d4 er;
-    if (q >= 0) er = D.eq[(q & 3) * NP + (q >> 2)];
-    else er = D.bq[-q - 1];
-    const double nx = (i == 0) ? f0.x : ((i == 1) ? f0.z : f1.x);
-    const double ny = (i == 0) ? f0.y : ((i == 1) ? f0.w : f1.y);
-    const double len = (i == 0) ? f1.z : ((i == 1) ? f1.w : f2.x);
-    edge_contribution<RW>(D, K, k, i, q, p.w, el, er, nx, ny, len, own, first, T);
-  }
-  } else {
-  d4 el[3];
-  el[0] = D.eq[k];
-  el[1] = D.eq[NP + k];
-  el[2] = D.eq[2 * NP + k];
-  const int pn[3] = {p.x, p.y, p.z};
-  d4 er[3];
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const int q = pn[i];
-    if (q >= 0) er[i] = D.eq[(q & 3) * NP + (q >> 2)];
-    else er[i] = D.bq[-q - 1];
-  }
-  const double nx[3] = {f0.x, f0.z, f1.x};
-  const double ny[3] = {f0.y, f0.w, f1.y};
-  const double len[3] = {f1.z, f1.w, f2.x};
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-    edge_contribution<RW>(D, K, k, i, pn[i], p.w, el[i], er[i], nx[i], ny[i], len[i], own, first, T);
-  }
-  finish_flux(T, f2.z, f2.y, first);
-#endif
   return T;
 }
 
@@ -913,7 +806,6 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Const
     D.eu[2 * D.NP + k] = T.yu;
     continue;
   }
-#if SWK_FU_RELOAD
   // only {h, z} of the own state live across the edge loop; the record is read again (L1) for the update
   Eff own;
   {
@@ -923,11 +815,6 @@ __global__ void __launch_bounds__(BLOCK, SWK_MINB_FU) k_flux_update(Dev D, Const
   const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, own, false);
   const d4 raw = D.cq[k];
   const Eff e = effective(raw, K);
-#else
-  const d4 raw = D.cq[k];
-  const Eff e = effective(raw, K);
-  const TriFlux T = triangle_flux<false, SWK_FU_ROLLED>(D, K, k, p, e, false);
-#endif
   triangle_update(D, K, U, k, raw, e, D.zflag[k], T.su, T.xu, T.yu, dt, D.cq, nullptr);
   }
 }

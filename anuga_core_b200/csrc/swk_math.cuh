@@ -29,48 +29,29 @@ __device__ __forceinline__ d4 ldg4(const d4 *p) { return *p; }
 // once per pass, so they bypass L1 allocation and are marked evict-first in L2, which leaves the
 // caches to the records that neighbours gather (cq in pass A, eq in pass B).
 // ---------------------------------------------------------------------------
-#ifndef SWK_HINTS
-#define SWK_HINTS 1
-#endif
 __device__ __forceinline__ d4 lds(const d4 *p)
 {
-#if SWK_HINTS
   d4 r;
   asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
                : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
   return r;
-#else
-  return *p;
-#endif
 }
 __device__ __forceinline__ i4 lds(const i4 *p)
 {
-#if SWK_HINTS
   i4 r;
   asm volatile("ld.global.cs.v4.s32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
-#else
-  return *p;
-#endif
 }
 __device__ __forceinline__ double lds(const double *p)
 {
-#if SWK_HINTS
   double r;
   asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(r) : "l"(p));
   return r;
-#else
-  return *p;
-#endif
 }
 __device__ __forceinline__ void sts(double *p, double v)
 {
-#if SWK_HINTS
   asm volatile("st.global.cs.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
-#else
-  *p = v;
-#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -80,9 +61,6 @@ __device__ __forceinline__ void sts(double *p, double v)
 // ---------------------------------------------------------------------------
 #ifndef SWK_PF_AHEAD          // 555 tiles = about 3/4 of a wave of resident CTAs; 92 ... 740 measure alike
 #define SWK_PF_AHEAD 555
-#endif
-#ifndef SWK_FU_L1PF
-#define SWK_FU_L1PF 0
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
@@ -96,13 +74,14 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes)
 // glibc's pow is accurate to ~0.52 ulp; CUDA's pow only to 2 ulp, which is the
 // one place where the device arithmetic could drift from the reference.  This
 // routine evaluates h^2 * cbrt(h) * (1 + delta ln h) in double-double
-// arithmetic (relative error ~2^-98) and rounds once, i.e. it returns the
-// correctly rounded value; it agrees with glibc on 99.92 % of arguments and is
-// 1 ulp away on the rest (measured on 2e7 random h in [1e-6, 1e3]).
+// arithmetic and rounds once.  The two small terms need little accuracy - ln h
+// only scales delta = y - 7/3 ~ 2^-53 (1e-6 absolute is plenty) and 1/(3c^2)
+// scales a Newton correction that is itself 2^-52 relative (20 bits are plenty) -
+// so they come from MUFU.LG2 / MUFU.RCP64H; the result has a relative error of
+// ~2^-72 before the final rounding, i.e. it is the correctly rounded value except
+// for ~7e-7 of arguments; it agrees with glibc on 99.92 % of arguments and is
+// 1 ulp away on the rest (2e7 random h in [1e-6, 1e4], CPU emulation).
 // ---------------------------------------------------------------------------
-#ifndef SWK_POW_FAST
-#define SWK_POW_FAST 1
-#endif
 // ln(h) to ~1e-6 absolute: exponent + MUFU.LG2 of the mantissa (it only scales the 2^-53-sized delta term)
 __device__ __forceinline__ double ln_rough(double h)
 {
@@ -132,11 +111,7 @@ __device__ __forceinline__ double pow_7_3(double h)
   double qe = __fma_rn(p, c, -q);
   qe = __fma_rn(pe, c, qe);
   const double r = (h - q) - qe;
-#if SWK_POW_FAST
   const double corr = r * rcp_rough(3.0 * p);             // |corr| <= ~2^-52 c: 20 good bits suffice
-#else
-  const double corr = r / (3.0 * p);
-#endif
   const double chi = c + corr;
   const double clo = corr - (chi - c);
   // h^2 exactly
@@ -147,11 +122,7 @@ __device__ __forceinline__ double pow_7_3(double h)
   double Pe = __fma_rn(s, chi, -P);
   Pe = __fma_rn(s, clo, Pe);
   Pe = __fma_rn(se, chi, Pe);
-#if SWK_POW_FAST
   Pe = __fma_rn(P, delta * ln_rough(h), Pe);
-#else
-  Pe = __fma_rn(P, delta * log(h), Pe);
-#endif
   return P + Pe;
 }
 
@@ -246,9 +217,6 @@ __device__ __forceinline__ Eff effective(const d4 c, const Consts &K)
 //     min_i fl(qmax/dq_i) = fl(qmax / max_i dq_i),   min_i fl(qmin/dq_i) = fl(qmin / min_i dq_i):
 // two branch-free divisions per quantity instead of the reference's three (the sign of dq differs from
 // thread to thread, so a branching form would execute every division in almost every warp anyway).
-#ifndef SWK_LIMITER_FAST
-#define SWK_LIMITER_FAST 1
-#endif
 __device__ __forceinline__ void limit_gradient(double &d0, double &d1, double &d2,
                                                double qmin, double qmax, double beta)
 {
@@ -256,7 +224,6 @@ __device__ __forceinline__ void limit_gradient(double &d0, double &d1, double &d
   const double dhi = dmax(d0, dmax(d1, d2));
   const double dlo = dmin(d0, dmin(d1, d2));
   const bool pos = dhi > TINY, neg = dlo < -TINY;
-#if SWK_LIMITER_FAST
   // Where the field is smooth nothing is limited: phi = min(r*beta, 1) is exactly 1 and d*1 = d.  That can
   // be decided without the two divisions: fl(fl(q/d)*beta) >= 1 whenever q*beta >= d*(1 + 1e-12) (the margin
   // swamps the three roundings involved), the inactive sides give r = 1000, and an invalid edge 0 caps r at
@@ -269,7 +236,6 @@ __device__ __forceinline__ void limit_gradient(double &d0, double &d1, double &d
                       (!pos | (qmax * beta >= dhi * m)) & (!neg | (qmin * beta <= dlo * m));
     if (__all_sync(__activemask(), fast)) return;
   }
-#endif
   const double rp = (pos ? qmax : 1000.0) / (pos ? dhi : 1.0);
   const double rn = (neg ? qmin : 1000.0) / (neg ? dlo : 1.0);
   double r = dmin(dmin(rp, rn), 1000.0);
