@@ -12,7 +12,7 @@ from .operators import (Rate_operator, Set_quantity, Set_stage, Set_quantity_ope
 from .structures import (Region, Inlet, Inlet_operator, Inlet_enquiry, Structure_operator,
                          Boyd_box_operator, Boyd_pipe_operator, Weir_orifice_trapezoid_operator)
 from .forcing import Wind_stress, General_forcing, Rainfall, Inflow
-from .file_boundary import File_boundary, Field_boundary, Time_space_boundary, file_function
+from .file_boundary import File_boundary, Field_boundary, Time_space_boundary, file_function, timefile2netcdf
 from .domain import Domain, rectangular_cross_domain, load_checkpoint_file, MODE_B200
 from .backend import SwkError, device_count
 from .attach import set_multiprocessor_mode_b200, B200_interface

@@ -97,18 +97,28 @@ def barycentric_weights(vertex_coordinates, triangles, points):
 
 class Interpolation_function:
     """f(t, point_id): frames of nodal values -> values at fixed points, linear in time
-    (fit_interpolate/interpolate.py:710-1110, the spatial-with-interpolation-points use)."""
+    (fit_interpolate/interpolate.py:710-1110, the spatial-with-interpolation-points use), or - without
+    vertex_coordinates - f(t): a plain time series with several attributes (TMS files)."""
 
-    def __init__(self, time, quantities, quantity_names, vertex_coordinates, triangles, interpolation_points,
-                 time_thinning=1):
+    def __init__(self, time, quantities, quantity_names, vertex_coordinates=None, triangles=None,
+                 interpolation_points=None, time_thinning=1):
         time = np.asarray(time, dtype=np.float64)
         if not np.all(time[1:] - time[:-1] >= 0):
             raise Exception("Time must be a monotonuosly increasing sequence %s" % time)
         self.time = np.array(time[::time_thinning])
         self.quantity_names = list(quantity_names)
+        self.index = 0
+        if vertex_coordinates is None:
+            self.spatial = False
+            self.interpolation_points = None
+            self.precomputed_values = {}
+            for name in self.quantity_names:
+                Q = np.asarray(quantities[name], dtype=np.float64)
+                assert Q.ndim == 1, "a time series without spatial information has one value per time"
+                self.precomputed_values[name] = np.array(Q[::time_thinning])
+            return
         self.interpolation_points = np.asarray(interpolation_points, dtype=np.float64)
         self.spatial = True
-        self.index = 0
         tri, sig = barycentric_weights(vertex_coordinates, triangles, self.interpolation_points)
         self.indices_outside_mesh = np.flatnonzero(tri < 0)
         T = np.asarray(triangles, dtype=np.int64)
@@ -132,20 +142,30 @@ class Interpolation_function:
                 out[i] = np.where(ok, r, NAN)
             self.precomputed_values[name] = out
 
-    def __call__(self, t, point_id=None):
-        if point_id is None:
+    def __call__(self, t, point_id=None, x=None, y=None):
+        if self.spatial and point_id is None:
             raise Exception("Either point_id or x and y must be specified")
         index, ratio = time_slot(self, t)
         q = np.zeros(len(self.quantity_names))
         for i, name in enumerate(self.quantity_names):
             Q = self.precomputed_values[name]
-            Q0 = Q[index, point_id]
+            Q0 = Q[index, point_id] if self.spatial else Q[index]
             if ratio > 0:
-                Q1 = Q[index + 1, point_id]
+                Q1 = Q[index + 1, point_id] if self.spatial else Q[index + 1]
                 q[i] = Q0 if (Q0 == NAN and Q1 == NAN) else Q0 + ratio * (Q1 - Q0)
             else:
                 q[i] = Q0
-        return q
+        if self.spatial or x is None or y is None:
+            return q
+        try:                                     # a time series asked at many points (e.g. by Wind_stress):
+            N = len(x)                           # one constant column per attribute (interpolate.py:1099-1116)
+        except TypeError:
+            return q
+        assert len(y) == N, "x and y must have same length"
+        return [col * np.ones(N, dtype=np.float64) for col in q]
+
+    def get_time(self):
+        return self.time
 
 
 def time_slot(F, t):
@@ -170,11 +190,15 @@ def file_function(filename, domain=None, quantities=None, interpolation_points=N
     """file_function.py:29-168 + get_netcdf_file_function :226-494 for SWW files: returns the
     Interpolation_function with attribute starttime; moves domain.starttime forward to the file's if the
     file starts later."""
+    if filename.endswith(".tms"):
+        return _tms_function(filename, domain, quantities, time_thinning, time_limit)
     if not filename.endswith(".sww"):
-        raise NotImplementedError("file_function: only SWW files are supported (got %s)" % filename)
+        raise NotImplementedError("file_function: SWW and TMS files are supported (got %s)" % filename)
     if boundary_polygon is not None:
         raise NotImplementedError("boundary_polygon applies to STS files only")
-    names = list(quantities) if quantities is not None else list(domain.conserved_quantities)
+    if interpolation_points is None:
+        raise NotImplementedError("file_function on an SWW file needs interpolation_points")
+    names = list(quantities) if quantities is not None else ["stage", "xmomentum", "ymomentum"]
     src = read_sww_series(filename, names)
     starttime = src["starttime"]
     time = src["time"]
@@ -201,6 +225,97 @@ def file_function(filename, domain=None, quantities=None, interpolation_points=N
     if domain is not None and starttime > domain.starttime:
         domain.set_starttime(starttime)
     return F
+
+
+def _tms_function(filename, domain, quantities, time_thinning, time_limit):
+    """a TMS file (NetCDF time series without spatial information, e.g. a tide gauge or a hydrograph) as f(t):
+    file_function.py:226-494 for spatial = False"""
+    from scipy.io import netcdf_file
+    if isinstance(quantities, str):
+        quantities = [quantities]
+    names = list(quantities) if quantities is not None else ["stage", "xmomentum", "ymomentum"]
+    fid = netcdf_file(filename, "r", mmap=False)
+    try:
+        missing = [q for q in ["time"] + names if q not in fid.variables]
+        if missing:
+            raise Exception("Quantities %s could not be found in file %s" % (str(missing), filename))
+        if "x" in fid.variables and "y" in fid.variables:
+            raise Exception("Files of type TMS must not contain spatial information")
+        starttime = float(np.asarray(fid.starttime).reshape(-1)[0])
+        time = np.array(fid.variables["time"][:], dtype=np.float64)
+        data = {n: np.array(fid.variables[n][:], dtype=np.float64) for n in names}
+    finally:
+        fid.close()
+    upper = len(time)
+    assert upper > 0, "Time vector obtained from file %s has length 0" % filename
+    if time_limit is not None:
+        limit = time_limit - starttime
+        for i, t in enumerate(time):
+            if t > limit:
+                upper = i
+                break
+        assert upper > 0, "Time vector is zero. Requested time limit is %f" % limit
+    time = time[:upper]
+    domain_starttime = None if domain is None else domain.starttime
+    if domain_starttime is not None and domain_starttime > starttime:
+        time = time - domain_starttime + starttime
+    F = Interpolation_function(time, {n: data[n][:upper] for n in names}, names, time_thinning=time_thinning)
+    F.starttime = starttime
+    F.filename = filename
+    if domain is not None and starttime > domain.starttime:
+        domain.set_starttime(starttime)
+    return F
+
+
+TIME_FORMAT = "%d/%m/%y %H:%M:%S"          # anuga/config.py: time_format
+
+
+def timefile2netcdf(file_text, file_out=None, quantity_names=None, time_as_seconds=False):
+    """text time series 'time, value0 value1 ...' (time as DD/MM/YY hh:mm:ss or, with time_as_seconds, as seconds)
+    -> NetCDF TMS file for file_function (file_conversion/file_conversion.py:89-217)"""
+    import calendar
+    import time as _time
+    from scipy.io import netcdf_file
+    if file_text[-4:] != ".txt":
+        raise IOError("Input file %s should be of type .txt." % file_text)
+    if file_out is None:
+        file_out = file_text[:-4] + ".tms"
+    with open(file_text) as fh:
+        lines = [ln for ln in fh.readlines()]
+    assert len(lines[0].split(",")) == 2, \
+        "File %s must have the format 'datetime, value0 value1 value2 ...'" % file_text
+
+    def seconds(field):
+        if time_as_seconds:
+            return float(field)
+        try:
+            return calendar.timegm(_time.strptime(field, TIME_FORMAT))
+        except ValueError:
+            raise Exception("First field in file %s must be date-time with format %s.\nI got %s instead."
+                            % (file_text, TIME_FORMAT, field))
+    starttime = seconds(lines[0].split(",")[0])
+    d = len(lines[0].split(",")[1].split())
+    T = np.zeros(len(lines))
+    Q = np.zeros((len(lines), d))
+    for i, line in enumerate(lines):
+        fields = line.split(",")
+        T[i] = seconds(fields[0]) - starttime
+        for j, value in enumerate(fields[1].split()):
+            Q[i, j] = float(value)
+    assert np.all(T[1:] - T[:-1] > 0), "File %s must list time as a monotonuosly increasing sequence" % file_text
+    fid = netcdf_file(file_out, "w", version=2)
+    fid.institution = "Geoscience Australia"
+    fid.description = "Time series"
+    fid.starttime = starttime
+    fid.createDimension("number_of_timesteps", len(T))
+    fid.createVariable("time", "d", ("number_of_timesteps",))[:] = T
+    for i in range(d):
+        try:
+            name = quantity_names[i]
+        except Exception:
+            name = "Attribute%d" % i
+        fid.createVariable(name, "d", ("number_of_timesteps",))[:] = Q[:, i]
+    fid.close()
 
 
 # ----------------------------------------------------------------------------------------
