@@ -84,3 +84,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(src), "%s reaches into oracle/" % f
+
+
+def test_enumerations_of_the_header_match_the_python_binding():
+    """boundary kinds and quantity ids are plain integers across the C ABI: every SWK_BC_* / SWK_Q_* of
+    include/swk.h must have the same value in anuga_core_b200/backend.py, and every boundary class must name a
+    kind the header knows"""
+    import re
+    from anuga_core_b200 import backend, boundaries, file_boundary
+    text = open(os.path.join(ROOT, "include", "swk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    enums = dict((k, int(v)) for k, v in re.findall(r"\b(SWK_(?:BC|Q)_[A-Z0-9_]+)\s*=\s*(\d+)", text))
+    bc = {k[len("SWK_"):]: v for k, v in enums.items() if k.startswith("SWK_BC_")}
+    assert len(bc) == 12 and sorted(bc.values()) == list(range(12))
+    for name, value in bc.items():
+        assert getattr(backend, name) == value, name
+    for name, value in enums.items():
+        if name.startswith("SWK_Q_"):
+            assert backend.Q[name[len("SWK_Q_"):]] == value, name
+    kinds = set()
+    for mod in (boundaries, file_boundary):
+        for obj in vars(mod).values():
+            if isinstance(obj, type) and issubclass(obj, boundaries.Boundary):
+                kinds.add(obj.device_kind)
+    assert kinds <= set(bc.values()) and kinds >= {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11}
