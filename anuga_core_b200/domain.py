@@ -557,6 +557,22 @@ class Domain:
         wet = self.get_wet_elements(indices)
         return self.quantities["elevation"].get_maximum_location(indices=wet)
 
+    def get_intersecting_segments(self, polyline, use_cache=False, verbose=False):
+        """segments of a polyline (absolute coordinates) inside the triangles it crosses
+        (neighbour_mesh.py:1124-1167)"""
+        from .cross_section import Cross_section
+        return Cross_section(self, polyline, verbose).segments
+
+    def get_flow_through_cross_section(self, polyline, verbose=False):
+        """total flow [m^3/s] across a polyline, left to right (shallow_water_domain.py:1750-1769)"""
+        from .cross_section import Cross_section
+        return Cross_section(self, polyline, verbose).get_flow_through_cross_section()
+
+    def get_energy_through_cross_section(self, polyline, kind="total", verbose=False):
+        """average energy head [m] along a polyline (shallow_water_domain.py:1772-1810)"""
+        from .cross_section import Cross_section
+        return Cross_section(self, polyline, verbose).get_energy_through_cross_section(kind)
+
     def compute_boundary_flows(self):
         """approximate flows across the boundary from the edge momenta (not the fluxes of evolve; see
         get_boundary_flux_integral for the exact figure): {tag: flow}, total inflow, total outflow"""
