@@ -10,7 +10,8 @@ from .boundaries import (Characteristic_stage_boundary, Dirichlet_discharge_boun
 from .operators import (Rate_operator, Set_quantity, Set_stage, Set_quantity_operator,
                         Set_stage_operator, Set_elevation, Set_elevation_operator)
 from .structures import (Region, Inlet, Inlet_operator, Inlet_enquiry, Structure_operator,
-                         Boyd_box_operator, Boyd_pipe_operator, Weir_orifice_trapezoid_operator)
+                         Boyd_box_operator, Boyd_pipe_operator, Weir_orifice_trapezoid_operator,
+                         Internal_boundary_operator, pumping_station_function)
 from .forcing import Wind_stress, General_forcing, Rainfall, Inflow
 from .file_boundary import File_boundary, Field_boundary, Time_space_boundary, file_function, timefile2netcdf
 from .domain import Domain, rectangular_cross_domain, load_checkpoint_file, MODE_B200

@@ -1333,3 +1333,167 @@ class Weir_orifice_trapezoid_operator(_Boyd_operator):
         kind, spec = _Boyd_operator.oracle_spec(self)
         spec.update(z1=self.culvert_z1, z2=self.culvert_z2)
         return kind, spec
+
+
+class Internal_boundary_operator(Structure_operator):
+    """anuga.Internal_boundary_operator(domain, internal_boundary_function, width, height, end_points |
+    exchange_lines, enquiry_points, invert_elevation, apron, enquiry_gap, use_velocity_head,
+    zero_outflow_momentum, force_constant_inlet_elevations, smoothing_timescale,
+    compute_discharge_implicitly)  (structures/internal_boundary_operator.py:15-308).
+
+    Q = internal_boundary_function(hw, tw), hw / tw the stage (or total energy) at enquiry points 0 / 1,
+    positive from 0 to 1; the transfer is Structure_operator's, without momentum jet.  The implicit form
+    solves for the change of both levels over the timestep (scipy.optimize.root, 'lm'), as the reference."""
+
+    def __init__(self, domain, internal_boundary_function, width=1.0, height=1.0, end_points=None,
+                 exchange_lines=None, enquiry_points=None, invert_elevation=None, apron=0.0, enquiry_gap=0.0,
+                 use_velocity_head=False, zero_outflow_momentum=False, force_constant_inlet_elevations=True,
+                 smoothing_timescale=0.0, compute_discharge_implicitly=True, description=None, label=None,
+                 structure_type="internal_boundary", logging=False, verbose=True):
+        Structure_operator.__init__(self, domain, end_points=end_points, exchange_lines=exchange_lines,
+                                    enquiry_points=enquiry_points,
+                                    invert_elevations=[invert_elevation, invert_elevation],
+                                    width=width, height=height, diameter=None, apron=apron, manning=None,
+                                    enquiry_gap=enquiry_gap, use_momentum_jet=False,
+                                    zero_outflow_momentum=zero_outflow_momentum, use_old_momentum_method=False,
+                                    always_use_Q_wetdry_adjustment=False,
+                                    force_constant_inlet_elevations=force_constant_inlet_elevations,
+                                    description=description, label=label, structure_type=structure_type,
+                                    logging=logging, verbose=verbose)
+        self.internal_boundary_function = internal_boundary_function
+        self.use_velocity_head = use_velocity_head
+        self.compute_discharge_implicitly = compute_discharge_implicitly
+        self.max_velocity = 99999999999.0
+        self.case = "N/A"
+        # one evaluation on the initial state primes the smoothed discharge (:107-116)
+        self.smoothing_timescale = 0.0
+        self.smooth_Q = 0.0
+        self.smooth_delta_total_energy = 0.0
+        _Boyd_operator._fetch_initial(self)
+        Qvd = self.discharge_routine()
+        self.smooth_Q = Qvd[0]
+        self.smoothing_timescale = smoothing_timescale
+        self._localise_from_patch()
+
+    def _levels(self):
+        a, b = self.inlets
+        if self.use_velocity_head:
+            self.inlet0_energy, self.inlet1_energy = a.get_enquiry_total_energy(), b.get_enquiry_total_energy()
+        else:
+            self.inlet0_energy, self.inlet1_energy = a.get_enquiry_stage(), b.get_enquiry_stage()
+        self.driving_energy = max(self.inlet0_energy, self.inlet1_energy)
+        self.delta_total_energy = self.inlet0_energy - self.inlet1_energy
+
+    def discharge_routine(self):
+        if self.compute_discharge_implicitly:
+            return self.discharge_routine_implicit()
+        return self.discharge_routine_explicit()
+
+    def discharge_routine_explicit(self):
+        """:136-218"""
+        if self.height <= 0.0:
+            self.case = "Structure is blocked"
+            self.inflow, self.outflow = self.inlets
+            return 0.0, 0.0, 0.0
+        self._levels()
+        dt = self.domain.timestep
+        ts = dt / max(dt, self.smoothing_timescale, 1.0e-30) if dt > 0.0 else 1.0
+        self.smooth_delta_total_energy += ts * (self.delta_total_energy - self.smooth_delta_total_energy)
+        if np.sign(self.smooth_delta_total_energy) != np.sign(self.delta_total_energy):
+            self.smooth_delta_total_energy = 0.0
+        if self.inlet0_energy >= self.inlet1_energy:
+            hw = 1.0 * self.inlet0_energy
+            tw = hw - self.smooth_delta_total_energy
+        else:
+            tw = 1.0 * self.inlet1_energy
+            hw = tw + self.smooth_delta_total_energy
+        Q = self.internal_boundary_function(hw, tw)
+        self.smooth_Q = self.smooth_Q + ts * (Q - self.smooth_Q)
+        if self.smooth_Q >= 0.0:
+            self.inflow, self.outflow = self.inlets
+        else:
+            self.outflow, self.inflow = self.inlets
+        if np.sign(self.smooth_Q) != np.sign(Q):
+            Q = 0.0
+        else:
+            Q = min(abs(self.smooth_Q), abs(Q))
+        return Q, np.nan, np.nan
+
+    def discharge_routine_implicit(self):
+        """:221-308: Q(H0 + dH, T0 + dT) with (dH, dT) the level changes that discharge causes over dt"""
+        import scipy.optimize as sco
+        self._levels()
+        f = self.internal_boundary_function
+        Q0 = f(self.inlet0_energy, self.inlet1_energy)
+        dt = self.domain.get_timestep()
+        if dt > 0.0:
+            E0, E1 = self.inlet0_energy, self.inlet1_energy
+            areas = np.array([self.inlets[0].get_area(), self.inlets[1].get_area()])
+            theta = 1.0
+            sign = np.array([-1.0, 1.0])
+
+            def residual(sol):
+                discharge = (1.0 - theta) * Q0 + theta * f(E0 + sol[0], E1 + sol[1])
+                return sol * areas - discharge * dt * sign
+            sol = sco.root(residual, np.array([0.0, 0.0]), method="lm").x
+            Q = (1.0 - theta) * Q0 + theta * f(E0 + sol[0], E1 + sol[1])
+            ts = dt / max(dt, self.smoothing_timescale, 1.0e-30)
+        else:
+            Q = Q0
+            ts = 1.0
+        self.smooth_Q = self.smooth_Q + ts * (Q - self.smooth_Q)
+        if Q >= 0.0:
+            self.inflow, self.outflow = self.inlets
+        else:
+            self.outflow, self.inflow = self.inlets
+        if np.sign(self.smooth_Q) != np.sign(Q):
+            Q = 0.0
+            self.smooth_Q = 0.0
+        else:
+            Q = min(abs(self.smooth_Q), abs(Q))
+        return Q, np.nan, np.nan
+
+    def oracle_spec(self):
+        raise NotImplementedError("Internal_boundary_operator carries a user function: no CPU-oracle scenario")
+
+
+class pumping_station_function:
+    """Rate of a pumping station as an internal_boundary_function: pumps ramp up to `pump_capacity` while the
+    headwater is above `hw_to_start_pumping` and down to zero below `hw_to_stop_pumping`
+    (structures/internal_boundary_functions.py:392-477)."""
+
+    def __init__(self, domain, pump_capacity, hw_to_start_pumping, hw_to_stop_pumping, initial_pump_rate=0.0,
+                 pump_rate_of_increase=1.0e+100, pump_rate_of_decrease=1.0e+100, verbose=True):
+        self.pump_capacity = pump_capacity
+        self.hw_to_start_pumping = hw_to_start_pumping
+        self.hw_to_stop_pumping = hw_to_stop_pumping
+        self.pump_rate_of_increase = pump_rate_of_increase
+        self.pump_rate_of_decrease = pump_rate_of_decrease
+        self.domain = domain
+        self.last_time_called = domain.get_time()
+        self.time = domain.get_time()
+        if hw_to_start_pumping < hw_to_stop_pumping:
+            raise Exception("hw_to_start_pumping should be >= hw_to_stop_pumping")
+        if initial_pump_rate > pump_capacity:
+            raise Exception("Initial pump rate is > pump capacity")
+        if pump_rate_of_increase < 0.0 or pump_rate_of_decrease < 0.0:
+            raise Exception("Pump rates of increase / decrease MUST be non-negative")
+        if pump_capacity < 0.0 or initial_pump_rate < 0.0:
+            raise Exception("Pump rates cannot be negative")
+        self.pump_rate = initial_pump_rate
+
+    def __call__(self, hw_in, tw_in):
+        self.time = self.domain.get_time()
+        if self.time > self.last_time_called:
+            dt = self.time - self.last_time_called
+            self.last_time_called = self.time
+        else:
+            dt = 0.0
+            if self.time != self.last_time_called:
+                raise Exception("Impossible timestepping: time %s before the last call at %s"
+                                % (self.time, self.last_time_called))
+        if hw_in < self.hw_to_stop_pumping:
+            self.pump_rate = max(0.0, self.pump_rate - dt * self.pump_rate_of_decrease)
+        elif hw_in > self.hw_to_start_pumping:
+            self.pump_rate = min(self.pump_capacity, self.pump_rate + dt * self.pump_rate_of_increase)
+        return self.pump_rate

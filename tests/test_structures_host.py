@@ -79,6 +79,9 @@ class _HostArrays:
         for k in range(3):
             self.a[k][ids] = v[:, k]
 
+    def set_time(self, t):
+        pass
+
 
 def _pair(seed):
     anuga = pyref.import_anuga()
@@ -200,3 +203,55 @@ def test_inlet_from_line_or_polygon_matches_reference():
         a = ab.Inlet_operator(mine, shape, Q=1.0).inlet.triangle_indices
         b = anuga.Inlet_operator(ref, shape, Q=1.0).inlet.triangle_indices
         assert np.array_equal(a, np.asarray(b, dtype=np.int64)) and len(a) > 3
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_internal_boundary_operator_equals_reference_object(seed):
+    """Internal_boundary_operator (explicit and implicit discharge, with and without smoothing / velocity head)
+    driven by a weir-like rating and by pumping_station_function: three applications == the reference's object
+    (structures/internal_boundary_operator.py, internal_boundary_functions.py:392-477)"""
+    anuga, build, rng = _pair(200 + seed)
+    from anuga.structures.internal_boundary_functions import pumping_station_function as ref_pump
+    ref, mine = build(anuga), build(ab)
+    crest = float(rng.uniform(0.02, 0.12))
+    k = float(rng.uniform(0.5, 2.0))
+
+    def weir(hw, tw):
+        head = max(hw, tw) - crest
+        if head <= 0.0:
+            return 0.0
+        sub = max(min(hw, tw) - crest, 0.0) / head
+        q = k * head ** 1.5 * (1.0 - sub ** 1.5) ** 0.385
+        return q if hw >= tw else -q
+    common = dict(width=float(rng.uniform(0.8, 2.0)), height=1.0, apron=0.55, enquiry_gap=0.4, verbose=False,
+                  force_constant_inlet_elevations=bool(rng.integers(0, 2)))
+    kw_weir = dict(compute_discharge_implicitly=bool(seed % 2), smoothing_timescale=float(rng.choice([0.0, 1.0])),
+                   use_velocity_head=bool(rng.integers(0, 2)), zero_outflow_momentum=bool(rng.integers(0, 2)))
+    ops = {}
+    for A, d, pump in ((anuga, ref, ref_pump), (ab, mine, ab.pumping_station_function)):
+        P = pump(d, pump_capacity=0.8, hw_to_start_pumping=0.3, hw_to_stop_pumping=0.1, initial_pump_rate=0.1,
+                 pump_rate_of_increase=0.7, pump_rate_of_decrease=0.9, verbose=False)
+        ops[A] = [A.Internal_boundary_operator(d, weir, end_points=[[4.3, 5.3], [9.7, 5.3]], **kw_weir, **common),
+                  A.Internal_boundary_operator(d, P, end_points=[[4.3, 2.3], [9.7, 2.3]],
+                                               compute_discharge_implicitly=False, **common)]
+    for key in ("stage", "elevation"):
+        assert np.array_equal(mine.quantities[key].centroid_values, ref.quantities[key].centroid_values), key
+    mine._dev = _HostArrays(mine)
+    t = 0.0
+    for step in range(3):
+        dt = float(rng.uniform(0.01, 0.3))
+        t += dt
+        for d in (ref, mine):
+            d.timestep = dt
+            d.yieldstep = 1.0
+            d.set_time(t)
+        for a, b in zip(ops[anuga], ops[ab]):
+            a()
+            b()
+        for key in ("stage", "xmomentum", "ymomentum"):
+            assert np.array_equal(mine.quantities[key].centroid_values, ref.quantities[key].centroid_values), (step, key)
+        for a, b in zip(ops[anuga], ops[ab]):
+            for key in ("discharge", "accumulated_flow", "delta_total_energy", "driving_energy", "smooth_Q",
+                        "smooth_delta_total_energy", "case"):
+                assert getattr(a, key) == getattr(b, key), (step, key, getattr(a, key), getattr(b, key))
+    assert ops[ab][1].accumulated_flow != 0.0      # (the weir moves water in 7 of the 8 seeds)
