@@ -79,6 +79,7 @@ class Domain:
             self.tri_full_flag[np.asarray(self.ghost_recv_dict[key][0], dtype=np.int64)] = 0
         self.number_of_full_triangles = int(self.tri_full_flag.sum()) if number_of_full_triangles is None \
             else number_of_full_triangles
+        self.number_of_full_nodes = self.number_of_nodes if number_of_full_nodes is None else number_of_full_nodes
 
         self.quantities = {}
         for name in ["stage", "xmomentum", "ymomentum", "elevation", "friction", "height", "xvelocity", "yvelocity"]:
@@ -193,12 +194,77 @@ class Domain:
         return self.timestepping_method
 
     def set_CFL(self, cfl=1.0):
+        """generic_domain.py:1069-1081: warns above 2, must be positive"""
         if cfl > 2.0:
-            raise Exception("Setting CFL condition to %g which is greater than 2 may cause instability" % cfl)
+            import warnings
+            warnings.warn("Setting CFL > 2.0")
+        assert cfl > 0.0
         self.CFL = cfl
         self._params_dirty = True
 
+    set_cfl = set_CFL
+
+    def get_CFL(self):
+        return self.CFL
+
+    get_cfl = get_CFL
+
+    def set_default_order(self, n):
+        """spatial order 1 or 2 (generic_domain.py:956-962)"""
+        assert n in [1, 2], "Default order must be either 1 or 2. I got %s" % n
+        self.default_order = n
+        self._order_ = self.default_order
+        self._params_dirty = True
+
+    def set_maximum_allowed_speed(self, maximum_allowed_speed):
+        # (any value but 0 is refused when the device handle is created: not part of the DE path)
+        self.maximum_allowed_speed = maximum_allowed_speed
+        self._params_dirty = True
+
+    def get_beta(self):
+        return self.beta
+
+    def get_minimum_allowed_height(self):
+        return self.minimum_allowed_height
+
+    def get_minimum_storable_height(self):
+        return self.minimum_storable_height
+
+    def get_evolve_max_timestep(self):
+        return self.evolve_max_timestep
+
+    def get_evolve_min_timestep(self):
+        return self.evolve_min_timestep
+
+    def get_centroid_transmissive_bc(self):
+        return self.centroid_transmissive_bc
+
+    def get_store_centroids(self):
+        return self.store_centroids
+
+    def get_algorithm_parameters(self):
+        """the parameters of the DE path that are currently set (shallow_water_domain.py:1031-1063)"""
+        return dict(minimum_allowed_height=self.minimum_allowed_height,
+                    maximum_allowed_speed=self.maximum_allowed_speed,
+                    minimum_storable_height=self.minimum_storable_height, g=self.g,
+                    optimise_dry_cells=self.optimise_dry_cells, low_froude=self.low_froude,
+                    use_sloped_mannings=self.use_sloped_mannings,
+                    compute_fluxes_method="DE", distribute_to_vertices_and_edges_method="DE",
+                    flow_algorithm=self.get_flow_algorithm(), CFL=self.get_CFL(),
+                    timestepping_method=self.get_timestepping_method(),
+                    extrapolate_velocity_second_order=self.extrapolate_velocity_second_order)
+
+    def print_algorithm_parameters(self):
+        print("#============================")
+        print("# Domain Algorithm Parameters ")
+        print("#============================")
+        parameters = self.get_algorithm_parameters()
+        for key in sorted(parameters.keys()):
+            print("# %-41s:  %s" % (key, parameters[key]))
+        print("#----------------------------")
+
     def set_beta(self, beta):
+        self.beta = beta
         self.beta_w = self.beta_uh = self.beta_vh = beta
         self.beta_w_dry = self.beta_uh_dry = self.beta_vh_dry = beta
         self._params_dirty = True
@@ -653,6 +719,104 @@ class Domain:
 
     def get_number_of_triangles(self):
         return self.number_of_triangles
+
+    # -- mesh accessors the reference forwards to its mesh (generic_domain.py:449-560, neighbour_mesh.py) ----
+    def get_number_of_full_triangles(self, *args, **kwargs):
+        return self.number_of_full_triangles
+
+    def get_full_centroid_coordinates(self, absolute=False):
+        return self.get_centroid_coordinates(absolute=absolute)[:self.number_of_full_triangles, :]
+
+    def get_full_vertex_coordinates(self, absolute=False):
+        return self.get_vertex_coordinates(absolute=absolute)[:3 * self.number_of_full_triangles, :]
+
+    def get_full_triangles(self, *args, **kwargs):
+        return self.get_triangles(*args, **kwargs)[:self.number_of_full_triangles, :]
+
+    def get_full_nodes(self, absolute=False):
+        return self.get_nodes(absolute=absolute)[:self.number_of_full_nodes, :]
+
+    def get_disconnected_triangles(self):
+        return np.reshape(np.arange(3 * self.number_of_triangles, dtype=int), (self.number_of_triangles, 3))
+
+    def get_area(self):
+        return np.sum(self.areas)
+
+    def get_radii(self):
+        return self.radii
+
+    def get_extent(self, absolute=False):
+        """xmin, xmax, ymin, ymax of the mesh"""
+        C = self.get_vertex_coordinates(absolute=absolute)
+        return np.min(C[:, 0]), np.max(C[:, 0]), np.min(C[:, 1]), np.max(C[:, 1])
+
+    def get_vertex_coordinate(self, i, j, absolute=False):
+        assert j in [0, 1, 2], "vertex id j must be an integer in [0,1,2]"
+        return self.get_vertex_coordinates(absolute=absolute)[3 * i + j, :]
+
+    def get_edge_midpoint_coordinate(self, i, j, absolute=False):
+        assert j in [0, 1, 2], "edge midpoint id j must be an integer in [0,1,2]"
+        return self.get_edge_midpoint_coordinates(absolute=absolute)[3 * i + j, :]
+
+    def get_triangle_containing_point(self, point):
+        """lowest id of a triangle that holds the point (neighbour_mesh.py:1057-1080)"""
+        from .structures import triangle_containing_point
+        return triangle_containing_point(self, point)
+
+    def get_triangles_inside_polygon(self, polygon):
+        """ids of the triangles whose centroid lies inside the polygon (neighbour_mesh.py:1083-1097)"""
+        from .compat import inside_polygon
+        return inside_polygon(self.get_centroid_coordinates(absolute=True), polygon)
+
+    def get_evolved_quantities(self, vol_id, vertex=None, edge=None):
+        """generic_domain.py:622-653; the evolved quantities of the shallow-water domain are its conserved ones"""
+        if not (vertex is None or edge is None):
+            raise Exception("Values for both vertex and edge was specified.Only one (or none) is allowed.")
+        return self.get_conserved_quantities(vol_id, vertex=vertex, edge=edge)
+
+    def get_starttime(self, datetime=False):
+        return self.get_datetime(self.starttime) if datetime else self.starttime
+
+    def get_evolve_starttime(self):
+        return self.evolve_starttime
+
+    def set_evolve_starttime(self, time):
+        self.evolve_starttime = float(time)
+        self.set_relative_time(self.evolve_starttime)
+
+    def set_timezone(self, tz=None):
+        """timezone of get_datetime: None (UTC), a tz database name or a ZoneInfo (shallow_water_domain.py:2453-2487)"""
+        from zoneinfo import ZoneInfo
+        if tz is None:
+            self.timezone = ZoneInfo("UTC")
+        elif isinstance(tz, str):
+            self.timezone = ZoneInfo(tz)
+        elif isinstance(tz, ZoneInfo):
+            self.timezone = tz
+        else:
+            raise Exception("Unknown timezone %s" % tz)
+
+    def get_timezone(self):
+        if getattr(self, "timezone", None) is None:
+            self.set_timezone()
+        return self.timezone
+
+    def get_datetime(self, timestamp=None):
+        """the model time as a datetime in the domain's timezone (shallow_water_domain.py:2496-2516)"""
+        from datetime import datetime, timezone
+        if timestamp is None:
+            timestamp = self.get_time()
+        return datetime.fromtimestamp(timestamp, timezone.utc).astimezone(self.get_timezone())
+
+    def set_institution(self, institution):
+        self.institution = institution
+
+    def evolve_to_end(self, finaltime=1.0):
+        for _ in self.evolve(yieldstep=None, finaltime=finaltime):
+            pass
+
+    def write_time(self, track_speeds=False):
+        print(self.timestepping_statistics(track_speeds))
 
     def get_number_of_nodes(self):
         return self.number_of_nodes
