@@ -557,6 +557,15 @@ class Domain:
         self.fractional_step_operators.append(operator)
         self._operators_dirty = True
 
+    def print_operator_timestepping_statistics(self):
+        """generic_domain.py:2320-2326"""
+        for operator in self.fractional_step_operators:
+            operator.print_timestepping_statistics()
+
+    def print_operator_statistics(self):
+        for operator in self.fractional_step_operators:
+            operator.print_statistics()
+
     def get_centroid_coordinates(self, absolute=False):
         return self.centroid_coordinates
 

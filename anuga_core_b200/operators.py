@@ -32,6 +32,9 @@ class Rate_operator:
         self.default_rate = default_rate
         self.default_rate_invoked = False
         self.op_id = None
+        self.description = description
+        self.label = ("rate_operator" if label is None else label) + "_%g" % len(domain.fractional_step_operators)
+        self.verbose = verbose
         domain.set_fractional_step_operator(self)
 
     @property
@@ -133,6 +136,63 @@ class Rate_operator:
 
     def current_factor(self, t):
         return float(self.factor(t)) if callable(self.factor) else float(self.factor)
+
+    def get_factor(self, t=None):
+        return self.current_factor(self.domain.get_time() if t is None else t)
+
+    def get_time(self):
+        return self.domain.get_time()
+
+    def get_timestep(self):
+        return self.domain.get_timestep()
+
+    def set_default_rate(self, default_rate):
+        """rate_operators.py:483-509"""
+        assert default_rate is None or isinstance(default_rate, (int, float)) or callable(default_rate), \
+            "Default_rate must be either None a scalar, or a function of time.\nI got %s." % str(default_rate)
+        self.default_rate = default_rate
+        self.default_rate_invoked = False
+
+    def _rates_now(self, t=None):
+        """the rate [m/s] over the operator's cells at time t (before the factor)"""
+        d = self.domain
+        t = d.get_time() if t is None else t
+        ids = np.arange(d.number_of_triangles, dtype=np.int64) if self.indices is None else self.indices
+        if self.rate_xyt is not None:
+            c = d.centroid_coordinates
+            return ids, np.asarray(self.rate_xyt(c[ids, 0], c[ids, 1], t), dtype=np.float64) * np.ones(len(ids))
+        if self.rate_array is not None:
+            return ids, self.rate_array[ids]
+        return ids, np.full(len(ids), self.current_rate(t))
+
+    def get_Q(self, full_only=True):
+        """current overall discharge [m^3/s] = sum(rate * area) * factor (rate_operators.py:444-481)"""
+        d = self.domain
+        ids, rate = self._rates_now()
+        keep = d.tri_full_flag[ids] == 1 if full_only else np.ones(len(ids), dtype=bool)
+        return np.sum(d.areas[ids][keep] * rate[keep]) * self.get_factor()
+
+    def statistics(self):
+        return "You need to implement operator statistics for your operator"
+
+    def timestepping_statistics(self):
+        """label: min and max rate over the cells and the volume of the last timestep (rate_operators.py:598-601)"""
+        from .compat import indent
+        ids, rate = self._rates_now()
+        full = self.domain.tri_full_flag[ids] == 1
+        per_second = (rate * self.get_factor())[full]
+        lo, hi = (float(np.min(per_second)), float(np.max(per_second))) if len(per_second) else (0.0, 0.0)
+        influx = float(np.sum(per_second * self.domain.areas[ids][full]) * self.domain.get_timestep())
+        return indent + self.label + ": Min rate = %g m/s, Max rate = %g m/s, Total Q = %g m^3" % (lo, hi, influx)
+
+    def print_statistics(self):
+        print(self.statistics())
+
+    def print_timestepping_statistics(self):
+        print(self.timestepping_statistics())
+
+    def set_label(self, label=None):
+        self.label = label
 
     def oracle_spec(self):
         if self.rate_xyt is not None:

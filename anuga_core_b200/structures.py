@@ -383,6 +383,31 @@ class Inlet:
         v = self.get_ymoms() * depths / (depths * depths + velocity_protection)
         return u, v
 
+    def get_xvelocities(self):
+        return self.get_velocities()[0]
+
+    def get_yvelocities(self):
+        return self.get_velocities()[1]
+
+    def get_average_speed(self):
+        u, v = self.get_velocities()
+        average_u = np.sum(u * self.get_areas()) / self.area
+        average_v = np.sum(v * self.get_areas()) / self.area
+        return math.sqrt(average_u ** 2 + average_v ** 2)
+
+    def get_average_velocity_head(self):
+        return 0.5 * self.get_average_speed() ** 2 / g
+
+    def get_average_total_energy(self):
+        return self.get_average_velocity_head() + self.get_average_stage()
+
+    def get_average_specific_energy(self):
+        return self.get_average_velocity_head() + self.get_average_depth()
+
+    def set_depths_evenly(self, volume):
+        """the volume spread as one extra depth over the region (inlet.py:230-236)"""
+        self.set_depths(self.get_average_depth() + volume / self.get_area())
+
     def set_depths(self, depth):
         self.values[:, 0] = self.get_elevations() + depth
 
@@ -446,6 +471,9 @@ class Inlet_operator:
         self.total_applied_volume = 0.0
         self.total_requested_volume = 0.0
         self.total_applied_volume = 0.0
+        self.description = " " if description is None else description
+        self.label = "inlet" if label is None else label
+        self.verbose = verbose
         domain.set_fractional_step_operator(self)
 
     def update_Q(self, t):
@@ -460,10 +488,58 @@ class Inlet_operator:
         self.Q = Q
 
     def get_Q(self):
+        return self.Q
+
+    def get_applied_Q(self):
         return self.applied_Q
+
+    def get_total_applied_volume(self):
+        return self.total_applied_volume
 
     def get_inlet(self):
         return self.inlet
+
+    def set_label(self, label):
+        self.label = label
+
+    # -- reporting (inlet_operator.py:186-233) ----------------------------------------------
+    def statistics(self):
+        inlet = self.inlet
+        message = "=====================================\n"
+        message += "Inlet Operator: %s\n" % self.label
+        message += "=====================================\n"
+        message += "Description\n"
+        message += "%s" % self.description
+        message += "\n"
+        message += "-------------------------------------\n"
+        message += "Inlet\n"
+        message += "-------------------------------------\n"
+        message += "inlet triangle indices and centres\n"
+        message += "%s" % inlet.triangle_indices
+        message += "\n"
+        message += "%s" % self.domain.get_centroid_coordinates()[inlet.triangle_indices]
+        message += "\n"
+        message += "region\n"
+        message += "%s" % inlet
+        message += "\n"
+        message += "=====================================\n"
+        return message
+
+    def print_statistics(self):
+        print(self.statistics())
+
+    def timestepping_statistics(self):
+        message = "---------------------------\n"
+        message += "Inlet report for %s:\n" % self.label
+        message += "--------------------------\n"
+        message += "Q [m^3/s]: %.2f\n" % self.applied_Q
+        message += "Total volume [m^3]: %.2f\n" % self.total_applied_volume
+        return message
+
+    def print_timestepping_statistics(self):
+        print(self.timestepping_statistics())
+
+    print_timestepping_statisitics = print_timestepping_statistics       # (the reference's spelling)
 
     def __call__(self):
         """inlet_operator.py:78-157; returns the volume added to fractional_step_volume_integral"""
@@ -609,6 +685,15 @@ class Inlet_enquiry(Inlet):
         u = depth * self.get_enquiry_xmom() / (depth ** 2 + velocity_protection)
         v = depth * self.get_enquiry_ymom() / (depth ** 2 + velocity_protection)
         return u, v
+
+    def get_enquiry_xvelocity(self):
+        return self.get_enquiry_velocity()[0]
+
+    def get_enquiry_yvelocity(self):
+        return self.get_enquiry_velocity()[1]
+
+    def get_enquiry_position(self):
+        return self.enquiry_pt
 
     def get_enquiry_speed(self):
         u, v = self.get_enquiry_velocity()
@@ -796,8 +881,182 @@ class Structure_operator:
     def get_inlets(self):
         return self.inlets
 
+    def get_culvert_diameter(self):
+        return self.diameter
+
+    def get_culvert_z1(self):
+        return self.z1
+
+    def get_culvert_z2(self):
+        return self.z2
+
+    def get_culvert_apron(self):
+        return self.apron
+
+    def get_culvert_slope(self):
+        a, b = self.inlets
+        return (b.get_enquiry_invert_elevation() - a.get_enquiry_invert_elevation()) / self.get_culvert_length()
+
+    def get_master_proc(self):
+        return 0
+
+    def _both(self, what):
+        return [getattr(i, "get_enquiry_" + what)() for i in self.inlets]
+
+    # the state of the two enquiry triangles as the last call of the structure saw it; refresh() re-reads
+    # it from the device (on a distributed domain: called by every rank)
+    def get_enquiry_stages(self):
+        return self._both("stage")
+
     def get_enquiry_depths(self):
-        return [i.get_enquiry_depth() for i in self.inlets]
+        return self._both("depth")
+
+    def get_enquiry_positions(self):
+        return self._both("position")
+
+    def get_enquiry_xmoms(self):
+        return self._both("xmom")
+
+    def get_enquiry_ymoms(self):
+        return self._both("ymom")
+
+    def get_enquiry_elevations(self):
+        return self._both("elevation")
+
+    def get_enquiry_water_depths(self):
+        return self._both("water_depth")
+
+    def get_enquiry_invert_elevations(self):
+        return self._both("invert_elevation")
+
+    def get_enquiry_velocitys(self):
+        return self._both("velocity")
+
+    def get_enquiry_xvelocitys(self):
+        return self._both("xvelocity")
+
+    def get_enquiry_yvelocitys(self):
+        return self._both("yvelocity")
+
+    def get_enquiry_speeds(self):
+        return self._both("speed")
+
+    def get_enquiry_velocity_heads(self):
+        return self._both("velocity_head")
+
+    def get_enquiry_total_energys(self):
+        return self._both("total_energy")
+
+    def get_enquiry_specific_energys(self):
+        return self._both("specific_energy")
+
+    def refresh(self):
+        """re-read both exchange regions and enquiry triangles (device -> host), e.g. before reporting at a yield"""
+        if getattr(self.domain, "_dev", None) is not None:
+            self._fetch()
+
+    # -- reporting (structure_operator.py:498-640) ------------------------------------------
+    def statistics(self):
+        message = "=====================================\n"
+        message += "Structure Operator: %s\n" % self.label
+        message += "=====================================\n"
+        message += "Structure Type: %s\n" % self.structure_type
+        message += "Description\n"
+        message += "%s" % self.description
+        if self.structure_type == "boyd_pipe":
+            message += "Culvert Diameter: %s\n" % self.diameter
+        elif self.structure_type == "boyd_box":
+            message += "Culvert  Height: %s\n" % self.height
+            message += "Culvert    Width: %s\n" % self.width
+        else:
+            message += "Culvert Height: %s\n" % self.height
+            message += "Culvert  Width: %s\n" % self.width
+            message += "Batter Slope 1: %s\n" % self.z1
+            message += "Batter Slope 2: %s\n" % self.z2
+        message += "Culvert Blockage: %s\n" % self.blockage
+        message += "No.  of  barrels: %s\n" % self.barrels
+        message += "\n"
+        for i, inlet in enumerate(self.inlets):
+            message += "-------------------------------------\n"
+            message += "Inlet %i\n" % i
+            message += "-------------------------------------\n"
+            message += "inlet triangle indices and centres and elevations\n"
+            message += "%s" % inlet.triangle_indices
+            message += "\n"
+            message += "%s" % self.domain.get_centroid_coordinates()[inlet.triangle_indices]
+            message += "\n"
+            elev = self.domain.quantities["elevation"].centroid_values[inlet.triangle_indices]
+            message += "%s" % elev
+            message += "\n"
+            if len(elev) and not np.allclose(elev.max() - elev.min(), 0.0):
+                message += "Warning: non-constant inlet elevation can cause well-balancing problems"
+            message += "region\n"
+            message += "%s" % inlet.region
+            message += "\n"
+        message += "=====================================\n"
+        return message
+
+    def print_statistics(self):
+        print(self.statistics())
+
+    def print_timestepping_statistics(self):
+        self.refresh()
+        message = "---------------------------\n"
+        message += "Structure report for %s:\n" % self.label
+        message += "--------------------------\n"
+        message += "Type: %s\n" % self.structure_type
+        for k in (0, 1):
+            inlet = self.inlets[k]
+            for what, unit in (("depth", "m"), ("speed", "m/s"), ("stage", "m"), ("elevation", "m")):
+                message += "inlets[%d]_enquiry_%s [%s]:  %.2f\n" % (k, what, unit, getattr(inlet, "get_enquiry_" + what)())
+            for what, unit in (("depth", "m"), ("speed", "m/s"), ("stage", "m"), ("elevation", "m")):
+                message += "inlets[%d]_average_%s [%s]:  %.2f\n" % (k, what, unit, getattr(inlet, "get_average_" + what)())
+            if k == 0:
+                message += "\n"
+        message += "Discharge [m^3/s]: %.2f\n" % self.discharge
+        message += "Discharge_function_value [m^3/s]: %.2f\n" % self.discharge_abs_timemean
+        message += "Velocity  [m/s]: %.2f\n" % self.velocity
+        message += "Outlet Depth  [m]: %.2f\n" % self.outlet_depth
+        message += "Accumulated Flow [m^3]: %.2f\n" % self.accumulated_flow
+        message += "Inlet Driving Energy %.2f\n" % self.driving_energy
+        message += "Delta Total Energy %.2f\n" % self.delta_total_energy
+        message += "Control at this instant: %s\n" % getattr(self, "case", "N/A")
+        print(message)
+
+    def timestepping_statistics(self):
+        """one csv row: time, discharge, its time mean since the last call, velocity, accumulated flow,
+        driving energy, head difference; the time mean starts again"""
+        message = "%.5f, " % self.domain.get_time()
+        message += "%.5f, " % self.discharge
+        message += "%.5f, " % self.discharge_abs_timemean
+        message += "%.5f, " % self.velocity
+        message += "%.5f, " % self.accumulated_flow
+        message += "%.5f, " % self.driving_energy
+        message += "%.5f" % self.delta_total_energy
+        self.discharge_abs_timemean = 0.0
+        return message
+
+    def set_label(self, label):
+        self.label = label
+
+    # used while evolving to close or resize a culvert (structure_operator.py:366-388): the rating reads culvert_*
+    def set_culvert_height(self, height):
+        self.culvert_height = height
+
+    def set_culvert_width(self, width):
+        self.culvert_width = width
+
+    def set_culvert_z1(self, z1):
+        self.culvert_z1 = z1
+
+    def set_culvert_z2(self, z2):
+        self.culvert_z2 = z2
+
+    def set_culvert_blockage(self, blockage):
+        self.culvert_blockage = blockage
+
+    def set_culvert_barrels(self, barrels):
+        self.culvert_barrels = barrels
 
     def discharge_routine(self):
         raise NotImplementedError

@@ -255,3 +255,65 @@ def test_internal_boundary_operator_equals_reference_object(seed):
                         "smooth_delta_total_energy", "case"):
                 assert getattr(a, key) == getattr(b, key), (step, key, getattr(a, key), getattr(b, key))
     assert ops[ab][1].accumulated_flow != 0.0      # (the weir moves water in 7 of the 8 seeds)
+
+
+def test_operator_reports_follow_the_reference(capsys):
+    """statistics / timestepping_statistics of the operators and the domain-level print_operator_* loops
+    (structure_operator.py:498-640, inlet_operator.py:186-233, rate_operators.py:444-481, 598-601,
+    generic_domain.py:2320-2326): same figures as the reference's objects after one application"""
+    anuga, build, rng = _pair(300)
+    ref, mine = build(anuga), build(ab)
+    ops = {}
+    for A, d in ((anuga, ref), (ab, mine)):
+        c = d.centroid_coordinates
+        ids = np.flatnonzero((c[:, 0] > 1.1) & (c[:, 0] < 3.2) & (c[:, 1] > 5.8))
+        ops[A] = [A.Rate_operator(d, rate=lambda t: 0.01 * (1.0 + t), factor=0.5, radius=2.0, center=[5.0, 3.0]),
+                  A.Inlet_operator(d, A.Region(d, indices=ids), Q=1.7, label="feed"),
+                  A.Boyd_box_operator(d, losses=1.5, width=1.2, height=0.8, end_points=[[4.3, 5.3], [9.7, 5.3]],
+                                      apron=0.55, enquiry_gap=0.4, label="box", verbose=False)]
+    mine._dev = _HostArrays(mine)
+    for d in (ref, mine):
+        d.timestep = 0.11
+        d.yieldstep = 1.0
+    keep = ref.quantities["stage"].centroid_values.copy()
+    ops[anuga][0]()          # (fills the reference's report; on the device this operator is a kernel, not a call)
+    ref.quantities["stage"].centroid_values[:] = keep
+    for a, b in zip(ops[anuga][1:], ops[ab][1:]):
+        a()
+        b()
+    ops[ab][2].refresh()     # the reference's getters read the live arrays: re-read ours from the "device"
+    rate_r, rate_m = ops[anuga][0], ops[ab][0]
+    assert np.isclose(rate_r.get_Q(), rate_m.get_Q(), rtol=1e-14) and rate_r.get_factor() == rate_m.get_factor()
+    # "label: Min rate = .., Max rate = .., Total Q = .." - the figures after the label agree
+    tail = lambda s: s.split(":", 1)[1]
+    assert tail(rate_r.timestepping_statistics()) == tail(rate_m.timestepping_statistics())
+    inl_r, inl_m = ops[anuga][1], ops[ab][1]
+    assert inl_r.get_Q() == inl_m.get_Q() == 1.7 and inl_r.get_applied_Q() == inl_m.get_applied_Q()
+    assert inl_r.get_total_applied_volume() == inl_m.get_total_applied_volume()
+    body = lambda s: s.split("\n", 3)[3]             # (after the header that carries the label's counter)
+    assert body(inl_r.timestepping_statistics()) == body(inl_m.timestepping_statistics())
+    box_r, box_m = ops[anuga][2], ops[ab][2]
+    for name in ("get_enquiry_stages", "get_enquiry_depths", "get_enquiry_xmoms", "get_enquiry_ymoms",
+                 "get_enquiry_elevations", "get_enquiry_water_depths", "get_enquiry_invert_elevations",
+                 "get_enquiry_speeds", "get_enquiry_velocity_heads", "get_enquiry_total_energys",
+                 "get_enquiry_specific_energys", "get_enquiry_xvelocitys", "get_enquiry_yvelocitys"):
+        assert np.allclose(getattr(box_r, name)(), getattr(box_m, name)(), rtol=1e-14, atol=0.0), name
+    for name in ("get_culvert_length", "get_culvert_width", "get_culvert_height", "get_culvert_apron",
+                 "get_culvert_slope", "get_culvert_blockage", "get_culvert_barrels", "get_master_proc"):
+        assert getattr(box_r, name)() == getattr(box_m, name)(), name
+    for k in (0, 1):
+        for name in ("get_average_speed", "get_average_velocity_head", "get_average_total_energy",
+                     "get_average_specific_energy"):
+            assert np.isclose(getattr(box_r.inlets[k], name)(), getattr(box_m.inlets[k], name)(), rtol=1e-13), name
+    assert box_r.timestepping_statistics() == box_m.timestepping_statistics()
+    assert box_m.discharge_abs_timemean == 0.0
+    box_r.print_timestepping_statistics()
+    out_r = capsys.readouterr().out
+    box_m.print_timestepping_statistics()
+    out_m = capsys.readouterr().out
+    assert out_r[out_r.index("Type:"):] == out_m[out_m.index("Type:"):]
+    upto = lambda s: body(s)[:body(s).index("region")]           # (then the Region objects print themselves)
+    assert upto(box_r.statistics()) == upto(box_m.statistics())
+    mine.print_operator_timestepping_statistics()
+    mine.print_operator_statistics()
+    assert "Inlet report for feed" in capsys.readouterr().out
