@@ -481,6 +481,9 @@ def main():
                                    "achieved_gbs": value / world * STEP_BYTES[alg] / 1e9,
                                    "frac_of_peak": value / world * STEP_BYTES[alg] / 1e9 / peak,
                                    "frac_of_8TBs": value / world * STEP_BYTES[alg] / 8.0e12},
+                    # halo pack / unpack, NCCL send / recv / allreduce waits, clock kernels and launch gaps: what the
+                    # step spends outside the four hot kernels (at N > 1 mostly waiting for the slowest rank)
+                    "outside_hot_kernels_ms_per_step": ms / a.steps - sum(t for t, n in ktime.values() if n > 0) / k_steps,
                     "kernels": kernels}
     line = {"metric": METRIC if alg == "DE1" else "triangle-steps/sec (%s, FP64)" % alg, "value": value,
             "unit": "triangle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
