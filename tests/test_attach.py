@@ -174,3 +174,49 @@ def test_real_reference_domain_on_the_device_equals_mode_2(name):
             e = rel_err(gpu.quantities[q].centroid_values, cpu.quantities[q].centroid_values)
             assert e <= 1e-9, (q, e)
     assert iface.dev_domain._dev.kernel_launch_count() > 0
+
+
+def _weir_rating(hw, tw):
+    head = max(hw, tw) - 0.3
+    if head <= 0.0:
+        return 0.0
+    sub = max(min(hw, tw) - 0.3, 0.0) / head
+    q = 1.2 * head ** 1.5 * (1.0 - sub ** 1.5) ** 0.385
+    return q if hw >= tw else -q
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyref.available(), reason="python reference not built (oracle/build_pyref.py -> baseline/_ref)")
+@pytest.mark.parametrize("implicit", [False, True])
+def test_internal_boundary_structures_on_the_device_equal_the_reference(implicit):
+    """Internal_boundary_operator with a weir rating and with a pumping station
+    (structures/internal_boundary_operator.py, internal_boundary_functions.py:392-477): this package's Domain
+    on the device next to the reference's Domain in mode 2, same process, two ponds and a dry embankment."""
+    anuga = pyref.import_anuga()
+    from anuga.structures.internal_boundary_functions import pumping_station_function as ref_pump
+
+    def build(A, pump):
+        d = cases._embankment(A)
+        A.Internal_boundary_operator(d, _weir_rating, width=1.5, height=1.0, end_points=[[6.1, 8.3], [9.9, 8.3]],
+                                     apron=0.55, enquiry_gap=0.4, smoothing_timescale=0.5,
+                                     compute_discharge_implicitly=implicit, verbose=False)
+        P = pump(d, pump_capacity=0.6, hw_to_start_pumping=0.5, hw_to_stop_pumping=0.3, initial_pump_rate=0.0,
+                 pump_rate_of_increase=0.4, pump_rate_of_decrease=0.4, verbose=False)
+        A.Internal_boundary_operator(d, P, width=1.0, height=1.0, end_points=[[6.1, 3.3], [9.9, 3.3]],
+                                     apron=0.55, enquiry_gap=0.4, compute_discharge_implicitly=False, verbose=False)
+        return d
+    cpu = build(anuga, ref_pump)
+    cpu.set_multiprocessor_mode(2)
+    gpu = build(ab, ab.pumping_station_function)
+    tc = [t for t in cpu.evolve(yieldstep=1.0, finaltime=4.0)]
+    tg = [t for t in gpu.evolve(yieldstep=1.0, finaltime=4.0)]
+    assert tc == tg
+    for q in ("stage", "xmomentum", "ymomentum"):
+        e = rel_err(gpu.quantities[q].centroid_values, cpu.quantities[q].centroid_values)
+        assert e <= 1e-9, (q, e)
+    structures = lambda d: [op for op in d.fractional_step_operators if hasattr(op, "accumulated_flow")]
+    assert len(structures(cpu)) == len(structures(gpu)) == 2
+    for a, b in zip(structures(cpu), structures(gpu)):
+        assert abs(a.accumulated_flow - b.accumulated_flow) <= 1e-9 * max(1.0, abs(a.accumulated_flow))
+        assert a.accumulated_flow > 0.05
+    assert gpu._dev.kernel_launch_count() > 0
