@@ -738,9 +738,6 @@ class Structure_operator:
         sub = None
         if is_distributed(domain):
             # build on the gathered patch around the culvert (identical on every rank), localise below
-            if force_constant_inlet_elevations:
-                raise NotImplementedError("force_constant_inlet_elevations on a distributed domain: set it before "
-                                          "distribute()")
             sub = domain
             reach = 2.0 * sum(abs(float(v)) for v in (width, height, diameter, apron, enquiry_gap) if v is not None)
             lo, hi = _bbox(end_points, exchange_lines, enquiry_points)
@@ -808,8 +805,15 @@ class Structure_operator:
                 inlet = self.inlets[-1]
                 z = domain.quantities["elevation"]
                 ids = inlet.triangle_indices
-                z.centroid_values[ids] = np.sum(z.centroid_values[ids] * inlet.areas) / inlet.area
+                level = np.sum(z.centroid_values[ids] * inlet.areas) / inlet.area
+                z.centroid_values[ids] = level
                 z.host_dirty = True
+                if sub is not None:
+                    # distributed: the same level on this rank's copies (full and ghost) of those triangles
+                    here = np.flatnonzero(np.isin(np.asarray(sub.tri_l2s, dtype=np.int64), domain.seq_ids[ids]))
+                    zs = sub.quantities["elevation"]
+                    zs.centroid_values[here] = level
+                    zs.host_dirty = True
         self.inflow, self.outflow = self.inlets
         if sub is None:
             domain.set_fractional_step_operator(self)

@@ -202,13 +202,16 @@ def add_ops(d):
                          apron=0.55, enquiry_gap=0.4)
     ab.Boyd_pipe_operator(d, losses=1.2, diameter=0.6, exchange_lines=[[[4.6, 4.4], [4.6, 5.3]], [[7.4, 4.6], [7.4, 5.4]]],
                           enquiry_points=[[3.9, 4.9], [8.1, 5.0]], smoothing_timescale=2.0)
+    # (levels the bed of its two exchange regions: force_constant_inlet_elevations is its default)
+    ab.Internal_boundary_operator(d, lambda hw, tw: 0.8 * (hw - tw), width=1.1, end_points=[[4.4, 1.2], [7.6, 1.2]],
+                                  apron=0.5, enquiry_gap=0.3, smoothing_timescale=1.0, verbose=False)
 
 subA = P.distribute(build2(True), size, ranks=[rank])[rank]          # sequential construction, localised
 subA.attach_communicator(comm)
 subB = P.distribute(build2(False), size, ranks=[rank])[rank]         # ... vs construction on the sub-domain
 subB.attach_communicator(comm)
 add_ops(subB)
-assert len(subA.fractional_step_operators) == len(subB.fractional_step_operators) == 4
+assert len(subA.fractional_step_operators) == len(subB.fractional_step_operators) == 5
 for a, b in zip(subA.fractional_step_operators, subB.fractional_step_operators):
     assert type(a) is type(b)
     for ia, ib in zip(getattr(a, "inlets", None) or [a.inlet], getattr(b, "inlets", None) or [b.inlet]):
@@ -222,8 +225,10 @@ for s_ in (subA, subB):
     s_._dev = HostArrays(s_); s_.timestep = 0.05; s_.yieldstep = 1.0
     for op in s_.fractional_step_operators:
         op()
-for k in ("stage", "xmomentum", "ymomentum"):
+for k in ("stage", "xmomentum", "ymomentum", "elevation"):
     assert np.array_equal(subA.quantities[k].centroid_values, subB.quantities[k].centroid_values), k
+assert comm.allreduce_sum(float(np.sum(subB.quantities["elevation"].centroid_values
+                                       != P.distribute(build2(False), size, ranks=[rank])[rank].quantities["elevation"].centroid_values))) > 4
 
 # anuga.distribute as the reference's parallel scripts use it: rank 0 holds the sequential domain
 def plain():
