@@ -134,6 +134,30 @@ def test_cuda_equals_reference_c_code_on_random_scenarios(seed):
     assert e <= TOL_FINAL, e
 
 
+@pytest.mark.parametrize("k", list(range(6)))
+def test_cuda_equals_reference_c_code_on_edge_cases(k):
+    """the smallest and the degenerate inputs (1 x 1 mesh = 4 triangles all on the boundary, one-cell-wide strips,
+    a dry bed with and without rain, stage below the bed; tests/test_oracle.py::_edge_case_domain, pinned there
+    against the live Python reference): device time loop vs the reference's C code - same timestep sequence,
+    state within the north_star tolerance"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "toracle", os.path.join(os.path.dirname(os.path.abspath(__file__)), "test_oracle.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    ev = dict(yieldstep=0.25, finaltime=0.75)
+    d = m._edge_case_domain(ab, k)
+    o = OracleDomain(domain_to_scenario(m._edge_case_domain(ab, k)), backend=REF)
+    d.record_timestep_history = True
+    tg = [t for t in d.evolve(**ev)]
+    to = [t for t in o.evolve(**ev)]
+    assert tg == to
+    assert d.total_steps == len(o.timestep_history) and d.timestep == o.timestep
+    w, uh, vh = conserved(d)
+    e = max(rel_err(w, o.stage_c), rel_err(uh, o.xmom_c), rel_err(vh, o.ymom_c))
+    assert e <= TOL_FINAL, e
+
+
 @pytest.mark.parametrize("name", ["dam_break_de1", "beach_de1", "rain_de1", "inlet_de1", "culvert_de1",
                                   "tsunami_set_stage"])
 def test_volume_balance(name):

@@ -201,6 +201,73 @@ def test_oracle_equals_live_python_reference_on_random_scenarios(oracle_libs, se
     assert np.array_equal(o.ymom_c, q["ymomentum"].centroid_values)
 
 
+EDGE_CASES = 6
+
+
+def _edge_case_domain(A, k):
+    """the smallest and the degenerate inputs: a 1 x 1 mesh (4 triangles, every one on the boundary), strips one
+    cell wide, a completely dry bed with and without rain, stage below the bed, more triangles than a block holds
+    by one row"""
+    m, n, alg = [(1, 1, "DE1"), (1, 1, "DE0"), (2, 1, "DE1"), (3, 2, "DE1"), (5, 3, "DE2"), (1, 3, "DE1_7")][k]
+    d = A.rectangular_cross_domain(m, n, len1=float(m), len2=float(n))
+    d.set_flow_algorithm(alg)
+    d.set_store(False)
+    d.set_quantity("elevation", lambda x, y: 0.1 * x - 0.05 * y)
+    d.set_quantity("friction", 0.03)
+    Br = A.Reflective_boundary(d)
+    bmap = {t: Br for t in d.get_boundary_tags()}
+    if k == 0:
+        d.set_quantity("stage", lambda x, y: 0.5 + 0.2 * x, location="centroids")
+    elif k == 1:
+        d.set_quantity("stage", 0.4, location="centroids")
+        bmap["left"] = A.Dirichlet_boundary([0.7, 0.1, 0.0])
+    elif k == 2:         # dry bed, rain wets it
+        d.set_quantity("stage", expression="elevation")
+        A.Rate_operator(d, rate=0.05)
+    elif k == 3:         # dry bed, nothing happens: the timestep is the maximal one, clipped by the yieldstep
+        d.set_quantity("stage", expression="elevation")
+    elif k == 4:         # stage below the bed in places (protect raises it), open boundaries
+        d.set_quantity("stage", lambda x, y: 0.15 + 0.0 * x - 0.1 * (y > 1.5), location="centroids")
+        bmap["right"] = A.Transmissive_boundary(d)
+        bmap["top"] = A.Transmissive_stage_zero_momentum_boundary(d)
+    else:
+        d.set_quantity("stage", lambda x, y: 0.3 + 0.1 * y, location="centroids")
+        d.set_quantity("ymomentum", 0.05, location="centroids")
+        bmap["top"] = A.Transmissive_stage_zero_momentum_boundary(d)
+    d.set_boundary(bmap)
+    return d
+
+
+@pytest.mark.parametrize("k", list(range(EDGE_CASES)))
+def test_oracle_equals_live_python_reference_on_edge_cases(oracle_libs, k):
+    """the pin on the smallest / degenerate inputs: the unmodified Python reference in this process and the oracle,
+    bit for bit (timestep sequence and state)"""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("python reference not built (oracle/build_pyref.py)")
+    anuga = pyref.import_anuga()
+    ref = _edge_case_domain(anuga, k)
+    ref.set_multiprocessor_mode(2)
+    ev = dict(yieldstep=0.25, finaltime=0.75)
+    dts = []
+    orig = ref.apply_fractional_steps
+
+    def hook():
+        orig()
+        dts.append(ref.timestep)
+    ref.apply_fractional_steps = hook
+    for _ in ref.evolve(**ev):
+        pass
+    o = OracleDomain(domain_to_scenario(_edge_case_domain(ab, k)), backend="port")
+    for _ in o.evolve(**ev):
+        pass
+    assert np.array_equal(np.array(o.timestep_history), np.array(dts)), (o.timestep_history, dts)
+    q = ref.quantities
+    assert np.array_equal(o.stage_c, q["stage"].centroid_values)
+    assert np.array_equal(o.xmom_c, q["xmomentum"].centroid_values)
+    assert np.array_equal(o.ymom_c, q["ymomentum"].centroid_values)
+
+
 import merimbula_case  # noqa: E402
 
 
