@@ -36,7 +36,8 @@ def read_sww_series(filename, quantity_names):
             time=np.array(fid.variables["time"][:], dtype=np.float64),
             x=np.array(fid.variables["x"][:], dtype=np.float64),
             y=np.array(fid.variables["y"][:], dtype=np.float64),
-            triangles=np.array(fid.variables["volumes"][:], dtype=np.int64),
+            triangles=(np.array(fid.variables["volumes"][:], dtype=np.int64) if "volumes" in fid.variables
+                       else None),          # STS files (time series at the gauges of a boundary) have no mesh
         )
         for name in quantity_names:
             if name not in fid.variables:
@@ -95,13 +96,68 @@ def barycentric_weights(vertex_coordinates, triangles, points):
     return found, sig
 
 
+def interpolate_polyline(data, polyline_nodes, gauge_neighbour_id, interpolation_points, rtol=1.0e-6, atol=1.0e-8):
+    """Values at points that lie on the polyline through the gauges: linear between a gauge and its neighbour,
+    0 for points on no segment (geometry/polygon.py:1069-1130, polygon.c:269-317)."""
+    from .cross_section import point_on_line
+    data = np.asarray(data, dtype=np.float64)
+    nodes = np.asarray(polyline_nodes, dtype=np.float64)
+    pts = np.asarray(interpolation_points, dtype=np.float64)
+    nb = np.asarray(gauge_neighbour_id, dtype=np.int64)
+    assert data.shape[0] == nodes.shape[0], "function value must be specified at every interpolation node"
+    assert data.shape[0] > 0, "Must define function value at one or more nodes"
+    if nodes.shape[0] == 1:
+        raise Exception("Polyline contained only one point. I need more. " + str(data))
+    out = np.zeros(len(pts), dtype=np.float64)
+    for j in range(nodes.shape[0]):
+        k = int(nb[j])
+        if k < 0:
+            continue
+        x0, y0 = float(nodes[j, 0]), float(nodes[j, 1])
+        x1, y1 = float(nodes[k, 0]), float(nodes[k, 1])
+        segment_len = np.sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0))
+        slope = (data[k] - data[j]) / segment_len
+        for i in range(len(pts)):
+            x, y = float(pts[i, 0]), float(pts[i, 1])
+            if point_on_line(x, y, x0, y0, x1, y1, rtol, atol):
+                alpha = np.sqrt((x - x0) * (x - x0) + (y - y0) * (y - y0))
+                out[i] = slope * alpha + data[j]
+    return out
+
+
+def gauges_on_boundary(vertex_coordinates, boundary_polygon):
+    """Which STS gauges are vertices of the boundary polygon, in the polygon's order, and for each the next gauge
+    along the boundary or -1 (file_function.py:378-418).  -> gauge ids, their coordinates (the polygon's),
+    neighbour ids."""
+    V = np.asarray(vertex_coordinates, dtype=np.float64)
+    P = np.asarray(boundary_polygon, dtype=np.float64)
+    temp, boundary_id, gauge_id = [], [], []
+    for i in range(len(P)):
+        close = np.all(np.abs(V - P[i]) <= 1e-4 + 1e-4 * np.abs(P[i]), axis=1)      # numpy.allclose(V[j], P[i])
+        hit = np.flatnonzero(close)
+        if len(hit):
+            temp.append(P[i])
+            gauge_id.append(int(hit[0]))
+            boundary_id.append(i)
+    if len(temp) == 0:
+        raise Exception("None of the sts gauges fall on the boundary")
+    neighbour = []
+    for i in range(len(boundary_id) - 1):
+        neighbour.append(i + 1 if boundary_id[i] + 1 == boundary_id[i + 1] else -1)
+    neighbour.append(0 if boundary_id[-1] == len(P) - 1 and boundary_id[0] == 0 else -1)
+    neighbour = np.asarray(neighbour, dtype=np.int64)
+    if int(np.sum(neighbour >= 0)) != len(temp) - 1:
+        raise Exception("incorrect number of segments")
+    return np.asarray(gauge_id, dtype=np.int64), np.asarray(temp, dtype=np.float64), neighbour
+
+
 class Interpolation_function:
     """f(t, point_id): frames of nodal values -> values at fixed points, linear in time
     (fit_interpolate/interpolate.py:710-1110, the spatial-with-interpolation-points use), or - without
     vertex_coordinates - f(t): a plain time series with several attributes (TMS files)."""
 
     def __init__(self, time, quantities, quantity_names, vertex_coordinates=None, triangles=None,
-                 interpolation_points=None, time_thinning=1):
+                 interpolation_points=None, time_thinning=1, gauge_neighbour_id=None):
         time = np.asarray(time, dtype=np.float64)
         if not np.all(time[1:] - time[:-1] >= 0):
             raise Exception("Time must be a monotonuosly increasing sequence %s" % time)
@@ -119,6 +175,21 @@ class Interpolation_function:
             return
         self.interpolation_points = np.asarray(interpolation_points, dtype=np.float64)
         self.spatial = True
+        if triangles is None:
+            # STS: values along the polyline of gauges (interpolate.py:985-994)
+            self.indices_outside_mesh = np.zeros(0, dtype=np.int64)
+            self.precomputed_values = {}
+            for name in self.quantity_names:
+                Q = np.asarray(quantities[name])
+                if Q.ndim == 2:
+                    Q = np.array(Q[::time_thinning, :])
+                frames = Q if Q.ndim == 2 else np.broadcast_to(Q, (len(self.time),) + Q.shape)
+                out = np.zeros((len(self.time), len(self.interpolation_points)))
+                for i in range(len(self.time)):
+                    out[i] = interpolate_polyline(np.asarray(frames[i], dtype=np.float64), vertex_coordinates,
+                                                  gauge_neighbour_id, self.interpolation_points)
+                self.precomputed_values[name] = out
+            return
         tri, sig = barycentric_weights(vertex_coordinates, triangles, self.interpolation_points)
         self.indices_outside_mesh = np.flatnonzero(tri < 0)
         T = np.asarray(triangles, dtype=np.int64)
@@ -192,14 +263,21 @@ def file_function(filename, domain=None, quantities=None, interpolation_points=N
     file starts later."""
     if filename.endswith(".tms"):
         return _tms_function(filename, domain, quantities, time_thinning, time_limit)
-    if not filename.endswith(".sww"):
-        raise NotImplementedError("file_function: SWW and TMS files are supported (got %s)" % filename)
-    if boundary_polygon is not None:
+    sts = filename.endswith(".sts")
+    if not (filename.endswith(".sww") or sts):
+        raise NotImplementedError("file_function: SWW, STS and TMS files are supported (got %s)" % filename)
+    if boundary_polygon is not None and not sts:
         raise NotImplementedError("boundary_polygon applies to STS files only")
+    if sts and boundary_polygon is None:
+        raise Exception("Files of type sts require boundary polygon")
     if interpolation_points is None:
-        raise NotImplementedError("file_function on an SWW file needs interpolation_points")
+        raise NotImplementedError("file_function on an SWW / STS file needs interpolation_points")
     names = list(quantities) if quantities is not None else ["stage", "xmomentum", "ymomentum"]
     src = read_sww_series(filename, names)
+    if sts and src["triangles"] is not None:
+        raise Exception("Files of type STS must not carry a mesh")
+    if not sts and src["triangles"] is None:
+        raise Exception("Files of type SWW must contain spatial information")
     starttime = src["starttime"]
     time = src["time"]
     upper = len(time)
@@ -219,8 +297,17 @@ def file_function(filename, domain=None, quantities=None, interpolation_points=N
     if domain_starttime is not None and domain_starttime > starttime:
         time = time - domain_starttime + starttime
     vertex_coordinates = np.stack([src["x"], src["y"]], axis=1)
-    F = Interpolation_function(time, {n: src[n][:upper] for n in names}, names, vertex_coordinates,
-                               src["triangles"], pts, time_thinning=time_thinning)
+    if sts:
+        poly = np.array(boundary_polygon, dtype=np.float64)
+        poly[:, 0] -= src["xllcorner"]
+        poly[:, 1] -= src["yllcorner"]
+        gauge_id, vertex_coordinates, neighbour = gauges_on_boundary(vertex_coordinates, poly)
+        F = Interpolation_function(time, {n: np.take(src[n][:upper], gauge_id, axis=1) for n in names}, names,
+                                   vertex_coordinates, None, pts, time_thinning=time_thinning,
+                                   gauge_neighbour_id=neighbour)
+    else:
+        F = Interpolation_function(time, {n: src[n][:upper] for n in names}, names, vertex_coordinates,
+                                   src["triangles"], pts, time_thinning=time_thinning)
     F.starttime = starttime
     if domain is not None and starttime > domain.starttime:
         domain.set_starttime(starttime)
